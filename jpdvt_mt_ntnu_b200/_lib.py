@@ -1,0 +1,135 @@
+"""ctypes binding of libjpdvt_sm100.so (C ABI declared in include/jpdvt_b200.h).
+
+There is NO fallback: if the shared library is missing and cannot be built, or the device is not sm_100, every entry
+point raises.  Non-zero C status codes become RuntimeError carrying jpdvt_last_error_string(), which keeps the
+reference callers' `try/except Exception` per-image behaviour (image_model/inference.py:257,367-370).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjpdvt_sm100.so")
+
+c_void_p, c_int, c_int64, c_double = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+
+class JpdvtError(RuntimeError):
+    pass
+
+
+class Weights(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("tokens", C.c_int32), ("image_size", C.c_int32), ("reserved", C.c_int32)] + [
+        (n, c_void_p) for n in (
+            "w_patch", "b_embed", "w_in_t", "pos", "t_w0", "t_b0", "t_w2", "t_b2", "w_ada", "b_ada",
+            "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+            "w_final", "b_final", "w_head1", "b_head1", "w_head2", "b_head2")]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cond_rows", C.c_int32), ("reserved", C.c_int32)] + [
+        (n, c_void_p) for n in ("x", "xn", "qkv", "attn", "hid", "y", "y32", "c", "silu_c", "silu_c_bf16", "mod")]
+
+
+class Sampler(C.Structure):
+    _fields_ = [("num_steps", C.c_int32), ("chain", C.c_int32)] + [
+        (n, c_void_p) for n in ("step_ids", "timestep_map", "coef1", "coef2", "logvar", "step_noise")] + [
+        ("step_noise_stride", C.c_int64)] + [(n, c_void_p) for n in ("x0", "sample", "traj_x0", "traj_sample")]
+
+
+P = c_void_p
+# name -> argument types (all return int status); kept in one table so tests can check it against the header
+PROTOTYPES = {
+    "jpdvt_device_check": [],
+    "jpdvt_ln_modulate_fwd": [P, P, P, c_int64, P, c_int64, c_int, P],
+    "jpdvt_gemm_bias": [P, P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_gemm_bias_f32": [P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_gemm_bias_gelu": [P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_gemm_bias_gate_residual": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
+    "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
+    "jpdvt_attention_fwd": [P, P, c_int, c_int, P],
+    "jpdvt_patchify": [P, P, c_int, c_int, P],
+    "jpdvt_unpatchify": [P, P, c_int, c_int, P],
+    "jpdvt_timestep_embed": [P, c_int, P, P, P, P, P, P, P, P, P],
+    "jpdvt_adaln_table": [P, c_int, P, P, P, c_int, P],
+    "jpdvt_posterior_step": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, P],
+    "jpdvt_ddim_step": [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, P],
+    "jpdvt_q_sample": [P, P, P, P, P, P, P, c_int64, c_int64, P],
+    "jpdvt_assign_from_scores": [P, c_int, c_int, c_double, P, P, P],
+    "jpdvt_assign_greedy_l1": [P, P, c_int, c_int, c_int, c_double, P, P, P, P],
+    "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
+    "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
+}
+OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string"]
+
+_lock = threading.Lock()
+_lib = None
+_device_ok = False
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the library (building it in-tree first when sources changed and nvcc is present)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if build_if_missing:
+            from . import build as _build
+            try:
+                if _build.needs_build():
+                    _build.build()
+            except Exception as e:  # no nvcc on this box: fall through to the prebuilt file, else fail loudly
+                if not os.path.exists(LIB_PATH):
+                    raise JpdvtError(f"libjpdvt_sm100.so is missing and could not be built: {e}") from e
+        if not os.path.exists(LIB_PATH):
+            raise JpdvtError(f"{LIB_PATH} not found - run `python -m jpdvt_mt_ntnu_b200.build` (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        lib.jpdvt_abi_version.restype = c_int
+        lib.jpdvt_last_error_string.restype = C.c_char_p
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    return load().jpdvt_last_error_string().decode("utf-8", "replace")
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise JpdvtError(f"{what} failed (status {status}): {last_error()}")
+
+
+def require_device() -> C.CDLL:
+    """Library handle, after verifying a B200-class device is current.  Raises otherwise (no CPU path)."""
+    global _device_ok
+    lib = load()
+    if not _device_ok:
+        import torch
+        if not torch.cuda.is_available():
+            raise JpdvtError("jpdvt_mt_ntnu_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        check(lib.jpdvt_device_check(), "jpdvt_device_check")
+        _device_ok = True
+    return lib
+
+
+def ptr(t) -> int:
+    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise JpdvtError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise JpdvtError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

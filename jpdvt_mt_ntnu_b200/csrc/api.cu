@@ -1,0 +1,319 @@
+// C ABI of libjpdvt_sm100.so (see include/jpdvt_b200.h) + the launch sequences for one denoiser forward and for the
+// whole reverse-diffusion loop.  Host code here only validates arguments and enqueues kernels on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/jpdvt_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jp {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(kErrCuda, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  return kOk;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(in)[i];
+}
+
+static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows, int n_mod, cudaStream_t st) {
+  if (rows <= 8) {
+    return launch_adaln_gemv(ws->silu_c, rows, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod, n_mod, st);
+  }
+  // many distinct conditioning rows (training / per-sample timesteps): tensor-core GEMM over bf16 silu(c)
+  const long long n = static_cast<long long>(rows) * kHidden;
+  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws->silu_c, reinterpret_cast<__nv_bfloat16*>(ws->silu_c_bf16), n);
+  int rc = check_launch("cast_bf16_kernel");
+  if (rc != kOk) return rc;
+  GemmParams p{};
+  p.M = rows; p.N = n_mod; p.K = kHidden; p.tokens = 1;
+  p.bias = w->b_ada; p.out = ws->mod; p.ldo = n_mod;
+  return launch_gemm(EPI_BIAS_F32, reinterpret_cast<const __nv_bfloat16*>(ws->silu_c_bf16), kHidden,
+                     reinterpret_cast<const __nv_bfloat16*>(w->w_ada), kHidden, p, st);
+}
+
+static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const float* img, const int64_t* t,
+                        const int32_t* step_ptr, const int32_t* map, const float* x_t, float* te_out, float* img_out,
+                        int batch, cudaStream_t st) {
+  if (w == nullptr || ws == nullptr) return set_error(kErrBadArg, "forward: null weights/workspace");
+  if (batch <= 0) return kOk;
+  const int T = w->tokens, depth = w->depth, S = w->image_size;
+  if (T != (S / 16) * (S / 16) || S % 16 != 0) return set_error(kErrBadArg, "forward: tokens %d do not match image size %d", T, S);
+  const long long M = static_cast<long long>(batch) * T;
+  if (M > ws->rows) return set_error(kErrBadArg, "forward: workspace holds %lld rows, need %lld", (long long)ws->rows, M);
+  if (M > 0x7fffffffLL) return set_error(kErrUnsupported, "forward: %lld token rows exceed the 32-bit tile index", M);
+  const int cond_rows = (t != nullptr) ? batch : 1;
+  if (cond_rows > ws->cond_rows) return set_error(kErrBadArg, "forward: workspace holds %d conditioning rows, need %d", ws->cond_rows, cond_rows);
+  if (img_out != nullptr && ws->y32 == nullptr) return set_error(kErrBadArg, "forward: image output requested but workspace.y32 is null");
+  const int n_mod = depth * 6 * kHidden + 2 * kHidden;
+  const long long mod_stride = (t != nullptr) ? n_mod : 0;
+  typedef const __nv_bfloat16* bfp;
+  int rc;
+#define JP_TRY(expr) do { rc = (expr); if (rc != kOk) return rc; } while (0)
+
+  // embeddings: x = patch_embed(img) + time_emb_in(x_t) + pos_embed       (models.py:280-281)
+  __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+  JP_TRY(launch_patchify(img, cols, batch, S, st));
+  {
+    GemmParams p{};
+    p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
+    p.bias = w->b_embed; p.out = ws->x; p.ldo = kHidden;
+    p.xt = x_t; p.w_in_t = w->w_in_t; p.pos = w->pos;
+    JP_TRY(launch_gemm(EPI_PATCH_EMBED_F32, cols, kHidden, reinterpret_cast<bfp>(w->w_patch), kHidden, p, st));
+  }
+  // conditioning: c = t_embedder(t); all 13 adaLN linears at once            (models.py:282-284,119,134)
+  JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), cond_rows, step_ptr, map, w->t_w0, w->t_b0, w->t_w2,
+                               w->t_b2, ws->c, ws->silu_c, st));
+  JP_TRY(adaln_all(w, ws, cond_rows, n_mod, st));
+
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws->xn);
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
+  __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws->attn);
+  __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+  for (int i = 0; i < depth; ++i) {
+    const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
+    // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120)
+    JP_TRY(launch_ln_modulate(ws->x, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    {
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
+      p.bias = w->b_qkv + static_cast<long long>(i) * 3 * kHidden; p.out = qkv; p.ldo = 3 * kHidden;
+      JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden, kHidden, p, st));
+    }
+    JP_TRY(launch_attention(qkv, att, batch, T, st));
+    {
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
+      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = ws->x; p.resid = ws->x; p.ldo = kHidden;
+      p.gate = mod + 2 * kHidden; p.gate_stride = mod_stride;
+      JP_TRY(launch_gemm(EPI_GATE_RESID_F32, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
+    }
+    // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
+    JP_TRY(launch_ln_modulate(ws->x, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
+    {
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
+      p.bias = w->b_fc1 + static_cast<long long>(i) * 4 * kHidden; p.out = hid; p.ldo = 4 * kHidden;
+      JP_TRY(launch_gemm(EPI_BIAS_GELU_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden, kHidden, p, st));
+    }
+    {
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = kHidden; p.K = 4 * kHidden; p.tokens = T;
+      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = ws->x; p.resid = ws->x; p.ldo = kHidden;
+      p.gate = mod + 5 * kHidden; p.gate_stride = mod_stride;
+      JP_TRY(launch_gemm(EPI_GATE_RESID_F32, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
+    }
+  }
+  // final layer + position head                                            (models.py:287-290)
+  {
+    const float* mod = ws->mod + static_cast<long long>(depth) * 6 * kHidden;   // shift, scale
+    JP_TRY(launch_ln_modulate(ws->x, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    GemmParams p{};
+    p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
+    p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
+    p.out2 = (img_out != nullptr) ? ws->y32 : nullptr;
+    JP_TRY(launch_gemm(EPI_BIAS_BF16_F32, xn, kHidden, reinterpret_cast<bfp>(w->w_final), kHidden, p, st));
+    GemmParams h{};
+    h.M = static_cast<int>(M); h.N = 64; h.K = kHidden; h.tokens = T;
+    h.bias = w->b_head1; h.out = te_out; h.ldo = kLatent; h.w2 = w->w_head2; h.b2 = w->b_head2;
+    JP_TRY(launch_gemm(EPI_HEAD, reinterpret_cast<bfp>(ws->y), kHidden, reinterpret_cast<bfp>(w->w_head1), kHidden, h, st));
+    if (img_out != nullptr) JP_TRY(launch_unpatchify(ws->y32, img_out, batch, S, st));   // models.py:291
+  }
+#undef JP_TRY
+  return kOk;
+}
+
+}  // namespace jp
+
+using namespace jp;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFM(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" {
+
+int jpdvt_abi_version(void) { return JPDVT_ABI_VERSION; }
+const char* jpdvt_last_error_string(void) { return g_err; }
+
+int jpdvt_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(kErrCuda, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) return set_error(kErrUnsupported, "device %d is sm_%d%d; libjpdvt_sm100 only runs on sm_100 (B200)", dev, major, minor);
+  return kOk;
+}
+
+int jpdvt_ln_modulate_fwd(const float* x, const float* shift, const float* scale, int64_t mod_stride, jpdvt_bf16* y,
+                          int64_t rows, int tokens, void* stream) {
+  if (!x || !shift || !scale || !y) return set_error(kErrBadArg, "ln_modulate: null pointer");
+  return launch_ln_modulate(x, shift, scale, mod_stride, BFM(y), rows, tokens, ST(stream));
+}
+
+static int gemm_simple(int epi, const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, void* out, float* out2,
+                       int64_t m, int n, int k, void* stream) {
+  if (!a || !w || !bias || !out) return set_error(kErrBadArg, "gemm: null pointer");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = 1;
+  p.bias = bias; p.out = out; p.ldo = n; p.out2 = out2;
+  return launch_gemm(epi, BF(a), k, BF(w), k, p, ST(stream));
+}
+
+int jpdvt_gemm_bias(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, jpdvt_bf16* out, float* out_f32_or_null,
+                    int64_t m, int n, int k, void* stream) {
+  return gemm_simple(out_f32_or_null ? EPI_BIAS_BF16_F32 : EPI_BIAS_BF16, a, w, bias, out, out_f32_or_null, m, n, k, stream);
+}
+int jpdvt_gemm_bias_f32(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, float* out, int64_t m, int n, int k,
+                        void* stream) {
+  return gemm_simple(EPI_BIAS_F32, a, w, bias, out, nullptr, m, n, k, stream);
+}
+int jpdvt_gemm_bias_gelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, jpdvt_bf16* out, int64_t m, int n,
+                         int k, void* stream) {
+  return gemm_simple(EPI_BIAS_GELU_BF16, a, w, bias, out, nullptr, m, n, k, stream);
+}
+int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                  int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream) {
+  if (!a || !w || !bias || !gate || !x) return set_error(kErrBadArg, "gemm_gate_residual: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_gate_residual: tokens must be positive");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
+  p.bias = bias; p.out = x; p.resid = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
+  return launch_gemm(EPI_GATE_RESID_F32, BF(a), k, BF(w), k, p, ST(stream));
+}
+int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
+                           const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {
+  if (!cols || !w_patch || !bias || !x_t || !w_in_t || !pos || !x) return set_error(kErrBadArg, "gemm_patch_embed: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_patch_embed: tokens must be positive");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = kHidden; p.K = kHidden; p.tokens = tokens;
+  p.bias = bias; p.out = x; p.ldo = kHidden; p.xt = x_t; p.w_in_t = w_in_t; p.pos = pos;
+  return launch_gemm(EPI_PATCH_EMBED_F32, BF(cols), kHidden, BF(w_patch), kHidden, p, ST(stream));
+}
+int jpdvt_final_head_fwd(const jpdvt_bf16* y, const jpdvt_bf16* w1, const float* b1, const float* w2, const float* b2,
+                         float* te_out, int64_t m, void* stream) {
+  if (!y || !w1 || !b1 || !w2 || !b2 || !te_out) return set_error(kErrBadArg, "final_head: null pointer");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = 64; p.K = kHidden; p.tokens = 1;
+  p.bias = b1; p.out = te_out; p.ldo = kLatent; p.w2 = w2; p.b2 = b2;
+  return launch_gemm(EPI_HEAD, BF(y), kHidden, BF(w1), kHidden, p, ST(stream));
+}
+
+int jpdvt_attention_fwd(const jpdvt_bf16* qkv, jpdvt_bf16* out, int batch, int tokens, void* stream) {
+  if (!qkv || !out) return set_error(kErrBadArg, "attention: null pointer");
+  return launch_attention(BF(qkv), BFM(out), batch, tokens, ST(stream));
+}
+int jpdvt_patchify(const float* img, jpdvt_bf16* cols, int batch, int image_size, void* stream) {
+  if (!img || !cols) return set_error(kErrBadArg, "patchify: null pointer");
+  return launch_patchify(img, BFM(cols), batch, image_size, ST(stream));
+}
+int jpdvt_unpatchify(const float* y, float* img, int batch, int image_size, void* stream) {
+  if (!y || !img) return set_error(kErrBadArg, "unpatchify: null pointer");
+  if (image_size % 16 != 0) return set_error(kErrBadArg, "unpatchify: image size %d is not a multiple of 16", image_size);
+  return launch_unpatchify(y, img, batch, image_size, ST(stream));
+}
+int jpdvt_timestep_embed(const int64_t* t, int n, const int32_t* step_ptr, const int32_t* map, const float* w0,
+                         const float* b0, const float* w2, const float* b2, float* c, float* silu_c, void* stream) {
+  if (!w0 || !b0 || !w2 || !b2 || !c || !silu_c) return set_error(kErrBadArg, "timestep_embed: null pointer");
+  return launch_timestep_embed(reinterpret_cast<const long long*>(t), n, step_ptr, map, w0, b0, w2, b2, c, silu_c, ST(stream));
+}
+int jpdvt_adaln_table(const float* silu_c, int rows, const jpdvt_bf16* w_all, const float* b_all, float* mod, int n_out,
+                      void* stream) {
+  if (!silu_c || !w_all || !b_all || !mod) return set_error(kErrBadArg, "adaln_table: null pointer");
+  return launch_adaln_gemv(silu_c, rows, BF(w_all), b_all, mod, n_out, ST(stream));
+}
+int jpdvt_posterior_step(const float* x0, const float* x_t, const float* noise, const float* coef1, const float* coef2,
+                         const float* logvar, const int64_t* t, const int32_t* step_ptr, float* mean_or_null,
+                         float* sample_or_null, int64_t n, int64_t per_sample, void* stream) {
+  if (!x0 || !x_t || !coef1 || !coef2 || !logvar) return set_error(kErrBadArg, "posterior_step: null pointer");
+  if (sample_or_null && !noise) return set_error(kErrBadArg, "posterior_step: sample requested without noise");
+  return launch_posterior(x0, x_t, noise, coef1, coef2, logvar, reinterpret_cast<const long long*>(t), step_ptr, mean_or_null,
+                          sample_or_null, n, per_sample, ST(stream));
+}
+int jpdvt_ddim_step(const float* x0, const float* x_t, const float* noise, const float* recip, const float* recipm1,
+                    const float* sqrt_abp, const float* dir, const float* sigma, const int64_t* t, const int32_t* step_ptr,
+                    float* sample, int64_t n, int64_t per_sample, void* stream) {
+  if (!x0 || !x_t || !noise || !recip || !recipm1 || !sqrt_abp || !dir || !sigma || !sample)
+    return set_error(kErrBadArg, "ddim_step: null pointer");
+  return launch_ddim(x0, x_t, noise, recip, recipm1, sqrt_abp, dir, sigma, reinterpret_cast<const long long*>(t), step_ptr,
+                     sample, n, per_sample, ST(stream));
+}
+int jpdvt_q_sample(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, const int64_t* t,
+                   const float* keep_or_null, float* out, int64_t n, int64_t per_sample, void* stream) {
+  if (!x0 || !noise || !sqrt_ac || !sqrt_1mac || !t || !out) return set_error(kErrBadArg, "q_sample: null pointer");
+  return launch_q_sample(x0, noise, sqrt_ac, sqrt_1mac, reinterpret_cast<const long long*>(t), keep_or_null, out, n, per_sample, ST(stream));
+}
+int jpdvt_assign_from_scores(const double* scores, int batch, int n, double sentinel, int32_t* order, int32_t* pred,
+                             void* stream) {
+  if (!scores || !order || !pred) return set_error(kErrBadArg, "assign_from_scores: null pointer");
+  return launch_assign_scores(scores, batch, n, sentinel, order, pred, ST(stream));
+}
+int jpdvt_assign_greedy_l1(const float* latents, const float* canon, int batch, int grid, int tokens_per_side,
+                           double sentinel, int32_t* order, int32_t* pred, double* scores_out_or_null, void* stream) {
+  if (!latents || !canon || !order || !pred) return set_error(kErrBadArg, "assign_greedy_l1: null pointer");
+  return launch_assign_latents(latents, canon, batch, grid, tokens_per_side, sentinel, order, pred, scores_out_or_null, ST(stream));
+}
+
+int jpdvt_denoiser_forward(const jpdvt_weights* w_host, const jpdvt_workspace* ws_host, const float* img,
+                           const int64_t* t, const int32_t* step_ptr, const int32_t* map, const float* x_t,
+                           float* te_out, float* img_out_or_null, int batch, void* stream) {
+  if (!img || !x_t || !te_out) return set_error(kErrBadArg, "denoiser_forward: null pointer");
+  if (!t && !step_ptr) return set_error(kErrBadArg, "denoiser_forward: need t or step_ptr");
+  return forward_impl(w_host, ws_host, img, t, step_ptr, map, x_t, te_out, img_out_or_null, batch, ST(stream));
+}
+
+int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const jpdvt_sampler* s, const float* condition,
+                      const float* noise, int batch, int first_step, int last_step, void* stream) {
+  if (!w || !ws || !s || !condition || !noise) return set_error(kErrBadArg, "sample_loop: null pointer");
+  if (!s->step_ids || !s->timestep_map || !s->coef1 || !s->coef2 || !s->logvar || !s->x0 || !s->sample || !s->step_noise)
+    return set_error(kErrBadArg, "sample_loop: sampler struct has null members");
+  if (first_step < 0 || last_step > s->num_steps || first_step > last_step)
+    return set_error(kErrBadArg, "sample_loop: bad step range [%d, %d) of %d", first_step, last_step, s->num_steps);
+  cudaStream_t st = ST(stream);
+  const long long per_sample = static_cast<long long>(w->tokens) * kLatent;
+  const long long n = per_sample * batch;
+  for (int k = first_step; k < last_step; ++k) {
+    // gaussian_diffusion.py:518-527: x_t of EVERY step is the initial noise unless chain mode is requested
+    const float* x_t = (s->chain && k > 0) ? s->sample : noise;
+    const int32_t* step_ptr = s->step_ids + k;
+    float* x0 = s->traj_x0 ? s->traj_x0 + static_cast<long long>(k) * n : s->x0;
+    int rc = forward_impl(w, ws, condition, nullptr, step_ptr, s->timestep_map, x_t, x0, nullptr, batch, st);
+    if (rc != kOk) return rc;
+    float* smp = s->traj_sample ? s->traj_sample + static_cast<long long>(k) * n : s->sample;
+    rc = launch_posterior(x0, x_t, s->step_noise + static_cast<long long>(k) * s->step_noise_stride, s->coef1, s->coef2,
+                          s->logvar, nullptr, step_ptr, nullptr, smp, n, per_sample, st);
+    if (rc != kOk) return rc;
+    if (s->traj_sample) {   // keep sampler->sample current (chain mode reads it; callers read the final result there)
+      copy_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(smp, s->sample, n / 4);
+      rc = check_launch("copy_f32_kernel");
+      if (rc != kOk) return rc;
+    }
+  }
+  return kOk;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Shared declarations between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jp {
+
+constexpr int kHidden = 768;   // JPDVT width (reference: models.py:409-410, hard-wired 8->768 / 768->64 heads at :176-179)
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 64;
+constexpr int kLatent = 8;     // width of the positional latent the diffusion runs on
+
+enum Status : int {
+  kOk = 0,
+  kErrBadArg = -1,
+  kErrCuda = -2,
+  kErrUnsupported = -3,
+  kErrDriver = -4,
+};
+
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+// GEMM epilogues (see gemm.cu)
+enum Epilogue : int {
+  EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias
+  EPI_BIAS_GELU_BF16 = 1,   // out_bf16 = gelu_tanh(acc + bias)
+  EPI_GATE_RESID_F32 = 2,   // out_f32 = resid + gate[row / tokens] * (acc + bias)
+  EPI_PATCH_EMBED_F32 = 3,  // out_f32 = acc + bias + pos[row % tokens] + x_t[row,:8] . w_in_t[:, n]
+  EPI_BIAS_F32 = 4,         // out_f32 = acc + bias
+  EPI_BIAS_BF16_F32 = 5,    // out_bf16 = acc + bias, and (if out2 != null) out2_f32 = acc + bias
+  EPI_HEAD = 6,             // out_f32[row, :8] = w2 . silu(acc[:, :64] + bias) + b2     (N == 64)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int tokens;            // rows per sample (row -> sample index = row / tokens)
+  const float* bias;     // [N]
+  void* out;             // primary output, row-major, leading dimension ldo (elements)
+  long long ldo;
+  float* out2;           // optional fp32 copy (EPI_BIAS_BF16_F32)
+  const float* resid;    // [M, N] fp32, leading dimension ldo (may alias out)
+  const float* gate;     // sample b reads gate + b * gate_stride, [N] contiguous
+  long long gate_stride;
+  const float* xt;       // [M, 8] fp32                     (patch embed)
+  const float* w_in_t;   // [8, N] fp32                     (patch embed)
+  const float* pos;      // [tokens, N] fp32                (patch embed)
+  const float* w2;       // [8, 64] fp32                    (head)
+  const float* b2;       // [8] fp32                        (head)
+};
+
+// a: bf16 [M, K] row-major (lda elements); w: bf16 [N, K] row-major (nn.Linear layout)
+int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
+                cudaStream_t stream);
+
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream);
+
+int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_stride, __nv_bfloat16* y,
+                       long long rows, int tokens, cudaStream_t stream);
+int launch_patchify(const float* img, __nv_bfloat16* cols, int batch, int size, cudaStream_t stream);
+int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStream_t stream);
+int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
+                          const float* w2, const float* b2, float* c, float* silu_c, cudaStream_t stream);
+int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, const float* bias, float* out, int n_out,
+                      cudaStream_t stream);
+int launch_posterior(const float* x0, const float* xt, const float* noise, const float* coef1, const float* coef2,
+                     const float* logvar, const long long* t, const int* step_ptr, float* mean, float* sample, long long n,
+                     long long per_sample, cudaStream_t stream);
+int launch_ddim(const float* x0, const float* xt, const float* noise, const float* recip, const float* recipm1,
+                const float* sqrt_abp, const float* dir, const float* sigma, const long long* t, const int* step_ptr,
+                float* sample, long long n, long long per_sample, cudaStream_t stream);
+int launch_q_sample(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, const long long* t,
+                    const float* keep_mask, float* out, long long n, long long per_sample, cudaStream_t stream);
+int launch_assign_scores(const double* scores, int batch, int n, double sentinel, int* order, int* pred,
+                         cudaStream_t stream);
+int launch_assign_latents(const float* latents, const float* canon, int batch, int grid, int tok, double sentinel,
+                          int* order, int* pred, double* scores_out, cudaStream_t stream);
+
+}  // namespace jp

@@ -1,0 +1,170 @@
+"""Device-side state of one JPDVT denoiser: packed bf16 weights, workspaces and the launch entry points.
+
+This is host plumbing around libjpdvt_sm100.so: PyTorch owns every allocation (weights, workspaces, outputs); the C
+side only sees raw pointers and the current CUDA stream (SURVEY.md 8b "Ownership").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import Sampler, Weights, Workspace, check, ptr
+
+HIDDEN = 768
+LATENT = 8
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class PackedWeights:
+    """Reference-keyed fp32 state dict -> the layouts the kernels read (include/jpdvt_b200.h: jpdvt_weights)."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], depth: int, image_size: int, device: torch.device):
+        self.depth, self.image_size = depth, image_size
+        self.tokens = (image_size // 16) ** 2
+        g = lambda k: state[k].to(device)
+        w = g("x_embedder.proj.weight")
+        if tuple(w.shape[1:]) != (3, 16, 16) or w.shape[0] != HIDDEN:
+            raise _lib.JpdvtError(
+                f"unsupported patch embedding {tuple(w.shape)}: the B200 path covers hidden 768 / patch 16 "
+                "(the only wiring the reference forward type-checks for, models.py:177,287-288)")
+        t: Dict[str, torch.Tensor] = {}
+        t["w_patch"] = _bf16(w.reshape(HIDDEN, -1))
+        t["b_embed"] = _f32(g("x_embedder.proj.bias") + g("time_emb_in.bias"))
+        t["w_in_t"] = _f32(g("time_emb_in.weight").t())
+        pos = g("pos_embed")
+        if pos.shape[1] != self.tokens:
+            raise _lib.JpdvtError(f"pos_embed has {pos.shape[1]} tokens, image size {image_size} needs {self.tokens}")
+        t["pos"] = _f32(pos[0])
+        t["t_w0"], t["t_b0"] = _f32(g("t_embedder.mlp.0.weight")), _f32(g("t_embedder.mlp.0.bias"))
+        t["t_w2"], t["t_b2"] = _f32(g("t_embedder.mlp.2.weight")), _f32(g("t_embedder.mlp.2.bias"))
+        blk = lambda i, k: g(f"blocks.{i}.{k}")
+        t["w_ada"] = _bf16(torch.cat([blk(i, "adaLN_modulation.1.weight") for i in range(depth)]
+                                     + [g("final_layer.adaLN_modulation.1.weight")], 0))
+        t["b_ada"] = _f32(torch.cat([blk(i, "adaLN_modulation.1.bias") for i in range(depth)]
+                                    + [g("final_layer.adaLN_modulation.1.bias")], 0))
+        for name, key in (("qkv", "attn.qkv"), ("proj", "attn.proj"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2")):
+            t["w_" + name] = _bf16(torch.stack([blk(i, key + ".weight") for i in range(depth)], 0))
+            t["b_" + name] = _f32(torch.stack([blk(i, key + ".bias") for i in range(depth)], 0))
+        t["w_final"], t["b_final"] = _bf16(g("final_layer.linear.weight")), _f32(g("final_layer.linear.bias"))
+        if t["w_final"].shape != (HIDDEN, HIDDEN):
+            raise _lib.JpdvtError("final_layer.linear must be 768x768 (patch 16, 3 channels)")
+        t["w_head1"], t["b_head1"] = _bf16(g("time_emb_out1.weight")), _f32(g("time_emb_out1.bias"))
+        t["w_head2"], t["b_head2"] = _f32(g("time_emb_out2.weight")), _f32(g("time_emb_out2.bias"))
+        self.tensors = t
+        self.n_mod = depth * 6 * HIDDEN + 2 * HIDDEN
+        s = Weights()
+        s.depth, s.tokens, s.image_size, s.reserved = depth, self.tokens, image_size, 0
+        for k, v in t.items():
+            setattr(s, k, ptr(v))
+        self.struct = s
+
+
+class DenoiserEngine:
+    def __init__(self, depth: int, image_size: int, device: torch.device):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.depth, self.image_size, self.device = depth, image_size, device
+        self.tokens = (image_size // 16) ** 2
+        self.weights: Optional[PackedWeights] = None
+        self._ws_key = None
+        self._ws_tensors: Dict[str, torch.Tensor] = {}
+        self._ws = None
+
+    # ------------------------------------------------------------------ weights / workspace
+    def load_state(self, state: Dict[str, torch.Tensor]) -> None:
+        self.weights = PackedWeights(state, self.depth, self.image_size, self.device)
+
+    def workspace(self, batch: int, cond_rows: int, need_image: bool) -> Workspace:
+        rows = batch * self.tokens
+        key = self._ws_key
+        if key is None or key[0] < rows or key[1] < cond_rows or (need_image and not key[2]):
+            rows_cap = max(rows, key[0] if key else 0)
+            cond_cap = max(cond_rows, key[1] if key else 0)
+            img = need_image or bool(key and key[2])
+            dev, bf, f32 = self.device, torch.bfloat16, torch.float32
+            n_mod = self.depth * 6 * HIDDEN + 2 * HIDDEN
+            t = {
+                "x": torch.empty(rows_cap, HIDDEN, device=dev, dtype=f32),
+                "xn": torch.empty(rows_cap, HIDDEN, device=dev, dtype=bf),
+                "qkv": torch.empty(rows_cap, 3 * HIDDEN, device=dev, dtype=bf),
+                "attn": torch.empty(rows_cap, HIDDEN, device=dev, dtype=bf),
+                "hid": torch.empty(rows_cap, 4 * HIDDEN, device=dev, dtype=bf),
+                "y": torch.empty(rows_cap, HIDDEN, device=dev, dtype=bf),
+                "y32": torch.empty(rows_cap, HIDDEN, device=dev, dtype=f32) if img else None,
+                "c": torch.empty(cond_cap, HIDDEN, device=dev, dtype=f32),
+                "silu_c": torch.empty(cond_cap, HIDDEN, device=dev, dtype=f32),
+                "silu_c_bf16": torch.empty(cond_cap, HIDDEN, device=dev, dtype=bf),
+                "mod": torch.empty(cond_cap, n_mod, device=dev, dtype=f32),
+            }
+            ws = Workspace()
+            ws.rows, ws.cond_rows, ws.reserved = rows_cap, cond_cap, 0
+            for k, v in t.items():
+                setattr(ws, k, ptr(v))
+            self._ws_tensors, self._ws, self._ws_key = t, ws, (rows_cap, cond_cap, img)
+        return self._ws
+
+    # ------------------------------------------------------------------ one forward
+    def forward(self, img: torch.Tensor, t: Optional[torch.Tensor], x_t: torch.Tensor, need_image: bool = True,
+                step_ptr: Optional[torch.Tensor] = None, tmap: Optional[torch.Tensor] = None):
+        """DiT.forward (image_model/models.py:273-293) -> (image or None, time_emb_out)."""
+        assert self.weights is not None, "load_state() first"
+        B = img.shape[0]
+        if tuple(img.shape[1:]) != (3, self.image_size, self.image_size):
+            raise _lib.JpdvtError(f"image batch {tuple(img.shape)} does not match input_size {self.image_size}")
+        if tuple(x_t.shape) != (B, self.tokens, LATENT):
+            raise _lib.JpdvtError(f"time_emb {tuple(x_t.shape)} must be [{B}, {self.tokens}, {LATENT}]")
+        img = img.to(torch.float32).contiguous()
+        x_t = x_t.to(torch.float32).contiguous()
+        if t is not None:
+            t = t.to(device=img.device, dtype=torch.int64).contiguous()
+            if t.shape != (B,):
+                raise _lib.JpdvtError(f"t {tuple(t.shape)} must be [{B}]")
+        ws = self.workspace(B, B if t is not None else 1, need_image)
+        te = torch.empty(B, self.tokens, LATENT, device=img.device, dtype=torch.float32)
+        out_img = torch.empty(B, 3, self.image_size, self.image_size, device=img.device, dtype=torch.float32) if need_image else None
+        check(self.lib.jpdvt_denoiser_forward(C.byref(self.weights.struct), C.byref(ws), ptr(img), ptr(t), ptr(step_ptr),
+                                              ptr(tmap), ptr(x_t), ptr(te), ptr(out_img), B, _lib.stream_ptr()),
+              "jpdvt_denoiser_forward")
+        return out_img, te
+
+    # ------------------------------------------------------------------ whole reverse loop
+    def sample_loop(self, tables: dict, condition: torch.Tensor, noise: torch.Tensor, step_noise: torch.Tensor,
+                    chain: bool = False, record: bool = False, first_step: int = 0, last_step: Optional[int] = None,
+                    state: Optional[dict] = None) -> dict:
+        """SpacedDiffusion.p_sample_loop on the device (diffusion/gaussian_diffusion.py:433-529)."""
+        assert self.weights is not None
+        B = condition.shape[0]
+        n_steps = tables["num_steps"]
+        last_step = n_steps if last_step is None else last_step
+        condition = condition.to(torch.float32).contiguous()
+        noise = noise.to(torch.float32).contiguous()
+        ws = self.workspace(B, 1, False)
+        dev = condition.device
+        if state is None:
+            state = {
+                "x0": torch.empty(B, self.tokens, LATENT, device=dev, dtype=torch.float32),
+                "sample": torch.empty(B, self.tokens, LATENT, device=dev, dtype=torch.float32),
+                "traj_x0": torch.empty(n_steps, B, self.tokens, LATENT, device=dev, dtype=torch.float32) if record else None,
+                "traj_sample": torch.empty(n_steps, B, self.tokens, LATENT, device=dev, dtype=torch.float32) if record else None,
+            }
+        s = Sampler()
+        s.num_steps, s.chain = n_steps, int(bool(chain))
+        s.step_ids, s.timestep_map = ptr(tables["step_ids"]), ptr(tables["timestep_map"])
+        s.coef1, s.coef2, s.logvar = ptr(tables["coef1"]), ptr(tables["coef2"]), ptr(tables["logvar"])
+        s.step_noise = ptr(step_noise)
+        s.step_noise_stride = step_noise.stride(0) if step_noise.dim() == noise.dim() + 1 and step_noise.shape[0] > 1 else 0
+        s.x0, s.sample = ptr(state["x0"]), ptr(state["sample"])
+        s.traj_x0, s.traj_sample = ptr(state["traj_x0"]), ptr(state["traj_sample"])
+        check(self.lib.jpdvt_sample_loop(C.byref(self.weights.struct), C.byref(ws), C.byref(s), ptr(condition), ptr(noise),
+                                         B, first_step, last_step, _lib.stream_ptr()), "jpdvt_sample_loop")
+        return state

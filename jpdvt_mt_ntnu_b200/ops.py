@@ -1,0 +1,213 @@
+"""One Python function per C-ABI kernel entry point (torch tensors in, torch tensors out).
+
+Used by the model/diffusion mirrors and by the parity tests; each wrapper only validates shapes, allocates the
+output with torch and forwards raw pointers + the current stream to libjpdvt_sm100.so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+HIDDEN, LATENT = 768, 8
+
+
+def _lib_dev():
+    return _lib.require_device()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if t.dtype != dtype:
+        raise _lib.JpdvtError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, tokens: int) -> torch.Tensor:
+    """x [rows,768] fp32; shift/scale [n_cond,768] fp32 with n_cond == rows/tokens or 1 -> bf16 [rows,768]."""
+    lib = _lib_dev()
+    x, shift, scale = _need(x, torch.float32, "x"), _need(shift, torch.float32, "shift"), _need(scale, torch.float32, "scale")
+    rows = x.shape[0]
+    stride = 0 if shift.shape[0] == 1 else HIDDEN
+    y = torch.empty(rows, HIDDEN, device=x.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_ln_modulate_fwd(ptr(x), ptr(shift), ptr(scale), stride, ptr(y), rows, tokens, stream_ptr()), "ln_modulate")
+    return y
+
+
+def gemm_bias(a, w, bias, want_f32_copy: bool = False):
+    lib = _lib_dev()
+    a, w, bias = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w"), _need(bias, torch.float32, "bias")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    out32 = torch.empty(m, n, device=a.device, dtype=torch.float32) if want_f32_copy else None
+    check(lib.jpdvt_gemm_bias(ptr(a), ptr(w), ptr(bias), ptr(out), ptr(out32), m, n, k, stream_ptr()), "gemm_bias")
+    return (out, out32) if want_f32_copy else out
+
+
+def gemm_bias_f32(a, w, bias):
+    lib = _lib_dev()
+    a, w, bias = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w"), _need(bias, torch.float32, "bias")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.float32)
+    check(lib.jpdvt_gemm_bias_f32(ptr(a), ptr(w), ptr(bias), ptr(out), m, n, k, stream_ptr()), "gemm_bias_f32")
+    return out
+
+
+def gemm_bias_gelu(a, w, bias):
+    lib = _lib_dev()
+    a, w, bias = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w"), _need(bias, torch.float32, "bias")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_gemm_bias_gelu(ptr(a), ptr(w), ptr(bias), ptr(out), m, n, k, stream_ptr()), "gemm_bias_gelu")
+    return out
+
+
+def gemm_bias_gate_residual_(x, a, w, bias, gate, tokens: int):
+    """In place: x[row] += gate[row // tokens] * (a @ w.T + bias).  gate [n_cond,768] with n_cond == rows/tokens or 1."""
+    lib = _lib_dev()
+    a, w = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w")
+    bias, gate = _need(bias, torch.float32, "bias"), _need(gate, torch.float32, "gate")
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise _lib.JpdvtError("x must be contiguous fp32")
+    m, k = a.shape
+    n = w.shape[0]
+    stride = 0 if gate.shape[0] == 1 else n
+    check(lib.jpdvt_gemm_bias_gate_residual(ptr(a), ptr(w), ptr(bias), ptr(gate), stride, ptr(x), m, n, k, tokens,
+                                            stream_ptr()), "gemm_bias_gate_residual")
+    return x
+
+
+def patchify(img: torch.Tensor) -> torch.Tensor:
+    lib = _lib_dev()
+    img = _need(img, torch.float32, "img")
+    b, _, s, _ = img.shape
+    cols = torch.empty(b * (s // 16) ** 2, HIDDEN, device=img.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_patchify(ptr(img), ptr(cols), b, s, stream_ptr()), "patchify")
+    return cols
+
+
+def unpatchify(y: torch.Tensor, batch: int, size: int) -> torch.Tensor:
+    lib = _lib_dev()
+    y = _need(y, torch.float32, "y")
+    img = torch.empty(batch, 3, size, size, device=y.device, dtype=torch.float32)
+    check(lib.jpdvt_unpatchify(ptr(y), ptr(img), batch, size, stream_ptr()), "unpatchify")
+    return img
+
+
+def gemm_patch_embed(cols, w_patch, bias, x_t, w_in_t, pos, tokens: int) -> torch.Tensor:
+    lib = _lib_dev()
+    m = cols.shape[0]
+    x = torch.empty(m, HIDDEN, device=cols.device, dtype=torch.float32)
+    check(lib.jpdvt_gemm_patch_embed(ptr(_need(cols, torch.bfloat16, "cols")), ptr(_need(w_patch, torch.bfloat16, "w")),
+                                     ptr(_need(bias, torch.float32, "bias")), ptr(_need(x_t, torch.float32, "x_t")),
+                                     ptr(_need(w_in_t, torch.float32, "w_in_t")), ptr(_need(pos, torch.float32, "pos")),
+                                     ptr(x), m, tokens, stream_ptr()), "gemm_patch_embed")
+    return x
+
+
+def final_head(y, w1, b1, w2, b2) -> torch.Tensor:
+    lib = _lib_dev()
+    m = y.shape[0]
+    out = torch.empty(m, LATENT, device=y.device, dtype=torch.float32)
+    check(lib.jpdvt_final_head_fwd(ptr(_need(y, torch.bfloat16, "y")), ptr(_need(w1, torch.bfloat16, "w1")),
+                                   ptr(_need(b1, torch.float32, "b1")), ptr(_need(w2, torch.float32, "w2")),
+                                   ptr(_need(b2, torch.float32, "b2")), ptr(out), m, stream_ptr()), "final_head")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, tokens: int) -> torch.Tensor:
+    lib = _lib_dev()
+    qkv = _need(qkv, torch.bfloat16, "qkv")
+    out = torch.empty(batch * tokens, HIDDEN, device=qkv.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_attention_fwd(ptr(qkv), ptr(out), batch, tokens, stream_ptr()), "attention")
+    return out
+
+
+def timestep_embed(t: torch.Tensor, w0, b0, w2, b2) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib_dev()
+    t = _need(t, torch.int64, "t")
+    n = t.shape[0]
+    c = torch.empty(n, HIDDEN, device=t.device, dtype=torch.float32)
+    sc = torch.empty_like(c)
+    check(lib.jpdvt_timestep_embed(ptr(t), n, None, None, ptr(_need(w0, torch.float32, "w0")), ptr(_need(b0, torch.float32, "b0")),
+                                   ptr(_need(w2, torch.float32, "w2")), ptr(_need(b2, torch.float32, "b2")), ptr(c), ptr(sc),
+                                   stream_ptr()), "timestep_embed")
+    return c, sc
+
+
+def adaln_table(silu_c, w_all, b_all) -> torch.Tensor:
+    lib = _lib_dev()
+    rows, n_out = silu_c.shape[0], w_all.shape[0]
+    out = torch.empty(rows, n_out, device=silu_c.device, dtype=torch.float32)
+    check(lib.jpdvt_adaln_table(ptr(_need(silu_c, torch.float32, "silu_c")), rows, ptr(_need(w_all, torch.bfloat16, "w_all")),
+                                ptr(_need(b_all, torch.float32, "b_all")), ptr(out), n_out, stream_ptr()), "adaln_table")
+    return out
+
+
+def posterior_step(x0, x_t, noise, coef1, coef2, logvar, t: torch.Tensor):
+    """-> (mean, sample); t int64 [B] respaced step indices."""
+    lib = _lib_dev()
+    x0, x_t, noise = _need(x0, torch.float32, "x0"), _need(x_t, torch.float32, "x_t"), _need(noise, torch.float32, "noise")
+    mean, sample = torch.empty_like(x0), torch.empty_like(x0)
+    n, per = x0.numel(), x0.numel() // x0.shape[0]
+    check(lib.jpdvt_posterior_step(ptr(x0), ptr(x_t), ptr(noise), ptr(coef1), ptr(coef2), ptr(logvar),
+                                   ptr(_need(t, torch.int64, "t")), None, ptr(mean), ptr(sample), n, per, stream_ptr()),
+          "posterior_step")
+    return mean, sample
+
+
+def ddim_step(x0, x_t, noise, tabs: dict, t: torch.Tensor) -> torch.Tensor:
+    """tabs: fp32 device tables recip/recipm1/sqrt_abp/dir/sigma indexed by respaced step."""
+    lib = _lib_dev()
+    x0, x_t, noise = _need(x0, torch.float32, "x0"), _need(x_t, torch.float32, "x_t"), _need(noise, torch.float32, "noise")
+    out = torch.empty_like(x0)
+    n, per = x0.numel(), x0.numel() // x0.shape[0]
+    check(lib.jpdvt_ddim_step(ptr(x0), ptr(x_t), ptr(noise), ptr(tabs["recip"]), ptr(tabs["recipm1"]), ptr(tabs["sqrt_abp"]),
+                              ptr(tabs["dir"]), ptr(tabs["sigma"]), ptr(_need(t, torch.int64, "t")), None, ptr(out), n, per,
+                              stream_ptr()), "ddim_step")
+    return out
+
+
+def q_sample(x0, noise, sqrt_ac, sqrt_1mac, t, keep: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib_dev()
+    x0, noise = _need(x0, torch.float32, "x0"), _need(noise, torch.float32, "noise")
+    out = torch.empty_like(x0)
+    n, per = x0.numel(), x0.numel() // x0.shape[0]
+    check(lib.jpdvt_q_sample(ptr(x0), ptr(noise), ptr(sqrt_ac), ptr(sqrt_1mac), ptr(_need(t, torch.int64, "t")),
+                             ptr(keep.contiguous()) if keep is not None else None, ptr(out), n, per, stream_ptr()), "q_sample")
+    return out
+
+
+def assign_from_scores(scores: torch.Tensor, sentinel: float = 1e9):
+    """scores fp64 [B,n,n] (rows = slots, cols = grid cells) -> (order, pred) int32 [B,n]  (inference.py:113-125,306)."""
+    lib = _lib_dev()
+    scores = _need(scores, torch.float64, "scores")
+    b, n, _ = scores.shape
+    order = torch.empty(b, n, device=scores.device, dtype=torch.int32)
+    pred = torch.empty_like(order)
+    check(lib.jpdvt_assign_from_scores(ptr(scores), b, n, float(sentinel), ptr(order), ptr(pred), stream_ptr()),
+          "assign_from_scores")
+    return order, pred
+
+
+def assign_greedy_l1(latents: torch.Tensor, canon: torch.Tensor, grid: int, sentinel: float = 1e9,
+                     return_scores: bool = False):
+    """latents fp32 [B,T,8] -> (order, pred[, scores])  (inference.py:294-306)."""
+    lib = _lib_dev()
+    latents, canon = _need(latents, torch.float32, "latents"), _need(canon, torch.float32, "canon")
+    b, t, _ = latents.shape
+    n = grid * grid
+    side = int(round((t // n) ** 0.5))
+    if n * side * side != t:
+        raise _lib.JpdvtError(f"{t} tokens do not tile a {grid}x{grid} puzzle (S/(16*G) must be integral, inference.py:295)")
+    order = torch.empty(b, n, device=latents.device, dtype=torch.int32)
+    pred = torch.empty_like(order)
+    scores = torch.empty(b, n, n, device=latents.device, dtype=torch.float64) if return_scores else None
+    check(lib.jpdvt_assign_greedy_l1(ptr(latents), ptr(canon), b, grid, side, float(sentinel), ptr(order), ptr(pred),
+                                     ptr(scores), stream_ptr()), "assign_greedy_l1")
+    return (order, pred, scores) if return_scores else (order, pred)
