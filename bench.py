@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the JPDVT hot path on B200: puzzles/s for 250-step p_sample_loop sampling + assignment.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5] [--batch B]
+
+One "step" = one pass of the hot path over one batch of synthetic puzzles: all 250 denoiser forwards of
+SpacedDiffusion.p_sample_loop (the reference's loop quirk preserved, none of the "dead" steps skipped), the fused
+posterior update after each, and the position-to-grid assignment of every puzzle.  Workload (BASELINE.json configs[1]):
+JPDVT 3x3 @192 px, batch 256 PER GPU (weak scaling: puzzles are independent, reference shards image_paths[rank::world]).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job puzzles/s with inputs resident in HBM; `e2e` = the same through the
+public API from pinned host buffers (H2D of the scrambled images + noise, D2H of the placements inside the timed
+region); `roofline` = the dominant kernel (fc1 tcgen05 GEMM) against the measured bf16 peak; `cpu_baseline` = the CPU
+oracle port (torch fp32, all host threads) on a bounded sample.  `--impl reference` times that CPU port as its own line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(name="JPDVT 3x3 @192px sampling, 250 steps, batch 256/GPU", size=192, grid=3, batch=256, steps=250),
+    "c4": dict(name="JPDVT 4x4 @256px sampling, 250 steps, batch 128/GPU", size=256, grid=4, batch=128, steps=250),
+    "c5": dict(name="JPDVT 3x3 @288px masked sampling, 250 steps, batch 128/GPU", size=288, grid=3, batch=128, steps=250),
+}
+DEPTH = 12
+
+
+def flops_per_forward(T: int) -> float:
+    """algorithmic FLOPs (2*MAC) of one denoiser forward per sample."""
+    D = 768
+    return (2 * T * D * D + 2 * T * 8 * D + 2 * (256 * D + D * D)
+            + 12 * (2 * D * 6 * D + 2 * T * D * 3 * D + 4 * T * T * D + 2 * T * D * D + 2 * (2 * T * D * 4 * D))
+            + 2 * D * 2 * D + 2 * T * D * D + 2 * T * D * 64 + 2 * T * 64 * 8)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def synthetic_inputs(wl, batch, seed=0):
+    """SURVEY.md 8(d) recipe: images rand*2-1 (manual_seed), per-puzzle np permutations, one randn(1,T,8) noise row
+    repeated over the batch (inferencetexmet.py:313); C5 additionally zeroes 1-2 random slots of the scrambled image."""
+    import numpy as np
+    import torch
+    G, S = wl["grid"], wl["size"]
+    T = (S // 16) ** 2
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(batch, 3, S, S, generator=g) * 2 - 1
+    rs = np.random.RandomState(seed)
+    perms = np.stack([rs.permutation(G * G) for _ in range(batch)])
+    p = S // G
+    pieces = img.reshape(batch, 3, G, p, G, p).permute(0, 1, 2, 4, 3, 5).reshape(batch, 3, G * G, p, p)
+    idx = torch.from_numpy(perms).long()
+    pieces = torch.gather(pieces, 2, idx[:, None, :, None, None].expand(batch, 3, G * G, p, p))
+    if wl is WORKLOADS["c5"]:
+        for b in range(batch):
+            for slot in rs.choice(G * G, size=rs.randint(1, 3), replace=False):
+                pieces[b, :, slot] = 0
+    cond = pieces.reshape(batch, 3, G, G, p, p).permute(0, 1, 2, 4, 3, 5).reshape(batch, 3, S, S).contiguous()
+    noise = torch.randn(1, T, 8, generator=g).repeat(batch, 1, 1)
+    return cond, noise, perms
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+_CPU_CACHE = {}
+
+
+def cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=4):
+    """The oracle port (torch fp32 CPU restatement of the reference path) on a BOUNDED sample: `sample_batch` puzzles x
+    `sample_steps` of the 250 diffusion steps (every step is identical work - the reference feeds the same
+    (condition, noise) to all of them) + the assignment, scaled to the full step count."""
+    import torch
+    from oracle import jpdvt_oracle as orc          # allowed here: bench.py's cpu_baseline / reference legs only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, G = wl["size"], wl["grid"]
+    T = (S // 16) ** 2
+    if S not in _CPU_CACHE:
+        _CPU_CACHE[S] = orc.OracleDenoiser(orc.seeded_state(orc.blank_state(S, DEPTH), seed=1234), depth=DEPTH)
+    model = _CPU_CACHE[S]
+    sched = orc.Schedule(str(wl["steps"]))
+    cond, noise, _ = synthetic_inputs(wl, sample_batch)
+    with torch.no_grad():
+        t = torch.full((sample_batch,), sched.num_timesteps - 1, dtype=torch.long)
+        sched.p_step(model, cond, noise, t, torch.randn_like(noise))          # warm-up (thread pools, allocator)
+        t0 = time.perf_counter()
+        out = None
+        for k in range(sample_steps):
+            t = torch.full((sample_batch,), sched.num_timesteps - 1 - k, dtype=torch.long)
+            out = sched.p_step(model, cond, noise, t, torch.randn_like(noise))
+        t_steps = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for b in range(sample_batch):
+            orc.solve(out["sample"][b], G, S // (16 * G))
+        t_assign = time.perf_counter() - t0
+    total = t_steps / sample_steps * wl["steps"] + t_assign
+    return sample_batch / total, cores, f"{sample_batch} puzzles x {sample_steps} of {wl['steps']} diffusion steps + assignment, scaled x{wl['steps']}/{sample_steps}", t_steps + t_assign
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference path's CPU implementation (oracle port; the Python reference cannot travel to
+    the GPU box) on the host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, spent = [], 0.0
+    for i in range(args.warmup + args.steps):
+        v, cores, sample, dt = cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=2)
+        if i >= args.warmup:
+            vals.append(v); spent += dt
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "puzzles/sec (3x3 @192px sampling)", "value": value, "unit": "puzzles/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * spent / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "diffusion_steps": wl["steps"], "grid": wl["grid"], "image_size": wl["size"]},
+        "cpu_baseline": {"value": value, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "puzzles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def kernel_roofline(model, wl, batch, peaks):
+    """Per-kernel CUDA-event timings of one denoiser forward at the bench shape, through the per-kernel C-ABI entry
+    points (ops.*) on the launching stream; inputs are larger than L2 at this batch.  Returns the roofline object of
+    the dominant kernel plus the full breakdown."""
+    import torch
+    from jpdvt_mt_ntnu_b200 import ops
+    T = (wl["size"] // 16) ** 2
+    M = batch * T
+    dev = torch.device("cuda")
+    eng = model.engine(dev)
+    W = eng.weights.tensors
+    xn = torch.randn(M, 768, device=dev).bfloat16()
+    x = torch.randn(M, 768, device=dev)
+    hid = torch.randn(M, 3072, device=dev).bfloat16() * 0.1
+    qkv = torch.randn(M, 2304, device=dev).bfloat16()
+    gate = torch.randn(1, 768, device=dev) * 0.1
+    shift, scale = torch.randn(1, 768, device=dev), torch.randn(1, 768, device=dev)
+    calls = {
+        "gemm_qkv (tcgen05, bias)": (lambda: ops.gemm_bias(xn, W["w_qkv"][0], W["b_qkv"][0]), 2.0 * M * 768 * 2304, "flop"),
+        "gemm_fc1 (tcgen05, bias+gelu)": (lambda: ops.gemm_bias_gelu(xn, W["w_fc1"][0], W["b_fc1"][0]), 2.0 * M * 768 * 3072, "flop"),
+        "gemm_fc2 (tcgen05, bias+gate+residual)": (lambda: ops.gemm_bias_gate_residual_(x, hid, W["w_fc2"][0], W["b_fc2"][0], gate, T), 2.0 * M * 3072 * 768, "flop"),
+        "gemm_proj (tcgen05, bias+gate+residual)": (lambda: ops.gemm_bias_gate_residual_(x, xn, W["w_proj"][0], W["b_proj"][0], gate, T), 2.0 * M * 768 * 768, "flop"),
+        "attention (mma.sync, smem K/V)": (lambda: ops.attention(qkv, batch, T), 4.0 * batch * 12 * T * T * 64, "flop"),
+        "ln_modulate (fp32->bf16)": (lambda: ops.ln_modulate(x, shift, scale, T), M * 768 * 6.0, "byte"),
+    }
+    out = {}
+    for name, (fn, work, kind) in calls.items():
+        for _ in range(3):
+            fn()
+        n = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if kind == "flop":
+            ach = work / (ms * 1e-3) / 1e12
+            out[name] = {"ms": ms, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"]}
+        else:
+            ach = work / (ms * 1e-3) / 1e9
+            out[name] = {"ms": ms, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+    top = "gemm_fc1 (tcgen05, bias+gelu)"
+    roof = {"bound": "tensor", "kernel": top, "achieved": out[top]["achieved"], "peak": peaks["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": out[top]["frac"], "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+            "how": "CUDA events on the launching stream over 10 back-to-back launches at the bench shape "
+                   f"(M={M}, activations > L2); algorithmic FLOPs 2*M*768*3072"}
+    return roof, out
+
+
+def run_ours(args, wl):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from jpdvt_mt_ntnu_b200 import assignment
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT_models
+    from jpdvt_mt_ntnu_b200.weights import seeded_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch or wl["batch"]
+    S, G = wl["size"], wl["grid"]
+    T = (S // 16) ** 2
+
+    model = DiT_models["JPDVT"](input_size=S)
+    model.load_state_dict(seeded_state(model.state_dict(), seed=1234))
+    model.to(dev)
+    diffusion = create_diffusion(str(wl["steps"]))
+    cond_h, noise_h, perms = synthetic_inputs(wl, batch, seed=rank)
+    cond_pin, noise_pin = cond_h.pin_memory(), noise_h.pin_memory()
+    cond, noise = cond_pin.to(dev), noise_pin.to(dev)
+    torch.manual_seed(rank)
+    step_noise = torch.randn(diffusion.num_timesteps, batch, T, 8, device=dev)   # per-step randn (parity-mode noise buffer)
+    gathered = [torch.empty(batch, G * G, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+
+    def one_step(c, z):
+        sample = diffusion.p_sample_loop(model.forward, c, z.shape, z, clip_denoised=False, model_kwargs=None,
+                                         progress=False, device=dev, step_noise=step_noise)
+        order, pred = assignment.solve_puzzles(sample, G)
+        if world > 1:
+            dist.all_gather(gathered, pred)          # the only cross-rank traffic: int32 placements (inference_ddp.py:485-495)
+        return pred
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    for _ in range(args.warmup):
+        one_step(cond, noise)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, pred = timed(lambda: one_step(cond, noise), args.steps)
+    value = batch * world * args.steps / (ms * 1e-3)
+
+    def e2e_step():
+        c = cond_pin.to(dev, non_blocking=True)
+        z = noise_pin.to(dev, non_blocking=True)
+        return one_step(c, z).cpu()
+
+    e2e_step()
+    ms_e2e, pred_host = timed(e2e_step, args.steps)
+    clock_info = clocks.stop()
+    e2e_value = batch * world * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        roof, breakdown = kernel_roofline(model, wl, batch, peaks)
+        cpu_v, cores, sample, _ = cpu_port_puzzles_per_s(wl)
+        fwd_launches = 4 + 7 * DEPTH + 3
+        launches = args.steps * (wl["steps"] * (fwd_launches + 1) + 1)
+        solved = float((pred_host.numpy() == perms).all(axis=1).mean())
+        flops = flops_per_forward(T) * wl["steps"] * batch * args.steps
+        line = {
+            "metric": "puzzles/sec (3x3 @192px sampling)" if wl is WORKLOADS["c2"] else f"puzzles/sec ({wl['name']})",
+            "value": value, "unit": "puzzles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": batch, "diffusion_steps": wl["steps"], "grid": G,
+                       "image_size": S, "tokens": T, "weights": "random N(0,0.02), seed 1234 (fresh init outputs zeros)",
+                       "l2": "activations per launch (>= 57 MB bf16 / 113 MB fp32 at M=36864) exceed L2; no flush needed",
+                       "denoiser_forwards_per_step": wl["steps"], "sharding": "independent puzzle batches per rank, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "puzzles/s", "h2d_bytes_per_step": int(cond_pin.numel() * 4 + noise_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(batch * G * G * 4), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clock_info,
+            "roofline": roof,
+            "kernels": breakdown,
+            "model_tflops": flops / (ms * 1e-3) / 1e12,
+            "model_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "cpu_baseline": {"value": cpu_v, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample},
+            "puzzles_solved_frac_random_weights": solved,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="puzzles per GPU (default: the workload's)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3            # timing rule: at least 3 warm-up steps
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

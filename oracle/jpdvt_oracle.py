@@ -81,48 +81,48 @@ class OracleDenoiser:
         g = S // p
         cols = img.reshape(B, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, C * p * p)
         wmat = self.w["x_embedder.proj.weight"].reshape(-1, C * p * p)
-        return cols @ wmat.t() + self.w["x_embedder.proj.bias"]
+        return F.linear(cols, wmat, self.w["x_embedder.proj.bias"])
 
     def conditioning(self, t: torch.Tensor) -> torch.Tensor:
         """models.py:61-64 - Linear(256,768) -> SiLU -> Linear(768,768)."""
-        h = timestep_features(t) @ self.w["t_embedder.mlp.0.weight"].t() + self.w["t_embedder.mlp.0.bias"]
-        return F.silu(h) @ self.w["t_embedder.mlp.2.weight"].t() + self.w["t_embedder.mlp.2.bias"]
+        h = F.linear(timestep_features(t), self.w["t_embedder.mlp.0.weight"], self.w["t_embedder.mlp.0.bias"])
+        return F.linear(F.silu(h), self.w["t_embedder.mlp.2.weight"], self.w["t_embedder.mlp.2.bias"])
 
     def attention(self, i: int, x: torch.Tensor) -> torch.Tensor:
         w = self.w
         B, T, D = x.shape
         hd = D // self.heads
-        qkv = x @ w[f"blocks.{i}.attn.qkv.weight"].t() + w[f"blocks.{i}.attn.qkv.bias"]
+        qkv = F.linear(x, w[f"blocks.{i}.attn.qkv.weight"], w[f"blocks.{i}.attn.qkv.bias"])
         q, k, v = qkv.reshape(B, T, 3, self.heads, hd).permute(2, 0, 3, 1, 4)
         p = torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1)
         o = (p @ v).transpose(1, 2).reshape(B, T, D)
-        return o @ w[f"blocks.{i}.attn.proj.weight"].t() + w[f"blocks.{i}.attn.proj.bias"]
+        return F.linear(o, w[f"blocks.{i}.attn.proj.weight"], w[f"blocks.{i}.attn.proj.bias"])
 
     def mlp(self, i: int, x: torch.Tensor) -> torch.Tensor:
         w = self.w
-        h = F.gelu(x @ w[f"blocks.{i}.mlp.fc1.weight"].t() + w[f"blocks.{i}.mlp.fc1.bias"], approximate="tanh")
-        return h @ w[f"blocks.{i}.mlp.fc2.weight"].t() + w[f"blocks.{i}.mlp.fc2.bias"]
+        h = F.gelu(F.linear(x, w[f"blocks.{i}.mlp.fc1.weight"], w[f"blocks.{i}.mlp.fc1.bias"]), approximate="tanh")
+        return F.linear(h, w[f"blocks.{i}.mlp.fc2.weight"], w[f"blocks.{i}.mlp.fc2.bias"])
 
     def forward(self, img: torch.Tensor, t: torch.Tensor, x_t: torch.Tensor, taps: Optional[dict] = None):
         """models.py:273-293.  Returns (image [B,3,S,S], time_emb_out [B,T,8])."""
         w = self.w
-        x = self.patch_embed(img.float()) + (x_t.float() @ w["time_emb_in.weight"].t() + w["time_emb_in.bias"]) + w["pos_embed"]
+        x = self.patch_embed(img.float()) + F.linear(x_t.float(), w["time_emb_in.weight"], w["time_emb_in.bias"]) + w["pos_embed"]
         c = self.conditioning(t)
         sc = F.silu(c)
         if taps is not None:
             taps["embed"] = x.clone(); taps["c"] = c.clone()
         for i in range(self.depth):
-            m = sc @ w[f"blocks.{i}.adaLN_modulation.1.weight"].t() + w[f"blocks.{i}.adaLN_modulation.1.bias"]
+            m = F.linear(sc, w[f"blocks.{i}.adaLN_modulation.1.weight"], w[f"blocks.{i}.adaLN_modulation.1.bias"])
             s1, k1, g1, s2, k2, g2 = m.chunk(6, dim=1)
             x = x + g1[:, None, :] * self.attention(i, _mod(_ln(x), s1, k1))
             x = x + g2[:, None, :] * self.mlp(i, _mod(_ln(x), s2, k2))
             if taps is not None:
                 taps[f"block{i}"] = x.clone()
-        m = sc @ w["final_layer.adaLN_modulation.1.weight"].t() + w["final_layer.adaLN_modulation.1.bias"]
+        m = F.linear(sc, w["final_layer.adaLN_modulation.1.weight"], w["final_layer.adaLN_modulation.1.bias"])
         shift, scale = m.chunk(2, dim=1)
-        y = _mod(_ln(x), shift, scale) @ w["final_layer.linear.weight"].t() + w["final_layer.linear.bias"]
-        h = F.silu(y @ w["time_emb_out1.weight"].t() + w["time_emb_out1.bias"])
-        te = h @ w["time_emb_out2.weight"].t() + w["time_emb_out2.bias"]
+        y = F.linear(_mod(_ln(x), shift, scale), w["final_layer.linear.weight"], w["final_layer.linear.bias"])
+        h = F.silu(F.linear(y, w["time_emb_out1.weight"], w["time_emb_out1.bias"]))
+        te = F.linear(h, w["time_emb_out2.weight"], w["time_emb_out2.bias"])
         if taps is not None:
             taps["final"] = y.clone()
         return self.unpatchify(y), te

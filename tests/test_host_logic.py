@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference interface: schedules, module layout, error behaviour, C-ABI exports (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from jpdvt_mt_ntnu_b200 import _lib, parallel
+from jpdvt_mt_ntnu_b200.diffusion import create_diffusion, space_timesteps
+from jpdvt_mt_ntnu_b200.diffusion import gaussian_diffusion as gd
+from jpdvt_mt_ntnu_b200.models import DiT, DiT_models, get_2d_sincos_pos_embed
+from jpdvt_mt_ntnu_b200.weights import seeded_state
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pos_embed_bit_exact(golden):
+    g = golden("static")
+    assert np.array_equal(get_2d_sincos_pos_embed(8, 3), g["pe_8_3"])
+    assert np.array_equal(get_2d_sincos_pos_embed(8, 4), g["pe_8_4"])
+    assert np.array_equal(get_2d_sincos_pos_embed(768, 12), g["pe_768_12"])
+
+
+@pytest.mark.parametrize("name,spec", [("full", ""), ("s250", "250"), ("s10", "10"), ("ddim50", "ddim50"), ("sec", "10,15,20")])
+def test_create_diffusion_tables_bit_exact(golden, name, spec):
+    g = golden("static")
+    d = create_diffusion(spec)
+    assert np.array_equal(np.asarray(d.timestep_map), g[f"{name}_map"])
+    for key, arr in (("betas", d.betas), ("sqrt_ac", d.sqrt_alphas_cumprod), ("sqrt_1mac", d.sqrt_one_minus_alphas_cumprod),
+                     ("post_var", d.posterior_variance), ("post_logvar", d.posterior_log_variance_clipped),
+                     ("coef1", d.posterior_mean_coef1), ("coef2", d.posterior_mean_coef2)):
+        assert np.array_equal(arr, g[f"{name}_{key}"]), key
+    assert d.num_timesteps == len(g[f"{name}_map"])
+
+
+def test_create_diffusion_defaults():
+    d = create_diffusion("250")
+    assert d.model_mean_type == gd.ModelMeanType.START_X
+    assert d.model_var_type == gd.ModelVarType.FIXED_SMALL
+    assert d.loss_type == gd.LossType.MSE
+    assert d.original_num_steps == 1000
+    assert create_diffusion(None).num_timesteps == 1000
+    assert create_diffusion("", predict_xstart=False).model_mean_type == gd.ModelMeanType.EPSILON
+
+
+def test_space_timesteps_errors_and_forms():
+    assert space_timesteps(1000, "250") == space_timesteps(1000, [250])
+    assert sorted(space_timesteps(300, [10, 15, 20]))[:3] == [0, 11, 22]
+    with pytest.raises(ValueError):
+        space_timesteps(10, "20")
+    with pytest.raises(ValueError):
+        space_timesteps(1000, "ddim999")
+
+
+def test_state_dict_layout_and_param_count(golden):
+    g = golden("static")
+    m = DiT_models["JPDVT"](input_size=192)
+    st = m.state_dict()
+    assert list(st.keys()) == [str(k) for k in g["state_keys"]]
+    assert [v.numel() for v in st.values()] == g["state_numel"].tolist()
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params_192"]) == 130857800
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == int(g["n_trainable_192"]) == 130747208
+    assert not m.pos_embed.requires_grad
+    assert sum(p.numel() for p in DiT_models["JPDVT"](input_size=288).parameters()) == 130996040
+
+
+def test_fresh_init_scheme():
+    torch.manual_seed(0)
+    m = DiT(input_size=96, depth=2, hidden_size=768, patch_size=16, num_heads=12)
+    for blk in m.blocks:                                     # adaLN-Zero (models.py:216-225)
+        assert blk.adaLN_modulation[-1].weight.abs().max() == 0 and blk.adaLN_modulation[-1].bias.abs().max() == 0
+    assert m.final_layer.linear.weight.abs().max() == 0 and m.final_layer.adaLN_modulation[-1].weight.abs().max() == 0
+    assert abs(m.time_emb_in.weight.std().item() - 0.02) < 2e-3
+    assert abs(m.t_embedder.mlp[0].weight.std().item() - 0.02) < 1e-3
+    w = m.blocks[0].attn.qkv.weight                          # xavier uniform: bound sqrt(6/(fan_in+fan_out))
+    assert w.abs().max().item() <= (6.0 / (768 + 2304)) ** 0.5 + 1e-6
+    assert m.blocks[0].attn.qkv.bias.abs().max() == 0
+    assert np.array_equal(m.pos_embed[0].numpy(), get_2d_sincos_pos_embed(768, 6).astype(np.float32))
+
+
+def test_state_dict_round_trip_and_deepcopy():
+    import copy
+    m = DiT(input_size=48, depth=1, hidden_size=768, patch_size=16, num_heads=12)
+    st = seeded_state(m.state_dict(), seed=3)
+    m.load_state_dict(st)
+    m2 = copy.deepcopy(m)                                    # EMA copy (train_JPDVT.py:235)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    missing = m2.load_state_dict({k: v for k, v in st.items() if "blocks" not in k}, strict=False)
+    assert all("blocks" in k for k in missing.missing_keys)
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a B200 - never silently compute on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    m = DiT(input_size=48, depth=1, hidden_size=768, patch_size=16, num_heads=12)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 48, 48), torch.zeros(1, dtype=torch.long), torch.zeros(1, 9, 8))
+    d = create_diffusion("10")
+    with pytest.raises(RuntimeError):
+        d.q_sample(torch.zeros(1, 9, 8), torch.zeros(1, dtype=torch.long), torch.zeros(1, 9, 8))
+    with pytest.raises(RuntimeError):
+        _lib.require_device()
+
+
+def test_unsupported_configs_raise():
+    m = DiT_models["JPDVT-T"](input_size=256)               # patch 64: the reference forward itself crashes (SURVEY headline 6)
+    with pytest.raises(NotImplementedError):
+        m._check_supported()
+    with pytest.raises(NotImplementedError):
+        DiT_models["DiT-S/2"](input_size=32)._check_supported()
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "jpdvt_b200.h")).read()
+    declared = set(re.findall(r"\b(jpdvt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"jpdvt_status"}
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/jpdvt_b200.h but not exported"
+    assert set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS) == declared
+    assert lib.jpdvt_abi_version() == 1
+    assert isinstance(lib.jpdvt_last_error_string(), bytes)
+
+
+def test_cabi_struct_layout_matches_header():
+    # 4 int32 + 24 pointers; int64 + 2 int32 + 11 pointers; 2 int32 + 6 ptr + int64 + 4 ptr
+    assert ctypes.sizeof(_lib.Weights) == 16 + 24 * 8
+    assert ctypes.sizeof(_lib.Workspace) == 16 + 11 * 8
+    assert ctypes.sizeof(_lib.Sampler) == 8 + 6 * 8 + 8 + 4 * 8
+    header = open(os.path.join(ROOT, "include", "jpdvt_b200.h")).read()
+    for struct, cls in (("jpdvt_weights", _lib.Weights), ("jpdvt_workspace", _lib.Workspace), ("jpdvt_sampler", _lib.Sampler)):
+        body = header[header.index(f"typedef struct {struct} {{"):header.index(f"}} {struct};")]
+        names = re.findall(r"\b([a-z_0-9]+);", body)
+        assert names == [f[0] for f in cls._fields_], struct
+
+
+def test_block_and_strided_shards():
+    for total, w in ((256, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [parallel.block_shard(total, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+    items = list(range(11))
+    got = sorted(sum((parallel.strided_shard(items, r, 4) for r in range(4)), []))
+    assert got == items
