@@ -173,6 +173,7 @@ int jpdvt_ln_modulate_fwd(const float* x, const float* shift, const float* scale
 
 static int gemm_simple(int epi, const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, void* out, float* out2,
                        int64_t m, int n, int k, void* stream) {
+  if (m == 0) return kOk;   // empty batch: nothing to launch (torch hands out null pointers for empty tensors)
   if (!a || !w || !bias || !out) return set_error(kErrBadArg, "gemm: null pointer");
   if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
   GemmParams p{};
