@@ -45,11 +45,13 @@ int jpdvt_device_check(void);
 
 /* ---- single kernels ------------------------------------------------------------------------------------------ */
 
-/* y = LayerNorm(x, eps=1e-6, no affine) * (1 + scale[b]) + shift[b], b = row / tokens; sample b reads its 768-wide
- * vectors at shift + b*mod_stride, scale + b*mod_stride (mod_stride 0 = one conditioning row for the whole batch).
+/* If delta != NULL: x += delta first (the gated branch output of the previous GEMM, bf16; x is updated in place - the
+ * residual add of models.py:120-121 rides on this pass).  Then y = LayerNorm(x, eps=1e-6, no affine) * (1 + scale[b]) +
+ * shift[b], b = row / tokens; sample b reads its 768-wide vectors at shift + b*mod_stride, scale + b*mod_stride
+ * (mod_stride 0 = one conditioning row for the whole batch).
  * Replaces nn.LayerNorm + modulate: models.py:19-20,107,109,120-121,131,140. */
-int jpdvt_ln_modulate_fwd(const float* x, const float* shift, const float* scale, int64_t mod_stride, jpdvt_bf16* y,
-                          int64_t rows, int tokens, void* stream);
+int jpdvt_ln_modulate_fwd(float* x, const jpdvt_bf16* delta_or_null, const float* shift, const float* scale,
+                          int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens, void* stream);
 
 /* tcgen05 GEMMs: out[M,N] = a[M,K] . w[N,K]^T + bias, a/w bf16 (w in nn.Linear layout), fp32 accumulate.
  * M arbitrary, K % 64 == 0, N % 128 == 0.  Replace timm Attention.qkv / Mlp.fc1 / FinalLayer.linear (models.py:108,112,132). */
@@ -60,10 +62,10 @@ int jpdvt_gemm_bias_f32(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* b
 /* out = gelu_tanh(a . w^T + bias)  (timm Mlp.fc1 + nn.GELU(approximate="tanh"), models.py:110-112) */
 int jpdvt_gemm_bias_gelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, jpdvt_bf16* out, int64_t m, int n,
                          int k, void* stream);
-/* x[row] += gate[row / tokens] * (a . w^T + bias)   in place on the fp32 residual stream
- * (attn.proj / mlp.fc2 + gated residual, models.py:120-121). */
-int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
-                                  int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream);
+/* out[row] = gate[row / tokens] * (a . w^T + bias) in bf16: the gated branch of attn.proj / mlp.fc2 (models.py:120-121);
+ * the `x +=` half is applied by the next jpdvt_ln_modulate_fwd(delta = out). */
+int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                         int64_t gate_stride, jpdvt_bf16* out, int64_t m, int n, int k, int tokens, void* stream);
 /* x = cols . w_patch^T + bias + pos_embed[row % tokens] + x_t[row] . w_in_t   (PatchEmbed conv as GEMM + time_emb_in +
  * pos_embed, models.py:280-281).  cols = jpdvt_patchify(img); bias = x_embedder.proj.bias + time_emb_in.bias;
  * w_in_t = time_emb_in.weight^T as [8,768] fp32; pos = pos_embed [tokens,768] fp32. */
@@ -158,7 +160,7 @@ typedef struct jpdvt_workspace {
   jpdvt_bf16* qkv;              /* [rows, 2304] */
   jpdvt_bf16* attn;             /* [rows, 768]  */
   jpdvt_bf16* hid;              /* [rows, 3072] (also holds the im2col tile of the patch embed) */
-  jpdvt_bf16* y;                /* [rows, 768] final-layer output */
+  jpdvt_bf16* y;                /* [rows, 768] gated branch outputs, then the final-layer output */
   float* y32;                   /* [rows, 768] fp32 copy for unpatchify, or NULL */
   float* c;                     /* [cond_rows, 768] */
   float* silu_c;                /* [cond_rows, 768] */

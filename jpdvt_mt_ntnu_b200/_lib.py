@@ -43,11 +43,11 @@ P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header
 PROTOTYPES = {
     "jpdvt_device_check": [],
-    "jpdvt_ln_modulate_fwd": [P, P, P, c_int64, P, c_int64, c_int, P],
+    "jpdvt_ln_modulate_fwd": [P, P, P, P, c_int64, P, c_int64, c_int, P],
     "jpdvt_gemm_bias": [P, P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gelu": [P, P, P, P, c_int64, c_int, c_int, P],
-    "jpdvt_gemm_bias_gate_residual": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_gemm_bias_gate": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
     "jpdvt_attention_fwd": [P, P, c_int, c_int, P],

@@ -89,10 +89,12 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws->attn);
   __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+  __nv_bfloat16* br = reinterpret_cast<__nv_bfloat16*>(ws->y);   // gated branch output, folded into x by the next LN
+  const __nv_bfloat16* pending = nullptr;                          // branch output not yet added to the residual stream
   for (int i = 0; i < depth; ++i) {
     const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
     // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120)
-    JP_TRY(launch_ln_modulate(ws->x, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, pending, mod, mod + kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
@@ -103,12 +105,12 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
-      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = ws->x; p.resid = ws->x; p.ldo = kHidden;
+      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
       p.gate = mod + 2 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_GATE_RESID_F32, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
+      JP_TRY(launch_gemm(EPI_GATE_BF16, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
     }
     // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
-    JP_TRY(launch_ln_modulate(ws->x, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, br, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
@@ -118,15 +120,16 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = 4 * kHidden; p.tokens = T;
-      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = ws->x; p.resid = ws->x; p.ldo = kHidden;
+      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
       p.gate = mod + 5 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_GATE_RESID_F32, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
+      JP_TRY(launch_gemm(EPI_GATE_BF16, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
     }
+    pending = br;
   }
   // final layer + position head                                            (models.py:287-290)
   {
     const float* mod = ws->mod + static_cast<long long>(depth) * 6 * kHidden;   // shift, scale
-    JP_TRY(launch_ln_modulate(ws->x, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, pending, mod, mod + kHidden, mod_stride, xn, M, T, st));
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
@@ -165,10 +168,11 @@ int jpdvt_device_check(void) {
   return kOk;
 }
 
-int jpdvt_ln_modulate_fwd(const float* x, const float* shift, const float* scale, int64_t mod_stride, jpdvt_bf16* y,
-                          int64_t rows, int tokens, void* stream) {
+int jpdvt_ln_modulate_fwd(float* x, const jpdvt_bf16* delta_or_null, const float* shift, const float* scale,
+                          int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens, void* stream) {
+  if (rows == 0) return kOk;
   if (!x || !shift || !scale || !y) return set_error(kErrBadArg, "ln_modulate: null pointer");
-  return launch_ln_modulate(x, shift, scale, mod_stride, BFM(y), rows, tokens, ST(stream));
+  return launch_ln_modulate(x, BF(delta_or_null), shift, scale, mod_stride, BFM(y), rows, tokens, ST(stream));
 }
 
 static int gemm_simple(int epi, const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, void* out, float* out2,
@@ -194,15 +198,16 @@ int jpdvt_gemm_bias_gelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* 
                          int k, void* stream) {
   return gemm_simple(EPI_BIAS_GELU_BF16, a, w, bias, out, nullptr, m, n, k, stream);
 }
-int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
-                                  int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream) {
-  if (!a || !w || !bias || !gate || !x) return set_error(kErrBadArg, "gemm_gate_residual: null pointer");
-  if (tokens <= 0) return set_error(kErrBadArg, "gemm_gate_residual: tokens must be positive");
+int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                         int64_t gate_stride, jpdvt_bf16* out, int64_t m, int n, int k, int tokens, void* stream) {
+  if (m == 0) return kOk;
+  if (!a || !w || !bias || !gate || !out) return set_error(kErrBadArg, "gemm_bias_gate: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_bias_gate: tokens must be positive");
   if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
   GemmParams p{};
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
-  p.bias = bias; p.out = x; p.resid = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
-  return launch_gemm(EPI_GATE_RESID_F32, BF(a), k, BF(w), k, p, ST(stream));
+  p.bias = bias; p.out = out; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
+  return launch_gemm(EPI_GATE_BF16, BF(a), k, BF(w), k, p, ST(stream));
 }
 int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
                            const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {

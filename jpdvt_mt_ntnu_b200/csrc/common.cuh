@@ -27,7 +27,7 @@ int check_launch(const char* what);
 enum Epilogue : int {
   EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias
   EPI_BIAS_GELU_BF16 = 1,   // out_bf16 = gelu_tanh(acc + bias)
-  EPI_GATE_RESID_F32 = 2,   // out_f32 = resid + gate[row / tokens] * (acc + bias)
+  EPI_GATE_BF16 = 2,        // out_bf16 = gate[row / tokens] * (acc + bias)   (the residual add is fused into the next LN)
   EPI_PATCH_EMBED_F32 = 3,  // out_f32 = acc + bias + pos[row % tokens] + x_t[row,:8] . w_in_t[:, n]
   EPI_BIAS_F32 = 4,         // out_f32 = acc + bias
   EPI_BIAS_BF16_F32 = 5,    // out_bf16 = acc + bias, and (if out2 != null) out2_f32 = acc + bias
@@ -41,7 +41,6 @@ struct GemmParams {
   void* out;             // primary output, row-major, leading dimension ldo (elements)
   long long ldo;
   float* out2;           // optional fp32 copy (EPI_BIAS_BF16_F32)
-  const float* resid;    // [M, N] fp32, leading dimension ldo (may alias out)
   const float* gate;     // sample b reads gate + b * gate_stride, [N] contiguous
   long long gate_stride;
   const float* xt;       // [M, 8] fp32                     (patch embed)
@@ -57,8 +56,9 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream);
 
-int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_stride, __nv_bfloat16* y,
-                       long long rows, int tokens, cudaStream_t stream);
+// x += delta (optional, bf16, written back to x), then y = LN(x) * (1 + scale) + shift
+int launch_ln_modulate(float* x, const __nv_bfloat16* delta, const float* shift, const float* scale, long long mod_stride,
+                       __nv_bfloat16* y, long long rows, int tokens, cudaStream_t stream);
 int launch_patchify(const float* img, __nv_bfloat16* cols, int batch, int size, cudaStream_t stream);
 int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStream_t stream);
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,

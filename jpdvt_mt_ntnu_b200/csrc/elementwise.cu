@@ -20,19 +20,35 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------- LN + modulate
 // One warp per 768-wide row: 6 float4 per lane (coalesced 512 B per warp load), two-pass statistics in registers,
-// 8-byte bf16x4 stores.  Algorithmic traffic per row: 3072 B read + 1536 B written.
+// 8-byte bf16x4 stores.  When `delta` is given the gated branch output of the previous GEMM is added to the fp32
+// residual stream first (x += delta, models.py:120-121) and x is written back, so the residual add costs no extra pass.
+// Algorithmic traffic per row: 3072 B read + 1536 B written (+ 1536 B read + 3072 B written with delta).
 constexpr int kLnWarps = 8;
 
+template <bool HAS_DELTA>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
-                   long long mod_stride, __nv_bfloat16* __restrict__ y, long long rows, int tokens) {
+ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const float* __restrict__ shift,
+                   const float* __restrict__ scale, long long mod_stride, __nv_bfloat16* __restrict__ y, long long rows,
+                   int tokens) {
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * kHidden);
+  float4* xr = reinterpret_cast<float4*>(x + row * kHidden);
   float4 v[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) v[j] = __ldcs(xr + lane + 32 * j);
+  if constexpr (HAS_DELTA) {
+    const uint2* dr = reinterpret_cast<const uint2*>(delta + row * kHidden);
+    uint2 d[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) d[j] = __ldcs(dr + lane + 32 * j);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      v[j].x += __uint_as_float(d[j].x << 16); v[j].y += __uint_as_float(d[j].x & 0xffff0000u);
+      v[j].z += __uint_as_float(d[j].y << 16); v[j].w += __uint_as_float(d[j].y & 0xffff0000u);
+      xr[lane + 32 * j] = v[j];
+    }
+  }
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -63,12 +79,15 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
   }
 }
 
-int launch_ln_modulate(const float* x, const float* shift, const float* scale, long long mod_stride, __nv_bfloat16* y,
-                       long long rows, int tokens, cudaStream_t stream) {
+int launch_ln_modulate(float* x, const __nv_bfloat16* delta, const float* shift, const float* scale, long long mod_stride,
+                       __nv_bfloat16* y, long long rows, int tokens, cudaStream_t stream) {
   if (rows <= 0) return kOk;
   if (tokens <= 0) return set_error(kErrBadArg, "ln_modulate: tokens must be positive");
-  const long long blocks = (rows + kLnWarps - 1) / kLnWarps;
-  ln_modulate_kernel<<<static_cast<unsigned>(blocks), kLnWarps * 32, 0, stream>>>(x, shift, scale, mod_stride, y, rows, tokens);
+  const unsigned blocks = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
+  if (delta != nullptr)
+    ln_modulate_kernel<true><<<blocks, kLnWarps * 32, 0, stream>>>(x, delta, shift, scale, mod_stride, y, rows, tokens);
+  else
+    ln_modulate_kernel<false><<<blocks, kLnWarps * 32, 0, stream>>>(x, delta, shift, scale, mod_stride, y, rows, tokens);
   return check_launch("ln_modulate_kernel");
 }
 
@@ -125,26 +144,28 @@ int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStrea
 }
 
 // ---------------------------------------------------------------------------------------------- timestep embedding
-// Up to kTeRows conditioning rows per CTA share every weight read.  Each warp owns output features; lanes stride the
-// reduction dimension (coalesced weight reads), then a warp reduction per (row, feature).
+// Two grid-wide phases (hidden = SiLU(W0 . sinusoid + b0), then c = W2 . hidden + b2) so the 2.4 MB + 0.8 MB of fp32
+// weights are streamed by ~96 CTAs instead of one.  Up to kTeRows conditioning rows per blockIdx.y share every weight
+// read; each warp owns one output feature, lanes stride the reduction dimension (coalesced), warp-shuffle reduction.
 constexpr int kTeRows = 8;
-constexpr int kTeThreads = 256;
+constexpr int kTeWarps = 8;
 
-__global__ void __launch_bounds__(kTeThreads)
-timestep_embed_kernel(const long long* __restrict__ t, int n, const int* __restrict__ step_ptr, const int* __restrict__ map,
-                      const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
-                      const float* __restrict__ b2, float* __restrict__ c_out, float* __restrict__ silu_out) {
+__device__ __forceinline__ long long te_timestep(const long long* t, int r, const int* step_ptr, const int* map) {
+  if (t != nullptr) return t[r];
+  return (map != nullptr) ? static_cast<long long>(map[*step_ptr]) : static_cast<long long>(*step_ptr);
+}
+
+__global__ void __launch_bounds__(kTeWarps * 32)
+timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __restrict__ step_ptr, const int* __restrict__ map,
+                       const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ hid) {
   __shared__ float feat[kTeRows][256];
-  __shared__ float hid[kTeRows][kHidden];
-  const int r0 = blockIdx.x * kTeRows;
+  const int r0 = blockIdx.y * kTeRows;
   const int nr = min(kTeRows, n - r0);
-  for (int i = threadIdx.x; i < kTeRows * 128; i += kTeThreads) {
+  for (int i = threadIdx.x; i < kTeRows * 128; i += kTeWarps * 32) {
     const int r = i >> 7, k = i & 127;
     float c = 0.f, s = 0.f;
     if (r < nr) {
-      long long tv;
-      if (t != nullptr) tv = t[r0 + r];
-      else tv = (map != nullptr) ? map[*step_ptr] : *step_ptr;
+      const long long tv = te_timestep(t, r0 + r, step_ptr, map);
       // models.py:52-56: freqs = exp(-ln(10000) * arange(128, fp32) / 128) in fp32, args = t.float() * freqs
       const float f = expf((-9.210340371976184f * static_cast<float>(k)) / 128.0f);
       const float a = static_cast<float>(tv) * f;
@@ -155,109 +176,144 @@ timestep_embed_kernel(const long long* __restrict__ t, int n, const int* __restr
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < kHidden; o += kTeThreads / 32) {
-    float acc[kTeRows];
+  const int o = blockIdx.x * kTeWarps + warp;
+  if (o >= kHidden) return;
+  float acc[kTeRows];
 #pragma unroll
-    for (int r = 0; r < kTeRows; ++r) acc[r] = 0.f;
-    for (int k = lane; k < 256; k += 32) {
-      const float w = __ldg(w0 + o * 256 + k);
+  for (int r = 0; r < kTeRows; ++r) acc[r] = 0.f;
 #pragma unroll
-      for (int r = 0; r < kTeRows; ++r) acc[r] = fmaf(w, feat[r][k], acc[r]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane + 32 * j;
+    const float w = __ldg(w0 + o * 256 + k);
 #pragma unroll
-    for (int r = 0; r < kTeRows; ++r) acc[r] = warp_sum(acc[r]);
-    if (lane == 0) {
-      const float b = __ldg(b0 + o);
-#pragma unroll
-      for (int r = 0; r < kTeRows; ++r) { const float v = acc[r] + b; hid[r][o] = v / (1.0f + expf(-v)); }
-    }
+    for (int r = 0; r < kTeRows; ++r) acc[r] = fmaf(w, feat[r][k], acc[r]);
   }
-  __syncthreads();
-  for (int o = warp; o < kHidden; o += kTeThreads / 32) {
-    float acc[kTeRows];
 #pragma unroll
-    for (int r = 0; r < kTeRows; ++r) acc[r] = 0.f;
-    for (int k = lane; k < kHidden; k += 32) {
-      const float w = __ldg(w2 + o * kHidden + k);
-#pragma unroll
-      for (int r = 0; r < kTeRows; ++r) acc[r] = fmaf(w, hid[r][k], acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kTeRows; ++r) acc[r] = warp_sum(acc[r]);
-    if (lane == 0) {
-      const float b = __ldg(b2 + o);
-      for (int r = 0; r < nr; ++r) {
-        const float v = acc[r] + b;
-        c_out[static_cast<long long>(r0 + r) * kHidden + o] = v;
-        silu_out[static_cast<long long>(r0 + r) * kHidden + o] = v / (1.0f + expf(-v));
-      }
+  for (int r = 0; r < kTeRows; ++r) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+    const float b = __ldg(b0 + o);
+    for (int r = 0; r < nr; ++r) {
+      const float v = acc[r] + b;
+      hid[static_cast<long long>(r0 + r) * kHidden + o] = v / (1.0f + expf(-v));
     }
   }
 }
 
+__global__ void __launch_bounds__(kTeWarps * 32)
+timestep_out_kernel(const float* __restrict__ hid, int n, const float* __restrict__ w2, const float* __restrict__ b2,
+                    float* __restrict__ c_out, float* __restrict__ silu_out) {
+  __shared__ float h[kTeRows][kHidden];
+  const int r0 = blockIdx.y * kTeRows;
+  const int nr = min(kTeRows, n - r0);
+  for (int i = threadIdx.x; i < kTeRows * kHidden; i += kTeWarps * 32) {
+    const int r = i / kHidden;
+    h[r][i - r * kHidden] = (r < nr) ? hid[static_cast<long long>(r0) * kHidden + i] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * kTeWarps + warp;
+  if (o >= kHidden) return;
+  float acc[kTeRows];
+#pragma unroll
+  for (int r = 0; r < kTeRows; ++r) acc[r] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < kHidden / 32; ++j) {
+    const int k = lane + 32 * j;
+    const float w = __ldg(w2 + o * kHidden + k);
+#pragma unroll
+    for (int r = 0; r < kTeRows; ++r) acc[r] = fmaf(w, h[r][k], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kTeRows; ++r) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+    const float b = __ldg(b2 + o);
+    for (int r = 0; r < nr; ++r) {
+      const float v = acc[r] + b;
+      c_out[static_cast<long long>(r0 + r) * kHidden + o] = v;
+      silu_out[static_cast<long long>(r0 + r) * kHidden + o] = v / (1.0f + expf(-v));
+    }
+  }
+}
+
+// `silu_c` doubles as the scratch for the hidden activations between the two phases.
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
                           const float* w2, const float* b2, float* c, float* silu_c, cudaStream_t stream) {
   if (n <= 0) return kOk;
   if (t == nullptr && step_ptr == nullptr) return set_error(kErrBadArg, "timestep_embed: need t or step_ptr");
-  timestep_embed_kernel<<<(n + kTeRows - 1) / kTeRows, kTeThreads, 0, stream>>>(t, n, step_ptr, map, w0, b0, w2, b2, c, silu_c);
-  return check_launch("timestep_embed_kernel");
+  dim3 grid(kHidden / kTeWarps, (n + kTeRows - 1) / kTeRows);
+  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, map, w0, b0, c);
+  int rc = check_launch("timestep_hidden_kernel");
+  if (rc != kOk) return rc;
+  timestep_out_kernel<<<grid, kTeWarps * 32, 0, stream>>>(c, n, w2, b2, c, silu_c);
+  return check_launch("timestep_out_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------- adaLN modulation GEMV
 // out[r, n] = bias[n] + sum_k silu_c[r, k] * W[n, k]   for r < rows <= kGvRows; W bf16 [n_out, 768] streamed once.
-// One warp per output feature: 3 x 16-byte loads per lane cover the 768-wide weight row (1536 B, coalesced).
+// Persistent grid: each warp walks output features with a grid stride; per feature 3 x 16-byte loads per lane cover the
+// 768-wide weight row (1536 B, coalesced).  Algorithmic traffic: n_out * 1536 B of weights (87 MB for JPDVT).
 constexpr int kGvRows = 8;
 constexpr int kGvWarps = 8;
 
+template <int ROWS>
 __global__ void __launch_bounds__(kGvWarps * 32)
-adaln_gemv_kernel(const float* __restrict__ silu_c, int rows, const __nv_bfloat16* __restrict__ w,
-                  const float* __restrict__ bias, float* __restrict__ out, int n_out) {
-  __shared__ float sc[kGvRows][kHidden];
-  for (int i = threadIdx.x; i < kGvRows * kHidden; i += kGvWarps * 32) {
-    const int r = i / kHidden;
-    sc[r][i - r * kHidden] = (r < rows) ? silu_c[i] : 0.f;
-  }
+adaln_gemv_kernel(const float* __restrict__ silu_c, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int n_out) {
+  __shared__ float sc[ROWS][kHidden];
+  for (int i = threadIdx.x; i < ROWS * kHidden; i += kGvWarps * 32) sc[i / kHidden][i % kHidden] = silu_c[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kGvWarps + (threadIdx.x >> 5);
-  if (n >= n_out) return;
-  float acc[kGvRows];
+  const int stride = gridDim.x * kGvWarps;
+  for (int n = blockIdx.x * kGvWarps + (threadIdx.x >> 5); n < n_out; n += stride) {
+    float acc[ROWS];
 #pragma unroll
-  for (int r = 0; r < kGvRows; ++r) acc[r] = 0.f;
-  const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * kHidden);
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * kHidden);
+    uint4 u[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const uint4 u = __ldcs(wr + lane + 32 * j);
-    const int k0 = (lane + 32 * j) * 8;
-    const uint32_t words[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < 3; ++j) u[j] = __ldcs(wr + lane + 32 * j);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float lo = __uint_as_float(words[e] << 16);
-      const float hi = __uint_as_float(words[e] & 0xffff0000u);
+    for (int j = 0; j < 3; ++j) {
+      const int k0 = (lane + 32 * j) * 8;
+      const uint32_t words[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
 #pragma unroll
-      for (int r = 0; r < kGvRows; ++r) {
-        acc[r] = fmaf(lo, sc[r][k0 + 2 * e], acc[r]);
-        acc[r] = fmaf(hi, sc[r][k0 + 2 * e + 1], acc[r]);
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(words[e] << 16);
+        const float hi = __uint_as_float(words[e] & 0xffff0000u);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          acc[r] = fmaf(lo, sc[r][k0 + 2 * e], acc[r]);
+          acc[r] = fmaf(hi, sc[r][k0 + 2 * e + 1], acc[r]);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int r = 0; r < kGvRows; ++r) acc[r] = warp_sum(acc[r]);
-  if (lane == 0) {
-    const float b = __ldg(bias + n);
-    for (int r = 0; r < rows; ++r) out[static_cast<long long>(r) * n_out + n] = acc[r] + b;
+    for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+      const float b = __ldg(bias + n);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) out[static_cast<long long>(r) * n_out + n] = acc[r] + b;
+    }
   }
 }
 
 int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, const float* bias, float* out, int n_out,
                       cudaStream_t stream) {
   if (rows <= 0 || n_out <= 0) return kOk;
-  for (int r0 = 0; r0 < rows; r0 += kGvRows) {
-    const int nr = rows - r0 < kGvRows ? rows - r0 : kGvRows;
-    adaln_gemv_kernel<<<(n_out + kGvWarps - 1) / kGvWarps, kGvWarps * 32, 0, stream>>>(
-        silu_c + static_cast<long long>(r0) * kHidden, nr, w, bias, out + static_cast<long long>(r0) * n_out, n_out);
+  int blocks = (n_out + kGvWarps - 1) / kGvWarps;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  for (int r0 = 0; r0 < rows;) {
+    const int left = rows - r0;
+    const float* s = silu_c + static_cast<long long>(r0) * kHidden;
+    float* o = out + static_cast<long long>(r0) * n_out;
+    int used;
+    if (left >= 8) { adaln_gemv_kernel<8><<<blocks, kGvWarps * 32, 0, stream>>>(s, w, bias, o, n_out); used = 8; }
+    else if (left >= 4) { adaln_gemv_kernel<4><<<blocks, kGvWarps * 32, 0, stream>>>(s, w, bias, o, n_out); used = 4; }
+    else if (left >= 2) { adaln_gemv_kernel<2><<<blocks, kGvWarps * 32, 0, stream>>>(s, w, bias, o, n_out); used = 2; }
+    else { adaln_gemv_kernel<1><<<blocks, kGvWarps * 32, 0, stream>>>(s, w, bias, o, n_out); used = 1; }
     int rc = check_launch("adaln_gemv_kernel");
     if (rc != kOk) return rc;
+    r0 += used;
   }
   return kOk;
 }

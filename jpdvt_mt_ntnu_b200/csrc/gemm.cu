@@ -1,168 +1,233 @@
 // Persistent warp-specialised tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue).
 //
-//   warp 0 : TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier complete_tx)
-//   warp 1 : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM, double buffered)
-//   warps 2-5 : epilogue    (tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / gated residual / ...)
+// CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2): one pair owns a 256 x BN output tile; each CTA loads its
+// own 128 rows of A and HALF of the W tile (BN/2 rows) with TMA and both halves feed one 256 x BN x 16 MMA, so the
+// L2->SM operand traffic per FLOP is 2/3 of a single-CTA 128 x 256 tile (the round-1 profile showed the single-CTA
+// kernel pinned at ~38 B/clk/SM of L2 reads, 48 % tensor-pipe active).
 //
-// Replaces the cuBLAS calls behind nn.Linear in the reference denoiser (image_model/models.py:108-121,132,176-179,
-// timm Attention.qkv/proj, Mlp.fc1/fc2, PatchEmbed.proj) - see SURVEY.md 2.1.
-// A and W are both K-major bf16, so both operands use the canonical K-major SWIZZLE_128B smem layout that a
-// {64 x rows} TMA box produces.  fp32 accumulation.
+//   warp 0    : TMA producer   (cp.async.bulk.tensor 2-D, 128B swizzle; both CTAs signal the LEADER's full barrier)
+//   warp 1    : MMA issuer     (leader CTA only: one lane issues tcgen05.mma.cta_group::2, accumulators in the TMEM
+//                               of both CTAs, double buffered; tcgen05.commit multicasts to both CTAs' barriers)
+//   warps 2-5 : epilogue       (tcgen05.ld 32 lanes x 32 columns, fused math, transpose through padded smem so every
+//                               global access is a full 128-byte row segment)
+//
+// Replaces the cuBLAS calls behind nn.Linear / Conv2d in the reference denoiser (image_model/models.py:108-121,132,
+// 169,176-179; timm Attention.qkv/proj, Mlp.fc1/fc2, PatchEmbed.proj) - see SURVEY.md 2.1.
+// A and W are both K-major bf16 ({64 x rows} TMA boxes -> canonical K-major SWIZZLE_128B smem tiles), fp32 accumulate.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace jp {
 
-constexpr int BM = 128;
+constexpr int BM = 128;         // rows per CTA (256 per pair)
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kStageRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free 16-byte accesses
+constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpose buffer per epilogue warp
 
-template <int BN>
+template <int BN, int CS>
 struct GemmCfg {
+  static constexpr int kBRows = BN / CS;                  // W rows this CTA loads
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two for BN in {64,128,256})
+  static constexpr int kPipeBudget = 194 * 1024;
+  static constexpr int kStagesRaw = kPipeBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStageWarpBytes + kBarBytes + 1024;
 };
 
-__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* dst, const float* v) {
-  uint4 u;
-  u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(dst) = u;
+// ---- cluster helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the completion bytes are credited to the barrier at `bar_cluster_addr`
+// (a shared::cluster address - the leader CTA's full barrier).
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all previously issued MMAs retire) on the barrier at the same smem offset in every CTA of `mask`.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 
-// One 32-column chunk of one accumulator row.  `acc` holds fp32 accumulators for columns [n0, n0+32).
+// ---- epilogue --------------------------------------------------------------------------------------------------------
+// The thread that owns accumulator row `row` holds fp32 values v[0..NC) for columns [n0, n0 + NC).
+// bf16 outputs are staged 64 columns (128 B per row) at a time, fp32 outputs 32 columns (128 B) at a time.
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&acc)[32], long long row, int n0, bool row_ok,
-                                               const float* xt_row) {
-  // bias (uniform across the warp -> broadcast loads served by L1)
+__device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], int row, int n0, bool row_ok) {
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 b = __ldg(b4 + j);
-    acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+  for (int j = 0; j < 16; ++j) {
+    const float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
   }
-  if (!row_ok) return;
-
   if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = gelu_tanh(acc[j]);
+    for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
   }
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_BF16_F32) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + n0;
+  if constexpr (EPI == EPI_GATE_BF16) {
+    const int sample = row_ok ? row / p.tokens : 0;
+    const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<long long>(sample) * p.gate_stride + n0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st_bf16x8(o + 8 * j, &acc[8 * j]);
-    if constexpr (EPI == EPI_BIAS_BF16_F32) {
-      if (p.out2 != nullptr) {
-        float4* o2 = reinterpret_cast<float4*>(p.out2 + row * p.ldo + n0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o2[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-      }
-    }
-  }
-  if constexpr (EPI == EPI_BIAS_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-  }
-  if constexpr (EPI == EPI_GATE_RESID_F32) {
-    const long long sample = row / p.tokens;
-    const float4* g4 = reinterpret_cast<const float4*>(p.gate + sample * p.gate_stride + n0);
-    const float4* r4 = reinterpret_cast<const float4*>(p.resid + row * p.ldo + n0);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 g = __ldg(g4 + j);
-      float4 r = r4[j];
-      r.x = fmaf(g.x, acc[4 * j + 0], r.x); r.y = fmaf(g.y, acc[4 * j + 1], r.y);
-      r.z = fmaf(g.z, acc[4 * j + 2], r.z); r.w = fmaf(g.w, acc[4 * j + 3], r.w);
-      o[j] = r;
-    }
-  }
-  if constexpr (EPI == EPI_PATCH_EMBED_F32) {
-    const int tok = static_cast<int>(row % p.tokens);
-    const float4* pos4 = reinterpret_cast<const float4*>(p.pos + static_cast<long long>(tok) * p.N + n0);
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 v = __ldg(pos4 + j);
-      v.x += acc[4 * j + 0]; v.y += acc[4 * j + 1]; v.z += acc[4 * j + 2]; v.w += acc[4 * j + 3];
-#pragma unroll
-      for (int d = 0; d < kLatent; ++d) {
-        float4 w = __ldg(reinterpret_cast<const float4*>(p.w_in_t + static_cast<long long>(d) * p.N + n0) + j);
-        v.x = fmaf(xt_row[d], w.x, v.x); v.y = fmaf(xt_row[d], w.y, v.y);
-        v.z = fmaf(xt_row[d], w.z, v.z); v.w = fmaf(xt_row[d], w.w, v.w);
-      }
-      o[j] = v;
+    for (int j = 0; j < 16; ++j) {
+      const float4 g = __ldg(g4 + j);
+      v[4 * j + 0] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
     }
   }
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// 32 rows x 64 bf16 columns of this warp -> global, every store instruction writes 4 full 128-byte row segments.
+__device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)[64], __nv_bfloat16* out, long long ldo,
+                                                int row0, int n0, int M, int lane) {
+  uint8_t* mine = stage + lane * kStageRowBytes;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]); u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(mine + 16 * j) = u;
+  }
+  __syncwarp();
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sub;
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
+    if (row0 + r < M) *reinterpret_cast<uint4*>(out + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch) = u;
+  }
+  __syncwarp();
+}
+
+// 32 rows x 32 fp32 columns of this warp -> staging buffer (row-per-thread in, coalesced row segments out).
+__device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[32], int lane) {
+  uint8_t* mine = stage + lane * kStageRowBytes;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+}
+
+template <int BN, int EPI, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + kEpiWarps * kStageWarpBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (p.M + BM - 1) / BM;
+  const uint32_t rank = (CS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int num_m = (p.M + CS * BM - 1) / (CS * BM);       // tiles of CS*128 rows
   const int num_n = p.N / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / BK;
+  const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS * kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CS == 2) { tmem_alloc2(tmem_slot, Cfg::kTmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int row_a = (m_blk * CS + static_cast<int>(rank)) * BM;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BK, m_blk * BM);
-          tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BK, n_blk * BN);
+          if constexpr (CS == 2) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
+            const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(&tma_a, bar, sa, kb * BK, row_a);
+            tma_load_2d_pair(&tma_b, bar, sb, kb * BK, row_b);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BK, row_a);
+            tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BK, row_b);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
+    __syncwarp();   // reconverge before the aligned cluster barrier at teardown
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -175,42 +240,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t db = umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if constexpr (CS == 2) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+        if constexpr (CS == 2) umma_commit_pair(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    uint8_t* stage = stage_buf + (warp - 2) * kStageWarpBytes;
     int acc = 0; uint32_t acc_phase = 0;
     __shared__ float s_w2[kLatent * 64];
     __shared__ float s_b2[kLatent];
     if constexpr (EPI == EPI_HEAD) {
-      for (int i = threadIdx.x - 64; i < kLatent * 64; i += 128) s_w2[i] = p.w2[i];
+      for (int i = threadIdx.x - 64; i < kLatent * 64; i += kEpiWarps * 32) s_w2[i] = p.w2[i];
       if (threadIdx.x - 64 < kLatent) s_b2[threadIdx.x - 64] = p.b2[threadIdx.x - 64];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const long long row = static_cast<long long>(m_blk) * BM + quad * 32 + lane;
+      const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;   // first row of this warp
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      float xt_row[kLatent];
-      if constexpr (EPI == EPI_PATCH_EMBED_F32) {
-        if (row_ok) {
-          const float4* x4 = reinterpret_cast<const float4*>(p.xt + row * kLatent);
-          float4 u = x4[0], v = x4[1];
-          xt_row[0] = u.x; xt_row[1] = u.y; xt_row[2] = u.z; xt_row[3] = u.w;
-          xt_row[4] = v.x; xt_row[5] = v.y; xt_row[6] = v.z; xt_row[7] = v.w;
-        }
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
       if constexpr (EPI == EPI_HEAD) {
         static_assert(EPI != EPI_HEAD || BN == 64, "head epilogue needs the whole 64-wide row");
         uint32_t r0[32], r1[32];
@@ -232,34 +294,118 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int j = 0; j < 64; ++j) s = fmaf(h[j], s_w2[d * 64 + j], s);
             o[d] = s;
           }
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row * p.ldo);
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo);
           dst[0] = make_float4(o[0], o[1], o[2], o[3]);
           dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
+      } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_BF16 || EPI == EPI_BIAS_BF16_F32) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + c * 64, r0);
+          tmem_ld_32x32(t_row + c * 64 + 32, r1);
+          tmem_ld_wait();
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          const int n0 = n_blk * BN + c * 64;
+          bf16_math<EPI>(p, v, row, n0, row_ok);
+          store_bf16_tile(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M, lane);
+          if constexpr (EPI == EPI_BIAS_BF16_F32) {
+            if (p.out2 != nullptr) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float w32[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w32[j] = v[32 * hh + j];
+                stage_f32_tile(stage, w32, lane);
+                const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int r = it * 4 + sub;
+                  const float4 u = *reinterpret_cast<const float4*>(stage + r * kStageRowBytes + 16 * ch);
+                  if (row0 + r < p.M)
+                    *reinterpret_cast<float4*>(p.out2 + static_cast<long long>(row0 + r) * p.ldo + n0 + 32 * hh + 4 * ch) = u;
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
       } else {
+        // fp32 outputs: EPI_BIAS_F32, EPI_PATCH_EMBED_F32
+        float xt_row[kLatent];
+        if constexpr (EPI == EPI_PATCH_EMBED_F32) {
+#pragma unroll
+          for (int d = 0; d < kLatent; ++d) xt_row[d] = 0.f;
+          if (row_ok) {
+            const float4* x4 = reinterpret_cast<const float4*>(p.xt + static_cast<long long>(row) * kLatent);
+            const float4 u = x4[0], w = x4[1];
+            xt_row[0] = u.x; xt_row[1] = u.y; xt_row[2] = u.z; xt_row[3] = u.w;
+            xt_row[4] = w.x; xt_row[5] = w.y; xt_row[6] = w.z; xt_row[7] = w.w;
+          }
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(t_row + c * 32, r);
           tmem_ld_wait();
-          float accv[32];
+          const int n0 = n_blk * BN + c * 32;
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) accv[j] = __uint_as_float(r[j]);
-          epilogue_chunk<EPI>(p, accv, row, n_blk * BN + c * 32, row_ok, xt_row);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+          }
+          if constexpr (EPI == EPI_PATCH_EMBED_F32) {
+            // + x_t[row, :8] . w_in_t[:, n]  (time_emb_in, models.py:280); 8 FMAs per output, weights broadcast from L1
+#pragma unroll
+            for (int d = 0; d < kLatent; ++d) {
+              const float4* w4 = reinterpret_cast<const float4*>(p.w_in_t + static_cast<long long>(d) * p.N + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = __ldg(w4 + j);
+                v[4 * j + 0] = fmaf(xt_row[d], w.x, v[4 * j + 0]); v[4 * j + 1] = fmaf(xt_row[d], w.y, v[4 * j + 1]);
+                v[4 * j + 2] = fmaf(xt_row[d], w.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(xt_row[d], w.w, v[4 * j + 3]);
+              }
+            }
+          }
+          stage_f32_tile(stage, v, lane);
+          const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            float4 u = *reinterpret_cast<const float4*>(stage + rr * kStageRowBytes + 16 * ch);
+            const int grow = row0 + rr;
+            if (grow < p.M) {
+              if constexpr (EPI == EPI_PATCH_EMBED_F32) {   // + pos_embed[row % tokens]  (coalesced 128-byte segments)
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(grow % p.tokens) * p.N + n0) + ch);
+                u.x += q.x; u.y += q.y; u.z += q.z; u.w += q.w;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + n0 + 4 * ch) = u;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CS == 2) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(acc) * 8u);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    __syncwarp();
+    if constexpr (CS == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -309,20 +455,42 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int EPI>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int cluster_size() {
+  static int cs = 0;
+  if (cs == 0) {
+    const char* e = getenv("JPDVT_GEMM_CLUSTER");   // debugging knob: 1 = single-CTA tiles, 2 = CTA pairs (default)
+    cs = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return cs;
+}
+
+template <int BN, int EPI, int CS>
+static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
+                      cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CS>;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, EPI>;
+  auto kern = gemm_kernel<BN, EPI, CS>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return set_error(kErrCuda, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_kmajor(&ta, a, p.M, p.K, lda, BM);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tb, w, p.N, p.K, ldw, Cfg::kBRows);
+  if (rc != kOk) return rc;
+  const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
+  const int max_groups = num_sms() / CS;
+  const int groups = tiles < max_groups ? tiles : max_groups;
+  kern<<<groups * CS, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return check_launch("gemm_kernel");
+}
+
+template <int BN, int EPI>
+static int launch_cs(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
+                     cudaStream_t stream) {
+  return cluster_size() == 2 ? launch_cfg<BN, EPI, 2>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 1>(a, lda, w, ldw, p, stream);
 }
 
 int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
@@ -335,23 +503,19 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   const int bn = (epi == EPI_HEAD) ? 64 : ((p.N % 256 == 0) ? 256 : 128);
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_kmajor(&ta, a, p.M, p.K, lda, BM);
-  if (rc != kOk) return rc;
-  rc = make_tmap_bf16_kmajor(&tb, w, p.N, p.K, ldw, bn);
-  if (rc != kOk) return rc;
+  if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
 #define JP_CASE(E)                                                             \
   case E:                                                                      \
-    return bn == 256 ? launch_cfg<256, E>(ta, tb, p, stream) : launch_cfg<128, E>(ta, tb, p, stream);
+    return bn == 256 ? launch_cs<256, E>(a, lda, w, ldw, p, stream) : launch_cs<128, E>(a, lda, w, ldw, p, stream);
   switch (epi) {
     JP_CASE(EPI_BIAS_BF16)
     JP_CASE(EPI_BIAS_GELU_BF16)
-    JP_CASE(EPI_GATE_RESID_F32)
+    JP_CASE(EPI_GATE_BF16)
     JP_CASE(EPI_PATCH_EMBED_F32)
     JP_CASE(EPI_BIAS_F32)
     JP_CASE(EPI_BIAS_BF16_F32)
     case EPI_HEAD:
-      return launch_cfg<64, EPI_HEAD>(ta, tb, p, stream);
+      return launch_cs<64, EPI_HEAD>(a, lda, w, ldw, p, stream);
     default:
       return set_error(kErrBadArg, "gemm: unknown epilogue %d", epi);
   }

@@ -25,14 +25,19 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, tokens: int) -> torch.Tensor:
-    """x [rows,768] fp32; shift/scale [n_cond,768] fp32 with n_cond == rows/tokens or 1 -> bf16 [rows,768]."""
+def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, tokens: int,
+                delta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [rows,768] fp32; shift/scale [n_cond,768] fp32 with n_cond == rows/tokens or 1 -> bf16 [rows,768].
+    With `delta` (bf16 [rows,768]) x is first updated IN PLACE: x += delta (the fused residual add)."""
     lib = _lib_dev()
-    x, shift, scale = _need(x, torch.float32, "x"), _need(shift, torch.float32, "shift"), _need(scale, torch.float32, "scale")
+    shift, scale = _need(shift, torch.float32, "shift"), _need(scale, torch.float32, "scale")
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise _lib.JpdvtError("x must be contiguous fp32")
     rows = x.shape[0]
     stride = 0 if shift.shape[0] == 1 else HIDDEN
     y = torch.empty(rows, HIDDEN, device=x.device, dtype=torch.bfloat16)
-    check(lib.jpdvt_ln_modulate_fwd(ptr(x), ptr(shift), ptr(scale), stride, ptr(y), rows, tokens, stream_ptr()), "ln_modulate")
+    check(lib.jpdvt_ln_modulate_fwd(ptr(x), ptr(_need(delta, torch.bfloat16, "delta")) if delta is not None else None,
+                                    ptr(shift), ptr(scale), stride, ptr(y), rows, tokens, stream_ptr()), "ln_modulate")
     return y
 
 
@@ -67,19 +72,18 @@ def gemm_bias_gelu(a, w, bias):
     return out
 
 
-def gemm_bias_gate_residual_(x, a, w, bias, gate, tokens: int):
-    """In place: x[row] += gate[row // tokens] * (a @ w.T + bias).  gate [n_cond,768] with n_cond == rows/tokens or 1."""
+def gemm_bias_gate(a, w, bias, gate, tokens: int) -> torch.Tensor:
+    """gate[row // tokens] * (a @ w.T + bias) -> bf16.  gate [n_cond,N] with n_cond == rows/tokens or 1."""
     lib = _lib_dev()
     a, w = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w")
     bias, gate = _need(bias, torch.float32, "bias"), _need(gate, torch.float32, "gate")
-    if x.dtype != torch.float32 or not x.is_contiguous():
-        raise _lib.JpdvtError("x must be contiguous fp32")
     m, k = a.shape
     n = w.shape[0]
     stride = 0 if gate.shape[0] == 1 else n
-    check(lib.jpdvt_gemm_bias_gate_residual(ptr(a), ptr(w), ptr(bias), ptr(gate), stride, ptr(x), m, n, k, tokens,
-                                            stream_ptr()), "gemm_bias_gate_residual")
-    return x
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_gemm_bias_gate(ptr(a), ptr(w), ptr(bias), ptr(gate), stride, ptr(out), m, n, k, tokens, stream_ptr()),
+          "gemm_bias_gate")
+    return out
 
 
 def patchify(img: torch.Tensor) -> torch.Tensor:

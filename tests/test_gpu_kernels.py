@@ -61,11 +61,9 @@ def test_gemm_epilogues(ops):
     b4 = torch.randn(3072, device="cuda")
     assert rel_l2(ops.gemm_bias_gelu(a, w4, b4).float(), F.gelu(a.float() @ w4.float().t() + b4, approximate="tanh")) < BF16_TOL
     for ncond in (3, 1):
-        x = torch.randn(m, n, device="cuda")
         gate = torch.randn(ncond, n, device="cuda")
         g = gate.repeat_interleave(T, 0) if ncond > 1 else gate
-        got = ops.gemm_bias_gate_residual_(x.clone(), a, w, bias, gate, T)
-        assert rel_l2(got, x + g * lin) < F32_TOL
+        assert rel_l2(ops.gemm_bias_gate(a, w, bias, gate, T).float(), g * lin) < BF16_TOL
 
 
 def test_patch_embed_head_and_patchify(ops):
@@ -98,6 +96,13 @@ def test_ln_modulate(ops, rows, T, ncond):
     got = ops.ln_modulate(x, sh, sc, T).float()
     assert rel_l2(got, ref) < BF16_TOL
     assert (got - ref).abs().max() <= 2.0 ** -8 * ref.abs().max() + 1e-6            # each element within bf16 rounding
+    # fused residual add: x += delta (in place, exact fp32 add of the bf16 branch), then the same LN + modulate
+    delta = torch.randn(rows, 768, device="cuda").bfloat16()
+    x2 = x.clone()
+    got2 = ops.ln_modulate(x2, sh, sc, T, delta=delta).float()
+    assert torch.equal(x2, x + delta.float())
+    ref2 = F.layer_norm(x2, (768,), eps=1e-6) * (1 + sc[idx]) + sh[idx]
+    assert rel_l2(got2, ref2) < BF16_TOL
 
 
 @pytest.mark.parametrize("B,T", [(2, 144), (3, 9), (2, 256), (2, 324), (1, 36), (5, 64), (2, 100), (1, 1), (1, 17)])

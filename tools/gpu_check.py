@@ -50,10 +50,9 @@ def g_gemm():
     res["bias_gelu"] = rel(ops.gemm_bias_gelu(a, w4, b4).float(),
                            torch.nn.functional.gelu(a.float() @ w4.float().t() + b4, approximate="tanh"))
     for ncond in (3, 1):
-        x = torch.randn(m, n, device=dev); gate = torch.randn(ncond, n, device=dev)
-        ref = x + gate.repeat_interleave(T, 0)[:m] * (a.float() @ w.float().t() + bias) if ncond > 1 else x + gate * (a.float() @ w.float().t() + bias)
-        got = ops.gemm_bias_gate_residual_(x.clone(), a, w, bias, gate, T)
-        res[f"gate_residual ncond={ncond}"] = rel(got, ref)
+        gate = torch.randn(ncond, n, device=dev)
+        g = gate.repeat_interleave(T, 0)[:m] if ncond > 1 else gate
+        res[f"gate_bf16 ncond={ncond}"] = rel(ops.gemm_bias_gate(a, w, bias, gate, T).float(), g * (a.float() @ w.float().t() + bias))
     img = torch.rand(3, 3, 192, 192, device=dev) * 2 - 1
     cols = ops.patchify(img)
     ref_cols = img.reshape(3, 3, 12, 16, 12, 16).permute(0, 2, 4, 1, 3, 5).reshape(432, 768)
@@ -86,6 +85,12 @@ def g_elementwise():
         idx = (torch.arange(rows, device=dev) // T).clamp_max(ncond - 1) if ncond > 1 else torch.zeros(rows, dtype=torch.long, device=dev)
         ref = ln * (1 + sc[idx]) + sh[idx]
         res[f"ln_modulate {rows}/{T}/{ncond}"] = rel(ops.ln_modulate(x, sh, sc, T).float(), ref)
+        delta = torch.randn(rows, 768, device=dev).bfloat16()
+        x2 = x.clone()
+        y2 = ops.ln_modulate(x2, sh, sc, T, delta=delta)
+        xr = x + delta.float()
+        res[f"ln_modulate+delta {rows}/{T}/{ncond}"] = (rel(y2.float(), torch.nn.functional.layer_norm(xr, (768,), eps=1e-6) * (1 + sc[idx]) + sh[idx]),
+                                                      bool(torch.equal(x2, xr)))
     t = torch.tensor([0, 1, 5, 250, 999, 37, 512, 4, 8, 991, 995], device=dev)
     w0, b0 = torch.randn(768, 256, device=dev) * 0.02, torch.randn(768, device=dev) * 0.02
     w2, b2 = torch.randn(768, 768, device=dev) * 0.02, torch.randn(768, device=dev) * 0.02
