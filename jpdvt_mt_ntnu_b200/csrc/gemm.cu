@@ -25,23 +25,23 @@ namespace jp {
 constexpr int BM = 128;         // rows per CTA (256 per pair)
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 4;
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kMaxSmem = 227 * 1024;
 constexpr int kStageRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free 16-byte accesses
 constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpose buffer per epilogue warp
 
-template <int BN, int CS>
+template <int BN, int CS, int EW>
 struct GemmCfg {
+  static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kBRows = BN / CS;                  // W rows this CTA loads
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kPipeBudget = 194 * 1024;
-  static constexpr int kStagesRaw = kPipeBudget / kStageBytes;
+  static constexpr int kFixedBytes = EW * kStageWarpBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStageWarpBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EW * kStageWarpBytes + kBarBytes + 1024;
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------------
@@ -155,14 +155,15 @@ __device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[
   __syncwarp();
 }
 
-template <int BN, int EPI, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int CS, int EW>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CS>;
+  using Cfg = GemmCfg<BN, CS, EW>;
+  constexpr int kColsPerWarp = BN / (EW / 4);        // EW/4 warps share a TMEM lane quadrant and split the columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + kEpiWarps * kStageWarpBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + EW * kStageWarpBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
@@ -182,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS * kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS * EW); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -252,16 +253,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2 .. 2+EW)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     uint8_t* stage = stage_buf + (warp - 2) * kStageWarpBytes;
+    const int col_base = ((warp - 2) >> 2) * kColsPerWarp;   // first accumulator column of this warp
     int acc = 0; uint32_t acc_phase = 0;
     __shared__ float s_w2[kLatent * 64];
     __shared__ float s_b2[kLatent];
     if constexpr (EPI == EPI_HEAD) {
-      for (int i = threadIdx.x - 64; i < kLatent * 64; i += kEpiWarps * 32) s_w2[i] = p.w2[i];
+      for (int i = threadIdx.x - 64; i < kLatent * 64; i += EW * 32) s_w2[i] = p.w2[i];
       if (threadIdx.x - 64 < kLatent) s_b2[threadIdx.x - 64] = p.b2[threadIdx.x - 64];
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
     const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
@@ -274,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
       if constexpr (EPI == EPI_HEAD) {
-        static_assert(EPI != EPI_HEAD || BN == 64, "head epilogue needs the whole 64-wide row");
+        static_assert(EPI != EPI_HEAD || (BN == 64 && EW == 4), "head epilogue needs the whole 64-wide row in one warp");
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_row, r0);
         tmem_ld_32x32(t_row + 32, r1);
@@ -300,15 +302,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_BF16 || EPI == EPI_BIAS_BF16_F32) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = 0; c < kColsPerWarp / 64; ++c) {
           uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_row + c * 64, r0);
-          tmem_ld_32x32(t_row + c * 64 + 32, r1);
+          tmem_ld_32x32(t_row + col_base + c * 64, r0);
+          tmem_ld_32x32(t_row + col_base + c * 64 + 32, r1);
           tmem_ld_wait();
           float v[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-          const int n0 = n_blk * BN + c * 64;
+          const int n0 = n_blk * BN + col_base + c * 64;
           bf16_math<EPI>(p, v, row, n0, row_ok);
           store_bf16_tile(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M, lane);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
@@ -346,11 +348,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
         }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < kColsPerWarp / 32; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_32x32(t_row + col_base + c * 32, r);
           tmem_ld_wait();
-          const int n0 = n_blk * BN + c * 32;
+          const int n0 = n_blk * BN + col_base + c * 32;
           float v[32];
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -455,21 +457,23 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int cluster_size() {
-  static int cs = 0;
-  if (cs == 0) {
-    const char* e = getenv("JPDVT_GEMM_CLUSTER");   // debugging knob: 1 = single-CTA tiles, 2 = CTA pairs (default)
-    cs = (e != nullptr && e[0] == '1') ? 1 : 2;
+static int epi_warps() {
+  static int ew = 0;
+  if (ew == 0) {
+    const char* e = getenv("JPDVT_GEMM_EPI_WARPS");   // tuning knob: 4 or 8 epilogue warps per CTA (default 8)
+    ew = (e != nullptr && e[0] == '4') ? 4 : 8;
   }
-  return cs;
+  return ew;
 }
 
-template <int BN, int EPI, int CS>
+template <int BN, int EPI, int EW>
 static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CS>;
+  constexpr int CS = 2;
+  using Cfg = GemmCfg<BN, CS, EW>;
+  static_assert(Cfg::kStages >= 3, "pipeline too shallow");
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, EPI, CS>;
+  auto kern = gemm_kernel<BN, EPI, CS, EW>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return set_error(kErrCuda, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(cudaGetLastError()));
@@ -483,14 +487,15 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return check_launch("gemm_kernel");
 }
 
 template <int BN, int EPI>
 static int launch_cs(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                      cudaStream_t stream) {
-  return cluster_size() == 2 ? launch_cfg<BN, EPI, 2>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 1>(a, lda, w, ldw, p, stream);
+  if constexpr (EPI == EPI_HEAD) return launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
+  else return epi_warps() == 8 ? launch_cfg<BN, EPI, 8>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
 }
 
 int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
