@@ -45,13 +45,14 @@ int jpdvt_device_check(void);
 
 /* ---- single kernels ------------------------------------------------------------------------------------------ */
 
-/* If delta != NULL: x += delta first (the gated branch output of the previous GEMM, bf16; x is updated in place - the
- * residual add of models.py:120-121 rides on this pass).  Then y = LayerNorm(x, eps=1e-6, no affine) * (1 + scale[b]) +
- * shift[b], b = row / tokens; sample b reads its 768-wide vectors at shift + b*mod_stride, scale + b*mod_stride
- * (mod_stride 0 = one conditioning row for the whole batch).
- * Replaces nn.LayerNorm + modulate: models.py:19-20,107,109,120-121,131,140. */
-int jpdvt_ln_modulate_fwd(float* x, const jpdvt_bf16* delta_or_null, const float* shift, const float* scale,
-                          int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens, void* stream);
+/* If delta != NULL: x_out = x_in + gate[b] * delta first (delta: bf16 branch output of the previous GEMM; gate: 768-wide
+ * adaLN gate of sample b at gate + b*mod_stride, NULL = 1; x_out may alias x_in) - the gated residual add of
+ * models.py:120-121 rides on this pass.  Then y = LayerNorm(x_out, eps=1e-6, no affine) * (1 + scale[b]) + shift[b],
+ * b = row / tokens; sample b reads its vectors at shift + b*mod_stride, scale + b*mod_stride (mod_stride 0 = one
+ * conditioning row for the whole batch).  Replaces nn.LayerNorm + modulate: models.py:19-20,107,109,120-121,131,140. */
+int jpdvt_ln_modulate_fwd(const float* x_in, float* x_out_or_null, const jpdvt_bf16* delta_or_null, const float* gate_or_null,
+                          const float* shift, const float* scale, int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens,
+                          void* stream);
 
 /* tcgen05 GEMMs: out[M,N] = a[M,K] . w[N,K]^T + bias, a/w bf16 (w in nn.Linear layout), fp32 accumulate.
  * M arbitrary, K % 64 == 0, N % 128 == 0.  Replace timm Attention.qkv / Mlp.fc1 / FinalLayer.linear (models.py:108,112,132). */
@@ -76,8 +77,9 @@ int jpdvt_final_head_fwd(const jpdvt_bf16* y, const jpdvt_bf16* w1, const float*
                          float* te_out, int64_t m, void* stream);
 
 /* softmax(q k^T / 8) v per (sample, head) on the fused QKV tensor [batch*tokens, 2304] -> [batch*tokens, 768]
- * (timm Attention.forward -> F.scaled_dot_product_attention, called from models.py:108,120). */
-int jpdvt_attention_fwd(const jpdvt_bf16* qkv, jpdvt_bf16* out, int batch, int tokens, void* stream);
+ * (timm Attention.forward -> F.scaled_dot_product_attention, called from models.py:108,120).  lse2 (nullable, fp32
+ * [batch, 12, tokens]): log2-domain log-sum-exp of the scaled scores, kept for jpdvt_attention_bwd. */
+int jpdvt_attention_fwd(const jpdvt_bf16* qkv, jpdvt_bf16* out, float* lse2_or_null, int batch, int tokens, void* stream);
 
 /* im2col of 16x16 patches, k = c*256 + py*16 + px (the flattened Conv2d weight order), fp32 -> bf16. */
 int jpdvt_patchify(const float* img, jpdvt_bf16* cols, int batch, int image_size, void* stream);
@@ -196,6 +198,109 @@ typedef struct jpdvt_sampler {
  * without any host round trip; the result of the last executed step is left in sampler->sample. */
 int jpdvt_sample_loop(const jpdvt_weights* w_host, const jpdvt_workspace* ws_host, const jpdvt_sampler* s_host,
                       const float* condition, const float* noise, int batch, int first_step, int last_step, void* stream);
+
+
+/* ---- training step (train_JPDVT.py:357-372: training_losses -> backward -> AdamW -> EMA) ----------------------------- */
+
+/* dW[out_rows, n_cols] (fp32, nn.Linear layout) = P[m, out_rows]^T . Q[m, n_cols]: weight gradients as a tcgen05 GEMM with
+ * MN-major operands and a split contraction.  scratch: jpdvt_wgrad_scratch_floats(...) floats (may be NULL when 0). */
+int jpdvt_gemm_wgrad(const jpdvt_bf16* p, const jpdvt_bf16* q, float* dw, float* scratch, int64_t m, int out_rows, int n_cols,
+                     void* stream);
+int64_t jpdvt_wgrad_scratch_floats(int64_t m, int out_rows, int n_cols);
+/* out = (a . w^T) * gelu_tanh'(pre)  - fc2 data gradient fused with the GELU derivative (timm Mlp, models.py:110-112) */
+int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16* pre, jpdvt_bf16* out, int64_t m, int n, int k,
+                     void* stream);
+/* dQ, dK, dV of softmax(q k^T / 8) v into dqkv [batch*tokens, 2304]; o / d_o: [batch*tokens, 768]; lse2 from the forward. */
+int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_bf16* d_o, const float* lse2, jpdvt_bf16* dqkv,
+                        int batch, int tokens, void* stream);
+/* x_out = x_in + gate[b]*y  =>  dy = gate[b]*dx (bf16); dgate[b] += sum_t dx*y; dbias += sum_rows dy (atomic accumulation) */
+int jpdvt_gate_bwd(const float* dx, const jpdvt_bf16* y, const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate,
+                   int64_t dgate_stride, float* dbias_or_null, int batch, int tokens, void* stream);
+/* backward of jpdvt_ln_modulate_fwd: dx (+)= LN'(dxn * (1 + scale[b])); dshift[b] += sum_t dxn; dscale[b] += sum_t dxn*xhat */
+int jpdvt_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
+                          float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, int batch, int tokens,
+                          void* stream);
+/* out[c] += sum_rows src[row, c]  (bias gradients) */
+int jpdvt_colsum_bf16(const jpdvt_bf16* src, int64_t rows, int cols, float* out, void* stream);
+int jpdvt_colsum_f32(const float* src, int64_t rows, int cols, float* out, void* stream);
+
+typedef struct jpdvt_weights_t {   /* transposed bf16 copies ([in, out]) read by the data-gradient GEMMs */
+  const jpdvt_bf16* w_qkv_t;    /* [depth, 768, 2304] */
+  const jpdvt_bf16* w_proj_t;   /* [depth, 768, 768]  */
+  const jpdvt_bf16* w_fc1_t;    /* [depth, 768, 3072] */
+  const jpdvt_bf16* w_fc2_t;    /* [depth, 3072, 768] */
+  const jpdvt_bf16* w_final_t;  /* [768, 768] */
+  const jpdvt_bf16* w_head1_t;  /* [768, 64]  */
+  const jpdvt_bf16* w_ada_t;    /* [768, depth*4608 + 1536] */
+  const jpdvt_bf16* t_w2_t;     /* [768, 768] */
+} jpdvt_weights_t;
+
+typedef struct jpdvt_tape {        /* activations kept by the training forward for the backward pass */
+  int64_t rows;                 /* batch * tokens */
+  int32_t batch;
+  int32_t reserved;
+  jpdvt_bf16* cols;             /* [rows, 768]              im2col of the condition image */
+  float* x;                     /* [2*depth + 1, rows, 768] input of every LayerNorm (residual stream snapshots) */
+  jpdvt_bf16* xn1;              /* [depth, rows, 768]   */
+  jpdvt_bf16* qkv;              /* [depth, rows, 2304]  */
+  float* lse2;                  /* [depth, batch, 12, tokens] */
+  jpdvt_bf16* att;              /* [depth, rows, 768]   */
+  jpdvt_bf16* y1;               /* [depth, rows, 768]   attn.proj output (before the gate) */
+  jpdvt_bf16* xn2;              /* [depth, rows, 768]   */
+  jpdvt_bf16* hpre;             /* [depth, rows, 3072]  fc1 output before GELU */
+  jpdvt_bf16* h;                /* [depth, rows, 3072]  */
+  jpdvt_bf16* y2;               /* [depth, rows, 768]   mlp.fc2 output (before the gate) */
+  jpdvt_bf16* xnf;              /* [rows, 768]  */
+  jpdvt_bf16* yfin;             /* [rows, 768]  final_layer.linear output */
+  float* yfin32;                /* [rows, 768]  fp32 copy (image head), or NULL */
+  float* headpre;               /* [rows, 64]   time_emb_out1 output */
+  float* feat;                  /* [batch, 256] sinusoid features */
+  float* tpre;                  /* [batch, 768] t_embedder.mlp.0 output */
+  float* c;                     /* [batch, 768] */
+  float* silu_c;                /* [batch, 768] */
+  jpdvt_bf16* silu_c_bf16;      /* [batch, 768] */
+  float* mod;                   /* [batch, depth*4608 + 1536] */
+} jpdvt_tape;
+
+typedef struct jpdvt_grads {       /* fp32 gradients in the parameters' own layouts; zero-filled by the caller before a backward */
+  float* w_patch;  float* b_patch;  float* w_in;  float* b_in;      /* [768,768] [768] [768,8] [768] */
+  float* t_w0;  float* t_b0;  float* t_w2;  float* t_b2;            /* [768,256] [768] [768,768] [768] */
+  float* w_ada;  float* b_ada;                                      /* [n_mod,768] [n_mod] */
+  float* w_qkv;  float* b_qkv;  float* w_proj;  float* b_proj;      /* stacked over depth */
+  float* w_fc1;  float* b_fc1;  float* w_fc2;  float* b_fc2;
+  float* w_final;  float* b_final;  float* w_head1;  float* b_head1;  float* w_head2;  float* b_head2;
+} jpdvt_grads;
+
+typedef struct jpdvt_bwd_scratch {
+  float* dx;                    /* [rows, 768] gradient of the residual stream */
+  float* dxn;                   /* [rows, 768] fp32 scratch (data gradients entering a LayerNorm) */
+  jpdvt_bf16* dy;               /* [rows, 768]  */
+  jpdvt_bf16* dh;               /* [rows, 3072] */
+  jpdvt_bf16* dqkv;             /* [rows, 2304] */
+  jpdvt_bf16* datt;             /* [rows, 768]  */
+  jpdvt_bf16* dpre;             /* [rows, 64]   */
+  float* dmod;                  /* [batch, n_mod] zero-filled by the caller */
+  jpdvt_bf16* dmod_bf16;        /* [batch, n_mod] */
+  float* small_f32;             /* [4, batch, 768] */
+  jpdvt_bf16* small_bf16;       /* [4, batch, 768] */
+  float* wgrad_scratch;         /* jpdvt_train_wgrad_scratch_floats(...) floats */
+  const float* zeros;           /* >= n_mod zeros (bias-free GEMM epilogues) */
+} jpdvt_bwd_scratch;
+
+int64_t jpdvt_train_wgrad_scratch_floats(int depth, int batch, int tokens);
+/* DiT.forward with every activation the backward needs written to the tape (per-sample timesteps t: int64[batch]). */
+int jpdvt_train_forward(const jpdvt_weights* w, const jpdvt_tape* tape, const float* img, const int64_t* t, const float* x_t,
+                        float* te_out, float* img_out_or_null, int batch, void* stream);
+/* Backward in three stages so the caller can overlap gradient all-reduces with the remaining stages:
+ * head (final layer + position head + image head), one call per block from depth-1 down to 0, then the embeddings and
+ * the conditioning path (adaLN linears, t_embedder). */
+int jpdvt_train_backward_head(const jpdvt_weights* w, const jpdvt_weights_t* wt, const jpdvt_tape* tape,
+                              const jpdvt_bwd_scratch* s, const jpdvt_grads* g, const float* d_te, const float* d_img_or_null,
+                              void* stream);
+int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt, const jpdvt_tape* tape,
+                               const jpdvt_bwd_scratch* s, const jpdvt_grads* g, int block, void* stream);
+int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt, const jpdvt_tape* tape,
+                               const jpdvt_bwd_scratch* s, const jpdvt_grads* g, const float* x_t, void* stream);
 
 #ifdef __cplusplus
 }

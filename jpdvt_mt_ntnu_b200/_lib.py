@@ -39,18 +39,42 @@ class Sampler(C.Structure):
         ("step_noise_stride", C.c_int64)] + [(n, c_void_p) for n in ("x0", "sample", "traj_x0", "traj_sample")]
 
 
+class WeightsT(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_qkv_t", "w_proj_t", "w_fc1_t", "w_fc2_t", "w_final_t", "w_head1_t", "w_ada_t", "t_w2_t")]
+
+
+class Tape(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("batch", C.c_int32), ("reserved", C.c_int32)] + [
+        (n, c_void_p) for n in ("cols", "x", "xn1", "qkv", "lse2", "att", "y1", "xn2", "hpre", "h", "y2", "xnf", "yfin", "yfin32",
+                                "headpre", "feat", "tpre", "c", "silu_c", "silu_c_bf16", "mod")]
+
+
+GRAD_FIELDS = ("w_patch", "b_patch", "w_in", "b_in", "t_w0", "t_b0", "t_w2", "t_b2", "w_ada", "b_ada", "w_qkv", "b_qkv",
+               "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2", "w_final", "b_final", "w_head1", "b_head1", "w_head2",
+               "b_head2")
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, c_void_p) for n in GRAD_FIELDS]
+
+
+class BwdScratch(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("dx", "dxn", "dy", "dh", "dqkv", "datt", "dpre", "dmod", "dmod_bf16", "small_f32",
+                                        "small_bf16", "wgrad_scratch", "zeros")]
+
+
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header
 PROTOTYPES = {
     "jpdvt_device_check": [],
-    "jpdvt_ln_modulate_fwd": [P, P, P, P, c_int64, P, c_int64, c_int, P],
+    "jpdvt_ln_modulate_fwd": [P, P, P, P, P, P, c_int64, P, c_int64, c_int, P],
     "jpdvt_gemm_bias": [P, P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gate": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
-    "jpdvt_attention_fwd": [P, P, c_int, c_int, P],
+    "jpdvt_attention_fwd": [P, P, P, c_int, c_int, P],
     "jpdvt_patchify": [P, P, c_int, c_int, P],
     "jpdvt_unpatchify": [P, P, c_int, c_int, P],
     "jpdvt_timestep_embed": [P, c_int, P, P, P, P, P, P, P, P, P],
@@ -60,10 +84,24 @@ PROTOTYPES = {
     "jpdvt_q_sample": [P, P, P, P, P, P, P, c_int64, c_int64, P],
     "jpdvt_assign_from_scores": [P, c_int, c_int, c_double, P, P, P],
     "jpdvt_assign_greedy_l1": [P, P, c_int, c_int, c_int, c_double, P, P, P, P],
+    "jpdvt_gemm_wgrad": [P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_gemm_dgelu": [P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],
+    "jpdvt_gate_bwd": [P, P, P, c_int64, P, P, c_int64, P, c_int, c_int, P],
+    "jpdvt_ln_modulate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, c_int, c_int, P],
+    "jpdvt_colsum_bf16": [P, c_int64, c_int, P, P],
+    "jpdvt_colsum_f32": [P, c_int64, c_int, P, P],
+    "jpdvt_train_forward": [C.POINTER(Weights), C.POINTER(Tape), P, P, P, P, P, c_int, P],
+    "jpdvt_train_backward_head": [C.POINTER(Weights), C.POINTER(WeightsT), C.POINTER(Tape), C.POINTER(BwdScratch),
+                                  C.POINTER(Grads), P, P, P],
+    "jpdvt_train_backward_block": [C.POINTER(Weights), C.POINTER(WeightsT), C.POINTER(Tape), C.POINTER(BwdScratch),
+                                   C.POINTER(Grads), c_int, P],
+    "jpdvt_train_backward_embed": [C.POINTER(Weights), C.POINTER(WeightsT), C.POINTER(Tape), C.POINTER(BwdScratch),
+                                   C.POINTER(Grads), P, P],
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
 }
-OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string"]
+OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats"]
 
 _lock = threading.Lock()
 _lib = None
@@ -91,6 +129,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = c_int
+        lib.jpdvt_wgrad_scratch_floats.argtypes = [c_int64, c_int, c_int]
+        lib.jpdvt_wgrad_scratch_floats.restype = c_int64
+        lib.jpdvt_train_wgrad_scratch_floats.argtypes = [c_int, c_int, c_int]
+        lib.jpdvt_train_wgrad_scratch_floats.restype = c_int64
         lib.jpdvt_abi_version.restype = c_int
         lib.jpdvt_last_error_string.restype = C.c_char_p
         _lib = lib

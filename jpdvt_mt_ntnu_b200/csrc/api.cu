@@ -82,7 +82,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   }
   // conditioning: c = t_embedder(t); all 13 adaLN linears at once            (models.py:282-284,119,134)
   JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), cond_rows, step_ptr, map, w->t_w0, w->t_b0, w->t_w2,
-                               w->t_b2, ws->c, ws->silu_c, st));
+                               w->t_b2, ws->c, ws->silu_c, nullptr, nullptr, st));
   JP_TRY(adaln_all(w, ws, cond_rows, n_mod, st));
 
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws->xn);
@@ -91,26 +91,26 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws->hid);
   __nv_bfloat16* br = reinterpret_cast<__nv_bfloat16*>(ws->y);   // gated branch output, folded into x by the next LN
   const __nv_bfloat16* pending = nullptr;                          // branch output not yet added to the residual stream
+  const float* pending_gate = nullptr;                             // ... and the adaLN gate it is scaled by (x += gate * branch)
   for (int i = 0; i < depth; ++i) {
     const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
     // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120)
-    JP_TRY(launch_ln_modulate(ws->x, pending, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, ws->x, pending, pending_gate, mod_stride, mod, mod + kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
       p.bias = w->b_qkv + static_cast<long long>(i) * 3 * kHidden; p.out = qkv; p.ldo = 3 * kHidden;
       JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden, kHidden, p, st));
     }
-    JP_TRY(launch_attention(qkv, att, batch, T, st));
+    JP_TRY(launch_attention(qkv, att, nullptr, batch, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
       p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
-      p.gate = mod + 2 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_GATE_BF16, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
+      JP_TRY(launch_gemm(EPI_BIAS_BF16, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
     }
     // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
-    JP_TRY(launch_ln_modulate(ws->x, br, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, ws->x, br, mod + 2 * kHidden, mod_stride, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
@@ -121,15 +121,15 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = 4 * kHidden; p.tokens = T;
       p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
-      p.gate = mod + 5 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_GATE_BF16, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
+      JP_TRY(launch_gemm(EPI_BIAS_BF16, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
     }
     pending = br;
+    pending_gate = mod + 5 * kHidden;
   }
   // final layer + position head                                            (models.py:287-290)
   {
     const float* mod = ws->mod + static_cast<long long>(depth) * 6 * kHidden;   // shift, scale
-    JP_TRY(launch_ln_modulate(ws->x, pending, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, ws->x, pending, pending_gate, mod_stride, mod, mod + kHidden, mod_stride, xn, M, T, st));
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
@@ -168,11 +168,13 @@ int jpdvt_device_check(void) {
   return kOk;
 }
 
-int jpdvt_ln_modulate_fwd(float* x, const jpdvt_bf16* delta_or_null, const float* shift, const float* scale,
-                          int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens, void* stream) {
+int jpdvt_ln_modulate_fwd(const float* x_in, float* x_out_or_null, const jpdvt_bf16* delta_or_null, const float* gate_or_null,
+                          const float* shift, const float* scale, int64_t mod_stride, jpdvt_bf16* y, int64_t rows, int tokens,
+                          void* stream) {
   if (rows == 0) return kOk;
-  if (!x || !shift || !scale || !y) return set_error(kErrBadArg, "ln_modulate: null pointer");
-  return launch_ln_modulate(x, BF(delta_or_null), shift, scale, mod_stride, BFM(y), rows, tokens, ST(stream));
+  if (!x_in || !shift || !scale || !y) return set_error(kErrBadArg, "ln_modulate: null pointer");
+  return launch_ln_modulate(x_in, x_out_or_null, BF(delta_or_null), gate_or_null, mod_stride, shift, scale, mod_stride, BFM(y),
+                            rows, tokens, ST(stream));
 }
 
 static int gemm_simple(int epi, const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, void* out, float* out2,
@@ -229,9 +231,9 @@ int jpdvt_final_head_fwd(const jpdvt_bf16* y, const jpdvt_bf16* w1, const float*
   return launch_gemm(EPI_HEAD, BF(y), kHidden, BF(w1), kHidden, p, ST(stream));
 }
 
-int jpdvt_attention_fwd(const jpdvt_bf16* qkv, jpdvt_bf16* out, int batch, int tokens, void* stream) {
+int jpdvt_attention_fwd(const jpdvt_bf16* qkv, jpdvt_bf16* out, float* lse2_or_null, int batch, int tokens, void* stream) {
   if (!qkv || !out) return set_error(kErrBadArg, "attention: null pointer");
-  return launch_attention(BF(qkv), BFM(out), batch, tokens, ST(stream));
+  return launch_attention(BF(qkv), BFM(out), lse2_or_null, batch, tokens, ST(stream));
 }
 int jpdvt_patchify(const float* img, jpdvt_bf16* cols, int batch, int image_size, void* stream) {
   if (!img || !cols) return set_error(kErrBadArg, "patchify: null pointer");
@@ -245,7 +247,7 @@ int jpdvt_unpatchify(const float* y, float* img, int batch, int image_size, void
 int jpdvt_timestep_embed(const int64_t* t, int n, const int32_t* step_ptr, const int32_t* map, const float* w0,
                          const float* b0, const float* w2, const float* b2, float* c, float* silu_c, void* stream) {
   if (!w0 || !b0 || !w2 || !b2 || !c || !silu_c) return set_error(kErrBadArg, "timestep_embed: null pointer");
-  return launch_timestep_embed(reinterpret_cast<const long long*>(t), n, step_ptr, map, w0, b0, w2, b2, c, silu_c, ST(stream));
+  return launch_timestep_embed(reinterpret_cast<const long long*>(t), n, step_ptr, map, w0, b0, w2, b2, c, silu_c, nullptr, nullptr, ST(stream));
 }
 int jpdvt_adaln_table(const float* silu_c, int rows, const jpdvt_bf16* w_all, const float* b_all, float* mod, int n_out,
                       void* stream) {

@@ -53,7 +53,8 @@ __device__ __forceinline__ float ex2(float x) {
 constexpr int kAttThreadsMax = 128;
 
 __global__ void __launch_bounds__(kAttThreadsMax, 4)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tp) {
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int T,
+                 int Tp) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   const int nthreads = blockDim.x;
   const int nw = nthreads >> 5;
@@ -187,6 +188,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    if (lse2 != nullptr && tq == 0) {   // training: log2-domain log-sum-exp of the scaled scores, [B, 12, T]
+      float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+      if (tile * 16 + g < T) lrow[tile * 16 + g] = fmaf(m0, sl2, log2f(l0));
+      if (tile * 16 + g + 8 < T) lrow[tile * 16 + g + 8] = fmaf(m1, sl2, log2f(l1));
+    }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -217,7 +223,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream) {
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
   if (batch > 65535) return set_error(kErrBadArg, "attention: batch %d exceeds gridDim.y limit", batch);
   const int mt = (tokens + 15) / 16;        // 16-row query tiles
@@ -235,8 +241,226 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, in
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   dim3 grid(kHeads, batch);
-  attention_kernel<<<grid, nw * 32, smem, stream>>>(qkv, out, tokens, Tp);
+  attention_kernel<<<grid, nw * 32, smem, stream>>>(qkv, out, lse2, tokens, Tp);
   return check_launch("attention_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention backward (training): dQ, dK, dV for softmax(Q K^T / 8) V, recomputing the probabilities from the forward's
+// log-sum-exp (flash-attention style).  One CTA per (sample, head); Q, K, V and dO of the head live in shared memory.
+//   phase A: each warp owns 16-key tiles and walks all query tiles  -> dK, dV   (S^T = K Q^T, dP^T = V dO^T)
+//   phase B: each warp owns 16-query tiles and walks all key groups  -> dQ       (S = Q K^T,  dP  = dO V^T)
+// Zero padding of rows >= T makes every padded contribution vanish, so no masks are needed.
+// qkv / dqkv: [B*T, 2304] bf16; o / d_o: [B*T, 768] bf16; lse2: [B, 12, T] fp32 (log2 domain, from the forward).
+__device__ __forceinline__ void store_tile_bf16(uint8_t* buf, const float (&acc)[8][4], __nv_bfloat16* gdst, long long ld,
+                                                int row0, int T, int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(buf + swz(g, j) + tq * 4) = pack_bf16(acc[j][0], acc[j][1]);
+    *reinterpret_cast<uint32_t*>(buf + swz(g + 8, j) + tq * 4) = pack_bf16(acc[j][2], acc[j][3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx >> 3, ch = idx & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(buf + swz(r, ch));
+    if (row0 + r < T) *reinterpret_cast<uint4*>(gdst + static_cast<long long>(row0 + r) * ld + ch * 8) = v;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kAttThreadsMax, 2)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+                     const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse2, __nv_bfloat16* __restrict__ dqkv,
+                     int T, int Tp) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int nthreads = blockDim.x;
+  const int nw = nthreads >> 5;
+  uint8_t* sQ = att_smem;
+  uint8_t* sK = sQ + Tp * 128;
+  uint8_t* sV = sK + Tp * 128;
+  uint8_t* sdO = sV + Tp * 128;
+  float* sD = reinterpret_cast<float*>(sdO + Tp * 128);
+  float* sL = sD + Tp;
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(sL + Tp);
+  const int b = blockIdx.y, h = blockIdx.x;
+  const long long tok0 = static_cast<long long>(b) * T;
+  const __nv_bfloat16* base = qkv + tok0 * kQkvLd + h * kHeadDim;
+  const __nv_bfloat16* obase = o + tok0 * kHidden + h * kHeadDim;
+  const __nv_bfloat16* dobase = d_o + tok0 * kHidden + h * kHeadDim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* mystage = sStage + warp * 2048;
+
+  for (int i = threadIdx.x; i < Tp * 8; i += nthreads) {
+    const int r = i >> 3, ch = i & 7;
+    const uint32_t off = swz(r, ch);
+    if (r < T) {
+      const __nv_bfloat16* src = base + static_cast<long long>(r) * kQkvLd + ch * 8;
+      cp_async16(sQ + off, src);
+      cp_async16(sK + off, src + kHidden);
+      cp_async16(sV + off, src + 2 * kHidden);
+      cp_async16(sdO + off, dobase + static_cast<long long>(r) * kHidden + ch * 8);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sQ + off) = z; *reinterpret_cast<uint4*>(sK + off) = z;
+      *reinterpret_cast<uint4*>(sV + off) = z; *reinterpret_cast<uint4*>(sdO + off) = z;
+    }
+  }
+  // D[r] = sum_d dO[r, d] * O[r, d]; one warp per row, 2 elements per lane
+  for (int r = warp; r < Tp; r += nw) {
+    float acc = 0.f;
+    if (r < T) {
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(dobase + static_cast<long long>(r) * kHidden + 2 * lane);
+      const uint32_t c = *reinterpret_cast<const uint32_t*>(obase + static_cast<long long>(r) * kHidden + 2 * lane);
+      acc = __uint_as_float(a << 16) * __uint_as_float(c << 16) + __uint_as_float(a & 0xffff0000u) * __uint_as_float(c & 0xffff0000u);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      sD[r] = acc;
+      sL[r] = (r < T) ? lse2[(static_cast<long long>(b) * kHeads + h) * T + r] : 0.f;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int g = lane >> 2, tq = lane & 3;
+  const int li = lane >> 3, lr = lane & 7;
+  const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), do_base = smem_u32(sdO);
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  const int mt = Tp >> 4;
+  __nv_bfloat16* dq_out = dqkv + tok0 * kQkvLd + h * kHeadDim;
+
+  // ------------------------------------------------------------------ phase A: dK, dV
+  for (int jt = warp; jt < mt; jt += nw) {
+    const int kb0 = jt * 16;
+    uint32_t kfA[4][4], vfA[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t off = swz(kb0 + lr + ((li & 1) ? 8 : 0), ks * 2 + (li >> 1));
+      ldsm_x4(kfA[ks], k_base + off);
+      ldsm_x4(vfA[ks], v_base + off);
+    }
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
+    for (int it = 0; it < mt; ++it) {
+      const int q0 = it * 16;
+      float st[2][4], dpt[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) { st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f; dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qB[4], oB[4];
+        const uint32_t off = swz(q0 + lr + ((li >> 1) ? 8 : 0), ks * 2 + (li & 1));
+        ldsm_x4(qB, q_base + off);
+        ldsm_x4(oB, do_base + off);
+        mma_bf16(st[0], kfA[ks], qB[0], qB[1]);
+        mma_bf16(st[1], kfA[ks], qB[2], qB[3]);
+        mma_bf16(dpt[0], vfA[ks], oB[0], oB[1]);
+        mma_bf16(dpt[1], vfA[ks], oB[2], oB[3]);
+      }
+      uint32_t pA[4], dsA[4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int qc = q0 + 8 * n + 2 * tq;
+        const float l0 = sL[qc], l1 = sL[qc + 1], d0 = sD[qc], d1 = sD[qc + 1];
+        const float p0 = ex2(fmaf(st[n][0], sl2, -l0)), p1 = ex2(fmaf(st[n][1], sl2, -l1));
+        const float p2 = ex2(fmaf(st[n][2], sl2, -l0)), p3 = ex2(fmaf(st[n][3], sl2, -l1));
+        pA[2 * n] = pack_bf16(p0, p1);
+        pA[2 * n + 1] = pack_bf16(p2, p3);
+        dsA[2 * n] = pack_bf16(p0 * (dpt[n][0] - d0) * 0.125f, p1 * (dpt[n][1] - d1) * 0.125f);
+        dsA[2 * n + 1] = pack_bf16(p2 * (dpt[n][2] - d0) * 0.125f, p3 * (dpt[n][3] - d1) * 0.125f);
+      }
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t of[4], qf[4];
+        const uint32_t off = swz(q0 + lr + ((li & 1) ? 8 : 0), dp * 2 + (li >> 1));
+        ldsm_x4_trans(of, do_base + off);
+        ldsm_x4_trans(qf, q_base + off);
+        mma_bf16(dv[2 * dp], pA, of[0], of[1]);
+        mma_bf16(dv[2 * dp + 1], pA, of[2], of[3]);
+        mma_bf16(dk[2 * dp], dsA, qf[0], qf[1]);
+        mma_bf16(dk[2 * dp + 1], dsA, qf[2], qf[3]);
+      }
+    }
+    store_tile_bf16(mystage, dk, dq_out + kHidden, kQkvLd, kb0, T, lane);
+    store_tile_bf16(mystage, dv, dq_out + 2 * kHidden, kQkvLd, kb0, T, lane);
+  }
+
+  // ------------------------------------------------------------------ phase B: dQ
+  for (int it = warp; it < mt; it += nw) {
+    const int q0 = it * 16;
+    uint32_t qfA[4][4], ofA[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t off = swz(q0 + lr + ((li & 1) ? 8 : 0), ks * 2 + (li >> 1));
+      ldsm_x4(qfA[ks], q_base + off);
+      ldsm_x4(ofA[ks], do_base + off);
+    }
+    const float l0 = sL[q0 + g], l1 = sL[q0 + g + 8], d0 = sD[q0 + g], d1 = sD[q0 + g + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
+    for (int jt = 0; jt < mt; ++jt) {
+      const int kb0 = jt * 16;
+      float sc[2][4], dp_[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) { sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f; dp_[n][0] = dp_[n][1] = dp_[n][2] = dp_[n][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kB[4], vB[4];
+        const uint32_t off = swz(kb0 + lr + ((li >> 1) ? 8 : 0), ks * 2 + (li & 1));
+        ldsm_x4(kB, k_base + off);
+        ldsm_x4(vB, v_base + off);
+        mma_bf16(sc[0], qfA[ks], kB[0], kB[1]);
+        mma_bf16(sc[1], qfA[ks], kB[2], kB[3]);
+        mma_bf16(dp_[0], ofA[ks], vB[0], vB[1]);
+        mma_bf16(dp_[1], ofA[ks], vB[2], vB[3]);
+      }
+      uint32_t dsA[4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const float p0 = ex2(fmaf(sc[n][0], sl2, -l0)), p1 = ex2(fmaf(sc[n][1], sl2, -l0));
+        const float p2 = ex2(fmaf(sc[n][2], sl2, -l1)), p3 = ex2(fmaf(sc[n][3], sl2, -l1));
+        dsA[2 * n] = pack_bf16(p0 * (dp_[n][0] - d0) * 0.125f, p1 * (dp_[n][1] - d0) * 0.125f);
+        dsA[2 * n + 1] = pack_bf16(p2 * (dp_[n][2] - d1) * 0.125f, p3 * (dp_[n][3] - d1) * 0.125f);
+      }
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t kf[4];
+        ldsm_x4_trans(kf, k_base + swz(kb0 + lr + ((li & 1) ? 8 : 0), dp * 2 + (li >> 1)));
+        mma_bf16(dq[2 * dp], dsA, kf[0], kf[1]);
+        mma_bf16(dq[2 * dp + 1], dsA, kf[2], kf[3]);
+      }
+    }
+    store_tile_bf16(mystage, dq, dq_out, kQkvLd, q0, T, lane);
+  }
+}
+
+int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                         __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream) {
+  if (batch <= 0 || tokens <= 0) return kOk;
+  if (batch > 65535) return set_error(kErrBadArg, "attention_bwd: batch %d exceeds gridDim.y limit", batch);
+  const int mt = (tokens + 15) / 16;
+  int nw = (mt % 3 == 0) ? 3 : 4;
+  if (nw > mt) nw = mt;
+  const int Tp = mt * 16;
+  const size_t smem = static_cast<size_t>(4 * Tp) * 128 + static_cast<size_t>(Tp) * 8 + static_cast<size_t>(nw) * 2048;
+  if (smem > 227 * 1024) return set_error(kErrUnsupported, "attention_bwd: %d tokens need %zu B of shared memory", tokens, smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return set_error(kErrCuda, "attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    configured = smem;
+    cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  dim3 grid(kHeads, batch);
+  attention_bwd_kernel<<<grid, nw * 32, smem, stream>>>(qkv, o, d_o, lse2, dqkv, tokens, Tp);
+  return check_launch("attention_bwd_kernel");
 }
 
 }  // namespace jp

@@ -31,7 +31,9 @@ enum Epilogue : int {
   EPI_PATCH_EMBED_F32 = 3,  // out_f32 = acc + bias + pos[row % tokens] + x_t[row,:8] . w_in_t[:, n]
   EPI_BIAS_F32 = 4,         // out_f32 = acc + bias
   EPI_BIAS_BF16_F32 = 5,    // out_bf16 = acc + bias, and (if out2 != null) out2_f32 = acc + bias
-  EPI_HEAD = 6,             // out_f32[row, :8] = w2 . silu(acc[:, :64] + bias) + b2     (N == 64)
+  EPI_HEAD = 6,             // out_f32[row, :8] = w2 . silu(acc[:, :64] + bias) + b2     (N == 64); optional pre-activation copy
+  EPI_DGELU_BF16 = 7,       // out_bf16 = acc * gelu_tanh'(aux_bf16[row, col])           (fc2 dgrad -> d(fc1 pre-activation))
+  EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
 };
 
 struct GemmParams {
@@ -48,21 +50,51 @@ struct GemmParams {
   const float* pos;      // [tokens, N] fp32                (patch embed)
   const float* w2;       // [8, 64] fp32                    (head)
   const float* b2;       // [8] fp32                        (head)
+  const __nv_bfloat16* aux;   // [M, N] bf16 (EPI_DGELU_BF16: fc1 pre-activations), leading dimension ldo
+  // EPI_WGRAD_F32: M = contraction length (token rows), N = output columns (in_features), wg_rows = output rows
+  int wg_rows, split, split_len;
 };
+
+// dW[wg_rows, n_cols] (fp32) = P[M, wg_rows]^T . Q[M, n_cols]   (both bf16 row-major); `partial` is scratch of
+// split * wg_rows * n_cols floats (see wgrad_scratch_floats)
+int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* qmat, long long ldq, float* out,
+                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream);
+long long wgrad_scratch_floats(long long m, int out_rows, int n_cols);
 
 // a: bf16 [M, K] row-major (lda elements); w: bf16 [N, K] row-major (nn.Linear layout)
 int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                 cudaStream_t stream);
 
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream);
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream);
+int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                         __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
 
-// x += delta (optional, bf16, written back to x), then y = LN(x) * (1 + scale) + shift
-int launch_ln_modulate(float* x, const __nv_bfloat16* delta, const float* shift, const float* scale, long long mod_stride,
-                       __nv_bfloat16* y, long long rows, int tokens, cudaStream_t stream);
+// backward.cu
+int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
+                    float* dgate, long long dgate_stride, float* dbias, int batch, int tokens, cudaStream_t stream);
+int launch_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx,
+                           int accumulate, float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16,
+                           int batch, int tokens, cudaStream_t stream);
+int launch_colsum_bf16(const __nv_bfloat16* src, long long ld, long long rows, int cols, float* out, cudaStream_t stream);
+int launch_colsum_f32(const float* src, long long ld, long long rows, int cols, float* out, cudaStream_t stream);
+int launch_head_bwd(const float* dte, const float* pre, const float* w2, __nv_bfloat16* dpre, float* dw2, float* db2,
+                    float* db1, long long rows, cudaStream_t stream);
+int launch_cast_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t stream);
+int launch_silu_bwd(const float* grad, const float* pre, float* out, __nv_bfloat16* out_bf16, long long n, cudaStream_t stream);
+int launch_win_grad(const float* dx0, const float* xt, float* dw, long long rows, cudaStream_t stream);
+int launch_unpatchify_bwd(const float* dimg, float* dy, int batch, int size, int accumulate, cudaStream_t stream);
+int launch_gelu(const __nv_bfloat16* pre, __nv_bfloat16* out, long long n, cudaStream_t stream);
+int launch_silu_fwd_bf16(const float* pre, __nv_bfloat16* out, long long n, cudaStream_t stream);
+
+// x_out = x_in + gate[b] * delta (optional: delta bf16, gate may be null = 1), then y = LN(x_out) * (1 + scale) + shift
+int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* delta, const float* gate, long long gate_stride,
+                       const float* shift, const float* scale, long long mod_stride, __nv_bfloat16* y, long long rows,
+                       int tokens, cudaStream_t stream);
 int launch_patchify(const float* img, __nv_bfloat16* cols, int batch, int size, cudaStream_t stream);
 int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStream_t stream);
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
-                          const float* w2, const float* b2, float* c, float* silu_c, cudaStream_t stream);
+                          const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
+                          cudaStream_t stream);
 int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, const float* bias, float* out, int n_out,
                       cudaStream_t stream);
 int launch_posterior(const float* x0, const float* xt, const float* noise, const float* coef1, const float* coef2,

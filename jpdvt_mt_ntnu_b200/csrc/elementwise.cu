@@ -27,26 +27,32 @@ constexpr int kLnWarps = 8;
 
 template <bool HAS_DELTA>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta, const float* __restrict__ shift,
+ln_modulate_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, const __nv_bfloat16* __restrict__ delta,
+                   const float* __restrict__ gate, long long gate_stride, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_stride, __nv_bfloat16* __restrict__ y, long long rows,
                    int tokens) {
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  float4* xr = reinterpret_cast<float4*>(x + row * kHidden);
+  const long long sample = row / tokens;
+  const float4* xr = reinterpret_cast<const float4*>(x_in + row * kHidden);
   float4 v[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) v[j] = __ldcs(xr + lane + 32 * j);
   if constexpr (HAS_DELTA) {
+    // residual update fused into this pass: x_out = x_in + gate[b] * delta   (models.py:120-121)
     const uint2* dr = reinterpret_cast<const uint2*>(delta + row * kHidden);
+    float4* xo = reinterpret_cast<float4*>(x_out + row * kHidden);
     uint2 d[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) d[j] = __ldcs(dr + lane + 32 * j);
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      v[j].x += __uint_as_float(d[j].x << 16); v[j].y += __uint_as_float(d[j].x & 0xffff0000u);
-      v[j].z += __uint_as_float(d[j].y << 16); v[j].w += __uint_as_float(d[j].y & 0xffff0000u);
-      xr[lane + 32 * j] = v[j];
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (gate != nullptr) g = __ldg(reinterpret_cast<const float4*>(gate + sample * gate_stride) + lane + 32 * j);
+      v[j].x = fmaf(g.x, __uint_as_float(d[j].x << 16), v[j].x); v[j].y = fmaf(g.y, __uint_as_float(d[j].x & 0xffff0000u), v[j].y);
+      v[j].z = fmaf(g.z, __uint_as_float(d[j].y << 16), v[j].z); v[j].w = fmaf(g.w, __uint_as_float(d[j].y & 0xffff0000u), v[j].w);
+      xo[lane + 32 * j] = v[j];
     }
   }
   float s = 0.f;
@@ -60,7 +66,6 @@ ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delt
     q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / kHidden) + 1e-6f);
-  const long long sample = row / tokens;
   const float4* sh = reinterpret_cast<const float4*>(shift + sample * mod_stride);
   const float4* sc = reinterpret_cast<const float4*>(scale + sample * mod_stride);
   uint2* yr = reinterpret_cast<uint2*>(y + row * kHidden);
@@ -79,15 +84,18 @@ ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delt
   }
 }
 
-int launch_ln_modulate(float* x, const __nv_bfloat16* delta, const float* shift, const float* scale, long long mod_stride,
-                       __nv_bfloat16* y, long long rows, int tokens, cudaStream_t stream) {
+// x_out may alias x_in (in-place residual update) or be a fresh buffer (training keeps every LN input for the backward).
+int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* delta, const float* gate, long long gate_stride,
+                       const float* shift, const float* scale, long long mod_stride, __nv_bfloat16* y, long long rows,
+                       int tokens, cudaStream_t stream) {
   if (rows <= 0) return kOk;
   if (tokens <= 0) return set_error(kErrBadArg, "ln_modulate: tokens must be positive");
+  if (delta != nullptr && x_out == nullptr) return set_error(kErrBadArg, "ln_modulate: residual update needs an output buffer");
   const unsigned blocks = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
   if (delta != nullptr)
-    ln_modulate_kernel<true><<<blocks, kLnWarps * 32, 0, stream>>>(x, delta, shift, scale, mod_stride, y, rows, tokens);
+    ln_modulate_kernel<true><<<blocks, kLnWarps * 32, 0, stream>>>(x_in, x_out, delta, gate, gate_stride, shift, scale, mod_stride, y, rows, tokens);
   else
-    ln_modulate_kernel<false><<<blocks, kLnWarps * 32, 0, stream>>>(x, delta, shift, scale, mod_stride, y, rows, tokens);
+    ln_modulate_kernel<false><<<blocks, kLnWarps * 32, 0, stream>>>(x_in, x_out, delta, gate, gate_stride, shift, scale, mod_stride, y, rows, tokens);
   return check_launch("ln_modulate_kernel");
 }
 
@@ -157,7 +165,8 @@ __device__ __forceinline__ long long te_timestep(const long long* t, int r, cons
 
 __global__ void __launch_bounds__(kTeWarps * 32)
 timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __restrict__ step_ptr, const int* __restrict__ map,
-                       const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ hid) {
+                       const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ hid,
+                       float* __restrict__ feat_out, float* __restrict__ pre_out) {
   __shared__ float feat[kTeRows][256];
   const int r0 = blockIdx.y * kTeRows;
   const int nr = min(kTeRows, n - r0);
@@ -173,6 +182,10 @@ timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __rest
     }
     feat[r][k] = c;          // cos first, then sin (models.py:56)
     feat[r][128 + k] = s;
+    if (feat_out != nullptr && blockIdx.x == 0 && r < nr) {   // training keeps the sinusoid features for the backward
+      feat_out[static_cast<long long>(r0 + r) * 256 + k] = c;
+      feat_out[static_cast<long long>(r0 + r) * 256 + 128 + k] = s;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,6 +208,7 @@ timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __rest
     for (int r = 0; r < nr; ++r) {
       const float v = acc[r] + b;
       hid[static_cast<long long>(r0 + r) * kHidden + o] = v / (1.0f + expf(-v));
+      if (pre_out != nullptr) pre_out[static_cast<long long>(r0 + r) * kHidden + o] = v;
     }
   }
 }
@@ -237,11 +251,12 @@ timestep_out_kernel(const float* __restrict__ hid, int n, const float* __restric
 
 // `silu_c` doubles as the scratch for the hidden activations between the two phases.
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
-                          const float* w2, const float* b2, float* c, float* silu_c, cudaStream_t stream) {
+                          const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
+                          cudaStream_t stream) {
   if (n <= 0) return kOk;
   if (t == nullptr && step_ptr == nullptr) return set_error(kErrBadArg, "timestep_embed: need t or step_ptr");
   dim3 grid(kHidden / kTeWarps, (n + kTeRows - 1) / kTeRows);
-  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, map, w0, b0, c);
+  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, map, w0, b0, c, feat_out, pre_out);
   int rc = check_launch("timestep_hidden_kernel");
   if (rc != kOk) return rc;
   timestep_out_kernel<<<grid, kTeWarps * 32, 0, stream>>>(c, n, w2, b2, c, silu_c);

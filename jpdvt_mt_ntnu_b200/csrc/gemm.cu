@@ -103,11 +103,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
 
 template <int EPI>
 __device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], int row, int n0, bool row_ok) {
-  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+  if constexpr (EPI != EPI_DGELU_BF16) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 b = __ldg(b4 + j);
-    v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    for (int j = 0; j < 16; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
   }
   if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
@@ -125,8 +127,9 @@ __device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], i
 }
 
 // 32 rows x 64 bf16 columns of this warp -> global, every store instruction writes 4 full 128-byte row segments.
-__device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)[64], __nv_bfloat16* out, long long ldo,
-                                                int row0, int n0, int M, int lane) {
+template <bool DGELU>
+__device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)[64], __nv_bfloat16* out,
+                                                const __nv_bfloat16* aux, long long ldo, int row0, int n0, int M, int lane) {
   uint8_t* mine = stage + lane * kStageRowBytes;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -140,8 +143,22 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + sub;
-    const uint4 u = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
-    if (row0 + r < M) *reinterpret_cast<uint4*>(out + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch) = u;
+    uint4 u = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
+    if (row0 + r < M) {
+      const long long off = static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch;
+      if constexpr (DGELU) {   // d(pre-activation) = d(activation) * gelu'(pre-activation), 8 coalesced bf16 per lane
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(aux + off));
+        uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float g0 = gelu_tanh_grad(__uint_as_float(aw[e] << 16)), g1 = gelu_tanh_grad(__uint_as_float(aw[e] & 0xffff0000u));
+          uw[e] = pack_bf16(__uint_as_float(uw[e] << 16) * g0, __uint_as_float(uw[e] & 0xffff0000u) * g1);
+        }
+        u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
+      }
+      *reinterpret_cast<uint4*>(out + off) = u;
+    }
   }
   __syncwarp();
 }
@@ -173,10 +190,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (CS == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const int num_m = (p.M + CS * BM - 1) / (CS * BM);       // tiles of CS*128 rows
+  constexpr bool WG = (EPI == EPI_WGRAD_F32);              // MN-major operands + split contraction (weight gradients)
+  const int out_rows = WG ? p.wg_rows : p.M;
+  const int num_m = (out_rows + CS * BM - 1) / (CS * BM);  // tiles of CS*128 rows
   const int num_n = p.N / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = p.K / BK;
+  const int tiles_mn = num_m * num_n;
+  const int num_tiles = WG ? tiles_mn * p.split : tiles_mn;
+  const int num_kb = WG ? p.split_len / BK : p.K / BK;
   const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
 
   if (warp == 0 && lane == 0) {
@@ -200,14 +220,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int split_idx = tile / tiles_mn, rem = tile - split_idx * tiles_mn;
+        const int m_blk = rem / num_n, n_blk = rem % num_n;
         const int row_a = (m_blk * CS + static_cast<int>(rank)) * BM;
         const int row_b = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if constexpr (CS == 2) {
+          if constexpr (WG) {
+            // operands are [contraction rows, features] row-major: {64 features x 64 rows} boxes stacked along the
+            // feature (MN) dimension, 8 KB each
+            static_assert(!WG || CS == 2, "wgrad mode is pair-only");
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            const int m0 = split_idx * p.split_len + kb * BK;
+#pragma unroll
+            for (int hh = 0; hh < BM / 64; ++hh) tma_load_2d_pair(&tma_a, bar, sa + hh * 8192, row_a + 64 * hh, m0);
+#pragma unroll
+            for (int hh = 0; hh < Cfg::kBRows / 64; ++hh) tma_load_2d_pair(&tma_b, bar, sb + hh * 8192, row_b + 64 * hh, m0);
+          } else if constexpr (CS == 2) {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
             const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_pair(&tma_a, bar, sa, kb * BK, row_a);
@@ -225,7 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN, WG ? 1 : 0, WG ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = group; tile < num_tiles; tile += num_groups) {
@@ -239,8 +271,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t db = umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            // K-major: 16 elements = 32 B inside the swizzle row; MN-major: 16 contraction rows = two 1024 B atoms
+            const uint64_t da = WG ? umma_desc_mn_sw128(a_addr + k * 2048) : umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t db = WG ? umma_desc_mn_sw128(b_addr + k * 2048) : umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
             if constexpr (CS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -267,10 +300,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int split_idx = tile / tiles_mn, rem = tile - split_idx * tiles_mn;
+      const int m_blk = rem / num_n, n_blk = rem % num_n;
       const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;   // first row of this warp
       const int row = row0 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < out_rows;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -287,6 +321,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           h[j] = silu(__uint_as_float(r0[j]) + __ldg(p.bias + j));
           h[32 + j] = silu(__uint_as_float(r1[j]) + __ldg(p.bias + 32 + j));
         }
+        if (row_ok && p.out2 != nullptr) {   // training: keep the pre-activations (time_emb_out1 output incl. bias)
+          float4* pre = reinterpret_cast<float4*>(p.out2 + static_cast<long long>(row) * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pre[j] = make_float4(__uint_as_float(r0[4 * j]) + __ldg(p.bias + 4 * j), __uint_as_float(r0[4 * j + 1]) + __ldg(p.bias + 4 * j + 1),
+                                 __uint_as_float(r0[4 * j + 2]) + __ldg(p.bias + 4 * j + 2), __uint_as_float(r0[4 * j + 3]) + __ldg(p.bias + 4 * j + 3));
+            pre[8 + j] = make_float4(__uint_as_float(r1[4 * j]) + __ldg(p.bias + 32 + 4 * j), __uint_as_float(r1[4 * j + 1]) + __ldg(p.bias + 33 + 4 * j),
+                                     __uint_as_float(r1[4 * j + 2]) + __ldg(p.bias + 34 + 4 * j), __uint_as_float(r1[4 * j + 3]) + __ldg(p.bias + 35 + 4 * j));
+          }
+        }
         if (row_ok) {
           float o[kLatent];
 #pragma unroll
@@ -300,7 +344,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           dst[0] = make_float4(o[0], o[1], o[2], o[3]);
           dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
-      } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_BF16 || EPI == EPI_BIAS_BF16_F32) {
+      } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_BF16 || EPI == EPI_BIAS_BF16_F32 ||
+                           EPI == EPI_DGELU_BF16) {
 #pragma unroll 1
         for (int c = 0; c < kColsPerWarp / 64; ++c) {
           uint32_t r0[32], r1[32];
@@ -312,7 +357,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
           bf16_math<EPI>(p, v, row, n0, row_ok);
-          store_bf16_tile(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M, lane);
+          store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
             if (p.out2 != nullptr) {
 #pragma unroll
@@ -354,12 +399,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tmem_ld_wait();
           const int n0 = n_blk * BN + col_base + c * 32;
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+          if constexpr (WG) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+            }
           }
           if constexpr (EPI == EPI_PATCH_EMBED_F32) {
             // + x_t[row, :8] . w_in_t[:, n]  (time_emb_in, models.py:280); 8 FMAs per output, weights broadcast from L1
@@ -381,12 +431,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int rr = it * 4 + sub;
             float4 u = *reinterpret_cast<const float4*>(stage + rr * kStageRowBytes + 16 * ch);
             const int grow = row0 + rr;
-            if (grow < p.M) {
+            if (grow < out_rows) {
               if constexpr (EPI == EPI_PATCH_EMBED_F32) {   // + pos_embed[row % tokens]  (coalesced 128-byte segments)
                 const float4 q = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(grow % p.tokens) * p.N + n0) + ch);
                 u.x += q.x; u.y += q.y; u.z += q.z; u.w += q.w;
               }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(grow) * p.ldo + n0 + 4 * ch) = u;
+              float* obase = reinterpret_cast<float*>(p.out);
+              if constexpr (WG) obase += static_cast<long long>(split_idx) * p.wg_rows * p.ldo;
+              *reinterpret_cast<float4*>(obase + static_cast<long long>(grow) * p.ldo + n0 + 4 * ch) = u;
             }
           }
           __syncwarp();
@@ -509,6 +561,7 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
   if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
+  if (epi == EPI_DGELU_BF16 && p.aux == nullptr) return set_error(kErrBadArg, "gemm: dgelu epilogue needs the pre-activations");
 #define JP_CASE(E)                                                             \
   case E:                                                                      \
     return bn == 256 ? launch_cs<256, E>(a, lda, w, ldw, p, stream) : launch_cs<128, E>(a, lda, w, ldw, p, stream);
@@ -519,12 +572,92 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     JP_CASE(EPI_PATCH_EMBED_F32)
     JP_CASE(EPI_BIAS_F32)
     JP_CASE(EPI_BIAS_BF16_F32)
+    JP_CASE(EPI_DGELU_BF16)
     case EPI_HEAD:
       return launch_cs<64, EPI_HEAD>(a, lda, w, ldw, p, stream);
     default:
       return set_error(kErrBadArg, "gemm: unknown epilogue %d", epi);
   }
 #undef JP_CASE
+}
+
+// ------------------------------------------------------------------------------------------- weight gradients
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n4, int split) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = reinterpret_cast<const float4*>(partial)[i];
+  for (int s = 1; s < split; ++s) {
+    const float4 v = reinterpret_cast<const float4*>(partial)[i + static_cast<long long>(s) * n4];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = acc;
+}
+
+static void wgrad_plan(long long m, int out_rows, int n_cols, int* split, int* split_len) {
+  const int bn = (n_cols % 256 == 0) ? 256 : 128;
+  const int tiles = ((out_rows + 255) / 256) * (n_cols / bn);
+  const int kb_total = static_cast<int>((m + BK - 1) / BK);
+  int s = (2 * (num_sms() / 2) + tiles - 1) / tiles;     // aim at ~2 work items per CTA pair
+  if (s > 16) s = 16;
+  if (s > kb_total) s = kb_total;
+  if (s < 1) s = 1;
+  const int kb_per = (kb_total + s - 1) / s;
+  *split = (kb_total + kb_per - 1) / kb_per;
+  *split_len = kb_per * BK;
+}
+
+long long wgrad_scratch_floats(long long m, int out_rows, int n_cols) {
+  int split, split_len;
+  wgrad_plan(m, out_rows, n_cols, &split, &split_len);
+  return split > 1 ? static_cast<long long>(split) * out_rows * n_cols : 0;
+}
+
+template <int BN>
+static int launch_wgrad_cfg(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* qmat, long long ldq,
+                            const GemmParams& p, cudaStream_t stream) {
+  constexpr int CS = 2, EW = 8;
+  using Cfg = GemmCfg<BN, CS, EW>;
+  static bool attr_set = false;
+  auto kern = gemm_kernel<BN, EPI_WGRAD_F32, CS, EW>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_kmajor(&ta, pmat, p.M, p.wg_rows, ldp, 64);   // {64 features x 64 contraction rows} boxes
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tb, qmat, p.M, p.N, ldq, 64);
+  if (rc != kOk) return rc;
+  const int tiles = ((p.wg_rows + 255) / 256) * (p.N / BN) * p.split;
+  const int max_groups = num_sms() / CS;
+  const int groups = tiles < max_groups ? tiles : max_groups;
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("gemm_kernel<wgrad>");
+}
+
+int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* qmat, long long ldq, float* out,
+                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream) {
+  if (out_rows <= 0 || n_cols <= 0) return kOk;
+  if (m <= 0) return set_error(kErrBadArg, "wgrad: empty contraction");
+  if (n_cols % 128 != 0) return set_error(kErrBadArg, "wgrad: n_cols=%d must be a multiple of 128", n_cols);
+  if ((ldp % 8) || (ldq % 8) || (out_rows % 8)) return set_error(kErrBadArg, "wgrad: leading dimensions / out_rows must be multiples of 8");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "wgrad: contraction too long");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n_cols; p.K = BK; p.tokens = 1;
+  p.wg_rows = out_rows; p.ldo = n_cols;
+  wgrad_plan(m, out_rows, n_cols, &p.split, &p.split_len);
+  if (p.split > 1 && partial == nullptr) return set_error(kErrBadArg, "wgrad: scratch buffer required (split=%d)", p.split);
+  p.out = (p.split > 1) ? partial : out;
+  int rc = (n_cols % 256 == 0) ? launch_wgrad_cfg<256>(pmat, ldp, qmat, ldq, p, stream)
+                               : launch_wgrad_cfg<128>(pmat, ldp, qmat, ldq, p, stream);
+  if (rc != kOk) return rc;
+  if (p.split > 1) {
+    const long long n4 = static_cast<long long>(out_rows) * n_cols / 4;
+    wgrad_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(partial, out, n4, p.split);
+    return check_launch("wgrad_reduce_kernel");
+  }
+  return kOk;
 }
 
 }  // namespace jp

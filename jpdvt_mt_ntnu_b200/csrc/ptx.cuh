@@ -148,6 +148,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand (the contraction index is the strided one), 128-byte swizzle, bf16, as laid down by {64 x 64} TMA
+// boxes stacked along MN: 64 MN-elements are contiguous (128 B), 8 K-rows form a 1024 B swizzle atom,
+// SBO = 1024 B steps to the next group of 8 K-rows, LBO = 8192 B steps to the next 64-wide MN block.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major (or MN-major via flags), dense.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
@@ -171,5 +183,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + tanh_fast(u));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// d/dx of gelu_tanh
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k0 * x * fmaf(k1, x2, 1.0f));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * fmaf(3.0f * k1, x2, 1.0f);
+}
 
 }  // namespace jp

@@ -26,9 +26,11 @@ def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 
 def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, tokens: int,
-                delta: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [rows,768] fp32; shift/scale [n_cond,768] fp32 with n_cond == rows/tokens or 1 -> bf16 [rows,768].
-    With `delta` (bf16 [rows,768]) x is first updated IN PLACE: x += delta (the fused residual add)."""
+                delta: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+                out_x: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [rows,768] fp32; shift/scale(/gate) [n_cond,768] fp32 with n_cond == rows/tokens or 1 -> bf16 [rows,768].
+    With `delta` (bf16 [rows,768]) the residual stream is updated first: out_x = x + gate * delta (gate None = 1);
+    out_x defaults to x itself (in place)."""
     lib = _lib_dev()
     shift, scale = _need(shift, torch.float32, "shift"), _need(scale, torch.float32, "scale")
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -36,7 +38,11 @@ def ln_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, token
     rows = x.shape[0]
     stride = 0 if shift.shape[0] == 1 else HIDDEN
     y = torch.empty(rows, HIDDEN, device=x.device, dtype=torch.bfloat16)
-    check(lib.jpdvt_ln_modulate_fwd(ptr(x), ptr(_need(delta, torch.bfloat16, "delta")) if delta is not None else None,
+    if delta is not None and out_x is None:
+        out_x = x
+    check(lib.jpdvt_ln_modulate_fwd(ptr(x), ptr(out_x) if out_x is not None else None,
+                                    ptr(_need(delta, torch.bfloat16, "delta")) if delta is not None else None,
+                                    ptr(_need(gate, torch.float32, "gate")) if gate is not None else None,
                                     ptr(shift), ptr(scale), stride, ptr(y), rows, tokens, stream_ptr()), "ln_modulate")
     return y
 
@@ -124,12 +130,13 @@ def final_head(y, w1, b1, w2, b2) -> torch.Tensor:
     return out
 
 
-def attention(qkv: torch.Tensor, batch: int, tokens: int) -> torch.Tensor:
+def attention(qkv: torch.Tensor, batch: int, tokens: int, return_lse: bool = False):
     lib = _lib_dev()
     qkv = _need(qkv, torch.bfloat16, "qkv")
     out = torch.empty(batch * tokens, HIDDEN, device=qkv.device, dtype=torch.bfloat16)
-    check(lib.jpdvt_attention_fwd(ptr(qkv), ptr(out), batch, tokens, stream_ptr()), "attention")
-    return out
+    lse = torch.empty(batch, 12, tokens, device=qkv.device, dtype=torch.float32) if return_lse else None
+    check(lib.jpdvt_attention_fwd(ptr(qkv), ptr(out), ptr(lse), batch, tokens, stream_ptr()), "attention")
+    return (out, lse) if return_lse else out
 
 
 def timestep_embed(t: torch.Tensor, w0, b0, w2, b2) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -215,3 +222,75 @@ def assign_greedy_l1(latents: torch.Tensor, canon: torch.Tensor, grid: int, sent
     check(lib.jpdvt_assign_greedy_l1(ptr(latents), ptr(canon), b, grid, side, float(sentinel), ptr(order), ptr(pred),
                                      ptr(scores), stream_ptr()), "assign_greedy_l1")
     return (order, pred, scores) if return_scores else (order, pred)
+
+
+# ------------------------------------------------------------------------------------------------- training kernels
+def gemm_wgrad(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """dW [out_rows, n_cols] fp32 = p[m, out_rows].T @ q[m, n_cols]  (bf16 operands, tcgen05 MN-major GEMM)."""
+    lib = _lib_dev()
+    p, q = _need(p, torch.bfloat16, "p"), _need(q, torch.bfloat16, "q")
+    m, out_rows = p.shape
+    n_cols = q.shape[1]
+    dw = torch.empty(out_rows, n_cols, device=p.device, dtype=torch.float32)
+    need = lib.jpdvt_wgrad_scratch_floats(m, out_rows, n_cols)
+    scratch = torch.empty(max(need, 1), device=p.device, dtype=torch.float32)
+    check(lib.jpdvt_gemm_wgrad(ptr(p), ptr(q), ptr(dw), ptr(scratch), m, out_rows, n_cols, stream_ptr()), "gemm_wgrad")
+    return dw
+
+
+def gemm_dgelu(a, w, pre) -> torch.Tensor:
+    """(a @ w.T) * gelu_tanh'(pre) -> bf16."""
+    lib = _lib_dev()
+    a, w, pre = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w"), _need(pre, torch.bfloat16, "pre")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_gemm_dgelu(ptr(a), ptr(w), ptr(pre), ptr(out), m, n, k, stream_ptr()), "gemm_dgelu")
+    return out
+
+
+def attention_bwd(qkv, o, d_o, lse2, batch: int, tokens: int) -> torch.Tensor:
+    lib = _lib_dev()
+    dqkv = torch.empty_like(qkv)
+    check(lib.jpdvt_attention_bwd(ptr(_need(qkv, torch.bfloat16, "qkv")), ptr(_need(o, torch.bfloat16, "o")),
+                                  ptr(_need(d_o, torch.bfloat16, "d_o")), ptr(_need(lse2, torch.float32, "lse2")), ptr(dqkv),
+                                  batch, tokens, stream_ptr()), "attention_bwd")
+    return dqkv
+
+
+def gate_bwd(dx, y, gate, tokens: int):
+    """-> (dy bf16, dgate [B,768], dbias [768])."""
+    lib = _lib_dev()
+    batch = dx.shape[0] // tokens
+    dy = torch.empty_like(y)
+    dgate = torch.zeros(batch, HIDDEN, device=dx.device, dtype=torch.float32)
+    dbias = torch.zeros(HIDDEN, device=dx.device, dtype=torch.float32)
+    check(lib.jpdvt_gate_bwd(ptr(_need(dx, torch.float32, "dx")), ptr(_need(y, torch.bfloat16, "y")),
+                             ptr(_need(gate, torch.float32, "gate")), HIDDEN, ptr(dy), ptr(dgate), HIDDEN, ptr(dbias), batch,
+                             tokens, stream_ptr()), "gate_bwd")
+    return dy, dgate, dbias
+
+
+def ln_modulate_bwd(x, dxn, scale, tokens: int, dx: Optional[torch.Tensor] = None):
+    """-> (dx fp32 (accumulated into `dx` when given), dshift [B,768], dscale [B,768], dx_bf16)."""
+    lib = _lib_dev()
+    batch = x.shape[0] // tokens
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x)
+    dshift = torch.zeros(batch, HIDDEN, device=x.device, dtype=torch.float32)
+    dscale = torch.zeros_like(dshift)
+    dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_ln_modulate_bwd(ptr(_need(x, torch.float32, "x")), ptr(_need(dxn, torch.float32, "dxn")),
+                                    ptr(_need(scale, torch.float32, "scale")), HIDDEN, ptr(dx), int(acc), ptr(dshift), ptr(dscale),
+                                    HIDDEN, ptr(dxb), batch, tokens, stream_ptr()), "ln_modulate_bwd")
+    return dx, dshift, dscale, dxb
+
+
+def colsum(src: torch.Tensor) -> torch.Tensor:
+    lib = _lib_dev()
+    rows, cols = src.shape
+    out = torch.zeros(cols, device=src.device, dtype=torch.float32)
+    fn = lib.jpdvt_colsum_bf16 if src.dtype == torch.bfloat16 else lib.jpdvt_colsum_f32
+    check(fn(ptr(src.contiguous()), rows, cols, ptr(out), stream_ptr()), "colsum")
+    return out
