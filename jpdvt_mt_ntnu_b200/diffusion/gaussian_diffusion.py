@@ -413,19 +413,23 @@ class GaussianDiffusion:
             model_kwargs = {}
         B = x_start.shape[0]
         G, n = grid_size, grid_size * grid_size
-        noise_x = th.randn_like(x_start)
-        perm = np.random.permutation(n)
+        draws = getattr(self, "_draws", None)      # parity tests inject the reference's CPU draws here
+        noise_x = th.randn_like(x_start) if draws is None else draws["noise_x"].to(x_start.device)
+        perm = np.random.permutation(n) if draws is None else np.asarray(draws["perm"])
         keep_slots = None
         if add_mask:
-            keep_slots = th.ones(B, n)
-            for i in range(B):
-                r = np.random.randint(0, G)
-                keep_slots[i, random.sample(range(n), r)] = 0
+            if draws is not None:
+                keep_slots = draws["masks"].clone()
+            else:
+                keep_slots = th.ones(B, n)
+                for i in range(B):
+                    r = np.random.randint(0, G)
+                    keep_slots[i, random.sample(range(n), r)] = 0
         x0 = self._scramble(x_start.float(), perm, G, block_size).contiguous()
         tok = block_size // patch_size
         te = time_emb_start.to(x_start.device).float().expand(B, -1, -1)[:, th.as_tensor(perm, device=x_start.device, dtype=th.long)]
         te0 = te.reshape(B, G, 1, G, 1, -1).expand(B, G, tok, G, tok, te.shape[-1]).reshape(B, n * tok * tok, -1).contiguous()
-        noise_te = th.randn_like(te0)
+        noise_te = th.randn_like(te0) if draws is None else draws["noise_te"].to(te0.device)
         t = t.to(th.int64)
         if keep_slots is None:
             # masks == 1 everywhere: x_t * 0 + 1 * x_start == x_start exactly, the image condition stays clean (:800);

