@@ -302,6 +302,15 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
 int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt, const jpdvt_tape* tape,
                                const jpdvt_bwd_scratch* s, const jpdvt_grads* g, const float* x_t, void* stream);
 
+/* One fused pass of torch.optim.AdamW.step() + update_ema() over a flat fp32 parameter buffer (train_JPDVT.py:281,371-372,
+ * 36-46): g is scaled by grad_scale first (1/world_size after a SUM all-reduce), `step` counts from 1; optionally refreshes
+ * the bf16 operand copy of the parameters in the same pass.  36 B of HBM traffic per parameter (+2 B for the bf16 copy). */
+int jpdvt_adamw_ema(float* p, const float* g, float* m, float* v, float* ema_or_null, jpdvt_bf16* p_bf16_or_null, int64_t n,
+                    int64_t step, float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float ema_decay, void* stream);
+/* out[b][c][r] = in[b][r][c]: refreshes the [in, out] weight copies of jpdvt_weights_t after an optimizer step. */
+int jpdvt_transpose_bf16(const jpdvt_bf16* in, jpdvt_bf16* out, int batch, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ PROTOTYPES = {
                                    C.POINTER(Grads), c_int, P],
     "jpdvt_train_backward_embed": [C.POINTER(Weights), C.POINTER(WeightsT), C.POINTER(Tape), C.POINTER(BwdScratch),
                                    C.POINTER(Grads), P, P],
+    "jpdvt_adamw_ema": [P, P, P, P, P, P, c_int64, c_int64] + [C.c_float] * 7 + [P],
+    "jpdvt_transpose_bf16": [P, P, c_int, c_int, c_int, P],
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
 }

@@ -178,7 +178,8 @@ class DiT(nn.Module):
                 "Linear(8,768) and time_emb_out1 is applied to the p*p*3-wide final layer, models.py:176-177,287-288)")
 
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # `_epoch` is bumped by the B200 Trainer, whose optimizer kernel updates parameters behind autograd's back
+        return (self.__dict__.get("_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, device: Optional[torch.device] = None):
         """The packed-weight engine for the parameters as they are now (re-packed when any parameter changed)."""
@@ -205,6 +206,8 @@ class DiT(nn.Module):
         if dev.type != "cuda":
             raise _lib.JpdvtError("JPDVT parameters are on the CPU: move the model to a B200 (`.cuda()`); no CPU path exists")
         eng = self.__dict__.get("_train_engine")
+        if eng is not None and self.__dict__.get("_adopted_by_trainer"):
+            return eng          # operand buffers are owned and refreshed by jpdvt_mt_ntnu_b200.trainer.Trainer
         key = self._weights_key()
         if eng is None or eng.device != dev:
             eng = TrainEngine(self.depth, self.input_size, dev)
@@ -220,7 +223,7 @@ class DiT(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_engine", "_engine_key", "_train_engine", "_train_engine_key", "_stage_hook") else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_engine_key", "_train_engine", "_train_engine_key", "_stage_hook", "_adopted_by_trainer") else copy.deepcopy(v, memo)
         return new
 
     def unpatchify(self, x: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,178 @@
+"""B200 training step: `training_losses -> backward -> gradient all-reduce -> AdamW -> EMA`
+(image_model/train_JPDVT.py:357-372 with DDP at :231, AdamW at :281, update_ema at :36-46) as one object.
+
+What it changes relative to running the reference loop on the drop-in modules (which also works, see
+tests/test_gpu_training.py::test_adamw_step_changes_outputs_and_engines_refresh):
+  * parameters, gradients, Adam moments and the EMA copy live in flat fp32 buffers with one shared layout, so the
+    optimizer + EMA (+ the bf16 operand refresh) is ONE kernel pass (jpdvt_adamw_ema, 38 B/param) instead of ~450 launches;
+  * the gradient all-reduce (NCCL over NVLink, SUM then 1/world inside the optimizer kernel) is issued per backward stage
+    on the communicator stream as soon as that stage's gradients exist, overlapping the remaining backward kernels -
+    the role DDP's bucketed hooks play in the reference;
+  * no per-step host sync (`loss.item()` is left to the caller's logging cadence, train_JPDVT.py:374).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import Weights, WeightsT, check, ptr
+from .engine import HIDDEN, LATENT
+from .training import TrainEngine, _grad_layout, param_grad_map
+
+_BF16_FIELDS = ("w_patch", "w_ada", "w_qkv", "w_proj", "w_fc1", "w_fc2", "w_final", "w_head1")
+_STAGE_FIELDS = {
+    "head": ("w_final", "b_final", "w_head1", "b_head1", "w_head2", "b_head2"),
+    "block": ("w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2"),
+    "embed": ("w_patch", "b_patch", "w_in", "b_in", "t_w0", "t_b0", "t_w2", "t_b2", "w_ada", "b_ada"),
+}
+
+
+class Trainer:
+    def __init__(self, model, diffusion, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 ema_decay: float = 0.9999, process_group=None):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.model, self.diffusion = model, diffusion
+        self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.step_count = 0
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.JpdvtError("Trainer needs the model on a B200 (`.cuda()`)")
+        self.device = dev
+        model._check_supported()
+        d = model.depth
+        self.layout = _grad_layout(d)
+        sizes = [int(torch.Size(s).numel()) for _, s in self.layout]
+        self.total = sum(sizes)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.p_flat = torch.zeros(self.total, **f32)
+        self.m_flat = torch.zeros(self.total, **f32)
+        self.v_flat = torch.zeros(self.total, **f32)
+        self.pb_flat = torch.zeros(self.total, device=dev, dtype=torch.bfloat16)
+        self.p_views, self.pb_views, self.offsets = {}, {}, {}
+        off = 0
+        for (name, shape), n in zip(self.layout, sizes):
+            self.p_views[name] = self.p_flat[off:off + n].view(shape)
+            self.pb_views[name] = self.pb_flat[off:off + n].view(shape)
+            self.offsets[name] = (off, n)
+            off += n
+        # adopt the module's parameters: copy into the flat buffer, then re-point .data at the slices
+        by_name = param_grad_map(model, self.p_views)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if name in by_name:
+                    by_name[name].copy_(p.data)
+                    p.data = by_name[name]
+        self.ema_flat = self.p_flat.clone()
+        self.pb_flat.copy_(self.p_flat)
+        self.pos = model.pos_embed.data[0].contiguous()
+        # small derived tensors + transposed copies
+        self.b_embed = torch.empty(HIDDEN, **f32)
+        self.w_in_t = torch.empty(LATENT, HIDDEN, **f32)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        n_mod = d * 6 * HIDDEN + 2 * HIDDEN
+        self.wt_t = {
+            "w_qkv_t": torch.empty(d, HIDDEN, 3 * HIDDEN, **bf), "w_proj_t": torch.empty(d, HIDDEN, HIDDEN, **bf),
+            "w_fc1_t": torch.empty(d, HIDDEN, 4 * HIDDEN, **bf), "w_fc2_t": torch.empty(d, 4 * HIDDEN, HIDDEN, **bf),
+            "w_final_t": torch.empty(HIDDEN, HIDDEN, **bf), "w_head1_t": torch.empty(HIDDEN, 64, **bf),
+            "w_ada_t": torch.empty(HIDDEN, n_mod, **bf), "t_w2_t": torch.empty(HIDDEN, HIDDEN, **bf),
+        }
+        self.t_w2_bf16 = torch.empty(HIDDEN, HIDDEN, **bf)
+        self.engine = TrainEngine(d, model.input_size, dev)
+        w = Weights()
+        w.depth, w.tokens, w.image_size, w.reserved = d, self.engine.tokens, model.input_size, 0
+        pv, bv = self.p_views, self.pb_views
+        for field, t in (("w_patch", bv["w_patch"]), ("b_embed", self.b_embed), ("w_in_t", self.w_in_t), ("pos", self.pos),
+                         ("t_w0", pv["t_w0"]), ("t_b0", pv["t_b0"]), ("t_w2", pv["t_w2"]), ("t_b2", pv["t_b2"]),
+                         ("w_ada", bv["w_ada"]), ("b_ada", pv["b_ada"]), ("w_qkv", bv["w_qkv"]), ("b_qkv", pv["b_qkv"]),
+                         ("w_proj", bv["w_proj"]), ("b_proj", pv["b_proj"]), ("w_fc1", bv["w_fc1"]), ("b_fc1", pv["b_fc1"]),
+                         ("w_fc2", bv["w_fc2"]), ("b_fc2", pv["b_fc2"]), ("w_final", bv["w_final"]), ("b_final", pv["b_final"]),
+                         ("w_head1", bv["w_head1"]), ("b_head1", pv["b_head1"]), ("w_head2", pv["w_head2"]), ("b_head2", pv["b_head2"])):
+            setattr(w, field, ptr(t))
+        wt = WeightsT()
+        for k, v in self.wt_t.items():
+            setattr(wt, k, ptr(v))
+        self.engine.adopt(w, wt, keepalive=(self,))
+        model.__dict__["_train_engine"] = self.engine
+        model.__dict__["_train_engine_key"] = "adopted"
+        model.__dict__["_adopted_by_trainer"] = True
+        self._refresh_derived()
+        self._works: List = []
+
+    # ------------------------------------------------------------------ derived operand copies
+    def _refresh_derived(self) -> None:
+        st = _lib.stream_ptr()
+        torch.add(self.p_views["b_patch"], self.p_views["b_in"], out=self.b_embed)
+        self.w_in_t.copy_(self.p_views["w_in"].t())
+        self.t_w2_bf16.copy_(self.p_views["t_w2"])
+        d = self.model.depth
+        bv = self.pb_views
+        for name, src, batch, rows, cols in (("w_qkv_t", bv["w_qkv"], d, 3 * HIDDEN, HIDDEN), ("w_proj_t", bv["w_proj"], d, HIDDEN, HIDDEN),
+                                            ("w_fc1_t", bv["w_fc1"], d, 4 * HIDDEN, HIDDEN), ("w_fc2_t", bv["w_fc2"], d, HIDDEN, 4 * HIDDEN),
+                                            ("w_final_t", bv["w_final"], 1, HIDDEN, HIDDEN), ("w_head1_t", bv["w_head1"], 1, 64, HIDDEN),
+                                            ("w_ada_t", bv["w_ada"], 1, bv["w_ada"].shape[0], HIDDEN), ("t_w2_t", self.t_w2_bf16, 1, HIDDEN, HIDDEN)):
+            check(self.lib.jpdvt_transpose_bf16(ptr(src), ptr(self.wt_t[name]), batch, rows, cols, st), "jpdvt_transpose_bf16")
+        self.model.__dict__["_epoch"] = self.model.__dict__.get("_epoch", 0) + 1      # invalidates the inference engine's packed copy
+
+    # ------------------------------------------------------------------ gradient all-reduce, one stage at a time
+    def _on_stage(self, stage: str, views: Dict[str, torch.Tensor]) -> None:
+        if self.world == 1:
+            return
+        if stage.startswith("block"):
+            i = int(stage[5:])
+            tensors = [views[f][i] for f in _STAGE_FIELDS["block"]]
+        else:
+            tensors = [views[f] for f in _STAGE_FIELDS[stage]]
+        try:
+            with dist._coalescing_manager(group=self.group, device=self.device, async_ops=True) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._works.append(cm)
+        except (AttributeError, TypeError, RuntimeError):
+            for t in tensors:
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    # ------------------------------------------------------------------ one optimisation step
+    def step(self, x: torch.Tensor, t: torch.Tensor, time_emb: torch.Tensor, **loss_kwargs) -> torch.Tensor:
+        """x [B,3,S,S] in [-1,1], t int64 [B], time_emb [1,G*G,8]  ->  mean loss (device scalar, no host sync)."""
+        model = self.model
+        model.__dict__["_stage_hook"] = self._on_stage
+        self._works = []
+        terms = self.diffusion.training_losses(model, x, t, time_emb, None, **loss_kwargs)
+        loss = terms["loss"].mean()
+        loss.backward()
+        flat = self.engine.last_flat
+        for wk in self._works:
+            wk.wait()
+        self._works = []
+        self.step_count += 1
+        check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
+                                       ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
+                                       self.betas[1], self.eps, self.weight_decay, self.ema_decay, _lib.stream_ptr()),
+              "jpdvt_adamw_ema")
+        self._refresh_derived()
+        for p in model.parameters():
+            p.grad = None
+        self.engine.last_flat = None
+        return loss.detach()
+
+    # ------------------------------------------------------------------ checkpoint views (train_JPDVT.py:410-416)
+    def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+        views, off = {}, 0
+        for (name, shape) in self.layout:
+            n = int(torch.Size(shape).numel())
+            views[name] = self.ema_flat[off:off + n].view(shape)
+            off += n
+        out = {k: v.clone() for k, v in param_grad_map(self.model, views).items()}
+        out["pos_embed"] = self.model.pos_embed.data.clone()
+        return {k: out[k] for k in self.model.state_dict().keys()}
+
+    def optimizer_state(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.m_flat, "exp_avg_sq": self.v_flat, "lr": self.lr, "betas": self.betas,
+                "eps": self.eps, "weight_decay": self.weight_decay}

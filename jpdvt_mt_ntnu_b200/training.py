@@ -53,6 +53,9 @@ class TrainEngine:
         self.tape = None
         self.scratch = None
         self.zeros = torch.zeros(max(self.n_mod, 4 * HIDDEN), device=device, dtype=torch.float32)
+        self.w_struct = None
+        self.last_flat = None
+        self._keepalive = None
         self.ticket = 0      # forward counter: a backward must match the forward whose activations are on the tape
 
     def __deepcopy__(self, memo):
@@ -73,6 +76,11 @@ class TrainEngine:
         for k, v in w.items():
             setattr(s, k, ptr(v))
         self.wt_tensors, self.wt = w, s
+        self.w_struct = self.weights.struct
+
+    def adopt(self, w_struct, wt_struct, keepalive=None) -> None:
+        """Use operand buffers owned by someone else (the Trainer's flat bf16 shadow + transposed copies)."""
+        self.w_struct, self.wt, self._keepalive = w_struct, wt_struct, keepalive
 
     # ------------------------------------------------------------------ buffers
     def _ensure(self, batch: int) -> None:
@@ -128,7 +136,7 @@ class TrainEngine:
         self.ticket += 1
         te = torch.empty(B, self.tokens, LATENT, device=self.device, dtype=torch.float32)
         out_img = torch.empty(B, 3, self.image_size, self.image_size, device=self.device, dtype=torch.float32)
-        check(self.lib.jpdvt_train_forward(C.byref(self.weights.struct), C.byref(self.tape), ptr(img), ptr(t), ptr(x_t), ptr(te),
+        check(self.lib.jpdvt_train_forward(C.byref(self.w_struct), C.byref(self.tape), ptr(img), ptr(t), ptr(x_t), ptr(te),
                                            ptr(out_img), B, _lib.stream_ptr()), "jpdvt_train_forward")
         return out_img, te
 
@@ -139,7 +147,7 @@ class TrainEngine:
         flat, g, views = self.new_grads()
         self.scr_t["dmod"].zero_()
         st = _lib.stream_ptr()
-        args = (C.byref(self.weights.struct), C.byref(self.wt), C.byref(self.tape), C.byref(self.scratch), C.byref(g))
+        args = (C.byref(self.w_struct), C.byref(self.wt), C.byref(self.tape), C.byref(self.scratch), C.byref(g))
         check(self.lib.jpdvt_train_backward_head(*args, ptr(d_te), ptr(d_img) if d_img is not None else None, st),
               "jpdvt_train_backward_head")
         if stage_done:
@@ -151,6 +159,7 @@ class TrainEngine:
         check(self.lib.jpdvt_train_backward_embed(*args, ptr(x_t), st), "jpdvt_train_backward_embed")
         if stage_done:
             stage_done("embed", views)
+        self.last_flat = flat
         return flat, views
 
 
