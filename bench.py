@@ -31,6 +31,9 @@ WORKLOADS = {
     "c2": dict(name="JPDVT 3x3 @192px sampling, 250 steps, batch 256/GPU", size=192, grid=3, batch=256, steps=250),
     "c4": dict(name="JPDVT 4x4 @256px sampling, 250 steps, batch 128/GPU", size=256, grid=4, batch=128, steps=250),
     "c5": dict(name="JPDVT 3x3 @288px masked sampling, 250 steps, batch 128/GPU", size=288, grid=3, batch=128, steps=250),
+    # BASELINE.json configs[2]: data-parallel training (fwd + bwd + NCCL gradient all-reduce + AdamW + EMA), metric train img/s
+    "c3": dict(name="train_JPDVT 3x3 @192px bf16 data-parallel training, batch 128/GPU", size=192, grid=3, batch=128, steps=0, train=True),
+    "c4t": dict(name="train_JPDVT 4x4 @256px bf16 data-parallel training, batch 64/GPU", size=256, grid=4, batch=64, steps=0, train=True),
 }
 DEPTH = 12
 
@@ -334,6 +337,128 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+
+def cpu_port_train_img_per_s(wl, sample_batch=2):
+    """CPU port of one training step (fp32 autograd through the oracle + torch AdamW) on a bounded sample."""
+    import numpy as np
+    import torch
+    from oracle import jpdvt_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, G = wl["size"], wl["grid"]
+    T = (S // 16) ** 2
+    st = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in orc.seeded_state(orc.blank_state(S, DEPTH), seed=1234).items()}
+    model = orc.OracleDenoiser.__new__(orc.OracleDenoiser)
+    model.w, model.depth, model.heads, model.patch = st, DEPTH, 12, 16
+    opt = torch.optim.AdamW([v for k, v in st.items() if k != "pos_embed"], lr=1e-4, weight_decay=0)
+    sched = orc.Schedule("")
+    piece = torch.from_numpy(orc.sincos_2d(8, G)).float().unsqueeze(0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(sample_batch, 3, S, S, generator=g) * 2 - 1
+    t = torch.randint(0, 1000, (sample_batch,), generator=g)
+    times = []
+    for it in range(2):
+        t0 = time.perf_counter()
+        o = orc.training_losses(sched, model, x, t, piece, np.random.RandomState(it).permutation(G * G), torch.randn_like(x),
+                                torch.randn(sample_batch, T, 8), block_size=S // G, grid=G, masks=None)
+        opt.zero_grad()
+        o["loss"].mean().backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return sample_batch / times[-1], cores, f"{sample_batch} images, one fwd+bwd+AdamW step (second of two)", sum(times)
+
+
+def run_train(args, wl):
+    import torch
+    import torch.distributed as dist
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT_models, get_2d_sincos_pos_embed
+    from jpdvt_mt_ntnu_b200.trainer import Trainer
+    from jpdvt_mt_ntnu_b200.weights import seeded_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch or wl["batch"]
+    S, G = wl["size"], wl["grid"]
+    T = (S // 16) ** 2
+    model = DiT_models["JPDVT"](input_size=S)
+    model.load_state_dict(seeded_state(model.state_dict(), seed=1234))
+    model.to(dev)
+    diffusion = create_diffusion("")
+    trainer = Trainer(model, diffusion, lr=1e-4, weight_decay=0.0, ema_decay=0.9999)
+    g = torch.Generator().manual_seed(rank)
+    x_pin = (torch.rand(batch, 3, S, S, generator=g) * 2 - 1).pin_memory()
+    x = x_pin.to(dev)
+    piece = torch.tensor(get_2d_sincos_pos_embed(8, G)).unsqueeze(0).float().to(dev)
+    kw = dict(block_size=S // G, patch_size=16, add_mask=False, grid_size=G)
+    torch.manual_seed(rank)
+
+    def one_step(xin):
+        t = torch.randint(0, diffusion.num_timesteps, (batch,), device=dev)          # train_JPDVT.py:354
+        return trainer.step(xin, t, piece, **kw)
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    steps = max(args.steps, 10)
+    for _ in range(max(args.warmup, 3)):
+        one_step(x)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, loss = timed(lambda: one_step(x), steps)
+    value = batch * world * steps / (ms * 1e-3)
+    ms_e2e, loss_h = timed(lambda: one_step(x_pin.to(dev, non_blocking=True)).cpu(), steps)
+    clock_info = clocks.stop()
+    if rank == 0:
+        peaks = measured_peaks()
+        flops = 3.0 * flops_per_forward(T) * batch * steps
+        cpu_obj = None
+        if world == 1:
+            v, cores, sample, _ = cpu_port_train_img_per_s(wl)
+            cpu_obj = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample}
+        n_params = trainer.total
+        line = {
+            "metric": "train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": batch, "image_size": S, "grid": G, "tokens": T,
+                       "optimizer": "AdamW lr 1e-4 wd 0 + EMA 0.9999 (fused, fp32 state)", "params": n_params,
+                       "allreduce": "NCCL SUM per backward stage, overlapped with the remaining backward" if world > 1 else "none (1 GPU)",
+                       "l2": "activations per launch exceed L2; no flush needed"},
+            "e2e": {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": steps * (12 * 8 + 8 + 12 * 21 + 40), "clocks": clock_info,
+            "model_tflops": flops / (ms * 1e-3) / 1e12, "model_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "roofline": {"bound": "tensor", "kernel": "whole training step (3 x forward FLOPs: fwd + dgrad + wgrad)",
+                         "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None},
+            "cpu_baseline": cpu_obj, "final_loss": float(loss_h),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,11 +477,12 @@ def main():
     if args.impl == "reference" or world == 1:
         for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ[var] = str(os.cpu_count() or 1)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("JPDVT_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the single JSON line the driver parses
+    if not os.environ.get("JPDVT_KEEP_NCCL_DEBUG"):
+        os.environ.pop("NCCL_DEBUG", None)     # NCCL prints its version banner on stdout; keep stdout to the one JSON line
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("train"):
+        run_train(args, wl)
     else:
         run_ours(args, wl)
 

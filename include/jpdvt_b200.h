@@ -207,8 +207,9 @@ int jpdvt_sample_loop(const jpdvt_weights* w_host, const jpdvt_workspace* ws_hos
 int jpdvt_gemm_wgrad(const jpdvt_bf16* p, const jpdvt_bf16* q, float* dw, float* scratch, int64_t m, int out_rows, int n_cols,
                      void* stream);
 int64_t jpdvt_wgrad_scratch_floats(int64_t m, int out_rows, int n_cols);
-/* out = (a . w^T) * gelu_tanh'(pre)  - fc2 data gradient fused with the GELU derivative (timm Mlp, models.py:110-112) */
-int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16* pre, jpdvt_bf16* out, int64_t m, int n, int k,
+/* out = (a . w^T) * gprime, gprime = gelu_tanh'(fc1 pre-activation) kept by the training forward - the fc2 data gradient
+ * fused with the GELU derivative (timm Mlp, models.py:110-112) */
+int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16* gprime, jpdvt_bf16* out, int64_t m, int n, int k,
                      void* stream);
 /* dQ, dK, dV of softmax(q k^T / 8) v into dqkv [batch*tokens, 2304]; o / d_o: [batch*tokens, 768]; lse2 from the forward. */
 int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_bf16* d_o, const float* lse2, jpdvt_bf16* dqkv,
@@ -247,7 +248,7 @@ typedef struct jpdvt_tape {        /* activations kept by the training forward f
   jpdvt_bf16* att;              /* [depth, rows, 768]   */
   jpdvt_bf16* y1;               /* [depth, rows, 768]   attn.proj output (before the gate) */
   jpdvt_bf16* xn2;              /* [depth, rows, 768]   */
-  jpdvt_bf16* hpre;             /* [depth, rows, 3072]  fc1 output before GELU */
+  jpdvt_bf16* hpre;             /* [depth, rows, 3072]  gelu'(fc1 output) (the pre-activations are overwritten in place) */
   jpdvt_bf16* h;                /* [depth, rows, 3072]  */
   jpdvt_bf16* y2;               /* [depth, rows, 768]   mlp.fc2 output (before the gate) */
   jpdvt_bf16* xnf;              /* [rows, 768]  */

@@ -59,7 +59,7 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
 int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
                     float* dgate, long long dgate_stride, float* dbias, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
-  int splits = (4 * 148 + batch - 1) / batch;
+  int splits = (16 * 148 + batch - 1) / batch;
   if (splits > tokens) splits = tokens;
   if (splits < 1) splits = 1;
   const int rows = (tokens + splits - 1) / splits;
@@ -72,7 +72,7 @@ int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, 
 // One warp per (sample, chunk of kLnbRows tokens): rows are processed one after the other so the per-sample sums for
 // dshift / dscale stay in registers (24 columns per lane) and hit global memory once per warp.
 constexpr int kLnbWarps = 8;
-constexpr int kLnbRows = 16;
+constexpr int kLnbRows = 4;
 
 __global__ void __launch_bounds__(kLnbWarps * 32)
 ln_modulate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, const float* __restrict__ scale,
@@ -356,22 +356,27 @@ int launch_unpatchify_bwd(const float* dimg, float* dy, int batch, int size, int
   return check_launch("unpatchify_bwd_kernel");
 }
 
-// h = gelu_tanh(pre), bf16 -> bf16 (training keeps both the fc1 pre-activations and the activations)
-__global__ void gelu_bf16_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long n8) {
+// h = gelu_tanh(pre) and, in place of pre, g' = gelu_tanh'(pre)  (bf16).  Training keeps g' so that the fc2 data-gradient
+// GEMM epilogue is a plain multiply instead of two transcendentals per element.
+__global__ void gelu_bf16_kernel(__nv_bfloat16* __restrict__ pre_to_grad, __nv_bfloat16* __restrict__ out, long long n8) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
-  const uint4 a = __ldcs(reinterpret_cast<const uint4*>(pre) + i);
+  const uint4 a = __ldcs(reinterpret_cast<const uint4*>(pre_to_grad) + i);
   const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-  uint32_t ow[4];
+  uint32_t ow[4], gw[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e)
-    ow[e] = pack_bf16(gelu_tanh(__uint_as_float(aw[e] << 16)), gelu_tanh(__uint_as_float(aw[e] & 0xffff0000u)));
+  for (int e = 0; e < 4; ++e) {
+    const float x0 = __uint_as_float(aw[e] << 16), x1 = __uint_as_float(aw[e] & 0xffff0000u);
+    ow[e] = pack_bf16(gelu_tanh(x0), gelu_tanh(x1));
+    gw[e] = pack_bf16(gelu_tanh_grad(x0), gelu_tanh_grad(x1));
+  }
   reinterpret_cast<uint4*>(out)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  reinterpret_cast<uint4*>(pre_to_grad)[i] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
 }
-int launch_gelu(const __nv_bfloat16* pre, __nv_bfloat16* out, long long n, cudaStream_t stream) {
+int launch_gelu(__nv_bfloat16* pre_to_grad, __nv_bfloat16* out, long long n, cudaStream_t stream) {
   if (n <= 0) return kOk;
   if (n & 7) return set_error(kErrBadArg, "gelu: element count must be a multiple of 8");
-  gelu_bf16_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(pre, out, n / 8);
+  gelu_bf16_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, stream>>>(pre_to_grad, out, n / 8);
   return check_launch("gelu_bf16_kernel");
 }
 

@@ -32,7 +32,7 @@ enum Epilogue : int {
   EPI_BIAS_F32 = 4,         // out_f32 = acc + bias
   EPI_BIAS_BF16_F32 = 5,    // out_bf16 = acc + bias, and (if out2 != null) out2_f32 = acc + bias
   EPI_HEAD = 6,             // out_f32[row, :8] = w2 . silu(acc[:, :64] + bias) + b2     (N == 64); optional pre-activation copy
-  EPI_DGELU_BF16 = 7,       // out_bf16 = acc * gelu_tanh'(aux_bf16[row, col])           (fc2 dgrad -> d(fc1 pre-activation))
+  EPI_DGELU_BF16 = 7,       // out_bf16 = acc * aux_bf16[row, col], aux = gelu_tanh'(fc1 pre-activation) kept by the forward
   EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
 };
 
@@ -83,7 +83,7 @@ int launch_cast_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStrea
 int launch_silu_bwd(const float* grad, const float* pre, float* out, __nv_bfloat16* out_bf16, long long n, cudaStream_t stream);
 int launch_win_grad(const float* dx0, const float* xt, float* dw, long long rows, cudaStream_t stream);
 int launch_unpatchify_bwd(const float* dimg, float* dy, int batch, int size, int accumulate, cudaStream_t stream);
-int launch_gelu(const __nv_bfloat16* pre, __nv_bfloat16* out, long long n, cudaStream_t stream);
+int launch_gelu(__nv_bfloat16* pre_to_grad, __nv_bfloat16* out, long long n, cudaStream_t stream);
 int launch_silu_fwd_bf16(const float* pre, __nv_bfloat16* out, long long n, cudaStream_t stream);
 
 // x_out = x_in + gate[b] * delta (optional: delta bf16, gate may be null = 1), then y = LN(x_out) * (1 + scale) + shift

@@ -146,14 +146,14 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
     uint4 u = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
     if (row0 + r < M) {
       const long long off = static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch;
-      if constexpr (DGELU) {   // d(pre-activation) = d(activation) * gelu'(pre-activation), 8 coalesced bf16 per lane
+      if constexpr (DGELU) {   // d(pre-activation) = d(activation) * gelu'(pre-activation) (kept by the forward), 8 coalesced bf16 per lane
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(aux + off));
         uint32_t uw[4] = {u.x, u.y, u.z, u.w};
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float g0 = gelu_tanh_grad(__uint_as_float(aw[e] << 16)), g1 = gelu_tanh_grad(__uint_as_float(aw[e] & 0xffff0000u));
-          uw[e] = pack_bf16(__uint_as_float(uw[e] << 16) * g0, __uint_as_float(uw[e] & 0xffff0000u) * g1);
+          uw[e] = pack_bf16(__uint_as_float(uw[e] << 16) * __uint_as_float(aw[e] << 16),
+                            __uint_as_float(uw[e] & 0xffff0000u) * __uint_as_float(aw[e] & 0xffff0000u));
         }
         u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
       }

@@ -239,7 +239,7 @@ def gemm_wgrad(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
 
 
 def gemm_dgelu(a, w, pre) -> torch.Tensor:
-    """(a @ w.T) * gelu_tanh'(pre) -> bf16."""
+    """(a @ w.T) * pre -> bf16, where `pre` holds gelu_tanh'(fc1 pre-activation) (kept by the training forward)."""
     lib = _lib_dev()
     a, w, pre = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w"), _need(pre, torch.bfloat16, "pre")
     m, k = a.shape

@@ -46,7 +46,7 @@ def g_elem():
     pre = torch.randn(m, 3072, device="cuda").bfloat16()
     x = pre.float().requires_grad_(True)
     F.gelu(x, approximate="tanh").sum().backward()
-    res["dgelu"] = rel(ops.gemm_dgelu(a, w, pre).float(), (a.float() @ w.float().t()) * x.grad)
+    res["dgelu"] = rel(ops.gemm_dgelu(a, w, x.grad.bfloat16()).float(), (a.float() @ w.float().t()) * x.grad.bfloat16().float())
     dx = torch.randn(m, 768, device="cuda")
     y = torch.randn(m, 768, device="cuda").bfloat16()
     gate = torch.randn(3, 768, device="cuda")
