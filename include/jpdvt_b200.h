@@ -214,13 +214,15 @@ int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16*
 /* dQ, dK, dV of softmax(q k^T / 8) v into dqkv [batch*tokens, 2304]; o / d_o: [batch*tokens, 768]; lse2 from the forward. */
 int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_bf16* d_o, const float* lse2, jpdvt_bf16* dqkv,
                         int batch, int tokens, void* stream);
-/* x_out = x_in + gate[b]*y  =>  dy = gate[b]*dx (bf16); dgate[b] += sum_t dx*y; dbias += sum_rows dy (atomic accumulation) */
+/* x_out = x_in + gate[b]*y  =>  dy = gate[b]*dx (bf16); dgate[b] += sum_t dx*y; dbias += sum_rows dy */
 int jpdvt_gate_bwd(const float* dx, const jpdvt_bf16* y, const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate,
-                   int64_t dgate_stride, float* dbias_or_null, int batch, int tokens, void* stream);
+                   int64_t dgate_stride, float* dbias_or_null, float* part, int batch, int tokens, void* stream);
+/* floats of `part` scratch the two reductions above/below need (per-sample partial sums instead of atomics) */
+int64_t jpdvt_bwd_part_floats(int batch, int tokens);
 /* backward of jpdvt_ln_modulate_fwd: dx (+)= LN'(dxn * (1 + scale[b])); dshift[b] += sum_t dxn; dscale[b] += sum_t dxn*xhat */
 int jpdvt_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
-                          float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, int batch, int tokens,
-                          void* stream);
+                          float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, float* part, int batch,
+                          int tokens, void* stream);
 /* out[c] += sum_rows src[row, c]  (bias gradients) */
 int jpdvt_colsum_bf16(const jpdvt_bf16* src, int64_t rows, int cols, float* out, void* stream);
 int jpdvt_colsum_f32(const float* src, int64_t rows, int cols, float* out, void* stream);
@@ -285,6 +287,7 @@ typedef struct jpdvt_bwd_scratch {
   float* small_f32;             /* [4, batch, 768] */
   jpdvt_bf16* small_bf16;       /* [4, batch, 768] */
   float* wgrad_scratch;         /* jpdvt_train_wgrad_scratch_floats(...) floats */
+  float* part;                  /* jpdvt_bwd_part_floats(batch, tokens) floats */
   const float* zeros;           /* >= n_mod zeros (bias-free GEMM epilogues) */
 } jpdvt_bwd_scratch;
 

@@ -60,7 +60,7 @@ class Grads(C.Structure):
 
 class BwdScratch(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("dx", "dxn", "dy", "dh", "dqkv", "datt", "dpre", "dmod", "dmod_bf16", "small_f32",
-                                        "small_bf16", "wgrad_scratch", "zeros")]
+                                        "small_bf16", "wgrad_scratch", "part", "zeros")]
 
 
 P = c_void_p
@@ -87,8 +87,8 @@ PROTOTYPES = {
     "jpdvt_gemm_wgrad": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_dgelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],
-    "jpdvt_gate_bwd": [P, P, P, c_int64, P, P, c_int64, P, c_int, c_int, P],
-    "jpdvt_ln_modulate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, c_int, c_int, P],
+    "jpdvt_gate_bwd": [P, P, P, c_int64, P, P, c_int64, P, P, c_int, c_int, P],
+    "jpdvt_ln_modulate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, c_int, c_int, P],
     "jpdvt_colsum_bf16": [P, c_int64, c_int, P, P],
     "jpdvt_colsum_f32": [P, c_int64, c_int, P, P],
     "jpdvt_train_forward": [C.POINTER(Weights), C.POINTER(Tape), P, P, P, P, P, c_int, P],
@@ -103,7 +103,7 @@ PROTOTYPES = {
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
 }
-OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats"]
+OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats", "jpdvt_bwd_part_floats"]
 
 _lock = threading.Lock()
 _lib = None
@@ -135,6 +135,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         lib.jpdvt_wgrad_scratch_floats.restype = c_int64
         lib.jpdvt_train_wgrad_scratch_floats.argtypes = [c_int, c_int, c_int]
         lib.jpdvt_train_wgrad_scratch_floats.restype = c_int64
+        lib.jpdvt_bwd_part_floats.argtypes = [c_int, c_int]
+        lib.jpdvt_bwd_part_floats.restype = c_int64
         lib.jpdvt_abi_version.restype = c_int
         lib.jpdvt_last_error_string.restype = C.c_char_p
         _lib = lib

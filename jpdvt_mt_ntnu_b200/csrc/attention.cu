@@ -252,27 +252,21 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, 
 //   phase B: each warp owns 16-query tiles and walks all key groups  -> dQ       (S = Q K^T,  dP  = dO V^T)
 // Zero padding of rows >= T makes every padded contribution vanish, so no masks are needed.
 // qkv / dqkv: [B*T, 2304] bf16; o / d_o: [B*T, 768] bf16; lse2: [B, 12, T] fp32 (log2 domain, from the forward).
-__device__ __forceinline__ void store_tile_bf16(uint8_t* buf, const float (&acc)[8][4], __nv_bfloat16* gdst, long long ld,
-                                                int row0, int T, int lane) {
+// accumulator tile (16 rows x 64 columns in mma.sync C layout) -> bf16 global rows; 4-byte stores, each 32-byte sector is
+// completed by the two d-tiles that share it (no shared-memory staging: the backward kernel needs the space for residency)
+__device__ __forceinline__ void store_tile_bf16(const float (&acc)[8][4], __nv_bfloat16* gdst, long long ld, int row0, int T,
+                                                int lane) {
   const int g = lane >> 2, tq = lane & 3;
-  __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    *reinterpret_cast<uint32_t*>(buf + swz(g, j) + tq * 4) = pack_bf16(acc[j][0], acc[j][1]);
-    *reinterpret_cast<uint32_t*>(buf + swz(g + 8, j) + tq * 4) = pack_bf16(acc[j][2], acc[j][3]);
+    if (row0 + g < T)
+      *reinterpret_cast<uint32_t*>(gdst + static_cast<long long>(row0 + g) * ld + 8 * j + 2 * tq) = pack_bf16(acc[j][0], acc[j][1]);
+    if (row0 + g + 8 < T)
+      *reinterpret_cast<uint32_t*>(gdst + static_cast<long long>(row0 + g + 8) * ld + 8 * j + 2 * tq) = pack_bf16(acc[j][2], acc[j][3]);
   }
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx >> 3, ch = idx & 7;
-    const uint4 v = *reinterpret_cast<const uint4*>(buf + swz(r, ch));
-    if (row0 + r < T) *reinterpret_cast<uint4*>(gdst + static_cast<long long>(row0 + r) * ld + ch * 8) = v;
-  }
-  __syncwarp();
 }
 
-__global__ void __launch_bounds__(kAttThreadsMax, 2)
+__global__ void __launch_bounds__(kAttThreadsMax, 3)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                      const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse2, __nv_bfloat16* __restrict__ dqkv,
                      int T, int Tp) {
@@ -285,14 +279,12 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   uint8_t* sdO = sV + Tp * 128;
   float* sD = reinterpret_cast<float*>(sdO + Tp * 128);
   float* sL = sD + Tp;
-  uint8_t* sStage = reinterpret_cast<uint8_t*>(sL + Tp);
   const int b = blockIdx.y, h = blockIdx.x;
   const long long tok0 = static_cast<long long>(b) * T;
   const __nv_bfloat16* base = qkv + tok0 * kQkvLd + h * kHeadDim;
   const __nv_bfloat16* obase = o + tok0 * kHidden + h * kHeadDim;
   const __nv_bfloat16* dobase = d_o + tok0 * kHidden + h * kHeadDim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* mystage = sStage + warp * 2048;
 
   for (int i = threadIdx.x; i < Tp * 8; i += nthreads) {
     const int r = i >> 3, ch = i & 7;
@@ -387,8 +379,8 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
         mma_bf16(dk[2 * dp + 1], dsA, qf[2], qf[3]);
       }
     }
-    store_tile_bf16(mystage, dk, dq_out + kHidden, kQkvLd, kb0, T, lane);
-    store_tile_bf16(mystage, dv, dq_out + 2 * kHidden, kQkvLd, kb0, T, lane);
+    store_tile_bf16(dk, dq_out + kHidden, kQkvLd, kb0, T, lane);
+    store_tile_bf16(dv, dq_out + 2 * kHidden, kQkvLd, kb0, T, lane);
   }
 
   // ------------------------------------------------------------------ phase B: dQ
@@ -437,7 +429,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
         mma_bf16(dq[2 * dp + 1], dsA, kf[2], kf[3]);
       }
     }
-    store_tile_bf16(mystage, dq, dq_out, kQkvLd, q0, T, lane);
+    store_tile_bf16(dq, dq_out, kQkvLd, q0, T, lane);
   }
 }
 
@@ -449,7 +441,7 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const
   int nw = (mt % 3 == 0) ? 3 : 4;
   if (nw > mt) nw = mt;
   const int Tp = mt * 16;
-  const size_t smem = static_cast<size_t>(4 * Tp) * 128 + static_cast<size_t>(Tp) * 8 + static_cast<size_t>(nw) * 2048;
+  const size_t smem = static_cast<size_t>(4 * Tp) * 128 + static_cast<size_t>(Tp) * 8;
   if (smem > 227 * 1024) return set_error(kErrUnsupported, "attention_bwd: %d tokens need %zu B of shared memory", tokens, smem);
   static size_t configured = 0;
   if (smem > configured) {

@@ -14,21 +14,40 @@
 
 namespace jp {
 
+int launch_colsum_f32(const float* src, long long ld, long long rows, int cols, float* out, cudaStream_t stream);
+
 __device__ __forceinline__ float warp_sum_b(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------- per-sample partial sums
+// part: [batch][slices][768] -> out[b][c] (+)= sum_slices part[b][s][c]; one block per sample, float4 per thread
+__global__ void __launch_bounds__(kHidden / 4)
+sum_parts_kernel(const float* __restrict__ part, int slices, float* __restrict__ out, long long out_stride) {
+  const int b = blockIdx.x, c4 = threadIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(part + static_cast<long long>(b) * slices * kHidden) + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < slices; ++s) {
+    const float4 v = src[static_cast<long long>(s) * (kHidden / 4)];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float4* dst = reinterpret_cast<float4*>(out + b * out_stride) + c4;
+  float4 o = *dst;
+  o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+  *dst = o;
+}
+
 // ---------------------------------------------------------------------------------------------- gate backward
-// grid (B, splits); 192 threads, each owns 4 consecutive columns of the 768-wide row and walks a slice of the sample's
-// tokens.  Per-sample sums go to dgate with one atomicAdd per (block, column); the bias gradient likewise.
+// grid (B, slices); 192 threads, each owns 4 consecutive columns of the 768-wide row and walks a slice of the sample's
+// tokens.  Per-(sample, slice) partial sums are written to scratch (no atomics) and folded by sum_parts / colsum.
 constexpr int kGateThreads = kHidden / 4;
 
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
-                long long gate_stride, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dgate_stride,
-                float* __restrict__ dbias, int tokens, int rows_per_block) {
+                long long gate_stride, __nv_bfloat16* __restrict__ dy, float* __restrict__ part_gate,
+                float* __restrict__ part_bias, int tokens, int rows_per_block) {
   const int b = blockIdx.x;
   const int t0 = blockIdx.y * rows_per_block;
   const int t1 = min(tokens, t0 + rows_per_block);
@@ -48,24 +67,38 @@ gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ 
     o.x = pack_bf16(o0, o1); o.y = pack_bf16(o2, o3);
     reinterpret_cast<uint2*>(dy + row * kHidden)[c4] = o;
   }
-  float* dg = dgate + b * dgate_stride + 4 * c4;
-  atomicAdd(dg + 0, sg.x); atomicAdd(dg + 1, sg.y); atomicAdd(dg + 2, sg.z); atomicAdd(dg + 3, sg.w);
-  if (dbias != nullptr) {
-    float* db = dbias + 4 * c4;
-    atomicAdd(db + 0, sb.x); atomicAdd(db + 1, sb.y); atomicAdd(db + 2, sb.z); atomicAdd(db + 3, sb.w);
-  }
+  const long long slot = (static_cast<long long>(b) * gridDim.y + blockIdx.y) * (kHidden / 4) + c4;
+  reinterpret_cast<float4*>(part_gate)[slot] = sg;
+  reinterpret_cast<float4*>(part_bias)[slot] = sb;
 }
 
-int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
-                    float* dgate, long long dgate_stride, float* dbias, int batch, int tokens, cudaStream_t stream) {
-  if (batch <= 0 || tokens <= 0) return kOk;
-  int splits = (16 * 148 + batch - 1) / batch;
+// part: scratch of 2 * batch * gate_bwd_slices(batch, tokens) * 768 floats
+int gate_bwd_slices(int batch, int tokens) {
+  int splits = (8 * 148 + batch - 1) / batch;
   if (splits > tokens) splits = tokens;
   if (splits < 1) splits = 1;
   const int rows = (tokens + splits - 1) / splits;
-  dim3 grid(batch, (tokens + rows - 1) / rows);
-  gate_bwd_kernel<<<grid, kGateThreads, 0, stream>>>(dx, y, gate, gate_stride, dy, dgate, dgate_stride, dbias, tokens, rows);
-  return check_launch("gate_bwd_kernel");
+  return (tokens + rows - 1) / rows;
+}
+
+int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
+                    float* dgate, long long dgate_stride, float* dbias, float* part, int batch, int tokens,
+                    cudaStream_t stream) {
+  if (batch <= 0 || tokens <= 0) return kOk;
+  if (part == nullptr) return set_error(kErrBadArg, "gate_bwd: scratch buffer required");
+  const int slices = gate_bwd_slices(batch, tokens);
+  const int rows = (tokens + slices - 1) / slices;
+  float* part_gate = part;
+  float* part_bias = part + static_cast<long long>(batch) * slices * kHidden;
+  dim3 grid(batch, slices);
+  gate_bwd_kernel<<<grid, kGateThreads, 0, stream>>>(dx, y, gate, gate_stride, dy, part_gate, part_bias, tokens, rows);
+  int rc = check_launch("gate_bwd_kernel");
+  if (rc != kOk) return rc;
+  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_gate, slices, dgate, dgate_stride);
+  rc = check_launch("sum_parts_kernel");
+  if (rc != kOk) return rc;
+  if (dbias != nullptr) return launch_colsum_f32(part_bias, kHidden, static_cast<long long>(batch) * slices, kHidden, dbias, stream);
+  return kOk;
 }
 
 // ---------------------------------------------------------------------------------------------- LN + modulate backward
@@ -76,9 +109,8 @@ constexpr int kLnbRows = 4;
 
 __global__ void __launch_bounds__(kLnbWarps * 32)
 ln_modulate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, const float* __restrict__ scale,
-                       long long mod_stride, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
-                       float* __restrict__ dscale, long long dmod_stride, __nv_bfloat16* __restrict__ dx_bf16, int batch,
-                       int tokens) {
+                       long long mod_stride, float* __restrict__ dx, int accumulate, float* __restrict__ part_shift,
+                       float* __restrict__ part_scale, __nv_bfloat16* __restrict__ dx_bf16, int batch, int tokens) {
   const int chunks = (tokens + kLnbRows - 1) / kLnbRows;
   const long long wid = static_cast<long long>(blockIdx.x) * kLnbWarps + (threadIdx.x >> 5);
   if (wid >= static_cast<long long>(batch) * chunks) return;
@@ -139,24 +171,36 @@ ln_modulate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dx
       if (db != nullptr) { uint2 u; u.x = pack_bf16(o.x, o.y); u.y = pack_bf16(o.z, o.w); db[lane + 32 * j] = u; }
     }
   }
-  float* dsh = dshift + b * dmod_stride;
-  float* dsc = dscale + b * dmod_stride;
+  // per-(sample, chunk) partial sums to scratch (no atomics); folded by sum_parts_kernel
+  float4* psh = reinterpret_cast<float4*>(part_shift + wid * kHidden);
+  float4* psc = reinterpret_cast<float4*>(part_scale + wid * kHidden);
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int c = 4 * (lane + 32 * j);
-    atomicAdd(dsh + c, ssh[j].x); atomicAdd(dsh + c + 1, ssh[j].y); atomicAdd(dsh + c + 2, ssh[j].z); atomicAdd(dsh + c + 3, ssh[j].w);
-    atomicAdd(dsc + c, ssc[j].x); atomicAdd(dsc + c + 1, ssc[j].y); atomicAdd(dsc + c + 2, ssc[j].z); atomicAdd(dsc + c + 3, ssc[j].w);
-  }
+  for (int j = 0; j < 6; ++j) { psh[lane + 32 * j] = ssh[j]; psc[lane + 32 * j] = ssc[j]; }
 }
 
+// part: scratch of 2 * batch * ceil(tokens / kLnbRows) * 768 floats
 int launch_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx,
                            int accumulate, float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16,
-                           int batch, int tokens, cudaStream_t stream) {
+                           float* part, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
-  const long long warps = static_cast<long long>(batch) * ((tokens + kLnbRows - 1) / kLnbRows);
+  if (part == nullptr) return set_error(kErrBadArg, "ln_modulate_bwd: scratch buffer required");
+  const int chunks = (tokens + kLnbRows - 1) / kLnbRows;
+  const long long warps = static_cast<long long>(batch) * chunks;
+  float* part_shift = part;
+  float* part_scale = part + warps * kHidden;
   ln_modulate_bwd_kernel<<<static_cast<unsigned>((warps + kLnbWarps - 1) / kLnbWarps), kLnbWarps * 32, 0, stream>>>(
-      x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride, dx_bf16, batch, tokens);
-  return check_launch("ln_modulate_bwd_kernel");
+      x, dxn, scale, mod_stride, dx, accumulate, part_shift, part_scale, dx_bf16, batch, tokens);
+  int rc = check_launch("ln_modulate_bwd_kernel");
+  if (rc != kOk) return rc;
+  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_shift, chunks, dshift, dmod_stride);
+  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_scale, chunks, dscale, dmod_stride);
+  return check_launch("sum_parts_kernel");
+}
+
+long long bwd_part_floats(int batch, int tokens) {
+  const long long a = 2LL * batch * ((tokens + kLnbRows - 1) / kLnbRows) * kHidden;
+  const long long b = 2LL * batch * gate_bwd_slices(batch, tokens) * kHidden;
+  return a > b ? a : b;
 }
 
 // ---------------------------------------------------------------------------------------------- column sums (bias grads)

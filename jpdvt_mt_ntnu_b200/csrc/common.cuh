@@ -70,11 +70,13 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
 
 // backward.cu
+// `part`: scratch of bwd_part_floats(batch, tokens) floats (per-sample partial sums; no atomics on the hot reductions)
+long long bwd_part_floats(int batch, int tokens);
 int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
-                    float* dgate, long long dgate_stride, float* dbias, int batch, int tokens, cudaStream_t stream);
+                    float* dgate, long long dgate_stride, float* dbias, float* part, int batch, int tokens, cudaStream_t stream);
 int launch_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx,
                            int accumulate, float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16,
-                           int batch, int tokens, cudaStream_t stream);
+                           float* part, int batch, int tokens, cudaStream_t stream);
 int launch_colsum_bf16(const __nv_bfloat16* src, long long ld, long long rows, int cols, float* out, cudaStream_t stream);
 int launch_colsum_f32(const float* src, long long ld, long long rows, int cols, float* out, cudaStream_t stream);
 int launch_head_bwd(const float* dte, const float* pre, const float* w2, __nv_bfloat16* dpre, float* dw2, float* db2,

@@ -130,6 +130,16 @@ __device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], i
 template <bool DGELU>
 __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)[64], __nv_bfloat16* out,
                                                 const __nv_bfloat16* aux, long long ldo, int row0, int n0, int M, int lane) {
+  const int sub = lane >> 3, ch = lane & 7;
+  uint4 auxv[8];
+  if constexpr (DGELU) {   // issue the coalesced gelu' loads first so their latency hides behind the staging round trip
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + sub;
+      auxv[it] = make_uint4(0, 0, 0, 0);
+      if (row0 + r < M) auxv[it] = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch));
+    }
+  }
   uint8_t* mine = stage + lane * kStageRowBytes;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -139,25 +149,21 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
     *reinterpret_cast<uint4*>(mine + 16 * j) = u;
   }
   __syncwarp();
-  const int sub = lane >> 3, ch = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + sub;
     uint4 u = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
     if (row0 + r < M) {
-      const long long off = static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch;
-      if constexpr (DGELU) {   // d(pre-activation) = d(activation) * gelu'(pre-activation) (kept by the forward), 8 coalesced bf16 per lane
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(aux + off));
+      if constexpr (DGELU) {   // d(pre-activation) = d(activation) * gelu'(pre-activation), 8 bf16 per lane
         uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t aw[4] = {auxv[it].x, auxv[it].y, auxv[it].z, auxv[it].w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 4; ++e)
           uw[e] = pack_bf16(__uint_as_float(uw[e] << 16) * __uint_as_float(aw[e] << 16),
                             __uint_as_float(uw[e] & 0xffff0000u) * __uint_as_float(aw[e] & 0xffff0000u));
-        }
         u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
       }
-      *reinterpret_cast<uint4*>(out + off) = u;
+      *reinterpret_cast<uint4*>(out + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch) = u;
     }
   }
   __syncwarp();

@@ -48,17 +48,19 @@ int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_
   if (!qkv || !o || !d_o || !lse2 || !dqkv) return set_error(kErrBadArg, "attention_bwd: null pointer");
   return launch_attention_bwd(BF(qkv), BF(o), BF(d_o), lse2, BFM(dqkv), batch, tokens, ST(stream));
 }
+int64_t jpdvt_bwd_part_floats(int batch, int tokens) { return bwd_part_floats(batch, tokens); }
+
 int jpdvt_gate_bwd(const float* dx, const jpdvt_bf16* y, const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate,
-                   int64_t dgate_stride, float* dbias_or_null, int batch, int tokens, void* stream) {
-  if (!dx || !y || !gate || !dy || !dgate) return set_error(kErrBadArg, "gate_bwd: null pointer");
-  return launch_gate_bwd(dx, BF(y), gate, gate_stride, BFM(dy), dgate, dgate_stride, dbias_or_null, batch, tokens, ST(stream));
+                   int64_t dgate_stride, float* dbias_or_null, float* part, int batch, int tokens, void* stream) {
+  if (!dx || !y || !gate || !dy || !dgate || !part) return set_error(kErrBadArg, "gate_bwd: null pointer");
+  return launch_gate_bwd(dx, BF(y), gate, gate_stride, BFM(dy), dgate, dgate_stride, dbias_or_null, part, batch, tokens, ST(stream));
 }
 int jpdvt_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
-                          float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, int batch, int tokens,
-                          void* stream) {
-  if (!x || !dxn || !scale || !dx || !dshift || !dscale) return set_error(kErrBadArg, "ln_modulate_bwd: null pointer");
+                          float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, float* part, int batch,
+                          int tokens, void* stream) {
+  if (!x || !dxn || !scale || !dx || !dshift || !dscale || !part) return set_error(kErrBadArg, "ln_modulate_bwd: null pointer");
   return launch_ln_modulate_bwd(x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride, BFM(dx_bf16_or_null),
-                                batch, tokens, ST(stream));
+                                part, batch, tokens, ST(stream));
 }
 int jpdvt_colsum_bf16(const jpdvt_bf16* src, int64_t rows, int cols, float* out, void* stream) {
   if (rows == 0) return kOk;
@@ -183,7 +185,7 @@ int jpdvt_train_backward_head(const jpdvt_weights* w, const jpdvt_weights_t* wt,
   const float* mod = tp->mod + static_cast<long long>(depth) * 6 * kHidden;
   float* dmod = s->dmod + static_cast<long long>(depth) * 6 * kHidden;
   JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * depth) * X, s->dxn, mod + kHidden, n_mod, s->dx, 0, dmod,
-                                dmod + kHidden, n_mod, depth == 0 ? BFM(s->dy) : nullptr, batch, T, st));
+                                dmod + kHidden, n_mod, depth == 0 ? BFM(s->dy) : nullptr, s->part, batch, T, st));
   return kOk;
 }
 
@@ -203,7 +205,7 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   bfm dy = BFM(s->dy), dh = BFM(s->dh), dqkv = BFM(s->dqkv), datt = BFM(s->datt);
 
   // ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(xn2)))            (models.py:121)
-  JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, batch, T, st));
+  JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   JP_TRY(launch_wgrad(dy, kHidden, h, H4, g->w_fc2 + static_cast<long long>(i) * kHidden * H4, s->wgrad_scratch, M, kHidden, static_cast<int>(H4), st));
   JP_TRY(gemm(EPI_DGELU_BF16, dy, kHidden, BF(wt->w_fc2_t) + static_cast<long long>(i) * H4 * kHidden, kHidden, nullptr, dh, H4, M,
               static_cast<int>(H4), kHidden, st, nullptr, hpre));
@@ -212,10 +214,10 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   JP_TRY(gemm(EPI_BIAS_F32, dh, H4, BF(wt->w_fc1_t) + static_cast<long long>(i) * kHidden * H4, H4, s->zeros, s->dxn, kHidden, M,
               kHidden, static_cast<int>(H4), st));
   JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * i + 1) * X, s->dxn, mod + 4 * kHidden, n_mod, s->dx, 1,
-                                dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, batch, T, st));
+                                dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, s->part, batch, T, st));
 
   // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(xn1)))     (models.py:120)
-  JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, batch, T, st));
+  JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   JP_TRY(launch_wgrad(dy, kHidden, att, kHidden, g->w_proj + static_cast<long long>(i) * kHidden * kHidden, s->wgrad_scratch, M, kHidden, kHidden, st));
   JP_TRY(gemm(EPI_BIAS_BF16, dy, kHidden, BF(wt->w_proj_t) + static_cast<long long>(i) * kHidden * kHidden, kHidden, s->zeros, datt,
               kHidden, M, kHidden, kHidden, st));
@@ -225,7 +227,7 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   JP_TRY(gemm(EPI_BIAS_F32, dqkv, H3, BF(wt->w_qkv_t) + static_cast<long long>(i) * kHidden * H3, H3, s->zeros, s->dxn, kHidden, M,
               kHidden, static_cast<int>(H3), st));
   JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * i) * X, s->dxn, mod + kHidden, n_mod, s->dx, 1, dmod,
-                                dmod + kHidden, n_mod, i == 0 ? dy : nullptr, batch, T, st));
+                                dmod + kHidden, n_mod, i == 0 ? dy : nullptr, s->part, batch, T, st));
   return kOk;
 }
 

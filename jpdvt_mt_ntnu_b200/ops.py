@@ -265,9 +265,10 @@ def gate_bwd(dx, y, gate, tokens: int):
     dy = torch.empty_like(y)
     dgate = torch.zeros(batch, HIDDEN, device=dx.device, dtype=torch.float32)
     dbias = torch.zeros(HIDDEN, device=dx.device, dtype=torch.float32)
+    part = torch.empty(max(int(lib.jpdvt_bwd_part_floats(batch, tokens)), 4), device=dx.device, dtype=torch.float32)
     check(lib.jpdvt_gate_bwd(ptr(_need(dx, torch.float32, "dx")), ptr(_need(y, torch.bfloat16, "y")),
-                             ptr(_need(gate, torch.float32, "gate")), HIDDEN, ptr(dy), ptr(dgate), HIDDEN, ptr(dbias), batch,
-                             tokens, stream_ptr()), "gate_bwd")
+                             ptr(_need(gate, torch.float32, "gate")), HIDDEN, ptr(dy), ptr(dgate), HIDDEN, ptr(dbias), ptr(part),
+                             batch, tokens, stream_ptr()), "gate_bwd")
     return dy, dgate, dbias
 
 
@@ -281,9 +282,10 @@ def ln_modulate_bwd(x, dxn, scale, tokens: int, dx: Optional[torch.Tensor] = Non
     dshift = torch.zeros(batch, HIDDEN, device=x.device, dtype=torch.float32)
     dscale = torch.zeros_like(dshift)
     dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    part = torch.empty(max(int(lib.jpdvt_bwd_part_floats(batch, tokens)), 4), device=x.device, dtype=torch.float32)
     check(lib.jpdvt_ln_modulate_bwd(ptr(_need(x, torch.float32, "x")), ptr(_need(dxn, torch.float32, "dxn")),
                                     ptr(_need(scale, torch.float32, "scale")), HIDDEN, ptr(dx), int(acc), ptr(dshift), ptr(dscale),
-                                    HIDDEN, ptr(dxb), batch, tokens, stream_ptr()), "ln_modulate_bwd")
+                                    HIDDEN, ptr(dxb), ptr(part), batch, tokens, stream_ptr()), "ln_modulate_bwd")
     return dx, dshift, dscale, dxb
 
 

@@ -107,6 +107,7 @@ class TrainEngine:
             "dqkv": e(M, 3 * HIDDEN), "datt": e(M, HIDDEN), "dpre": e(M, 64), "dmod": e(batch, self.n_mod, dtype=f32),
             "dmod_bf16": e(batch, self.n_mod), "small_f32": e(4, batch, HIDDEN, dtype=f32), "small_bf16": e(4, batch, HIDDEN),
             "wgrad_scratch": e(max(need, 4), dtype=f32),
+            "part": e(max(int(self.lib.jpdvt_bwd_part_floats(batch, T)), 4), dtype=f32),
         }
         scratch = BwdScratch()
         for k, v in sc.items():
