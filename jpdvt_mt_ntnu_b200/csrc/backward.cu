@@ -25,8 +25,11 @@ __device__ __forceinline__ float warp_sum_b(float v) {
 // ---------------------------------------------------------------------------------------------- per-sample partial sums
 // part: [batch][slices][768] -> out[b][c] (+)= sum_slices part[b][s][c]; one block per sample, float4 per thread
 __global__ void __launch_bounds__(kHidden / 4)
-sum_parts_kernel(const float* __restrict__ part, int slices, float* __restrict__ out, long long out_stride) {
+sum_parts_kernel(const float* __restrict__ part0, float* __restrict__ out0, const float* __restrict__ part1,
+                 float* __restrict__ out1, int slices, long long out_stride) {
   const int b = blockIdx.x, c4 = threadIdx.x;
+  const float* part = blockIdx.y == 0 ? part0 : part1;
+  float* out = blockIdx.y == 0 ? out0 : out1;
   const float4* src = reinterpret_cast<const float4*>(part + static_cast<long long>(b) * slices * kHidden) + c4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < slices; ++s) {
@@ -94,7 +97,7 @@ int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, 
   gate_bwd_kernel<<<grid, kGateThreads, 0, stream>>>(dx, y, gate, gate_stride, dy, part_gate, part_bias, tokens, rows);
   int rc = check_launch("gate_bwd_kernel");
   if (rc != kOk) return rc;
-  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_gate, slices, dgate, dgate_stride);
+  sum_parts_kernel<<<dim3(batch, 1), kHidden / 4, 0, stream>>>(part_gate, dgate, nullptr, nullptr, slices, dgate_stride);
   rc = check_launch("sum_parts_kernel");
   if (rc != kOk) return rc;
   if (dbias != nullptr) return launch_colsum_f32(part_bias, kHidden, static_cast<long long>(batch) * slices, kHidden, dbias, stream);
@@ -107,7 +110,7 @@ int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, 
 constexpr int kLnbWarps = 8;
 constexpr int kLnbRows = 4;
 
-__global__ void __launch_bounds__(kLnbWarps * 32)
+__global__ void __launch_bounds__(kLnbWarps * 32, 2)
 ln_modulate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, const float* __restrict__ scale,
                        long long mod_stride, float* __restrict__ dx, int accumulate, float* __restrict__ part_shift,
                        float* __restrict__ part_scale, __nv_bfloat16* __restrict__ dx_bf16, int batch, int tokens) {
@@ -192,8 +195,7 @@ int launch_ln_modulate_bwd(const float* x, const float* dxn, const float* scale,
       x, dxn, scale, mod_stride, dx, accumulate, part_shift, part_scale, dx_bf16, batch, tokens);
   int rc = check_launch("ln_modulate_bwd_kernel");
   if (rc != kOk) return rc;
-  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_shift, chunks, dshift, dmod_stride);
-  sum_parts_kernel<<<batch, kHidden / 4, 0, stream>>>(part_scale, chunks, dscale, dmod_stride);
+  sum_parts_kernel<<<dim3(batch, 2), kHidden / 4, 0, stream>>>(part_shift, dshift, part_scale, dscale, chunks, dmod_stride);
   return check_launch("sum_parts_kernel");
 }
 
