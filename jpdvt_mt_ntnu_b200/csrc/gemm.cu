@@ -28,6 +28,7 @@ constexpr int UMMA_K = 16;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kStageRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free 16-byte accesses
 constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpose buffer per epilogue warp
+constexpr int kBiasWarpBytes = 256 * 4;                   // this tile's bias slice of the warp, staged once per tile
 
 template <int BN, int CS, int EW>
 struct GemmCfg {
@@ -36,12 +37,12 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kFixedBytes = EW * kStageWarpBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kBiasWarpBytes) + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + EW * kStageWarpBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kBiasWarpBytes) + kBarBytes + 1024;
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------------
@@ -59,7 +60,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the only thing this arrive publishes is "my tcgen05.ld reads of the accumulator are done", which the
+  // preceding tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order; a release here would drain every
+  // outstanding global store of the epilogue first (ncu r1c: 18 % of the kernel's warp samples sat in that MEMBAR)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the completion bytes are credited to the barrier at `bar_cluster_addr`
 // (a shared::cluster address - the leader CTA's full barrier).
@@ -102,12 +106,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
 // bf16 outputs are staged 64 columns (128 B per row) at a time, fp32 outputs 32 columns (128 B) at a time.
 
 template <int EPI>
-__device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], int row, int n0, bool row_ok) {
+__device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], int row, int n0, bool row_ok,
+                                          const float* bias_smem) {
   if constexpr (EPI != EPI_DGELU_BF16) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+    const float4* b4 = reinterpret_cast<const float4*>(bias_smem);   // broadcast reads of the staged bias slice
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float4 b = __ldg(b4 + j);
+      const float4 b = b4[j];
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
@@ -186,7 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + EW * kStageWarpBytes);
+  uint8_t* bias_buf = stage_buf + EW * kStageWarpBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * kBiasWarpBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
@@ -311,6 +317,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;   // first row of this warp
       const int row = row0 + lane;
       const bool row_ok = row < out_rows;
+      float* bias_smem = reinterpret_cast<float*>(bias_buf + (warp - 2) * kBiasWarpBytes);
+      if constexpr (EPI != EPI_DGELU_BF16 && EPI != EPI_WGRAD_F32 && EPI != EPI_HEAD) {
+        // this warp's bias slice -> smem while the MMAs of the tile are still running
+        for (int i = lane; i < kColsPerWarp / 4; i += 32)
+          reinterpret_cast<float4*>(bias_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base) + i);
+        __syncwarp();
+      }
+      auto release_tmem = [&]() {   // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CS == 2) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(acc) * 8u);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      };
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -321,6 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_ld_32x32(t_row, r0);
         tmem_ld_32x32(t_row + 32, r1);
         tmem_ld_wait();
+        release_tmem();
         float h[64];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -358,11 +380,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tmem_ld_32x32(t_row + col_base + c * 64, r0);
           tmem_ld_32x32(t_row + col_base + c * 64 + 32, r1);
           tmem_ld_wait();
+          if (c == kColsPerWarp / 64 - 1) release_tmem();
           float v[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
-          bf16_math<EPI>(p, v, row, n0, row_ok);
+          bf16_math<EPI>(p, v, row, n0, row_ok, bias_smem + c * 64);
           store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
             if (p.out2 != nullptr) {
@@ -403,16 +426,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           uint32_t r[32];
           tmem_ld_32x32(t_row + col_base + c * 32, r);
           tmem_ld_wait();
+          if (c == kColsPerWarp / 32 - 1) release_tmem();
           const int n0 = n_blk * BN + col_base + c * 32;
           float v[32];
           if constexpr (WG) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           } else {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+            const float4* b4 = reinterpret_cast<const float4*>(bias_smem + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
+              const float4 b = b4[j];
               v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
               v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
             }
@@ -450,12 +474,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           __syncwarp();
         }
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if constexpr (CS == 2) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(acc) * 8u);
-        else mbar_arrive(&tempty_bar[acc]);
-      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
