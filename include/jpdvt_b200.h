@@ -67,6 +67,11 @@ int jpdvt_gemm_bias_gelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* 
  * the `x +=` half is applied by the next jpdvt_ln_modulate_fwd(delta = out). */
 int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
                          int64_t gate_stride, jpdvt_bf16* out, int64_t m, int n, int k, int tokens, void* stream);
+/* x[row] += gate[row / tokens] * (a . w^T + bias), in place on the fp32 residual stream: the whole adaLN-Zero gated
+ * residual update `x = x + gate.unsqueeze(1) * branch(...)` of attn.proj / mlp.fc2 (models.py:120-121) as the GEMM
+ * epilogue (coalesced read-modify-write, overlapped with the next tile's MMAs).  n must be a multiple of 128. */
+int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                  int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream);
 /* x = cols . w_patch^T + bias + pos_embed[row % tokens] + x_t[row] . w_in_t   (PatchEmbed conv as GEMM + time_emb_in +
  * pos_embed, models.py:280-281).  cols = jpdvt_patchify(img); bias = x_embedder.proj.bias + time_emb_in.bias;
  * w_in_t = time_emb_in.weight^T as [8,768] fp32; pos = pos_embed [tokens,768] fp32. */

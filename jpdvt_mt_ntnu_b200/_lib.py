@@ -72,6 +72,7 @@ PROTOTYPES = {
     "jpdvt_gemm_bias_f32": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gate": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_gemm_bias_gate_residual": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
     "jpdvt_attention_fwd": [P, P, P, c_int, c_int, P],
@@ -116,6 +117,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
+        override = os.environ.get("JPDVT_LIB_PATH")        # developer knob: A/B-time an alternative build of the library
+        if override:
+            if not os.path.exists(override):
+                raise JpdvtError(f"JPDVT_LIB_PATH={override} does not exist")
+            build_if_missing = False
         if build_if_missing:
             from . import build as _build
             try:
@@ -126,7 +132,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                     raise JpdvtError(f"libjpdvt_sm100.so is missing and could not be built: {e}") from e
         if not os.path.exists(LIB_PATH):
             raise JpdvtError(f"{LIB_PATH} not found - run `python -m jpdvt_mt_ntnu_b200.build` (no CPU fallback exists)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(override or LIB_PATH)
         for name, args in PROTOTYPES.items():
             fn = getattr(lib, name)
             fn.argtypes = args

@@ -89,13 +89,10 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws->attn);
   __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws->hid);
-  __nv_bfloat16* br = reinterpret_cast<__nv_bfloat16*>(ws->y);   // gated branch output, folded into x by the next LN
-  const __nv_bfloat16* pending = nullptr;                          // branch output not yet added to the residual stream
-  const float* pending_gate = nullptr;                             // ... and the adaLN gate it is scaled by (x += gate * branch)
   for (int i = 0; i < depth; ++i) {
     const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
     // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120)
-    JP_TRY(launch_ln_modulate(ws->x, ws->x, pending, pending_gate, mod_stride, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod, mod + kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
@@ -103,14 +100,15 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
       JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden, kHidden, p, st));
     }
     JP_TRY(launch_attention(qkv, att, nullptr, batch, T, st));
-    {
+    {   // the gated residual update is the GEMM epilogue: fp32 read-modify-write of x under the next tile's MMAs
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
-      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
-      JP_TRY(launch_gemm(EPI_BIAS_BF16, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
+      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = ws->x; p.ldo = kHidden;
+      p.gate = mod + 2 * kHidden; p.gate_stride = mod_stride;
+      JP_TRY(launch_gemm(EPI_RESID_F32, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
     }
     // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
-    JP_TRY(launch_ln_modulate(ws->x, ws->x, br, mod + 2 * kHidden, mod_stride, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
@@ -120,16 +118,15 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = kHidden; p.K = 4 * kHidden; p.tokens = T;
-      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = br; p.ldo = kHidden;
-      JP_TRY(launch_gemm(EPI_BIAS_BF16, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
+      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = ws->x; p.ldo = kHidden;
+      p.gate = mod + 5 * kHidden; p.gate_stride = mod_stride;
+      JP_TRY(launch_gemm(EPI_RESID_F32, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
     }
-    pending = br;
-    pending_gate = mod + 5 * kHidden;
   }
   // final layer + position head                                            (models.py:287-290)
   {
     const float* mod = ws->mod + static_cast<long long>(depth) * 6 * kHidden;   // shift, scale
-    JP_TRY(launch_ln_modulate(ws->x, ws->x, pending, pending_gate, mod_stride, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod, mod + kHidden, mod_stride, xn, M, T, st));
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
@@ -210,6 +207,17 @@ int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* 
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
   p.bias = bias; p.out = out; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
   return launch_gemm(EPI_GATE_BF16, BF(a), k, BF(w), k, p, ST(stream));
+}
+int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                  int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream) {
+  if (m == 0) return kOk;
+  if (!a || !w || !bias || !gate || !x) return set_error(kErrBadArg, "gemm_bias_gate_residual: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_bias_gate_residual: tokens must be positive");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
+  p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
+  return launch_gemm(EPI_RESID_F32, BF(a), k, BF(w), k, p, ST(stream));
 }
 int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
                            const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {

@@ -34,6 +34,7 @@ enum Epilogue : int {
   EPI_HEAD = 6,             // out_f32[row, :8] = w2 . silu(acc[:, :64] + bias) + b2     (N == 64); optional pre-activation copy
   EPI_DGELU_BF16 = 7,       // out_bf16 = acc * aux_bf16[row, col], aux = gelu_tanh'(fc1 pre-activation) kept by the forward
   EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
+  EPI_RESID_F32 = 9,        // out_f32 += gate[row / tokens] * (acc + bias): the adaLN-Zero gated residual update, in place, fp32
 };
 
 struct GemmParams {

@@ -28,7 +28,6 @@ constexpr int UMMA_K = 16;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kStageRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free 16-byte accesses
 constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpose buffer per epilogue warp
-constexpr int kBiasWarpBytes = 256 * 4;                   // this tile's bias slice of the warp, staged once per tile
 
 template <int BN, int CS, int EW>
 struct GemmCfg {
@@ -37,12 +36,14 @@ struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kBiasWarpBytes) + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  static constexpr int kColsPerWarp = BN / (EW / 4);      // EW/4 warps share a TMEM lane quadrant and split the columns
+  static constexpr int kVecWarpBytes = 3 * kColsPerWarp * 4;   // per warp and tile: bias slice + gate slices of <= 2 samples
+  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kVecWarpBytes) + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kBiasWarpBytes) + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kVecWarpBytes) + kBarBytes + 1024;
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------------
@@ -105,9 +106,8 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
 // The thread that owns accumulator row `row` holds fp32 values v[0..NC) for columns [n0, n0 + NC).
 // bf16 outputs are staged 64 columns (128 B per row) at a time, fp32 outputs 32 columns (128 B) at a time.
 
-template <int EPI>
-__device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], int row, int n0, bool row_ok,
-                                          const float* bias_smem) {
+template <int EPI, typename GateFn>
+__device__ __forceinline__ void bf16_math(float (&v)[64], const float* bias_smem, GateFn gate4, int col4) {
   if constexpr (EPI != EPI_DGELU_BF16) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_smem);   // broadcast reads of the staged bias slice
 #pragma unroll
@@ -121,11 +121,9 @@ __device__ __forceinline__ void bf16_math(const GemmParams& p, float (&v)[64], i
     for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
   }
   if constexpr (EPI == EPI_GATE_BF16) {
-    const int sample = row_ok ? row / p.tokens : 0;
-    const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<long long>(sample) * p.gate_stride + n0);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float4 g = __ldg(g4 + j);
+      const float4 g = gate4(col4 + j);
       v[4 * j + 0] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
     }
   }
@@ -187,12 +185,14 @@ template <int BN, int EPI, int CS, int EW>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using Cfg = GemmCfg<BN, CS, EW>;
-  constexpr int kColsPerWarp = BN / (EW / 4);        // EW/4 warps share a TMEM lane quadrant and split the columns
+  constexpr int kColsPerWarp = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by OFFSETTING the shared-space pointer (integer round-trips make the compiler lose the address
+  // space and emit generic LD/ST for every staging access)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
   uint8_t* bias_buf = stage_buf + EW * kStageWarpBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * kBiasWarpBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * Cfg::kVecWarpBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
@@ -317,13 +317,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;   // first row of this warp
       const int row = row0 + lane;
       const bool row_ok = row < out_rows;
-      float* bias_smem = reinterpret_cast<float*>(bias_buf + (warp - 2) * kBiasWarpBytes);
+      float* bias_smem = reinterpret_cast<float*>(bias_buf + (warp - 2) * Cfg::kVecWarpBytes);
+      float* gate_smem = bias_smem + kColsPerWarp;        // [2][kColsPerWarp]: gate rows of the first / last sample of the warp
       if constexpr (EPI != EPI_DGELU_BF16 && EPI != EPI_WGRAD_F32 && EPI != EPI_HEAD) {
-        // this warp's bias slice -> smem while the MMAs of the tile are still running
+        // this warp's bias (and gate) slices -> smem while the MMAs of the tile are still running, so the per-chunk
+        // epilogue math never queues a global load behind the streaming residual prefetch
         for (int i = lane; i < kColsPerWarp / 4; i += 32)
           reinterpret_cast<float4*>(bias_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base) + i);
+        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_GATE_BF16) {
+          const int last = out_rows - 1;
+          const int s_first = (row0 < last ? row0 : last) / p.tokens, s_last = (row0 + 31 < last ? row0 + 31 : last) / p.tokens;
+          const float* ga = p.gate + static_cast<long long>(s_first) * p.gate_stride + n_blk * BN + col_base;
+          const float* gb = p.gate + static_cast<long long>(s_last) * p.gate_stride + n_blk * BN + col_base;
+          for (int i = lane; i < kColsPerWarp / 4; i += 32) {
+            reinterpret_cast<float4*>(gate_smem)[i] = __ldg(reinterpret_cast<const float4*>(ga) + i);
+            reinterpret_cast<float4*>(gate_smem + kColsPerWarp)[i] = __ldg(reinterpret_cast<const float4*>(gb) + i);
+          }
+        }
         __syncwarp();
       }
+      // gate row of this thread's sample: the staged copy when the warp's 32 rows span at most two samples (tokens >= 32),
+      // else straight from global memory (kept as two typed pointers so the staged reads stay LDS)
+      uint32_t gate_sm = smem_u32(gate_smem);
+      const float* gate_gl = nullptr;
+      const bool gate_staged = p.tokens >= 32;
+      if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_GATE_BF16) {
+        const int last = out_rows - 1;
+        const int s_first = (row0 < last ? row0 : last) / p.tokens;
+        const int s_mine = row_ok ? row / p.tokens : s_first;
+        if (s_mine != s_first) gate_sm += kColsPerWarp * 4;
+        gate_gl = p.gate + static_cast<long long>(s_mine) * p.gate_stride + n_blk * BN + col_base;
+      }
+      auto gate4 = [&](int col4) -> float4 {   // 4 gate values of this thread's sample at warp-local column 4 * col4
+        if (gate_staged) return lds_f4(gate_sm + 16u * static_cast<uint32_t>(col4));
+        return __ldg(reinterpret_cast<const float4*>(gate_gl) + col4);
+      };
       auto release_tmem = [&]() {   // accumulator fully read into registers: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
@@ -332,6 +360,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           else mbar_arrive(&tempty_bar[acc]);
         }
       };
+      // EPI_RESID_F32: the residual-stream tile this warp updates, as coalesced 128-byte row segments (lane -> row
+      // it*4 + lane/8, 16-byte chunk lane%8), double buffered so chunk c+1 streams in while chunk c is processed; the
+      // first chunk is requested before the accumulator is even complete
+      auto load_x = [&](float4 (&buf)[8], int c) {
+        const float* xb = reinterpret_cast<const float*>(p.out) + n_blk * BN + col_base + c * 32 + 4 * (lane & 7);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + (lane >> 3);
+          buf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < out_rows) buf[it] = __ldcs(reinterpret_cast<const float4*>(xb + static_cast<long long>(grow) * p.ldo));
+        }
+      };
+      float4 xa[8], xb[8];
+      if constexpr (EPI == EPI_RESID_F32) load_x(xa, 0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -385,7 +427,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
-          bf16_math<EPI>(p, v, row, n0, row_ok, bias_smem + c * 64);
+          bf16_math<EPI>(v, bias_smem + c * 64, gate4, c * 16);
           store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
             if (p.out2 != nullptr) {
@@ -408,8 +450,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
           }
         }
+      } else if constexpr (EPI == EPI_RESID_F32) {
+        // x[row, n] += gate[row / tokens, n] * (acc + bias[n])  -  fp32 read-modify-write of the residual stream
+        constexpr int NC = kColsPerWarp / 32;
+        const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          float4 (&cur)[8] = (c & 1) ? xb : xa;
+          float4 (&nxt)[8] = (c & 1) ? xa : xb;
+          if (c + 1 < NC) load_x(nxt, c + 1);
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + col_base + c * 32, r);
+          tmem_ld_wait();
+          if (c == NC - 1) release_tmem();
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_smem + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            const float4 g = gate4(c * 8 + j);
+            v[4 * j + 0] = g.x * (__uint_as_float(r[4 * j + 0]) + b.x); v[4 * j + 1] = g.y * (__uint_as_float(r[4 * j + 1]) + b.y);
+            v[4 * j + 2] = g.z * (__uint_as_float(r[4 * j + 2]) + b.z); v[4 * j + 3] = g.w * (__uint_as_float(r[4 * j + 3]) + b.w);
+          }
+          stage_f32_tile(stage, v, lane);
+          float* ob = reinterpret_cast<float*>(p.out) + n_blk * BN + col_base + c * 32 + 4 * ch;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            float4 u = *reinterpret_cast<const float4*>(stage + rr * kStageRowBytes + 16 * ch);
+            u.x += cur[it].x; u.y += cur[it].y; u.z += cur[it].z; u.w += cur[it].w;
+            if (row0 + rr < out_rows) *reinterpret_cast<float4*>(ob + static_cast<long long>(row0 + rr) * p.ldo) = u;
+          }
+          __syncwarp();
+        }
       } else {
-        // fp32 outputs: EPI_BIAS_F32, EPI_PATCH_EMBED_F32
+        // fp32 outputs: EPI_BIAS_F32, EPI_PATCH_EMBED_F32, EPI_WGRAD_F32
         float xt_row[kLatent];
         if constexpr (EPI == EPI_PATCH_EMBED_F32) {
 #pragma unroll
@@ -423,11 +498,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
 #pragma unroll 1
         for (int c = 0; c < kColsPerWarp / 32; ++c) {
+          const int n0 = n_blk * BN + col_base + c * 32;
           uint32_t r[32];
           tmem_ld_32x32(t_row + col_base + c * 32, r);
           tmem_ld_wait();
           if (c == kColsPerWarp / 32 - 1) release_tmem();
-          const int n0 = n_blk * BN + col_base + c * 32;
           float v[32];
           if constexpr (WG) {
 #pragma unroll
@@ -585,7 +660,8 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   const int bn = (epi == EPI_HEAD) ? 64 : ((p.N % 256 == 0) ? 256 : 128);
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
-  if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
+  if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32 || epi == EPI_RESID_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
+  if (epi == EPI_RESID_F32 && p.gate == nullptr) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate");
   if (epi == EPI_DGELU_BF16 && p.aux == nullptr) return set_error(kErrBadArg, "gemm: dgelu epilogue needs the pre-activations");
 #define JP_CASE(E)                                                             \
   case E:                                                                      \
@@ -598,6 +674,7 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     JP_CASE(EPI_BIAS_F32)
     JP_CASE(EPI_BIAS_BF16_F32)
     JP_CASE(EPI_DGELU_BF16)
+    JP_CASE(EPI_RESID_F32)
     case EPI_HEAD:
       return launch_cs<64, EPI_HEAD>(a, lda, w, ldw, p, stream);
     default:

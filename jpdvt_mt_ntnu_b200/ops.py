@@ -92,6 +92,21 @@ def gemm_bias_gate(a, w, bias, gate, tokens: int) -> torch.Tensor:
     return out
 
 
+def gemm_bias_gate_residual(x, a, w, bias, gate, tokens: int) -> torch.Tensor:
+    """x += gate[row // tokens] * (a @ w.T + bias), in place on the fp32 residual stream x [M,N]; returns x."""
+    lib = _lib_dev()
+    a, w = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w")
+    bias, gate = _need(bias, torch.float32, "bias"), _need(gate, torch.float32, "gate")
+    m, k = a.shape
+    n = w.shape[0]
+    if x.dtype != torch.float32 or not x.is_contiguous() or tuple(x.shape) != (m, n) or not x.is_cuda:
+        raise _lib.JpdvtError("gemm_bias_gate_residual: x must be a contiguous fp32 CUDA tensor of shape [M, N]")
+    stride = 0 if gate.shape[0] == 1 else n
+    check(lib.jpdvt_gemm_bias_gate_residual(ptr(a), ptr(w), ptr(bias), ptr(gate), stride, ptr(x), m, n, k, tokens,
+                                            stream_ptr()), "gemm_bias_gate_residual")
+    return x
+
+
 def patchify(img: torch.Tensor) -> torch.Tensor:
     lib = _lib_dev()
     img = _need(img, torch.float32, "img")

@@ -64,6 +64,12 @@ def test_gemm_epilogues(ops):
         gate = torch.randn(ncond, n, device="cuda")
         g = gate.repeat_interleave(T, 0) if ncond > 1 else gate
         assert rel_l2(ops.gemm_bias_gate(a, w, bias, gate, T).float(), g * lin) < BF16_TOL
+        # the gated residual update as the GEMM epilogue: fp32 read-modify-write of x, in place (models.py:120-121)
+        x0 = torch.randn(m, n, device="cuda")
+        x = x0.clone()
+        assert ops.gemm_bias_gate_residual(x, a, w, bias, gate, T) is x
+        assert rel_l2(x, x0 + g * lin) < F32_TOL
+        assert rel_l2(x - x0, g * lin) < 1e-4          # the update itself, not hidden behind |x0|
 
 
 def test_patch_embed_head_and_patchify(ops):
