@@ -172,6 +172,22 @@ def run_reference(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1d_ncu_full_kernels.json")
+
+
+def ncu_traffic(label):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `label` from the committed `ncu --set full` capture
+    (tools/ncu_summary.py output; same shape as the bench: M = 36864).  None when the capture is absent."""
+    try:
+        for d in json.load(open(NCU_SUMMARY)):
+            if d.get("launch") == label:
+                mb = float(d["dram__bytes_read.sum [Mbyte]"]) + float(d["dram__bytes_write.sum [Mbyte]"])
+                return mb * 1e6, os.path.relpath(NCU_SUMMARY, ROOT)
+    except Exception:
+        pass
+    return None, None
+
+
 def kernel_roofline(model, wl, batch, peaks):
     """Per-kernel CUDA-event timings of one denoiser forward at the bench shape, through the per-kernel C-ABI entry
     points (ops.*) on the launching stream; inputs are larger than L2 at this batch.  Returns the roofline object of
@@ -217,8 +233,10 @@ def kernel_roofline(model, wl, batch, peaks):
             ach = work / (ms * 1e-3) / 1e9
             out[name] = {"ms": ms, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
     top = "gemm_fc1 (tcgen05, bias+gelu)"
+    traffic, traffic_src = ncu_traffic("fc1")
     roof = {"bound": "tensor", "kernel": top, "achieved": out[top]["achieved"], "peak": peaks["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": out[top]["frac"], "traffic": None,
+            "unit": "TFLOP/s", "frac": out[top]["frac"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read + write)",
+            "traffic_source": traffic_src, "algorithmic_bytes": M * 768 * 2.0 + 3072 * 768 * 2.0 + M * 3072 * 2.0,
             "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
             "how": "CUDA events on the launching stream over 10 back-to-back launches at the bench shape "
                    f"(M={M}, activations > L2); algorithmic FLOPs 2*M*768*3072"}

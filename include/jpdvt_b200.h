@@ -107,8 +107,8 @@ int jpdvt_posterior_step(const float* x0, const float* x_t, const float* noise, 
                          const float* logvar, const int64_t* t, const int32_t* step_ptr, float* mean_or_null,
                          float* sample_or_null, int64_t n, int64_t per_sample, void* stream);
 /* DDIM update (gaussian_diffusion.py:559-578, with the `condition` argument the reference call at :547 forgot):
- * eps = (recip[t]*x_t - x0)/recipm1[t]; sample = sqrt_abp[t]*x0 + dir[t]*eps + [t != 0]*sigma[t]*noise.  PARITY UNPINNED:
- * the reference's ddim_sample raises TypeError, so only the oracle restatement of those lines checks this kernel. */
+ * eps = (recip[t]*x_t - x0)/recipm1[t]; sample = sqrt_abp[t]*x0 + dir[t]*eps + [t != 0]*sigma[t]*noise.  Pinned against
+ * the reference's own DDIM code run with that argument supplied (tests/golden/ddim_*.npz). */
 int jpdvt_ddim_step(const float* x0, const float* x_t, const float* noise, const float* recip, const float* recipm1,
                     const float* sqrt_abp, const float* dir, const float* sigma, const int64_t* t, const int32_t* step_ptr,
                     float* sample, int64_t n, int64_t per_sample, void* stream);

@@ -2,6 +2,7 @@
 // whole reverse-diffusion loop.  Host code here only validates arguments and enqueues kernels on the caller's stream.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/jpdvt_b200.h"

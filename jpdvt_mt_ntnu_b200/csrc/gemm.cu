@@ -373,7 +373,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       };
       float4 xa[8], xb[8];
-      if constexpr (EPI == EPI_RESID_F32) load_x(xa, 0);
+      if constexpr (EPI == EPI_RESID_F32) {
+        load_x(xa, 0);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);

@@ -352,7 +352,8 @@ class GaussianDiffusion:
     def ddim_sample(self, model, condition, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                     eta=0.0, noise=None):
         """gaussian_diffusion.py:531-578 with the `condition` argument threaded through (the reference omits it at
-        :547 and raises TypeError).  PARITY UNPINNED against the reference; pinned against the oracle restatement."""
+        :547 and raises TypeError).  Pinned against the reference's own DDIM code run with that one argument supplied
+        (tests/golden/ddim_*.npz, oracle/make_golden.py golden_ddim)."""
         if cond_fn is not None:
             raise NotImplementedError("cond_fn guidance is never used by the reference callers")
         out = self.p_mean_variance(model, condition, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,

@@ -32,6 +32,15 @@ SAMPLING_CASES = {
     "full192_s250": dict(size=192, depth=12, batch=2, grid=3, wseed=1234, seed=204, respacing="250", loop_seed=8),
 }
 
+# DDIM: the reference's ddim_sample calls p_mean_variance without `condition` (gaussian_diffusion.py:546-553, TypeError);
+# the goldens run the reference's OWN ddim_sample / ddim_sample_loop_progressive code (lines 531-698, unmodified) with
+# the missing argument supplied at that single call site (oracle/make_golden.py: golden_ddim)
+DDIM_CASES = {
+    "tiny48_ddim10_eta0":  dict(size=48,  depth=2, batch=3, grid=3, wseed=21, seed=201, respacing="10",     loop_seed=9,  eta=0.0),
+    "tiny48_ddim10_eta05": dict(size=48,  depth=2, batch=3, grid=3, wseed=21, seed=201, respacing="10",     loop_seed=10, eta=0.5),
+    "d2_192_ddim25_eta1":  dict(size=192, depth=2, batch=2, grid=3, wseed=22, seed=202, respacing="ddim25", loop_seed=11, eta=1.0),
+}
+
 TRAINING_CASES = {
     "tiny96":      dict(size=96,  depth=2, batch=3, grid=3, wseed=31, seed=301, add_mask=False),
     "tiny96_mask": dict(size=96,  depth=2, batch=3, grid=3, wseed=32, seed=302, add_mask=True),

@@ -284,7 +284,8 @@ class Schedule:
 
     def ddim_step(self, model, condition, x_t, t, noise, eta=0.0):
         """gaussian_diffusion.py:559-578 arithmetic with `condition` threaded through (the reference call
-        at :547 omits it and raises TypeError, so this branch is PARITY UNPINNED)."""
+        at :547 omits it and raises TypeError; pinned against the reference's DDIM code run with that argument supplied,
+        oracle/make_golden.py golden_ddim)."""
         ts = torch.tensor(self.timestep_map, dtype=t.dtype)[t]
         _, x0 = model(condition, ts, x_t)
         g = lambda tab: self.gather(tab, t, x_t)

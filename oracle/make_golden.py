@@ -140,6 +140,38 @@ def golden_sampling():
         np.savez_compressed(os.path.join(OUT, f"sampling_{name}.npz"), **out)
 
 
+def golden_ddim():
+    """The reference's DDIM loop (gaussian_diffusion.py:531-578,636-698) run as committed, with the one argument its
+    p_mean_variance call forgets (`condition`, :546) supplied by wrapping that bound method on the instance."""
+    for name, case in cases.DDIM_CASES.items():
+        m, st = build_ref(case)
+        d = create_diffusion(case["respacing"])
+        cond, noise = cases.sampling_inputs(case)
+        inner = d.p_mean_variance
+        d.p_mean_variance = lambda model, x, t, **kw: inner(model, cond, x, t, **kw)
+        torch.manual_seed(case["loop_seed"])   # ddim_sample's randn_like stream (gaussian_diffusion.py:569)
+        outs = list(d.ddim_sample_loop_progressive(m.forward, noise.shape, noise=noise, clip_denoised=False,
+                                                   model_kwargs=None, device="cpu", progress=False, eta=case["eta"]))
+        keep = cases.kept_steps(len(outs))
+        out = {"final": outs[-1]["sample"].numpy()}
+        for n in keep:
+            out[f"step{n}_sample"] = outs[n]["sample"].numpy()
+            out[f"step{n}_x0"] = outs[n]["pred_xstart"].numpy()
+        sched = orc.Schedule(case["respacing"])
+        torch.manual_seed(case["loop_seed"])
+        step_noise = [torch.randn_like(noise) for _ in range(sched.num_timesteps)]
+        model = orc.OracleDenoiser(st, depth=case["depth"])
+        x, e1 = noise, 0.0
+        for k, i in enumerate(range(sched.num_timesteps - 1, -1, -1)):
+            o = sched.ddim_step(model, cond, x, torch.full((noise.shape[0],), i, dtype=torch.long), step_noise[k], case["eta"])
+            x = o["sample"]
+            if k in keep:
+                e1 = max(e1, (o["sample"] - outs[k]["sample"]).abs().max().item(), (o["pred_xstart"] - outs[k]["pred_xstart"]).abs().max().item())
+        print(f"ddim[{name}] oracle-vs-reference max abs err {e1:.3e} over {len(outs)} steps")
+        assert e1 < 5e-5
+        np.savez_compressed(os.path.join(OUT, f"ddim_{name}.npz"), **out)
+
+
 def golden_training():
     for name, case in cases.TRAINING_CASES.items():
         m, st = build_ref(case)
@@ -230,6 +262,6 @@ def golden_assignment():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["static", "assignment", "forward", "training", "sampling"]
+    which = sys.argv[1:] or ["static", "assignment", "forward", "training", "sampling", "ddim"]
     for w in which:
         globals()["golden_" + w]()

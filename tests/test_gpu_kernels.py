@@ -159,7 +159,7 @@ def test_diffusion_elementwise_bit_exact(ops):
 
 
 def test_ddim_step_vs_oracle(ops):
-    """PARITY UNPINNED against the reference (its ddim_sample raises TypeError); pinned against the oracle restatement."""
+    """One DDIM update against the oracle restatement (itself pinned to the reference's DDIM code: test_oracle_golden.py)."""
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from oracle import jpdvt_oracle as orc
     torch.manual_seed(4)

@@ -123,6 +123,28 @@ def test_generic_callable_path_matches_fast_path(cuda):
     _check(chained, want)
 
 
+@pytest.mark.parametrize("name", sorted(cases.DDIM_CASES))
+def test_ddim_loop_vs_reference_golden(cuda, golden, name):
+    """ddim_sample_loop against the reference's own DDIM arithmetic (fixtures from oracle/make_golden.py golden_ddim)."""
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    case = cases.DDIM_CASES[name]
+    g = golden("ddim_" + name)
+    m = _model(case)
+    d = create_diffusion(case["respacing"])
+    cond, noise = cases.sampling_inputs(case)
+    torch.manual_seed(case["loop_seed"])
+    step_noise = torch.stack([torch.randn_like(noise) for _ in range(d.num_timesteps)]).cuda()
+    outs = list(d.ddim_sample_loop_progressive(m.forward, cond.cuda(), noise.shape, noise=noise.cuda(), clip_denoised=False,
+                                               eta=case["eta"], step_noise=step_noise))
+    assert len(outs) == d.num_timesteps
+    for n in cases.kept_steps(len(outs)):
+        _check(outs[n]["pred_xstart"], g[f"step{n}_x0"])
+        _check(outs[n]["sample"], g[f"step{n}_sample"])
+    _check(outs[-1]["sample"], g["final"])
+    got = d.ddim_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, eta=case["eta"], step_noise=step_noise)
+    _check(got, g["final"])
+
+
 def test_ddim_loop_vs_oracle(cuda):
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     case = cases.SAMPLING_CASES["tiny48_s10"]

@@ -135,3 +135,26 @@ def test_perfect_latents_round_trip():
         lat = orc.expand_piece_embeddings(canon[perm][None], G, tok)[0]
         _, pred, _ = orc.solve(lat, G, tok)
         assert pred.tolist() == perm.tolist()
+
+
+@pytest.mark.parametrize("name", sorted(cases.DDIM_CASES))
+def test_ddim_loop_matches_reference(golden, name):
+    """The reference's own DDIM code (gaussian_diffusion.py:531-578,636-698) with `condition` supplied at its
+    p_mean_variance call (fixtures: oracle/make_golden.py golden_ddim) vs the oracle's ddim_step."""
+    case = cases.DDIM_CASES[name]
+    g = golden("ddim_" + name)
+    cond, noise = cases.sampling_inputs(case)
+    sched = orc.Schedule(case["respacing"])
+    torch.manual_seed(case["loop_seed"])
+    step_noise = [torch.randn_like(noise) for _ in range(sched.num_timesteps)]
+    model = orc.OracleDenoiser(cases.state_for(case), depth=case["depth"])
+    keep = cases.kept_steps(sched.num_timesteps)
+    x = noise
+    with torch.no_grad():
+        for k, i in enumerate(range(sched.num_timesteps - 1, -1, -1)):
+            o = sched.ddim_step(model, cond, x, torch.full((case["batch"],), i, dtype=torch.long), step_noise[k], case["eta"])
+            x = o["sample"]
+            if k in keep:
+                _close(o["sample"].numpy(), g[f"step{k}_sample"], 5e-5)
+                _close(o["pred_xstart"].numpy(), g[f"step{k}_x0"], 5e-5)
+    _close(x.numpy(), g["final"], 5e-5)
