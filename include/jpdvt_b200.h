@@ -125,6 +125,19 @@ int jpdvt_assign_from_scores(const double* scores, int batch, int n, double sent
 int jpdvt_assign_greedy_l1(const float* latents, const float* canon, int batch, int grid, int tokens_per_side,
                            double sentinel, int32_t* order, int32_t* pred, double* scores_out_or_null, void* stream);
 
+/* ---- puzzle plumbing either side of the sampling loop, batched on the device --------------------
+ * dst slot i (row-major G x G grid of (size/G)-pixel pieces) = src piece perm[b, i]; slots with keep[b, i] == 0 are zeroed
+ * (keep may be NULL).  With perm = the scramble indices this is the reference's scramble
+ * (inference_ddp.py:382-395 = inference.py:266-278, batched inferencetexmet.py:318-338; masked-puzzle inference zeroes
+ * slots); with perm = `order` from the assignment it is the reconstruction reconstructed[pred[i]] = piece i
+ * (inference_ddp.py:449-455).  src/dst [batch, channels, size, size] fp32, perm [batch, G*G] int32, keep [batch, G*G] u8. */
+int jpdvt_gather_pieces(const float* src, float* dst, const int32_t* perm, const uint8_t* keep_or_null, int batch,
+                        int channels, int size, int grid, void* stream);
+/* matches[b] = #{i : pred[b,i] == truth[b,i]}, correct[b] = (matches[b] == n); totals (NULL or int64[3]) accumulates
+ * (puzzles correct, pieces correct, puzzles) - the counters of inference_ddp.py:431-447 / :485-490. */
+int jpdvt_score_placements(const int32_t* pred, const int32_t* truth, int batch, int n, int32_t* correct, int32_t* matches,
+                           int64_t* totals_or_null, void* stream);
+
 /* ---- whole denoiser / whole sampling loop --------------------------------------------------------------------- */
 
 typedef struct jpdvt_weights {

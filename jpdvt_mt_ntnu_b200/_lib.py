@@ -85,6 +85,8 @@ PROTOTYPES = {
     "jpdvt_q_sample": [P, P, P, P, P, P, P, c_int64, c_int64, P],
     "jpdvt_assign_from_scores": [P, c_int, c_int, c_double, P, P, P],
     "jpdvt_assign_greedy_l1": [P, P, c_int, c_int, c_int, c_double, P, P, P, P],
+    "jpdvt_gather_pieces": [P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "jpdvt_score_placements": [P, P, c_int, c_int, P, P, P, P],
     "jpdvt_gemm_wgrad": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_dgelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],

@@ -295,6 +295,19 @@ int jpdvt_assign_greedy_l1(const float* latents, const float* canon, int batch, 
   return launch_assign_latents(latents, canon, batch, grid, tokens_per_side, sentinel, order, pred, scores_out_or_null, ST(stream));
 }
 
+int jpdvt_gather_pieces(const float* src, float* dst, const int32_t* perm, const uint8_t* keep_or_null, int batch,
+                        int channels, int size, int grid, void* stream) {
+  if (batch == 0) return kOk;
+  if (!src || !dst || !perm) return set_error(kErrBadArg, "gather_pieces: null pointer");
+  return launch_gather_pieces(src, dst, perm, keep_or_null, batch, channels, size, grid, ST(stream));
+}
+int jpdvt_score_placements(const int32_t* pred, const int32_t* truth, int batch, int n, int32_t* correct, int32_t* matches,
+                           int64_t* totals_or_null, void* stream) {
+  if (batch == 0) return kOk;
+  if (!pred || !truth || !correct || !matches) return set_error(kErrBadArg, "score_placements: null pointer");
+  return launch_score_placements(pred, truth, batch, n, correct, matches, reinterpret_cast<long long*>(totals_or_null), ST(stream));
+}
+
 int jpdvt_denoiser_forward(const jpdvt_weights* w_host, const jpdvt_workspace* ws_host, const float* img,
                            const int64_t* t, const int32_t* step_ptr, const int32_t* map, const float* x_t,
                            float* te_out, float* img_out_or_null, int batch, void* stream) {

@@ -70,6 +70,12 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, 
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
 
+// puzzle.cu
+int launch_gather_pieces(const float* src, float* dst, const int* perm, const unsigned char* keep, int batch, int channels,
+                         int size, int grid, cudaStream_t stream);
+int launch_score_placements(const int* pred, const int* truth, int batch, int n, int* correct, int* matches, long long* totals,
+                            cudaStream_t stream);
+
 // backward.cu
 // `part`: scratch of bwd_part_floats(batch, tokens) floats (per-sample partial sums; no atomics on the hot reductions)
 long long bwd_part_floats(int batch, int tokens);

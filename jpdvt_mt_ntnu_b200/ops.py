@@ -239,6 +239,43 @@ def assign_greedy_l1(latents: torch.Tensor, canon: torch.Tensor, grid: int, sent
     return (order, pred, scores) if return_scores else (order, pred)
 
 
+def gather_pieces(images: torch.Tensor, perm: torch.Tensor, grid: int, keep: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out slot i = images piece perm[b, i]; slots with keep[b, i] == 0 are zeroed.  images fp32 [B,C,S,S], perm int32
+    [B,G*G], keep uint8 [B,G*G] or None.  perm = scramble indices -> the scramble of inference_ddp.py:382-395;
+    perm = `order` of the assignment -> the reconstruction of inference_ddp.py:449-455."""
+    lib = _lib_dev()
+    images, perm = _need(images, torch.float32, "images"), _need(perm, torch.int32, "perm")
+    b, c, s, s2 = images.shape
+    if s != s2 or tuple(perm.shape) != (b, grid * grid):
+        raise _lib.JpdvtError(f"gather_pieces: images {tuple(images.shape)} / perm {tuple(perm.shape)} do not fit a {grid}x{grid} puzzle")
+    if keep is not None:
+        keep = _need(keep, torch.uint8, "keep")
+        if tuple(keep.shape) != tuple(perm.shape):
+            raise _lib.JpdvtError("gather_pieces: keep must have the shape of perm")
+    if out is None:
+        out = torch.empty_like(images)
+    check(lib.jpdvt_gather_pieces(ptr(images), ptr(out), ptr(perm), ptr(keep), b, c, s, grid, stream_ptr()), "gather_pieces")
+    return out
+
+
+def score_placements(pred: torch.Tensor, truth: torch.Tensor, totals: Optional[torch.Tensor] = None):
+    """(correct int32 [B], matches int32 [B]) for pred/truth int32 [B,n] (inference_ddp.py:431-447); `totals` (int64 [3],
+    optional) accumulates (puzzles correct, pieces correct, puzzles)."""
+    lib = _lib_dev()
+    pred, truth = _need(pred, torch.int32, "pred"), _need(truth, torch.int32, "truth")
+    if pred.shape != truth.shape or pred.dim() != 2:
+        raise _lib.JpdvtError("score_placements: pred and truth must both be [B, n]")
+    if totals is not None and (totals.dtype != torch.int64 or totals.numel() != 3 or not totals.is_contiguous()):
+        raise _lib.JpdvtError("score_placements: totals must be a contiguous int64 tensor of 3 elements")
+    b, n = pred.shape
+    correct = torch.empty(b, device=pred.device, dtype=torch.int32)
+    matches = torch.empty_like(correct)
+    check(lib.jpdvt_score_placements(ptr(pred), ptr(truth), b, n, ptr(correct), ptr(matches), ptr(totals), stream_ptr()),
+          "score_placements")
+    return correct, matches
+
+
 # ------------------------------------------------------------------------------------------------- training kernels
 def gemm_wgrad(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
     """dW [out_rows, n_cols] fp32 = p[m, out_rows].T @ q[m, n_cols]  (bf16 operands, tcgen05 MN-major GEMM)."""
