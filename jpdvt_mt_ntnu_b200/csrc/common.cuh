@@ -67,6 +67,11 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
                 cudaStream_t stream);
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream);
+// attention_tc.cu: tcgen05 / TMEM forward for the sizes attention_tc_supported() names (inference path, no log-sum-exp)
+bool attention_tc_supported(int tokens);
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream);
+// K-major bf16 [rows, cols] tensor map, {64 cols x box_rows} boxes, 128-byte swizzle (gemm.cu)
+int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
 
