@@ -12,11 +12,18 @@
 //   warp 5    : MMA issuer   - S = Q K^T  (M = 128 query rows, N = T keys, K = 64)  -> TMEM columns [0, T)
 //                              O = P V    (M = 128, N = 64, K = T; P is the bf16 probability tile the softmax warps
 //                              wrote to shared memory in K-major swizzled form, V is read MN-major as loaded)
-// T = 144 is 128 + 16 query rows.  The 16-row remainder is a second 128-row MMA tile whose A operand starts
-// 32 q rows before the end (q = unit index mod 4), so the 16 live rows land in TMEM lanes [32q, 32q+16) and the warp
-// that pays for the remainder rotates from unit to unit; its P tile is stored compactly (only those rows exist).
+// T = 144 is 128 + 16 query rows.  The 16-row remainder is NOT given to one warp (one thread per row would leave half
+// a warp idle and three SM sub-partitions waiting): its scores are produced by four small MMA groups, group j multiplying
+// the Q rows shifted by 32 j against keys [32j, 32j+32) (the last group takes 48), so TMEM lanes [32j, 32j+16) - lane
+// quadrant j - hold rows 128..143 x its own quarter of the keys.  All four softmax warps then work on the remainder, a
+// quarter of the columns each, and combine the row maximum / row sum through shared memory.  Its P tile only has 16 live
+// rows and is stored compactly (2 KB per 64-key block).
 // TMEM per CTA: S [0,T) shared by both tiles in turn, O0 [T,T+64), O1 aliases S[0,64) -> 256 columns at T = 144, two
 // CTAs per SM, so one CTA's loads / MMA latencies hide behind the other's softmax.
+#include <cstdio>
+#include <cstdlib>
+#include <initializer_list>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -45,23 +52,51 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// tcgen05.mma from split descriptor words.  The issuing thread is alone in its warp: every instruction it spends building
+// a 64-bit descriptor costs several cycles of exposed latency, and the MMAs of one unit are tiny, so the descriptors are
+// formed as (precomputed low word + compile-time offset, constant high word) and the accumulate flag is compile-time.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);        // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16); }
+template <bool ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi)
+      : "memory");
+}
+
 template <int T>
 struct TcCfg {
   static_assert(T % 16 == 0 && T >= 16 && T <= 256, "tokens must be a multiple of 16, at most 256");
   static constexpr int kTiles = T > 128 ? 2 : 1;
   static constexpr int kRem = T - 128;                       // live rows of tile 1
-  static constexpr bool kCompact = kTiles == 2 && kRem <= 32;   // remainder fits one warp: rotate it, store P1 compactly
+  static constexpr bool kSplit = kTiles == 2 && kRem <= 16;    // 16-row remainder: split its key columns over the four warps
+  static_assert(!kSplit || T == 144, "the split remainder is laid out for 128 + 16 rows");
+  static_assert(kTiles == 1 || kSplit || kRem == 128, "other remainders are not instantiated");
   static constexpr int kKBlocks = (T + 63) / 64;             // 64-key blocks of the P tile (128 B per row and block)
   static constexpr int kTileBytes = T * 128;                 // one of Q / K / V
   static constexpr int kPBytes = kKBlocks * 16384;           // P0: 128 rows x kKBlocks x 128 B
-  static constexpr int kOffQ = 0, kOffK = kTileBytes, kOffV = 2 * kTileBytes, kOffP = 3 * kTileBytes;
+  // split remainder: its compact P tile (16 live rows x kKBlocks x 2 KB) sits right before P0, so the 128-row A operand the
+  // MMA reads for it runs on into P0 (dead rows, read only) and tile 1 need not wait for the O0 MMAs to release P0
+  static constexpr int kP1Bytes = (kTiles == 2 && kRem <= 16) ? kKBlocks * 2048 : 0;
+  static constexpr int kOffQ = 0, kOffK = kTileBytes, kOffV = 2 * kTileBytes, kOffP1 = 3 * kTileBytes, kOffP = kOffP1 + kP1Bytes;
   // the tile-1 A operand reads Q rows up to 255: keep that inside the allocation (it may run into K / V / P, read only)
-  static constexpr int kDataBytes = (kOffP + kPBytes) > 256 * 128 ? (kOffP + kPBytes) : 256 * 128;
+  // output staging (4 KB per softmax warp): inside P0 when the remainder is split (P0 is idle once the O0 MMAs are done and
+  // P1 lives elsewhere), its own 16 KB otherwise (a full second tile keeps P1 in P0's place until the O1 MMAs finish)
+  static constexpr int kOffStage = (kTiles == 2 && kRem > 16) ? kOffP + kPBytes : kOffP;
+  static constexpr int kEndBytes = (kTiles == 2 && kRem > 16) ? kOffStage + 16384 : kOffP + kPBytes;
+  static constexpr int kDataBytes = kEndBytes > 256 * 128 ? kEndBytes : 256 * 128;
   static constexpr int kBarOff = kDataBytes;
-  static constexpr int kSmemBytes = kDataBytes + 128 + 1024; // + barriers / TMEM slot + alignment slack
+  static constexpr int kXchOff = kBarOff + 128;              // [2][4][16] floats: row max / row sum of the split remainder
+  static constexpr int kSmemBytes = kXchOff + 512 + 1024;    // + alignment slack
   static constexpr int kTmemCols = (T + 64 <= 256) ? 256 : 512;
   static constexpr int kCtasPerSm = (T + 64 <= 256 && 2 * (kSmemBytes + 1024) <= 227 * 1024) ? 2 : 1;
-  static_assert(kOffP % 1024 == 0 && kTileBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
+  static_assert(kOffP % 1024 == 0 && kOffP1 % 1024 == 0 && kTileBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
 };
 
 // One softmax pass of the thread's S row (TMEM lane = row, columns [0,T)): exact row maximum, then
@@ -70,23 +105,34 @@ template <int T>
 __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row_addr, uint32_t blk_stride, int sw, bool store) {
   constexpr float sl2 = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
   constexpr int kFull = T / 32, kTail = T % 32;              // kTail is 0 or 16
-  float mx = -INFINITY;
+  // chunk c = columns [32c, 32c+32) (the last one may be 16 wide); the load of chunk c+1 is in flight while chunk c is
+  // processed (tcgen05.wait::ld after the math, not before it)
+  constexpr int kChunks = kFull + (kTail ? 1 : 0);
+  uint32_t ra[32], rb[32];
+  auto load_chunk = [&](uint32_t (&r)[32], int c) {
+    if (c < kFull) tmem_ld_32x32(t_row + c * 32, r);
+    else tmem_ld_32x16(t_row + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
+  };
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  load_chunk(ra, 0);
+  tmem_ld_wait();
 #pragma unroll
-  for (int c = 0; c < kFull; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(t_row + c * 32, r);
-    tmem_ld_wait();
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+    for (int j = 0; j < n; j += 8) {
+      m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+      m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+      m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
+      m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+    }
+    if (c + 1 < kChunks) tmem_ld_wait();
   }
-  if constexpr (kTail != 0) {
-    uint32_t r[16];
-    tmem_ld_32x16(t_row + kFull * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-  }
-  const float ms = mx * sl2;
+  load_chunk(ra, 0);                                          // second pass: its first chunk is in flight during the reduction
+  const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
   float sum = 0.f;
   auto emit8 = [&](const uint32_t* r, int chunk) {            // 8 consecutive keys -> one 16-byte chunk of the P row
     float p[8];
@@ -96,51 +142,112 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
     const uint4 u = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
     if (store) sts_u4(p_row_addr + static_cast<uint32_t>(chunk >> 3) * blk_stride + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4), u);
   };
+  tmem_ld_wait();
 #pragma unroll
-  for (int c = 0; c < kFull; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(t_row + c * 32, r);
-    tmem_ld_wait();
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) emit8(r + 8 * g, c * 4 + g);
-  }
-  if constexpr (kTail != 0) {
-    uint32_t r[16];
-    tmem_ld_32x16(t_row + kFull * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int g = 0; g < 2; ++g) emit8(r + 8 * g, kFull * 4 + g);
+    for (int g = 0; g < n / 8; ++g) emit8(cur + 8 * g, c * 4 + g);
+    if (c + 1 < kChunks) tmem_ld_wait();
   }
   return sum;
 }
 
-// O tile row (64 fp32 columns in TMEM) * inv -> bf16 -> 128 contiguous bytes of the output row
-__device__ __forceinline__ void store_o_row(uint32_t t_row, float inv, __nv_bfloat16* dst, bool live) {
-  uint32_t a[32], b[32];
+// Split remainder: this warp's NCJ key columns of the 16 remainder rows (live in lanes 0..15 of the warp's TMEM quadrant).
+// Row maximum and row sum are combined across the four warps through `xch`; p goes out as bf16 into the compact P tile
+// (row = lane, 2 KB per 64-key block).  Returns the full row sum.
+template <int NCJ>
+__device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_row_addr, int chunk0, int sw, float* xch, int warp,
+                                                  int lane) {
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  static_assert(NCJ == 32 || NCJ == 48, "remainder column split is 32/32/32/48");
+  uint32_t sreg[48];
+  tmem_ld_32x32(t_addr, reinterpret_cast<uint32_t (&)[32]>(sreg[0]));
+  if constexpr (NCJ == 48) tmem_ld_32x16(t_addr + 32, reinterpret_cast<uint32_t (&)[16]>(sreg[32]));
+  tmem_ld_wait();
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NCJ; j += 4) {
+    m0 = fmaxf(m0, fmaxf(__uint_as_float(sreg[j]), __uint_as_float(sreg[j + 1])));
+    m1 = fmaxf(m1, fmaxf(__uint_as_float(sreg[j + 2]), __uint_as_float(sreg[j + 3])));
+  }
+  const int l = lane & 15;
+  if (lane < 16) xch[warp * 16 + lane] = fmaxf(m0, m1);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const float mx = fmaxf(fmaxf(xch[l], xch[16 + l]), fmaxf(xch[32 + l], xch[48 + l]));
+  const float ms = mx * sl2;
+  float sum = 0.f;
+#pragma unroll
+  for (int g = 0; g < NCJ / 8; ++g) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = ex2f(fmaf(__uint_as_float(sreg[8 * g + j]), sl2, -ms));
+    sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    const uint4 u = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    const int ch = chunk0 + g;
+    if (lane < 16) sts_u4(p_row_addr + static_cast<uint32_t>(ch >> 3) * 2048u + static_cast<uint32_t>(((ch & 7) ^ sw) << 4), u);
+  }
+  if (lane < 16) xch[64 + warp * 16 + lane] = sum;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  return (xch[64 + l] + xch[80 + l]) + (xch[96 + l] + xch[112 + l]);
+}
+
+// O tile rows of this warp (TMEM lane = row, 64 fp32 columns) * inv -> bf16 -> global.  One thread per row would make every
+// store instruction touch 32 different lines, so the 32 x 128 B tile is transposed through a 4 KB staging tile (XOR-swizzled
+// 16-byte chunks, conflict free both ways) and leaves as 4 full 128-byte rows per instruction.
+__device__ __forceinline__ void load_o_row(uint32_t t_row, uint32_t (&a)[32], uint32_t (&b)[32]) {
   tmem_ld_32x32(t_row, a);
   tmem_ld_32x32(t_row + 32, b);
   tmem_ld_wait();
-  if (live) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+}
+__device__ __forceinline__ void store_o_rows(const uint32_t (&a)[32], const uint32_t (&b)[32], float inv, uint32_t stage,
+                                             __nv_bfloat16* dst_row0, int live_rows, int lane) {
+  const uint32_t mine = stage + lane * 128, sw = lane & 7;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      d4[j] = make_uint4(pack_bf16(__uint_as_float(a[8 * j]) * inv, __uint_as_float(a[8 * j + 1]) * inv),
-                         pack_bf16(__uint_as_float(a[8 * j + 2]) * inv, __uint_as_float(a[8 * j + 3]) * inv),
-                         pack_bf16(__uint_as_float(a[8 * j + 4]) * inv, __uint_as_float(a[8 * j + 5]) * inv),
-                         pack_bf16(__uint_as_float(a[8 * j + 6]) * inv, __uint_as_float(a[8 * j + 7]) * inv));
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      d4[4 + j] = make_uint4(pack_bf16(__uint_as_float(b[8 * j]) * inv, __uint_as_float(b[8 * j + 1]) * inv),
-                             pack_bf16(__uint_as_float(b[8 * j + 2]) * inv, __uint_as_float(b[8 * j + 3]) * inv),
-                             pack_bf16(__uint_as_float(b[8 * j + 4]) * inv, __uint_as_float(b[8 * j + 5]) * inv),
-                             pack_bf16(__uint_as_float(b[8 * j + 6]) * inv, __uint_as_float(b[8 * j + 7]) * inv));
+  for (int j = 0; j < 4; ++j) {
+    sts_u4(mine + ((j ^ sw) << 4),
+           make_uint4(pack_bf16(__uint_as_float(a[8 * j]) * inv, __uint_as_float(a[8 * j + 1]) * inv),
+                      pack_bf16(__uint_as_float(a[8 * j + 2]) * inv, __uint_as_float(a[8 * j + 3]) * inv),
+                      pack_bf16(__uint_as_float(a[8 * j + 4]) * inv, __uint_as_float(a[8 * j + 5]) * inv),
+                      pack_bf16(__uint_as_float(a[8 * j + 6]) * inv, __uint_as_float(a[8 * j + 7]) * inv)));
+    sts_u4(mine + (((4 + j) ^ sw) << 4),
+           make_uint4(pack_bf16(__uint_as_float(b[8 * j]) * inv, __uint_as_float(b[8 * j + 1]) * inv),
+                      pack_bf16(__uint_as_float(b[8 * j + 2]) * inv, __uint_as_float(b[8 * j + 3]) * inv),
+                      pack_bf16(__uint_as_float(b[8 * j + 4]) * inv, __uint_as_float(b[8 * j + 5]) * inv),
+                      pack_bf16(__uint_as_float(b[8 * j + 6]) * inv, __uint_as_float(b[8 * j + 7]) * inv)));
   }
+  __syncwarp();
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub;
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                 : "r"(stage + r * 128 + ((ch ^ (r & 7)) << 4)));
+    if (r < live_rows) *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(r) * kHidden + ch * 8) = u;
+  }
+  __syncwarp();
 }
 
-template <int T>
+// TRACE (developer path, JPDVT_ATTN_TRACE=1): lane 0 of the MMA warp and of two softmax warps of CTA 0 log clock64() at the
+// pipeline events of the first units into `trace` [role][unit][event]
+constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: MMA warp, softmax warp 0, softmax warp 3, TMA warp
+
+template <int T, bool TRACE>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int num_units) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int num_units,
+                    long long* __restrict__ trace) {
   using Cfg = TcCfg<T>;
+  auto mark = [&](int role, int it, int ev) {
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < kTraceUnits && role >= 0)
+        trace[(role * kTraceUnits + it) * kTraceEvents + ev] = clock64();
+    }
+  };
   extern __shared__ uint8_t att_tc_smem[];
   uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
@@ -151,6 +258,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   uint64_t* o_full = bars + 6;         // [2] MMA: O tile t is in TMEM
   uint64_t* epi_done = bars + 8;       // softmax warps: every TMEM read of the unit is done (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kXchOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -166,7 +274,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
-                 sP = smem_u32(smem + Cfg::kOffP);
+                 sP = smem_u32(smem + Cfg::kOffP), sP1 = smem_u32(smem + Cfg::kOffP1);
   constexpr int kLast = Cfg::kTiles - 1;
 
   if (warp == 4) {
@@ -176,11 +284,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
         const int b = unit / kHeads, h = unit - b * kHeads;
         const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        mark(3, it, 0);
         if (it > 0) mbar_wait(&s_full[kLast], prev);          // every score MMA of the previous unit has read Q, K
+        mark(3, it, 1);
         mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
         tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        mark(3, it, 2);
         if (it > 0) mbar_wait(&o_full[kLast], prev);          // ... and every P V MMA has read V
+        mark(3, it, 3);
         mbar_expect_tx(v_full, Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
       }
@@ -191,38 +303,70 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);   // B = V, MN-major (keys are the strided index)
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), p_lo = desc_lo_k(sP), v_lo = desc_lo_mn(sV);
+      const uint32_t p1_lo = Cfg::kSplit ? desc_lo_k(sP1) : p_lo;
       int it = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
         const uint32_t ph = static_cast<uint32_t>(it & 1);
-        const int q = Cfg::kCompact ? (unit & 3) : 0;
+        mark(0, it, 0);
         mbar_wait(qk_full, ph);
+        mark(0, it, 1);
         if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O of the previous unit has left TMEM
+        mark(0, it, 2);
         tc_fence_after();
-        auto issue_s = [&](int row0) {
+        auto issue_o = [&](uint32_t d_col, uint32_t pa_lo, uint32_t blk_words) {   // blk_words = P block stride / 16 bytes
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k)
-            umma_bf16(tmem_base, umma_desc_k_sw128(sQ + row0 * 128 + k * 32), umma_desc_k_sw128(sK + k * 32), idesc_s, k != 0);
+          for (int j = 0; j < T / 16; ++j) {
+            const uint32_t a = pa_lo + (j >> 2) * blk_words + (j & 3) * 2, bq = v_lo + j * 128;
+            if (j == 0) umma_lohi<false>(tmem_base + d_col, a, bq, idesc_o);
+            else umma_lohi<true>(tmem_base + d_col, a, bq, idesc_o);
+          }
         };
-        auto issue_o = [&](uint32_t d_col, uint32_t p_addr, uint32_t blk_stride) {
 #pragma unroll
-          for (int j = 0; j < T / 16; ++j)
-            umma_bf16(tmem_base + d_col, umma_desc_k_sw128(p_addr + (j >> 2) * blk_stride + (j & 3) * 32),
-                      umma_desc_mn_sw128(sV + j * 2048), idesc_o, j != 0);
-        };
-        issue_s(0);
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
+        }
         umma_commit(&s_full[0]);
+        mark(0, it, 3);
         mbar_wait(&p_full[0], ph);                            // softmax has consumed S and written P0
-        mbar_wait(v_full, ph);
+        mark(0, it, 4);
         tc_fence_after();
-        issue_o(T, sP, 16384);
-        umma_commit(&o_full[0]);
-        if constexpr (Cfg::kTiles == 2) {
-          issue_s(Cfg::kCompact ? 128 - 32 * q : 128);
+        if constexpr (Cfg::kTiles == 2) {                       // remainder scores first: the softmax warps wait for them
+          if constexpr (Cfg::kSplit) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                       // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
+              constexpr uint32_t idesc_a = umma_idesc_bf16(128, 32), idesc_b = umma_idesc_bf16(128, T - 96);
+              const uint32_t idesc_j = j < 3 ? idesc_a : idesc_b;
+              const uint32_t a0 = q_lo + (128 - 32 * j) * 8, b0 = k_lo + 32 * j * 8;
+#pragma unroll
+              for (int k = 0; k < kHeadDim / 16; ++k) {
+                if (k == 0) umma_lohi<false>(tmem_base + 32 * j, a0, b0, idesc_j);
+                else umma_lohi<true>(tmem_base + 32 * j, a0 + 2 * k, b0 + 2 * k, idesc_j);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kHeadDim / 16; ++k) {
+              if (k == 0) umma_lohi<false>(tmem_base, q_lo + 128 * 8, k_lo, idesc_s);
+              else umma_lohi<true>(tmem_base, q_lo + 128 * 8 + 2 * k, k_lo + 2 * k, idesc_s);
+            }
+          }
           umma_commit(&s_full[1]);
+        }
+        mark(0, it, 5);
+        mbar_wait(v_full, ph);
+        mark(0, it, 6);
+        issue_o(T, p_lo, 1024);
+        umma_commit(&o_full[0]);
+        mark(0, it, 7);
+        if constexpr (Cfg::kTiles == 2) {
           mbar_wait(&p_full[1], ph);
+          mark(0, it, 8);
           tc_fence_after();
-          issue_o(0, sP, Cfg::kCompact ? 2048 : 16384);
+          issue_o(0, p1_lo, Cfg::kSplit ? 128 : 1024);
           umma_commit(&o_full[1]);
+          mark(0, it, 9);
         }
       }
     }
@@ -235,49 +379,65 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const uint32_t ph = static_cast<uint32_t>(it & 1);
       const int b = unit / kHeads, h = unit - b * kHeads;
-      const int q = Cfg::kCompact ? (unit & 3) : 0;
       __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+      const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
       // ---- tile 0
+      mark(role, it, 0);
       mbar_wait(&s_full[0], ph);
+      mark(role, it, 1);
       tc_fence_after();
       const float sum0 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true);
       fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[0]);
+      mark(role, it, 2);
       // ---- tile 1 (the 16- or 128-row remainder)
       float sum1 = 1.f;
-      bool mine1 = false;                                     // does this WARP take part in tile 1
-      int row1 = 0;                                           // query row of this thread in tile 1
       if constexpr (Cfg::kTiles == 2) {
-        mine1 = Cfg::kCompact ? (warp == q) : (warp * 32 < Cfg::kRem);
-        row1 = Cfg::kCompact ? 128 + lane : 128 + r_tile;
-        if (mine1) {
-          mbar_wait(&s_full[1], ph);
-          mbar_wait(&o_full[0], ph);                          // P1 reuses P0's shared memory: the O0 MMAs must have read it
-          tc_fence_after();
-          // compact P1: the 2 KB blocks of successive key groups abut, so only live rows may be written
-          sum1 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, Cfg::kCompact ? 2048 : 16384, r_tile & 7, row1 < T);
-          fence_proxy_async_smem();
-          tc_fence_before();
+        mbar_wait(&s_full[1], ph);
+        mark(role, it, 3);
+        if constexpr (!Cfg::kSplit) mbar_wait(&o_full[0], ph); // full second tile: P1 reuses P0, the O0 MMAs must have read it
+        mark(role, it, 4);
+        tc_fence_after();
+        if constexpr (Cfg::kSplit) {
+          if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane);
+          else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane);
+        } else {
+          sum1 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[1]);
+        fence_proxy_async_smem();
       }
-      // ---- outputs
+      // ---- outputs.  O0 is pulled into registers BEFORE the remainder's P tile is handed to the MMA warp: a tcgen05.ld
+      // issued while the O1 MMAs run waits for them, so the other order parks every softmax warp behind the tensor pipe
+      const uint32_t o_stage = smem_u32(smem + Cfg::kOffStage) + static_cast<uint32_t>(warp) * 4096u;
+      uint32_t oa[32], ob[32];
       mbar_wait(&o_full[0], ph);
       tc_fence_after();
-      store_o_row(t_lane + T, 1.0f / sum0, obase + static_cast<long long>(r_tile) * kHidden, r_tile < T);
+      load_o_row(t_lane + T, oa, ob);
       if constexpr (Cfg::kTiles == 2) {
-        if (mine1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[1]);
+        mark(role, it, 5);
+      }
+      store_o_rows(oa, ob, 1.0f / sum0, o_stage, obase + static_cast<long long>(warp * 32) * kHidden,
+                   T - warp * 32 < 32 ? T - warp * 32 : 32, lane);
+      if constexpr (Cfg::kTiles == 2) {
+        if (!Cfg::kSplit || warp == 0) {                       // split remainder: O1 rows 128..143 sit in lanes 0..15 of quadrant 0
+          mark(role, it, 6);
           mbar_wait(&o_full[1], ph);
+          mark(role, it, 7);
           tc_fence_after();
-          store_o_row(t_lane, 1.0f / sum1, obase + static_cast<long long>(row1) * kHidden, row1 < T);
+          load_o_row(t_lane, oa, ob);
+          store_o_rows(oa, ob, 1.0f / sum1, o_stage, obase + static_cast<long long>(Cfg::kSplit ? 128 : 128 + warp * 32) * kHidden,
+                       Cfg::kSplit ? 16 : 32, lane);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(epi_done);
+      mark(role, it, 8);
     }
   }
 
@@ -293,12 +453,17 @@ template <int T>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStream_t stream) {
   using Cfg = TcCfg<T>;
   static bool configured = false;
-  auto kern = attention_tc_kernel<T>;
+  static int trace_mode = -1;
+  if (trace_mode < 0) { const char* e = getenv("JPDVT_ATTN_TRACE"); trace_mode = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  auto kern = attention_tc_kernel<T, false>;
+  auto kern_trace = attention_tc_kernel<T, true>;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
-      return set_error(kErrCuda, "attention_tc: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
-                       cudaGetErrorString(cudaGetLastError()));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (auto k : {kern, kern_trace}) {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+        return set_error(kErrCuda, "attention_tc: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                         cudaGetErrorString(cudaGetLastError()));
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     configured = true;
   }
   CUtensorMap tm;
@@ -310,7 +475,32 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStrea
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = batch * kHeads;
   const int slots = sms * Cfg::kCtasPerSm;
-  kern<<<units < slots ? units : slots, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, units);
+  const int grid = units < slots ? units : slots;
+  if (trace_mode) {   // developer path: synchronous, prints the event clocks of CTA 0 (relative to its first event)
+    constexpr int n = kTraceRoles * kTraceUnits * kTraceEvents;
+    long long* d = nullptr;
+    cudaMalloc(&d, n * sizeof(long long));
+    cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
+    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, units, d);
+    long long h[n];
+    cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d);
+    long long t0 = 0;
+    for (int i = 0; i < n; ++i) if (h[i] != 0 && (t0 == 0 || h[i] < t0)) t0 = h[i];
+    const char* names[kTraceRoles] = {"mma  ", "sm_w0", "sm_w3", "tma  "};
+    for (int r = 0; r < kTraceRoles; ++r)
+      for (int u = 0; u < kTraceUnits; ++u) {
+        fprintf(stderr, "trace %s unit %d:", names[r], u);
+        for (int e = 0; e < kTraceEvents; ++e) {
+          const long long v = h[(r * kTraceUnits + u) * kTraceEvents + e];
+          fprintf(stderr, " %7lld", v ? v - t0 : -1LL);
+        }
+        fprintf(stderr, "\n");
+      }
+    return check_launch("attention_tc_kernel<trace>");
+  }
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, units, nullptr);
   return check_launch("attention_tc_kernel");
 }
 
