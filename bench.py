@@ -459,7 +459,7 @@ def run_train(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "image_size": S, "grid": G, "tokens": T,
                        "optimizer": "AdamW lr 1e-4 wd 0 + EMA 0.9999 (fused, fp32 state)", "params": n_params,
-                       "allreduce": "NCCL SUM per backward stage, overlapped with the remaining backward" if world > 1 else "none (1 GPU)",
+                       "allreduce": ("NCCL SUM per backward stage, overlapped with the remaining backward" if trainer.allreduce == "stage" else "one NCCL SUM of the flat fp32 gradient buffer (523 MB) after the backward") if world > 1 else "none (1 GPU)",
                        "l2": "activations per launch exceed L2; no flush needed"},
             "e2e": {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
