@@ -72,6 +72,15 @@ int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* 
  * epilogue (coalesced read-modify-write, overlapped with the next tile's MMAs).  n must be a multiple of 128. */
 int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
                                   int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream);
+/* jpdvt_gemm_bias_gate_residual followed, in the same kernel, by the LayerNorm-modulate that consumes the updated rows:
+ * x[row] += gate[row / tokens] * (a . w^T + bias);  xn[row] = LN(x[row]) * (1 + ln_scale[row / tokens]) + ln_shift[...]
+ * i.e. one whole `x = x + gate * branch(...)` line of DiTBlock.forward plus the `modulate(norm(x), shift, scale)` that opens
+ * the next line (models.py:19-20,120-121).  n must be 768; each CTA pair owns whole 256-row blocks, so the rows it
+ * normalises are the ones it has just written (read back from L2, not HBM).  ln_shift/ln_scale: [n_cond, 768] fp32 with
+ * row stride mod_stride (0 = one row for every sample). */
+int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                     int64_t gate_stride, float* x, const float* ln_shift, const float* ln_scale,
+                                     int64_t mod_stride, jpdvt_bf16* xn, int64_t m, int n, int k, int tokens, void* stream);
 /* x = cols . w_patch^T + bias + pos_embed[row % tokens] + x_t[row] . w_in_t   (PatchEmbed conv as GEMM + time_emb_in +
  * pos_embed, models.py:280-281).  cols = jpdvt_patchify(img); bias = x_embedder.proj.bias + time_emb_in.bias;
  * w_in_t = time_emb_in.weight^T as [8,768] fp32; pos = pos_embed [tokens,768] fp32. */

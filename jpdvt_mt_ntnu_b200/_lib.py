@@ -73,6 +73,7 @@ PROTOTYPES = {
     "jpdvt_gemm_bias_gelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_bias_gate": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_bias_gate_residual": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_gemm_bias_gate_residual_ln": [P, P, P, P, c_int64, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
     "jpdvt_attention_fwd": [P, P, P, c_int, c_int, P],

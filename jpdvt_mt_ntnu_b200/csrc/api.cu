@@ -90,10 +90,29 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws->attn);
   __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+  // JPDVT_LN_FUSED=1 fuses every LayerNorm-modulate but the first into the GEMM that produces its input rows (the
+  // EPI_RESID_LN_F32 epilogue).  Measured slower at M = 36,864 (proj 138 us vs 70 + 27, fc2 205 us vs 139 + 27: the eight
+  // epilogue warps are latency-bound on the row read-back), so the default keeps the separate, HBM-rate LN launches.
+  static int ln_fused = -1;
+  if (ln_fused < 0) { const char* e = getenv("JPDVT_LN_FUSED"); ln_fused = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  auto resid_gemm = [&](bfp a, long long lda, bfp wt, const float* bias, int k, const float* gate, const float* shift,
+                        const float* scale) -> int {
+    GemmParams p{};
+    p.M = static_cast<int>(M); p.N = kHidden; p.K = k; p.tokens = T;
+    p.bias = bias; p.out = ws->x; p.ldo = kHidden; p.gate = gate; p.gate_stride = mod_stride;
+    if (ln_fused) {
+      p.ln_out = xn; p.ln_shift = shift; p.ln_scale = scale; p.ln_stride = mod_stride;
+      return launch_gemm(EPI_RESID_LN_F32, a, lda, wt, lda, p, st);
+    }
+    int r = launch_gemm(EPI_RESID_F32, a, lda, wt, lda, p, st);
+    if (r != kOk) return r;
+    return launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, shift, scale, mod_stride, xn, M, T, st);
+  };
+  JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, ws->mod, ws->mod + kHidden, mod_stride, xn, M, T, st));
   for (int i = 0; i < depth; ++i) {
     const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
-    // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120)
-    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod, mod + kHidden, mod_stride, xn, M, T, st));
+    const float* nxt = mod + 6 * kHidden;                                   // next block's (or the final layer's) shift, scale
+    // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120); xn holds modulate(LN(x), ...)
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
@@ -101,33 +120,22 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
       JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden, kHidden, p, st));
     }
     JP_TRY(launch_attention(qkv, att, nullptr, batch, T, st));
-    {   // the gated residual update is the GEMM epilogue: fp32 read-modify-write of x under the next tile's MMAs
-      GemmParams p{};
-      p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
-      p.bias = w->b_proj + static_cast<long long>(i) * kHidden; p.out = ws->x; p.ldo = kHidden;
-      p.gate = mod + 2 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_RESID_F32, att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, kHidden, p, st));
-    }
+    // the gated residual update AND the LayerNorm-modulate of the MLP branch are the proj GEMM's epilogue
+    JP_TRY(resid_gemm(att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden,
+                      w->b_proj + static_cast<long long>(i) * kHidden, kHidden, mod + 2 * kHidden, mod + 3 * kHidden, mod + 4 * kHidden));
     // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
-    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod + 3 * kHidden, mod + 4 * kHidden, mod_stride, xn, M, T, st));
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
       p.bias = w->b_fc1 + static_cast<long long>(i) * 4 * kHidden; p.out = hid; p.ldo = 4 * kHidden;
       JP_TRY(launch_gemm(EPI_BIAS_GELU_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden, kHidden, p, st));
     }
-    {
-      GemmParams p{};
-      p.M = static_cast<int>(M); p.N = kHidden; p.K = 4 * kHidden; p.tokens = T;
-      p.bias = w->b_fc2 + static_cast<long long>(i) * kHidden; p.out = ws->x; p.ldo = kHidden;
-      p.gate = mod + 5 * kHidden; p.gate_stride = mod_stride;
-      JP_TRY(launch_gemm(EPI_RESID_F32, hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden, p, st));
-    }
+    // ... and fc2's epilogue also produces the next block's (or the final layer's) modulate(LN(x), shift, scale)
+    JP_TRY(resid_gemm(hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden,
+                      w->b_fc2 + static_cast<long long>(i) * kHidden, 4 * kHidden, mod + 5 * kHidden, nxt, nxt + kHidden));
   }
   // final layer + position head                                            (models.py:287-290)
   {
-    const float* mod = ws->mod + static_cast<long long>(depth) * 6 * kHidden;   // shift, scale
-    JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod, mod + kHidden, mod_stride, xn, M, T, st));
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
@@ -219,6 +227,19 @@ int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, cons
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
   p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
   return launch_gemm(EPI_RESID_F32, BF(a), k, BF(w), k, p, ST(stream));
+}
+int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                     int64_t gate_stride, float* x, const float* ln_shift, const float* ln_scale,
+                                     int64_t mod_stride, jpdvt_bf16* xn, int64_t m, int n, int k, int tokens, void* stream) {
+  if (m == 0) return kOk;
+  if (!a || !w || !bias || !gate || !x || !ln_shift || !ln_scale || !xn) return set_error(kErrBadArg, "gemm_bias_gate_residual_ln: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_bias_gate_residual_ln: tokens must be positive");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
+  p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
+  p.ln_out = BFM(xn); p.ln_shift = ln_shift; p.ln_scale = ln_scale; p.ln_stride = mod_stride;
+  return launch_gemm(EPI_RESID_LN_F32, BF(a), k, BF(w), k, p, ST(stream));
 }
 int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
                            const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {

@@ -35,6 +35,8 @@ enum Epilogue : int {
   EPI_DGELU_BF16 = 7,       // out_bf16 = acc * aux_bf16[row, col], aux = gelu_tanh'(fc1 pre-activation) kept by the forward
   EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
   EPI_RESID_F32 = 9,        // out_f32 += gate[row / tokens] * (acc + bias): the adaLN-Zero gated residual update, in place, fp32
+  EPI_RESID_LN_F32 = 10,    // EPI_RESID_F32 (N == 768) + the NEXT LayerNorm-modulate of the updated rows:
+                            // ln_out_bf16 = LN(out_f32) * (1 + ln_scale[sample]) + ln_shift[sample]
 };
 
 struct GemmParams {
@@ -54,6 +56,11 @@ struct GemmParams {
   const __nv_bfloat16* aux;   // [M, N] bf16 (EPI_DGELU_BF16: fc1 pre-activations), leading dimension ldo
   // EPI_WGRAD_F32: M = contraction length (token rows), N = output columns (in_features), wg_rows = output rows
   int wg_rows, split, split_len;
+  // EPI_RESID_LN_F32: the LayerNorm-modulate that consumes the updated residual rows (models.py:120-121, 19-20)
+  __nv_bfloat16* ln_out;      // [M, N] bf16
+  const float* ln_shift;      // sample b reads ln_shift + b * ln_stride, [N]
+  const float* ln_scale;
+  long long ln_stride;
 };
 
 // dW[wg_rows, n_cols] (fp32) = P[M, wg_rows]^T . Q[M, n_cols]   (both bf16 row-major); `partial` is scratch of

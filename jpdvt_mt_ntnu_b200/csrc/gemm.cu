@@ -38,12 +38,13 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColsPerWarp = BN / (EW / 4);      // EW/4 warps share a TMEM lane quadrant and split the columns
   static constexpr int kVecWarpBytes = 3 * kColsPerWarp * 4;   // per warp and tile: bias slice + gate slices of <= 2 samples
-  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kVecWarpBytes) + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  static constexpr int kLnStatsBytes = 2 * 2 * BM * 8;    // EPI_RESID_LN_F32: (mean, M2) per row, per column half, 2 M-block parities
+  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kVecWarpBytes) + kLnStatsBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kVecWarpBytes) + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kVecWarpBytes) + kLnStatsBytes + kBarBytes + 1024;
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------------
@@ -192,7 +193,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
   uint8_t* bias_buf = stage_buf + EW * kStageWarpBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * Cfg::kVecWarpBytes);
+  float2* ln_stats = reinterpret_cast<float2*>(bias_buf + EW * Cfg::kVecWarpBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * Cfg::kVecWarpBytes + Cfg::kLnStatsBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
@@ -210,6 +212,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int num_tiles = WG ? tiles_mn * p.split : tiles_mn;
   const int num_kb = WG ? p.split_len / BK : p.K / BK;
   const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
+  constexpr bool kLN = (EPI == EPI_RESID_LN_F32);           // residual update + the next LayerNorm of the same rows
+  constexpr bool kResid = (EPI == EPI_RESID_F32) || kLN;
+  // s-th work item of this CTA group.  Normally tiles are dealt round robin; the LayerNorm-fused epilogue needs whole rows,
+  // so there a group owns M-blocks and walks the N tiles of each one in turn.
+  auto tile_at = [&](int s, int& split_idx, int& m_blk, int& n_blk) -> bool {
+    if constexpr (kLN) {
+      split_idx = 0;
+      m_blk = group + (s / num_n) * num_groups;
+      n_blk = s % num_n;
+      return m_blk < num_m;
+    } else {
+      const int tile = group + s * num_groups;
+      if (tile >= num_tiles) return false;
+      split_idx = tile / tiles_mn;
+      const int rem = tile - split_idx * tiles_mn;
+      m_blk = rem / num_n;
+      n_blk = rem % num_n;
+      return true;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -231,9 +253,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ------------------------------------------------------------------ TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int split_idx = tile / tiles_mn, rem = tile - split_idx * tiles_mn;
-        const int m_blk = rem / num_n, n_blk = rem % num_n;
+      for (int s = 0;; ++s) {
+        int split_idx, m_blk, n_blk;
+        if (!tile_at(s, split_idx, m_blk, n_blk)) break;
         const int row_a = (m_blk * CS + static_cast<int>(rank)) * BM;
         const int row_b = n_blk * BN + static_cast<int>(rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -272,7 +294,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN, WG ? 1 : 0, WG ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
+      for (int s = 0;; ++s) {
+        int split_idx, m_blk, n_blk;
+        if (!tile_at(s, split_idx, m_blk, n_blk)) break;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -311,9 +335,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
     const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
-    for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int split_idx = tile / tiles_mn, rem = tile - split_idx * tiles_mn;
-      const int m_blk = rem / num_n, n_blk = rem % num_n;
+    float ln_mean = 0.f, ln_m2 = 0.f;     // kLN: running (mean, sum of squared deviations) of this thread's row over its columns
+    int ln_cnt = 0;
+    for (int s = 0;; ++s) {
+      int split_idx, m_blk, n_blk;
+      if (!tile_at(s, split_idx, m_blk, n_blk)) break;
       const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;   // first row of this warp
       const int row = row0 + lane;
       const bool row_ok = row < out_rows;
@@ -324,7 +350,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // epilogue math never queues a global load behind the streaming residual prefetch
         for (int i = lane; i < kColsPerWarp / 4; i += 32)
           reinterpret_cast<float4*>(bias_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base) + i);
-        if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_GATE_BF16) {
+        if constexpr (kResid || EPI == EPI_GATE_BF16) {
           const int last = out_rows - 1;
           const int s_first = (row0 < last ? row0 : last) / p.tokens, s_last = (row0 + 31 < last ? row0 + 31 : last) / p.tokens;
           const float* ga = p.gate + static_cast<long long>(s_first) * p.gate_stride + n_blk * BN + col_base;
@@ -341,7 +367,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t gate_sm = smem_u32(gate_smem);
       const float* gate_gl = nullptr;
       const bool gate_staged = p.tokens >= 32;
-      if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_GATE_BF16) {
+      if constexpr (kResid || EPI == EPI_GATE_BF16) {
         const int last = out_rows - 1;
         const int s_first = (row0 < last ? row0 : last) / p.tokens;
         const int s_mine = row_ok ? row / p.tokens : s_first;
@@ -373,7 +399,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       };
       float4 xa[8], xb[8];
-      if constexpr (EPI == EPI_RESID_F32) {
+      if constexpr (kResid) {
         load_x(xa, 0);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -452,10 +478,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
           }
         }
-      } else if constexpr (EPI == EPI_RESID_F32) {
+      } else if constexpr (kResid) {
         // x[row, n] += gate[row / tokens, n] * (acc + bias[n])  -  fp32 read-modify-write of the residual stream
         constexpr int NC = kColsPerWarp / 32;
         const int sub = lane >> 3, ch = lane & 7;
+        if constexpr (kLN) {
+          if (n_blk == 0) { ln_mean = 0.f; ln_m2 = 0.f; ln_cnt = 0; }
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           float4 (&cur)[8] = (c & 1) ? xb : xa;
@@ -482,8 +511,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             float4 u = *reinterpret_cast<const float4*>(stage + rr * kStageRowBytes + 16 * ch);
             u.x += cur[it].x; u.y += cur[it].y; u.z += cur[it].z; u.w += cur[it].w;
             if (row0 + rr < out_rows) *reinterpret_cast<float4*>(ob + static_cast<long long>(row0 + rr) * p.ldo) = u;
+            if constexpr (kLN) *reinterpret_cast<float4*>(stage + rr * kStageRowBytes + 16 * ch) = u;   // updated values back
           }
           __syncwarp();
+          if constexpr (kLN) {
+            // row statistics in the row-per-thread view of the staging tile: exact two-pass moments of these 32 values,
+            // merged into the running (count, mean, M2) of the row (Chan et al.) - no E[x^2] - mean^2 cancellation
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = *reinterpret_cast<const float4*>(stage + lane * kStageRowBytes + 16 * j);
+              w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+            }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { s0 += w[j]; s1 += w[j + 1]; }
+            const float mc = (s0 + s1) * (1.0f / 32.0f);
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float d0 = w[j] - mc, d1 = w[j + 1] - mc;
+              q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+            }
+            const float delta = mc - ln_mean;
+            const float n_old = static_cast<float>(ln_cnt), n_new = n_old + 32.0f;
+            ln_mean = fmaf(delta, 32.0f / n_new, ln_mean);
+            ln_m2 += (q0 + q1) + delta * delta * (n_old * 32.0f / n_new);
+            ln_cnt += 32;
+            __syncwarp();
+          }
+        }
+        if constexpr (kLN) {
+          if (n_blk == num_n - 1) {
+            // ---- the M-block is complete: LayerNorm-modulate its rows (models.py:19-20,120-121) while they are still in L2
+            const int par = (s / num_n) & 1;
+            const int half = (warp - 2) >> 2;
+            ln_stats[(par * 2 + half) * BM + quad * 32 + lane] = make_float2(ln_mean, ln_m2);
+            __threadfence_block();                               // this warp's residual stores before the other warps' reads
+            asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");
+            const int wi = warp - 2;                             // 16 rows per warp
+            const float inv_n = 1.0f / static_cast<float>(p.N), half_n = 0.25f * static_cast<float>(p.N);
+            long long cur_sample = -1;
+            float4 sh[6], sc[6];
+#pragma unroll 1
+            for (int i = 0; i < BM / EW; ++i) {
+              const int rr = wi * (BM / EW) + i;
+              const int grow = (m_blk * CS + static_cast<int>(rank)) * BM + rr;
+              if (grow >= out_rows) break;
+              const float2 a = ln_stats[(par * 2 + 0) * BM + rr], b = ln_stats[(par * 2 + 1) * BM + rr];
+              const float dm = b.x - a.x;
+              const float mean = 0.5f * (a.x + b.x);
+              const float rstd = rsqrtf((a.y + b.y + dm * dm * half_n) * inv_n + 1e-6f);     // two halves of N/2 columns each
+              const long long sample = grow / p.tokens;
+              if (sample != cur_sample) {
+                cur_sample = sample;
+                const float4* s4 = reinterpret_cast<const float4*>(p.ln_shift + sample * p.ln_stride);
+                const float4* c4 = reinterpret_cast<const float4*>(p.ln_scale + sample * p.ln_stride);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { sh[j] = __ldg(s4 + lane + 32 * j); sc[j] = __ldg(c4 + lane + 32 * j); }
+              }
+              const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + static_cast<long long>(grow) * p.ldo);
+              float4 xv[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) xv[j] = __ldcg(xr + lane + 32 * j);
+              uint2* yr = reinterpret_cast<uint2*>(p.ln_out + static_cast<long long>(grow) * p.ldo);
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                uint2 o;
+                o.x = pack_bf16(fmaf((xv[j].x - mean) * rstd, 1.0f + sc[j].x, sh[j].x), fmaf((xv[j].y - mean) * rstd, 1.0f + sc[j].y, sh[j].y));
+                o.y = pack_bf16(fmaf((xv[j].z - mean) * rstd, 1.0f + sc[j].z, sh[j].z), fmaf((xv[j].w - mean) * rstd, 1.0f + sc[j].w, sh[j].w));
+                yr[lane + 32 * j] = o;
+              }
+            }
+          }
         }
       } else {
         // fp32 outputs: EPI_BIAS_F32, EPI_PATCH_EMBED_F32, EPI_WGRAD_F32
@@ -662,8 +762,13 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   const int bn = (epi == EPI_HEAD) ? 64 : ((p.N % 256 == 0) ? 256 : 128);
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
-  if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32 || epi == EPI_RESID_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
-  if (epi == EPI_RESID_F32 && p.gate == nullptr) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate");
+  if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32 || epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
+  if ((epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.gate == nullptr) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate");
+  if (epi == EPI_RESID_LN_F32) {
+    if (p.N != kHidden || p.ldo != kHidden) return set_error(kErrBadArg, "gemm: the LayerNorm-fused epilogue needs N == ldo == %d", kHidden);
+    if (!p.ln_out || !p.ln_shift || !p.ln_scale) return set_error(kErrBadArg, "gemm: LayerNorm-fused epilogue: null pointer");
+    return launch_cfg<256, EPI_RESID_LN_F32, 8>(a, lda, w, ldw, p, stream);     // two warps per lane quadrant split the columns
+  }
   if (epi == EPI_DGELU_BF16 && p.aux == nullptr) return set_error(kErrBadArg, "gemm: dgelu epilogue needs the pre-activations");
 #define JP_CASE(E)                                                             \
   case E:                                                                      \

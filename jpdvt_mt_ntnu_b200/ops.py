@@ -107,6 +107,26 @@ def gemm_bias_gate_residual(x, a, w, bias, gate, tokens: int) -> torch.Tensor:
     return x
 
 
+def gemm_bias_gate_residual_ln(x, a, w, bias, gate, shift, scale, tokens: int):
+    """x += gate[row // tokens] * (a @ w.T + bias) in place (fp32 [M,768]), then xn = LN(x) * (1 + scale) + shift in the same
+    kernel; returns (x, xn bf16 [M,768]).  gate / shift / scale: [n_cond,768] with n_cond == rows/tokens or 1."""
+    lib = _lib_dev()
+    a, w = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w")
+    bias, gate = _need(bias, torch.float32, "bias"), _need(gate, torch.float32, "gate")
+    shift, scale = _need(shift, torch.float32, "shift"), _need(scale, torch.float32, "scale")
+    m, k = a.shape
+    n = w.shape[0]
+    if x.dtype != torch.float32 or not x.is_contiguous() or tuple(x.shape) != (m, n) or not x.is_cuda:
+        raise _lib.JpdvtError("gemm_bias_gate_residual_ln: x must be a contiguous fp32 CUDA tensor of shape [M, N]")
+    if shift.shape != scale.shape or gate.shape[0] != shift.shape[0]:
+        raise _lib.JpdvtError("gemm_bias_gate_residual_ln: gate / shift / scale must have the same number of conditioning rows")
+    g_stride = 0 if gate.shape[0] == 1 else n
+    xn = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_gemm_bias_gate_residual_ln(ptr(a), ptr(w), ptr(bias), ptr(gate), g_stride, ptr(x), ptr(shift), ptr(scale),
+                                               g_stride, ptr(xn), m, n, k, tokens, stream_ptr()), "gemm_bias_gate_residual_ln")
+    return x, xn
+
+
 def patchify(img: torch.Tensor) -> torch.Tensor:
     lib = _lib_dev()
     img = _need(img, torch.float32, "img")

@@ -111,7 +111,8 @@ def test_ln_modulate(ops, rows, T, ncond):
     assert rel_l2(got2, ref2) < BF16_TOL
 
 
-@pytest.mark.parametrize("B,T", [(2, 144), (3, 9), (2, 256), (2, 324), (1, 36), (5, 64), (2, 100), (1, 1), (1, 17)])
+@pytest.mark.parametrize("B,T", [(2, 144), (3, 9), (2, 256), (2, 324), (1, 36), (5, 64), (2, 100), (1, 1), (1, 17),
+                                 (1, 144), (7, 144), (31, 144), (1, 256), (5, 256)])   # T in {144, 256}: tcgen05 kernel
 def test_attention(ops, B, T):
     torch.manual_seed(T)
     qkv = (torch.randn(B * T, 2304, device="cuda") * 1.5).bfloat16()
@@ -214,3 +215,26 @@ def test_assignment_perfect_latents_round_trip(ops):
         assert np.array_equal(pred.cpu().numpy(), perms)
         ok, matches = assignment.accuracy(pred, torch.from_numpy(perms))
         assert bool(ok.all()) and int(matches.sum()) == B * G * G
+
+
+@pytest.mark.parametrize("m,k,T", [(432, 768, 144), (1000, 3072, 100), (36864, 768, 144), (300, 768, 9), (256, 768, 256), (77, 3072, 77)])
+def test_gemm_residual_layernorm_fused(ops, m, k, T):
+    """One `x = x + gate * branch(...)` line plus the modulate(LN(x)) that opens the next one, in one kernel
+    (models.py:19-20,120-121): x against fp32 torch on the same bf16 operands, xn within bf16 rounding."""
+    torch.manual_seed(m + k)
+    n = 768
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    ncond = (m + T - 1) // T
+    for nc in (ncond, 1):
+        gate, shift, scale = (torch.randn(nc, n, device="cuda") * 0.5 for _ in range(3))
+        idx = torch.arange(m, device="cuda") // T if nc > 1 else torch.zeros(m, dtype=torch.long, device="cuda")
+        x0 = torch.randn(m, n, device="cuda") * 2 + 0.7            # non-zero mean: exercises the merged-moment statistics
+        x = x0.clone()
+        x_out, xn = ops.gemm_bias_gate_residual_ln(x, a, w, bias, gate, shift, scale, T)
+        ref_x = x0 + gate[idx] * (a.float() @ w.float().t() + bias)
+        ref_xn = F.layer_norm(ref_x, (n,), eps=1e-6) * (1 + scale[idx]) + shift[idx]
+        assert x_out is x and rel_l2(x, ref_x) < F32_TOL
+        assert rel_l2(xn.float(), ref_xn) < BF16_TOL
+        assert (xn.float() - ref_xn).abs().max() < 0.05 * ref_xn.abs().max()

@@ -49,6 +49,8 @@ KERNELS = {
     "proj_bf16": (lambda: ops.gemm_bias_gate(att, w_proj, b_proj, gate, T), 2.0 * M * 768 * 768, "flop"),
     "fc2_resid": (lambda: ops.gemm_bias_gate_residual(x, hid, w_fc2, b_fc2, gate, T), 2.0 * M * 3072 * 768, "flop"),
     "proj_resid": (lambda: ops.gemm_bias_gate_residual(x, att, w_proj, b_proj, gate, T), 2.0 * M * 768 * 768, "flop"),
+    "fc2_resid_ln": (lambda: ops.gemm_bias_gate_residual_ln(x, hid, w_fc2, b_fc2, gate, shift, scale, T), 2.0 * M * 3072 * 768, "flop"),
+    "proj_resid_ln": (lambda: ops.gemm_bias_gate_residual_ln(x, att, w_proj, b_proj, gate, shift, scale, T), 2.0 * M * 768 * 768, "flop"),
     "attn": (lambda: ops.attention(qkv, B, T), 4.0 * B * 12 * T * T * 64, "flop"),
     "ln": (lambda: ops.ln_modulate(x, shift, scale, T), M * 768 * 6.0, "byte"),
     "ln_res": (lambda: ops.ln_modulate(x, shift, scale, T, delta=xn), M * 768 * 12.0, "byte"),
