@@ -142,6 +142,11 @@ int jpdvt_assign_greedy_l1(const float* latents, const float* canon, int batch, 
  * (inference_ddp.py:449-455).  src/dst [batch, channels, size, size] fp32, perm [batch, G*G] int32, keep [batch, G*G] u8. */
 int jpdvt_gather_pieces(const float* src, float* dst, const int32_t* perm, const uint8_t* keep_or_null, int batch,
                         int channels, int size, int grid, void* stream);
+/* Crop-gap erosion of the training loader (train_JPDVT.py:345-349): every piece of the G x G puzzle is centre-cropped from
+ * in_piece to out_piece pixels (offset `off` = torchvision CenterCrop's int(round((in - out) / 2))) and the crops are
+ * re-tiled.  src [batch, channels, G*in_piece, G*in_piece] -> dst [batch, channels, G*out_piece, G*out_piece], fp32. */
+int jpdvt_crop_pieces(const float* src, float* dst, int batch, int channels, int grid, int in_piece, int out_piece, int off,
+                      void* stream);
 /* matches[b] = #{i : pred[b,i] == truth[b,i]}, correct[b] = (matches[b] == n); totals (NULL or int64[3]) accumulates
  * (puzzles correct, pieces correct, puzzles) - the counters of inference_ddp.py:431-447 / :485-490. */
 int jpdvt_score_placements(const int32_t* pred, const int32_t* truth, int batch, int n, int32_t* correct, int32_t* matches,

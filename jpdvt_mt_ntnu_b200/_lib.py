@@ -88,6 +88,7 @@ PROTOTYPES = {
     "jpdvt_assign_greedy_l1": [P, P, c_int, c_int, c_int, c_double, P, P, P, P],
     "jpdvt_gather_pieces": [P, P, P, P, c_int, c_int, c_int, c_int, P],
     "jpdvt_score_placements": [P, P, c_int, c_int, P, P, P, P],
+    "jpdvt_crop_pieces": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "jpdvt_gemm_wgrad": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_dgelu": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],

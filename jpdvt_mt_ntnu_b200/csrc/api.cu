@@ -322,6 +322,12 @@ int jpdvt_gather_pieces(const float* src, float* dst, const int32_t* perm, const
   if (!src || !dst || !perm) return set_error(kErrBadArg, "gather_pieces: null pointer");
   return launch_gather_pieces(src, dst, perm, keep_or_null, batch, channels, size, grid, ST(stream));
 }
+int jpdvt_crop_pieces(const float* src, float* dst, int batch, int channels, int grid, int in_piece, int out_piece, int off,
+                      void* stream) {
+  if (batch == 0) return kOk;
+  if (!src || !dst) return set_error(kErrBadArg, "crop_pieces: null pointer");
+  return launch_crop_pieces(src, dst, batch, channels, grid, in_piece, out_piece, off, ST(stream));
+}
 int jpdvt_score_placements(const int32_t* pred, const int32_t* truth, int batch, int n, int32_t* correct, int32_t* matches,
                            int64_t* totals_or_null, void* stream) {
   if (batch == 0) return kOk;

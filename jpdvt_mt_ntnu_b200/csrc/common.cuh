@@ -85,6 +85,8 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const
 // puzzle.cu
 int launch_gather_pieces(const float* src, float* dst, const int* perm, const unsigned char* keep, int batch, int channels,
                          int size, int grid, cudaStream_t stream);
+int launch_crop_pieces(const float* src, float* dst, int batch, int channels, int grid, int in_piece, int out_piece, int off,
+                       cudaStream_t stream);
 int launch_score_placements(const int* pred, const int* truth, int batch, int n, int* correct, int* matches, long long* totals,
                             cudaStream_t stream);
 

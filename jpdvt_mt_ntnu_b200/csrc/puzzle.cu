@@ -56,6 +56,31 @@ int launch_gather_pieces(const float* src, float* dst, const int* perm, const un
   return check_launch("gather_pieces_kernel");
 }
 
+// Crop-gap erosion of the training loader (image_model/train_JPDVT.py:345-349): every piece of a G x G puzzle is centre-cropped
+// from in_piece to out_piece pixels and the crops are re-tiled, so neighbouring pieces no longer share a boundary:
+// dst[b, c, gy*out + y, gx*out + x] = src[b, c, gy*in + off + y, gx*in + off + x]   (off = torchvision CenterCrop's offset)
+__global__ void crop_pieces_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total, int grid, int in_piece,
+                                   int out_piece, int off) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int so = grid * out_piece, si = grid * in_piece;
+  const int X = static_cast<int>(idx % so);
+  const int Y = static_cast<int>((idx / so) % so);
+  const long long bc = idx / (static_cast<long long>(so) * so);
+  const int gy = Y / out_piece, y = Y - gy * out_piece, gx = X / out_piece, x = X - gx * out_piece;
+  dst[idx] = __ldg(src + (bc * si + gy * in_piece + off + y) * static_cast<long long>(si) + gx * in_piece + off + x);
+}
+
+int launch_crop_pieces(const float* src, float* dst, int batch, int channels, int grid, int in_piece, int out_piece, int off,
+                       cudaStream_t stream) {
+  if (batch <= 0) return kOk;
+  if (grid <= 0 || in_piece <= 0 || out_piece <= 0 || out_piece > in_piece || off < 0 || off + out_piece > in_piece)
+    return set_error(kErrBadArg, "crop_pieces: cannot crop %d-pixel pieces to %d at offset %d", in_piece, out_piece, off);
+  const long long total = static_cast<long long>(batch) * channels * grid * out_piece * grid * out_piece;
+  crop_pieces_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src, dst, total, grid, in_piece, out_piece, off);
+  return check_launch("crop_pieces_kernel");
+}
+
 // One warp per puzzle: matches[b] = #{i : pred[b,i] == truth[b,i]}, correct[b] = (matches[b] == n); totals[0..2] +=
 // (puzzles correct, pieces correct, puzzles) - the three counters the reference all-reduces (inference_ddp.py:485-490).
 __global__ void score_placements_kernel(const int* __restrict__ pred, const int* __restrict__ truth, int batch, int n,

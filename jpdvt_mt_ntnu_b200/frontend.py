@@ -17,7 +17,10 @@ from __future__ import annotations
 
 import csv
 import os
+import queue
+import threading
 import time
+from concurrent.futures import Future
 from dataclasses import dataclass
 from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -143,21 +146,25 @@ class PuzzleSolver:
 
     @torch.no_grad()
     def solve(self, images: torch.Tensor, indices=None, keep=None, step_noise: Optional[torch.Tensor] = None,
-              want_images: bool = False) -> SolveResult:
+              want_images: bool = False, prescrambled: bool = False) -> SolveResult:
         """images [B,3,S,S] fp32 in [-1,1] (host - pinned or not - or device).  indices [B,G*G] (default: drawn), keep
-        [B,G*G] 0/1 (default: drawn from `missing_per_puzzle`, None = nothing missing)."""
+        [B,G*G] 0/1 (default: drawn from `missing_per_puzzle`, None = nothing missing).  prescrambled=True: the images
+        ARE the puzzles (api/app.py:350-451 receives them that way); `indices` is then only the ground truth to score
+        against (required)."""
         B = images.shape[0]
         n = self.grid * self.grid
         if tuple(images.shape[1:]) != (3, self.size, self.size):
             raise ValueError(f"expected images [B,3,{self.size},{self.size}], got {tuple(images.shape)}")
         x = images.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         if indices is None:
+            if prescrambled:
+                raise ValueError("prescrambled puzzles need their scramble indices to be scored")
             indices = self.draw_indices(B)
-        if keep is None:
+        if keep is None and not prescrambled:
             keep = self.draw_missing(B)
         idx = torch.as_tensor(np.asarray(indices), dtype=torch.int32).reshape(B, n).to(self.device)
         keep_t = None if keep is None else torch.as_tensor(np.asarray(keep), dtype=torch.uint8).reshape(B, n).to(self.device)
-        scrambled = ops.gather_pieces(x, idx, self.grid, keep=keep_t)
+        scrambled = x if prescrambled else ops.gather_pieces(x, idx, self.grid, keep=keep_t)
         noise = self.noise_row.expand(B, -1, -1).contiguous()
         latents = self.diffusion.p_sample_loop(self.model.forward, scrambled, noise.shape, noise, clip_denoised=False,
                                                model_kwargs=None, progress=False, device=self.device, step_noise=step_noise)
@@ -212,3 +219,104 @@ def solve_files(solver: PuzzleSolver, paths: Sequence[str], csv_path: str, batch
     (gp, gm, gc), wall = parallel.reduce_stats(puzzles, pieces, count, time.time() - t_start, solver.device)
     return {"puzzles": gc, "puzzle_accuracy": gp / gc if gc else 0.0, "patch_accuracy": gm / (gc * n) if gc else 0.0,
             "wall_s": wall, "puzzles_per_s": gc / wall if wall > 0 else 0.0}
+
+
+# ----------------------------------------------------------------------------------------------- request micro-batching
+class MicroBatcher:
+    """Groups single-puzzle requests into batches for one PuzzleSolver: the serving path of
+    api/app.py:250-451 solves one upload per call; here concurrent callers `submit()` an image and get a Future, a worker
+    thread collects up to `max_batch` requests - or whatever arrived within `max_wait_ms` of the first - and runs them as
+    ONE `solver.solve` call.  Each Future resolves to the per-request fields the API returns (`metrics` / `details`,
+    app.py:335-345) plus the reconstructed image tensor.
+    """
+
+    def __init__(self, solver, max_batch: int = 64, max_wait_ms: float = 5.0):
+        self.solver, self.max_batch, self.max_wait = solver, int(max_batch), float(max_wait_ms) / 1000.0
+        self._q: "queue.Queue" = queue.Queue()
+        self._stop = threading.Event()
+        self.batches_run = 0
+        self._thread = threading.Thread(target=self._loop, name="jpdvt-microbatch", daemon=True)
+        self._thread.start()
+
+    def submit(self, image: torch.Tensor, indices=None, prescrambled: bool = False) -> Future:
+        """image [3,S,S] fp32 in [-1,1]; indices: optional scramble ground truth (required when prescrambled)."""
+        if self._stop.is_set():
+            raise RuntimeError("MicroBatcher is closed")
+        if prescrambled and indices is None:
+            raise ValueError("prescrambled puzzles need their scramble indices")
+        fut: Future = Future()
+        self._q.put((image, None if indices is None else np.asarray(indices, dtype=np.int32), bool(prescrambled), fut))
+        return fut
+
+    def close(self) -> None:
+        self._stop.set()
+        self._q.put(None)
+        self._thread.join()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _collect(self):
+        first = self._q.get()
+        if first is None:
+            return None
+        items, deadline = [first], time.monotonic() + self.max_wait
+        while len(items) < self.max_batch:
+            left = deadline - time.monotonic()
+            if left <= 0:
+                break
+            try:
+                nxt = self._q.get(timeout=left)
+            except queue.Empty:
+                break
+            if nxt is None:
+                self._q.put(None)           # leave the stop marker for the loop
+                break
+            items.append(nxt)
+        return items
+
+    def _run(self, items) -> None:
+        n = self.solver.grid * self.solver.grid
+        # one solve per kind: scrambling is a per-batch switch in PuzzleSolver.solve
+        for kind in (False, True):
+            group = [it for it in items if it[2] == kind]
+            if not group:
+                continue
+            try:
+                images = torch.stack([it[0] for it in group])
+                have = [it[1] is not None for it in group]
+                idx = None
+                if all(have):
+                    idx = np.stack([it[1] for it in group])
+                elif any(have):                               # draw the missing ones so the batch stays one call
+                    drawn = self.solver.draw_indices(len(group))
+                    idx = np.stack([it[1] if it[1] is not None else drawn[i] for i, it in enumerate(group)])
+                res = self.solver.solve(images, indices=idx, want_images=True, prescrambled=kind)
+                ok, matches = res.puzzle_correct.tolist(), res.patch_matches.tolist()
+                truth, pred = res.indices.tolist(), res.pred.tolist()
+                for i, it in enumerate(group):
+                    it[3].set_result({"puzzle_correct": int(ok[i]), "patch_matches": int(matches[i]), "total_patches": n,
+                                      "patch_accuracy": matches[i] / n, "indices": truth[i], "predicted_order": pred[i],
+                                      "solution_image": res.reconstructed[i], "scrambled_image": res.scrambled[i]})
+            except Exception as e:                            # the API answers every request, failed or not (app.py:346-348)
+                for it in group:
+                    if not it[3].done():
+                        it[3].set_exception(e)
+        self.batches_run += 1
+
+    def _loop(self) -> None:
+        while not self._stop.is_set():
+            items = self._collect()
+            if items is None:
+                break
+            self._run(items)
+        while True:                                            # fail whatever is still queued
+            try:
+                it = self._q.get_nowait()
+            except queue.Empty:
+                break
+            if it is not None and not it[3].done():
+                it[3].set_exception(RuntimeError("MicroBatcher closed"))

@@ -279,6 +279,23 @@ def gather_pieces(images: torch.Tensor, perm: torch.Tensor, grid: int, keep: Opt
     return out
 
 
+def crop_pieces(images: torch.Tensor, grid: int, out_piece: int) -> torch.Tensor:
+    """Crop-gap erosion (train_JPDVT.py:345-349): centre-crop every piece of the grid x grid puzzle to out_piece pixels and
+    re-tile.  images fp32 [B,C,S,S] with S % grid == 0 -> [B,C,grid*out_piece,grid*out_piece]."""
+    lib = _lib_dev()
+    images = _need(images, torch.float32, "images")
+    b, c, s, s2 = images.shape
+    if s != s2 or s % grid != 0:
+        raise _lib.JpdvtError(f"crop_pieces: {s}x{s2} images do not tile a {grid}x{grid} puzzle")
+    in_piece = s // grid
+    if not 0 < out_piece <= in_piece:
+        raise _lib.JpdvtError(f"crop_pieces: cannot crop {in_piece}-pixel pieces to {out_piece}")
+    off = int(round((in_piece - out_piece) / 2.0))            # torchvision.transforms.functional.center_crop
+    out = torch.empty(b, c, grid * out_piece, grid * out_piece, device=images.device, dtype=torch.float32)
+    check(lib.jpdvt_crop_pieces(ptr(images), ptr(out), b, c, grid, in_piece, out_piece, off, stream_ptr()), "crop_pieces")
+    return out
+
+
 def score_placements(pred: torch.Tensor, truth: torch.Tensor, totals: Optional[torch.Tensor] = None):
     """(correct int32 [B], matches int32 [B]) for pred/truth int32 [B,n] (inference_ddp.py:431-447); `totals` (int64 [3],
     optional) accumulates (puzzles correct, pieces correct, puzzles)."""

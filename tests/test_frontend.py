@@ -60,6 +60,60 @@ def test_solver_rejects_ill_formed_grid():
         fe.PuzzleSolver(m, 4)
 
 
+class _FakeSolver:
+    """Duck-typed PuzzleSolver for the micro-batcher's host logic: 'predicts' the truth for even-sum images."""
+    grid = 3
+
+    def __init__(self):
+        self.calls = []
+
+    def draw_indices(self, batch):
+        return np.stack([np.roll(np.arange(9), b + 1) for b in range(batch)]).astype(np.int32)
+
+    def solve(self, images, indices=None, want_images=False, prescrambled=False, **kw):
+        from jpdvt_mt_ntnu_b200.frontend import SolveResult
+        B = images.shape[0]
+        self.calls.append((B, prescrambled))
+        idx = torch.as_tensor(indices if indices is not None else self.draw_indices(B), dtype=torch.int32)
+        pred = idx.clone()
+        wrong = images.reshape(B, -1)[:, 0] < 0                 # requests flagged by a negative first pixel are mis-solved
+        pred[wrong] = pred[wrong].roll(1, dims=1)
+        eq = pred == idx
+        return SolveResult(indices=idx, pred=pred, order=pred.argsort(1).int(), puzzle_correct=eq.all(1).int(),
+                           patch_matches=eq.sum(1).int(), latents=torch.zeros(B, 1, 8), scrambled=images, reconstructed=images + 1)
+
+
+def test_microbatcher_groups_requests_and_routes_results():
+    import threading
+    from jpdvt_mt_ntnu_b200 import frontend as fe
+    fake = _FakeSolver()
+    with fe.MicroBatcher(fake, max_batch=8, max_wait_ms=200.0) as mb:
+        futs = {}
+        def client(i):
+            img = torch.full((3, 4, 4), float(i) if i % 3 else -1.0 - i)
+            futs[i] = mb.submit(img, indices=np.roll(np.arange(9), i))
+        threads = [threading.Thread(target=client, args=(i,)) for i in range(12)]
+        [t.start() for t in threads]; [t.join() for t in threads]
+        res = {i: f.result(timeout=30) for i, f in futs.items()}
+    assert sum(b for b, _ in fake.calls) == 12 and max(b for b, _ in fake.calls) <= 8 and len(fake.calls) < 12   # batched
+    for i, r in res.items():                                     # every caller gets ITS puzzle back
+        assert r["indices"] == np.roll(np.arange(9), i).tolist() and r["total_patches"] == 9
+        assert r["puzzle_correct"] == (1 if i % 3 else 0) and r["patch_accuracy"] == r["patch_matches"] / 9
+        assert float(r["solution_image"][0, 0, 0]) == (float(i) if i % 3 else -1.0 - i) + 1
+    # prescrambled requests need their indices, run as their own solve call, and errors reach the caller
+    with fe.MicroBatcher(fake, max_batch=4, max_wait_ms=20.0) as mb:
+        with pytest.raises(ValueError):
+            mb.submit(torch.zeros(3, 4, 4), prescrambled=True)
+        a = mb.submit(torch.ones(3, 4, 4), indices=np.arange(9), prescrambled=True)
+        b = mb.submit(torch.ones(3, 4, 4))
+        assert a.result(timeout=30)["puzzle_correct"] == 1 and b.result(timeout=30)["total_patches"] == 9
+        fake.solve = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("boom"))
+        with pytest.raises(RuntimeError):
+            mb.submit(torch.ones(3, 4, 4)).result(timeout=30)
+    with pytest.raises(RuntimeError):
+        mb.submit(torch.ones(3, 4, 4))                           # closed
+
+
 # ------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("size,grid,batch", [(192, 3, 5), (256, 4, 3), (288, 3, 2), (192, 4, 2), (90, 3, 2), (48, 3, 1)])
@@ -96,6 +150,21 @@ def test_gather_pieces_rejects_bad_arguments(cuda):
     with pytest.raises(JpdvtError):                    # wrong permutation shape
         ops.gather_pieces(img, torch.zeros(2, 9, dtype=torch.int32, device="cuda"), 5)
     assert ops.gather_pieces(img[:0], torch.zeros(0, 25, dtype=torch.int32, device="cuda"), 5).shape[0] == 0   # empty batch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,in_piece,out_piece", [(3, 96, 64), (4, 64, 48), (3, 33, 20), (2, 10, 10), (3, 7, 4)])
+def test_crop_pieces_matches_reference_erosion(cuda, grid, in_piece, out_piece):
+    """train_JPDVT.py:345-349: rearrange -> torchvision CenterCrop -> rearrange, bit-exact (pure data movement)."""
+    from einops import rearrange
+    from torchvision import transforms
+    from jpdvt_mt_ntnu_b200 import ops
+    g = torch.Generator().manual_seed(grid * in_piece)
+    x = torch.rand(3, 3, grid * in_piece, grid * in_piece, generator=g)
+    patchs = rearrange(x, "b c (p1 h1) (p2 w1)-> b c (p1 p2) h1 w1", p1=grid, p2=grid, h1=in_piece, w1=in_piece)
+    patchs = transforms.CenterCrop((out_piece, out_piece))(patchs)
+    want = rearrange(patchs, "b c (p1 p2) h1 w1-> b c (p1 h1) (p2 w1)", p1=grid, p2=grid, h1=out_piece, w1=out_piece)
+    assert torch.equal(ops.crop_pieces(x.cuda(), grid, out_piece).cpu(), want)
 
 
 @pytest.mark.gpu
@@ -178,3 +247,34 @@ def test_solve_files_csv_resume_and_masking(cuda, tmp_path):
     assert count == 7 and done == {f"im{i}.png" for i in range(7)}
     assert stats["puzzles"] == 7 and 0.0 <= stats["patch_accuracy"] <= 1.0       # resumed counters folded in
     assert fe.solve_files(solver, paths, csv_path, batch_size=4)["puzzles"] == 7  # nothing left to do: totals from the CSV
+
+
+@pytest.mark.gpu
+def test_microbatcher_and_prescrambled_on_device(cuda):
+    from jpdvt_mt_ntnu_b200 import frontend as fe, ops
+    from jpdvt_mt_ntnu_b200.models import DiT
+    m = DiT(input_size=96, depth=2, hidden_size=768, patch_size=16, num_heads=12)
+    m.load_state_dict(orc.seeded_state(m.state_dict(), seed=5))
+    m.cuda()
+    solver = fe.PuzzleSolver(m, 3, sampling_steps=4)
+    g = torch.Generator().manual_seed(2)
+    imgs = torch.rand(6, 3, 96, 96, generator=g) * 2 - 1
+    perms = np.stack([np.random.RandomState(i).permutation(9) for i in range(6)]).astype(np.int32)
+    # prescrambled: the images pass through untouched and are scored against the given truth
+    pre = ops.gather_pieces(imgs.cuda(), torch.from_numpy(perms).cuda(), 3)
+    torch.manual_seed(0)
+    r1 = solver.solve(pre, indices=perms, prescrambled=True, want_images=True)
+    torch.manual_seed(0)
+    r2 = solver.solve(imgs, indices=perms, want_images=True)
+    assert torch.equal(r1.scrambled, pre) and torch.equal(r2.scrambled, pre)
+    assert torch.equal(r1.pred, r2.pred) and torch.equal(r1.patch_matches, r2.patch_matches)      # same puzzles, same loop noise
+    with pytest.raises(ValueError):
+        solver.solve(pre, prescrambled=True)
+    with fe.MicroBatcher(solver, max_batch=4, max_wait_ms=50.0) as mb:
+        futs = [mb.submit(imgs[i], indices=perms[i]) for i in range(6)]
+        out = [f.result(timeout=120) for f in futs]
+    for i, r in enumerate(out):
+        assert r["indices"] == perms[i].tolist() and sorted(r["predicted_order"]) == list(range(9))
+        assert torch.equal(r["scrambled_image"], pre[i]) and tuple(r["solution_image"].shape) == (3, 96, 96)
+        assert r["patch_matches"] == int((np.asarray(r["predicted_order"]) == perms[i]).sum())
+    assert 2 <= mb.batches_run <= 6
