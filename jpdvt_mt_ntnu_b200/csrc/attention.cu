@@ -227,10 +227,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
-  if (lse2 == nullptr && attention_tc_supported(tokens)) {
+  if (attention_tc_supported(tokens)) {
     static int legacy = -1;            // JPDVT_ATTN_LEGACY=1 keeps the mma.sync kernel for every size (A/B timing knob)
     if (legacy < 0) { const char* e = getenv("JPDVT_ATTN_LEGACY"); legacy = (e != nullptr && e[0] == '1') ? 1 : 0; }
-    if (!legacy) return launch_attention_tc(qkv, out, batch, tokens, stream);
+    if (!legacy) return launch_attention_tc(qkv, out, lse2, batch, tokens, stream);
   }
   if (batch > 65535) return set_error(kErrBadArg, "attention: batch %d exceeds gridDim.y limit", batch);
   const int mt = (tokens + 15) / 16;        // 16-row query tiles

@@ -1,9 +1,9 @@
 // tcgen05 attention for the JPDVT piece tokens: softmax(Q K^T / 8) V per (sample, head) with both contractions on the
 // 5th-generation tensor cores and the scores / outputs living in TMEM.
 //
-// Replaces timm Attention.forward's F.scaled_dot_product_attention (image_model/models.py:108,120) for the inference
-// path, T <= 256 tokens and T % 16 == 0 (144 @192 px, 256 @256 px); the mma.sync kernel in attention.cu keeps the other
-// sizes and the training forward (which also wants the log-sum-exp).
+// Replaces timm Attention.forward's F.scaled_dot_product_attention (image_model/models.py:108,120) for T = 144 (192 px)
+// and T = 256 (256 px), inference and training forward (optionally writes the per-row log-sum-exp the backward reads);
+// the mma.sync kernel in attention.cu keeps the other sizes.
 //
 // One CTA works on one (sample, head) unit at a time, several units per CTA (persistent grid):
 //   warps 0-3 : softmax + output epilogue; warp w owns TMEM lanes [32w, 32w+32) = 32 query rows of a 128-row tile
@@ -102,7 +102,8 @@ struct TcCfg {
 // One softmax pass of the thread's S row (TMEM lane = row, columns [0,T)): exact row maximum, then
 // p = 2^((s - max) * log2(e) / 8) written as bf16 into the K-major swizzled P tile; returns sum(p) (fp32, unrounded p).
 template <int T>
-__device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row_addr, uint32_t blk_stride, int sw, bool store) {
+__device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row_addr, uint32_t blk_stride, int sw, bool store,
+                                                  float& ms_out) {
   constexpr float sl2 = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
   constexpr int kFull = T / 32, kTail = T % 32;              // kTail is 0 or 16
   // chunk c = columns [32c, 32c+32) (the last one may be 16 wide); the load of chunk c+1 is in flight while chunk c is
@@ -133,6 +134,7 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
   }
   load_chunk(ra, 0);                                          // second pass: its first chunk is in flight during the reduction
   const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+  ms_out = ms;
   float sum = 0.f;
   auto emit8 = [&](const uint32_t* r, int chunk) {            // 8 consecutive keys -> one 16-byte chunk of the P row
     float p[8];
@@ -161,7 +163,7 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
 // (row = lane, 2 KB per 64-key block).  Returns the full row sum.
 template <int NCJ>
 __device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_row_addr, int chunk0, int sw, float* xch, int warp,
-                                                  int lane) {
+                                                  int lane, float& ms_out) {
   constexpr float sl2 = 0.125f * 1.4426950408889634f;
   static_assert(NCJ == 32 || NCJ == 48, "remainder column split is 32/32/32/48");
   uint32_t sreg[48];
@@ -179,6 +181,7 @@ __device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_ro
   asm volatile("bar.sync 1, 128;" ::: "memory");
   const float mx = fmaxf(fmaxf(xch[l], xch[16 + l]), fmaxf(xch[32 + l], xch[48 + l]));
   const float ms = mx * sl2;
+  ms_out = ms;
   float sum = 0.f;
 #pragma unroll
   for (int g = 0; g < NCJ / 8; ++g) {
@@ -239,8 +242,8 @@ constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: M
 
 template <int T, bool TRACE>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int num_units,
-                    long long* __restrict__ trace) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                    int num_units, long long* __restrict__ trace) {
   using Cfg = TcCfg<T>;
   auto mark = [&](int role, int it, int ev) {
     if constexpr (TRACE) {
@@ -386,7 +389,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       mbar_wait(&s_full[0], ph);
       mark(role, it, 1);
       tc_fence_after();
-      const float sum0 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true);
+      float ms0, ms1 = 0.f;
+      const float sum0 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms0);
       fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's reads
       tc_fence_before();
       __syncwarp();
@@ -401,12 +405,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mark(role, it, 4);
         tc_fence_after();
         if constexpr (Cfg::kSplit) {
-          if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane);
-          else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane);
+          if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane, ms1);
+          else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane, ms1);
         } else {
-          sum1 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true);
+          sum1 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms1);
         }
         fence_proxy_async_smem();
+      }
+      if (lse2 != nullptr) {   // training: log2-domain log-sum-exp of the scaled scores, [B, 12, T] (read by the attention backward)
+        float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+        if (r_tile < T) lrow[r_tile] = ms0 + log2f(sum0);
+        if constexpr (Cfg::kTiles == 2) {
+          if constexpr (Cfg::kSplit) { if (warp == 0 && lane < 16) lrow[128 + lane] = ms1 + log2f(sum1); }
+          else if (128 + r_tile < T) lrow[128 + r_tile] = ms1 + log2f(sum1);
+        }
       }
       // ---- outputs.  O0 is pulled into registers BEFORE the remainder's P tile is handed to the MMA warp: a tcgen05.ld
       // issued while the O1 MMAs run waits for them, so the other order parks every softmax warp behind the tensor pipe
@@ -450,7 +462,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 }
 
 template <int T>
-int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStream_t stream) {
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = TcCfg<T>;
   static bool configured = false;
   static int trace_mode = -1;
@@ -481,7 +493,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStrea
     long long* d = nullptr;
     cudaMalloc(&d, n * sizeof(long long));
     cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
-    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, units, d);
+    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, d);
     long long h[n];
     cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -500,7 +512,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStrea
       }
     return check_launch("attention_tc_kernel<trace>");
   }
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, units, nullptr);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, nullptr);
   return check_launch("attention_tc_kernel");
 }
 
@@ -508,13 +520,13 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, cudaStrea
 
 bool attention_tc_supported(int tokens) { return tokens == 144 || tokens == 256; }
 
-int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream) {
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0) return kOk;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(kErrBadArg, "attention_tc: pointers must be 16-byte aligned");
   switch (tokens) {
-    case 144: return launch_tc<144>(qkv, out, batch, stream);
-    case 256: return launch_tc<256>(qkv, out, batch, stream);
+    case 144: return launch_tc<144>(qkv, out, lse2, batch, stream);
+    case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
   }
 }

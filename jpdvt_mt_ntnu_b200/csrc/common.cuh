@@ -35,6 +35,7 @@ enum Epilogue : int {
   EPI_DGELU_BF16 = 7,       // out_bf16 = acc * aux_bf16[row, col], aux = gelu_tanh'(fc1 pre-activation) kept by the forward
   EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
   EPI_RESID_F32 = 9,        // out_f32 += gate[row / tokens] * (acc + bias): the adaLN-Zero gated residual update, in place, fp32
+  EPI_BIAS_GELU_GRAD_BF16 = 11,   // training fc1: out_bf16 = gelu_tanh(acc + bias) and out_aux_bf16 = gelu_tanh'(acc + bias)
   EPI_RESID_LN_F32 = 10,    // EPI_RESID_F32 (N == 768) + the NEXT LayerNorm-modulate of the updated rows:
                             // ln_out_bf16 = LN(out_f32) * (1 + ln_scale[sample]) + ln_shift[sample]
 };
@@ -57,6 +58,7 @@ struct GemmParams {
   // EPI_WGRAD_F32: M = contraction length (token rows), N = output columns (in_features), wg_rows = output rows
   int wg_rows, split, split_len;
   // EPI_RESID_LN_F32: the LayerNorm-modulate that consumes the updated residual rows (models.py:120-121, 19-20)
+  __nv_bfloat16* out_aux;     // EPI_BIAS_GELU_GRAD_BF16: [M, N] bf16, leading dimension ldo
   __nv_bfloat16* ln_out;      // [M, N] bf16
   const float* ln_shift;      // sample b reads ln_shift + b * ln_stride, [N]
   const float* ln_scale;
@@ -74,9 +76,9 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
                 cudaStream_t stream);
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream);
-// attention_tc.cu: tcgen05 / TMEM forward for the sizes attention_tc_supported() names (inference path, no log-sum-exp)
+// attention_tc.cu: tcgen05 / TMEM forward for the sizes attention_tc_supported() names (lse2 optional, as launch_attention)
 bool attention_tc_supported(int tokens);
-int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int batch, int tokens, cudaStream_t stream);
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream);
 // K-major bf16 [rows, cols] tensor map, {64 cols x box_rows} boxes, 128-byte swizzle (gemm.cu)
 int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,

@@ -173,6 +173,23 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
   __syncwarp();
 }
 
+// same transposition for values that are already packed bf16 pairs (32 words = 64 columns of this thread's row)
+__device__ __forceinline__ void store_packed_tile(uint8_t* stage, const uint32_t (&u)[32], __nv_bfloat16* out, long long ldo,
+                                                  int row0, int n0, int M, int lane) {
+  const int sub = lane >> 3, ch = lane & 7;
+  uint8_t* mine = stage + lane * kStageRowBytes;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(mine + 16 * j) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sub;
+    const uint4 q = *reinterpret_cast<const uint4*>(stage + r * kStageRowBytes + 16 * ch);
+    if (row0 + r < M) *reinterpret_cast<uint4*>(out + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch) = q;
+  }
+  __syncwarp();
+}
+
 // 32 rows x 32 fp32 columns of this warp -> staging buffer (row-per-thread in, coalesced row segments out).
 __device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[32], int lane) {
   uint8_t* mine = stage + lane * kStageRowBytes;
@@ -443,7 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
       } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_BF16 || EPI == EPI_BIAS_BF16_F32 ||
-                           EPI == EPI_DGELU_BF16) {
+                           EPI == EPI_DGELU_BF16 || EPI == EPI_BIAS_GELU_GRAD_BF16) {
 #pragma unroll 1
         for (int c = 0; c < kColsPerWarp / 64; ++c) {
           uint32_t r0[32], r1[32];
@@ -456,6 +473,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
           bf16_math<EPI>(v, bias_smem + c * 64, gate4, c * 16);
+          if constexpr (EPI == EPI_BIAS_GELU_GRAD_BF16) {   // activation and its derivative from one tanh; derivative tile first
+            uint32_t gp[32];
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              float y0, d0, y1, d1;
+              gelu_tanh_both(v[j], y0, d0);
+              gelu_tanh_both(v[j + 1], y1, d1);
+              v[j] = y0; v[j + 1] = y1;
+              gp[j >> 1] = pack_bf16(d0, d1);
+            }
+            store_packed_tile(stage, gp, p.out_aux, p.ldo, row0, n0, p.M, lane);
+          }
           store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
             if (p.out2 != nullptr) {
@@ -769,6 +798,7 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     if (!p.ln_out || !p.ln_shift || !p.ln_scale) return set_error(kErrBadArg, "gemm: LayerNorm-fused epilogue: null pointer");
     return launch_cfg<256, EPI_RESID_LN_F32, 8>(a, lda, w, ldw, p, stream);     // two warps per lane quadrant split the columns
   }
+  if (epi == EPI_BIAS_GELU_GRAD_BF16 && p.out_aux == nullptr) return set_error(kErrBadArg, "gemm: gelu+grad epilogue needs the derivative buffer");
   if (epi == EPI_DGELU_BF16 && p.aux == nullptr) return set_error(kErrBadArg, "gemm: dgelu epilogue needs the pre-activations");
 #define JP_CASE(E)                                                             \
   case E:                                                                      \
@@ -782,6 +812,7 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     JP_CASE(EPI_BIAS_BF16_F32)
     JP_CASE(EPI_DGELU_BF16)
     JP_CASE(EPI_RESID_F32)
+    JP_CASE(EPI_BIAS_GELU_GRAD_BF16)
     case EPI_HEAD:
       return launch_cs<64, EPI_HEAD>(a, lda, w, ldw, p, stream);
     default:

@@ -223,4 +223,14 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * fmaf(3.0f * k1, x2, 1.0f);
 }
 
+// gelu_tanh(x) and its derivative from ONE tanh
+__device__ __forceinline__ void gelu_tanh_both(float x, float& y, float& dy) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(k0 * x * fmaf(k1, x2, 1.0f));
+  const float h = 0.5f * (1.0f + t);
+  y = x * h;
+  dy = fmaf(0.5f * x * (1.0f - t * t), k0 * fmaf(3.0f * k1, x2, 1.0f), h);
+}
+
 }  // namespace jp

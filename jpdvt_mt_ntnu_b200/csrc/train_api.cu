@@ -136,9 +136,13 @@ int jpdvt_train_forward(const jpdvt_weights* w, const jpdvt_tape* tp, const floa
                 w->b_proj + static_cast<long long>(i) * kHidden, y1, kHidden, M, kHidden, kHidden, st));
     JP_TRY(launch_ln_modulate(x_a, x_b, y1, mod + 2 * kHidden, n_mod, mod + 3 * kHidden, mod + 4 * kHidden, n_mod, xn2, M, T, st));
     // fc1: pre-activations (kept for gelu') and activations
-    JP_TRY(gemm(EPI_BIAS_BF16, xn2, kHidden, BF(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden, kHidden,
-                w->b_fc1 + static_cast<long long>(i) * 4 * kHidden, hpre, 4 * kHidden, M, 4 * kHidden, kHidden, st));
-    JP_TRY(launch_gelu(hpre, h, M * 4 * kHidden, st));
+    {   // fc1 with the activation AND its derivative (kept for the backward's dGELU epilogue) as one epilogue
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = 1;
+      p.bias = w->b_fc1 + static_cast<long long>(i) * 4 * kHidden; p.out = h; p.ldo = 4 * kHidden; p.out_aux = hpre;
+      JP_TRY(launch_gemm(EPI_BIAS_GELU_GRAD_BF16, xn2, kHidden, BF(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden,
+                         kHidden, p, st));
+    }
     JP_TRY(gemm(EPI_BIAS_BF16, h, 4 * kHidden, BF(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden, 4 * kHidden,
                 w->b_fc2 + static_cast<long long>(i) * kHidden, y2, kHidden, M, kHidden, 4 * kHidden, st));
     pending = y2;
