@@ -82,19 +82,25 @@ struct TcCfg {
   static constexpr int kTileBytes = T * 128;                 // one of Q / K / V
   static constexpr int kPBytes = kKBlocks * 16384;           // P0: 128 rows x kKBlocks x 128 B
   // split remainder: its compact P tile (16 live rows x kKBlocks x 2 KB) sits right before P0, so the 128-row A operand the
-  // MMA reads for it runs on into P0 (dead rows, read only) and tile 1 need not wait for the O0 MMAs to release P0
-  static constexpr int kP1Bytes = (kTiles == 2 && kRem <= 16) ? kKBlocks * 2048 : 0;
-  static constexpr int kOffQ = 0, kOffK = kTileBytes, kOffV = 2 * kTileBytes, kOffP1 = 3 * kTileBytes, kOffP = kOffP1 + kP1Bytes;
-  // the tile-1 A operand reads Q rows up to 255: keep that inside the allocation (it may run into K / V / P, read only)
-  // output staging (4 KB per softmax warp): inside P0 when the remainder is split (P0 is idle once the O0 MMAs are done and
-  // P1 lives elsewhere), its own 16 KB otherwise (a full second tile keeps P1 in P0's place until the O1 MMAs finish)
-  static constexpr int kOffStage = (kTiles == 2 && kRem > 16) ? kOffP + kPBytes : kOffP;
-  static constexpr int kEndBytes = (kTiles == 2 && kRem > 16) ? kOffStage + 16384 : kOffP + kPBytes;
+  // MMA reads for it runs on into P0 (dead rows, read only) and tile 1 need not wait for the O0 MMAs to release P0.
+  // dual (two full tiles, T = 256): both score tiles are computed up front into the two halves of TMEM and each tile has
+  // its own P buffer, so the second tile's softmax starts the moment the first is done and O0's MMAs run underneath it.
+  static constexpr bool kDual = kTiles == 2 && kRem > 16;
+  static_assert(!kDual || 2 * T <= 512, "two score tiles must fit the 512 TMEM columns");
+  static constexpr int kP1Bytes = kSplit ? kKBlocks * 2048 : (kDual ? kPBytes : 0);
+  static constexpr int kOffQ = 0, kOffK = kTileBytes, kOffV = 2 * kTileBytes;
+  static constexpr int kOffP1 = kSplit ? 3 * kTileBytes : 3 * kTileBytes + kPBytes;
+  static constexpr int kOffP = kSplit ? kOffP1 + kP1Bytes : 3 * kTileBytes;
+  // output staging (4 KB per softmax warp) lives in the P buffer of the tile being written out: it is idle once that
+  // tile's O MMAs are done
+  static constexpr int kEndBytes = (kOffP > kOffP1 ? kOffP + kPBytes : kOffP1 + kP1Bytes);
   static constexpr int kDataBytes = kEndBytes > 256 * 128 ? kEndBytes : 256 * 128;
+  // TMEM columns: scores of tile 0 / tile 1, outputs of tile 0 / tile 1
+  static constexpr int kColS1 = kDual ? 256 : 0, kColO0 = kDual ? 0 : T, kColO1 = kDual ? 256 : 0;
   static constexpr int kBarOff = kDataBytes;
   static constexpr int kXchOff = kBarOff + 128;              // [2][4][16] floats: row max / row sum of the split remainder
   static constexpr int kSmemBytes = kXchOff + 512 + 1024;    // + alignment slack
-  static constexpr int kTmemCols = (T + 64 <= 256) ? 256 : 512;
+  static constexpr int kTmemCols = (!kDual && T + 64 <= 256) ? 256 : 512;
   static constexpr int kCtasPerSm = (T + 64 <= 256 && 2 * (kSmemBytes + 1024) <= 227 * 1024) ? 2 : 1;
   static_assert(kOffP % 1024 == 0 && kOffP1 % 1024 == 0 && kTileBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
 };
@@ -307,7 +313,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);   // B = V, MN-major (keys are the strided index)
       const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), p_lo = desc_lo_k(sP), v_lo = desc_lo_mn(sV);
-      const uint32_t p1_lo = Cfg::kSplit ? desc_lo_k(sP1) : p_lo;
+      const uint32_t p1_lo = (Cfg::kSplit || Cfg::kDual) ? desc_lo_k(sP1) : p_lo;
       int it = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
         const uint32_t ph = static_cast<uint32_t>(it & 1);
@@ -331,11 +337,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
         }
         umma_commit(&s_full[0]);
+        if constexpr (Cfg::kDual) {                            // second score tile right behind the first, into its own columns
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColS1, q_lo + 128 * 8, k_lo, idesc_s);
+            else umma_lohi<true>(tmem_base + Cfg::kColS1, q_lo + 128 * 8 + 2 * k, k_lo + 2 * k, idesc_s);
+          }
+          umma_commit(&s_full[1]);
+        }
         mark(0, it, 3);
         mbar_wait(&p_full[0], ph);                            // softmax has consumed S and written P0
         mark(0, it, 4);
         tc_fence_after();
-        if constexpr (Cfg::kTiles == 2) {                       // remainder scores first: the softmax warps wait for them
+        if constexpr (Cfg::kTiles == 2 && !Cfg::kDual) {        // remainder scores first: the softmax warps wait for them
           if constexpr (Cfg::kSplit) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                       // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
@@ -360,14 +374,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mark(0, it, 5);
         mbar_wait(v_full, ph);
         mark(0, it, 6);
-        issue_o(T, p_lo, 1024);
+        issue_o(Cfg::kColO0, p_lo, 1024);
         umma_commit(&o_full[0]);
         mark(0, it, 7);
         if constexpr (Cfg::kTiles == 2) {
           mbar_wait(&p_full[1], ph);
           mark(0, it, 8);
           tc_fence_after();
-          issue_o(0, p1_lo, Cfg::kSplit ? 128 : 1024);
+          issue_o(Cfg::kColO1, p1_lo, Cfg::kSplit ? 128 : 1024);
           umma_commit(&o_full[1]);
           mark(0, it, 9);
         }
@@ -401,14 +415,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       if constexpr (Cfg::kTiles == 2) {
         mbar_wait(&s_full[1], ph);
         mark(role, it, 3);
-        if constexpr (!Cfg::kSplit) mbar_wait(&o_full[0], ph); // full second tile: P1 reuses P0, the O0 MMAs must have read it
+        if constexpr (!Cfg::kSplit && !Cfg::kDual) mbar_wait(&o_full[0], ph);   // P1 would reuse P0: the O0 MMAs must have read it
         mark(role, it, 4);
         tc_fence_after();
         if constexpr (Cfg::kSplit) {
           if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane, ms1);
           else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane, ms1);
         } else {
-          sum1 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms1);
+          sum1 = softmax_row_to_p<T>(t_lane + Cfg::kColS1, (Cfg::kDual ? sP1 : sP) + r_tile * 128, 16384, r_tile & 7, true, ms1);
         }
         fence_proxy_async_smem();
       }
@@ -422,11 +436,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       }
       // ---- outputs.  O0 is pulled into registers BEFORE the remainder's P tile is handed to the MMA warp: a tcgen05.ld
       // issued while the O1 MMAs run waits for them, so the other order parks every softmax warp behind the tensor pipe
-      const uint32_t o_stage = smem_u32(smem + Cfg::kOffStage) + static_cast<uint32_t>(warp) * 4096u;
+      const uint32_t o_stage = sP + static_cast<uint32_t>(warp) * 4096u;                     // P0 is idle after o_full[0]
+      const uint32_t o_stage1 = (Cfg::kDual ? sP1 : sP) + static_cast<uint32_t>(warp) * 4096u;   // dual: P1 after o_full[1]
       uint32_t oa[32], ob[32];
       mbar_wait(&o_full[0], ph);
       tc_fence_after();
-      load_o_row(t_lane + T, oa, ob);
+      load_o_row(t_lane + Cfg::kColO0, oa, ob);
       if constexpr (Cfg::kTiles == 2) {
         tc_fence_before();
         __syncwarp();
@@ -441,8 +456,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           mbar_wait(&o_full[1], ph);
           mark(role, it, 7);
           tc_fence_after();
-          load_o_row(t_lane, oa, ob);
-          store_o_rows(oa, ob, 1.0f / sum1, o_stage, obase + static_cast<long long>(Cfg::kSplit ? 128 : 128 + warp * 32) * kHidden,
+          load_o_row(t_lane + Cfg::kColO1, oa, ob);
+          store_o_rows(oa, ob, 1.0f / sum1, o_stage1, obase + static_cast<long long>(Cfg::kSplit ? 128 : 128 + warp * 32) * kHidden,
                        Cfg::kSplit ? 16 : 32, lane);
         }
       }
