@@ -69,7 +69,8 @@ int jpdvt_gemm_bias_gate(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* 
                          int64_t gate_stride, jpdvt_bf16* out, int64_t m, int n, int k, int tokens, void* stream);
 /* x[row] += gate[row / tokens] * (a . w^T + bias), in place on the fp32 residual stream: the whole adaLN-Zero gated
  * residual update `x = x + gate.unsqueeze(1) * branch(...)` of attn.proj / mlp.fc2 (models.py:120-121) as the GEMM
- * epilogue (coalesced read-modify-write, overlapped with the next tile's MMAs).  n must be a multiple of 128. */
+ * epilogue (overlapped with the next tile's MMAs): short contractions move the residual tile with TMA through a
+ * shared-memory ring, long ones prefetch it into registers.  n must be a multiple of 128; x 16-byte aligned. */
 int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
                                   int64_t gate_stride, float* x, int64_t m, int n, int k, int tokens, void* stream);
 /* jpdvt_gemm_bias_gate_residual followed, in the same kernel, by the LayerNorm-modulate that consumes the updated rows:

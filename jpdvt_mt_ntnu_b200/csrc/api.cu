@@ -36,6 +36,17 @@ __global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict_
   if (i < n4) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(in)[i];
 }
 
+// Which gated-residual epilogue.  Short contractions (proj, K = 768) are bound by the residual read-modify-write itself and
+// gain from moving the tile with TMA through a shared-memory ring (58 vs 69 us at M = 36,864); long ones (fc2, K = 3072) hide
+// the register-prefetch RMW under their MMAs and would only lose the pipeline stage the ring costs (144 vs 141 us).
+// JPDVT_RESID_TMA=0 / 1 forces one or the other (A/B timing knob).
+int resid_epilogue(int n, int k) {
+  static int mode = -2;
+  if (mode == -2) { const char* e = getenv("JPDVT_RESID_TMA"); mode = (e == nullptr) ? -1 : (e[0] == '1' ? 1 : 0); }
+  if (n % 256 != 0 || mode == 0) return EPI_RESID_F32;
+  return (mode == 1 || k <= 1024) ? EPI_RESID_TMA_F32 : EPI_RESID_F32;
+}
+
 static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows, int n_mod, cudaStream_t st) {
   if (rows <= 8) {
     return launch_adaln_gemv(ws->silu_c, rows, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod, n_mod, st);
@@ -104,7 +115,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
       p.ln_out = xn; p.ln_shift = shift; p.ln_scale = scale; p.ln_stride = mod_stride;
       return launch_gemm(EPI_RESID_LN_F32, a, lda, wt, lda, p, st);
     }
-    int r = launch_gemm(EPI_RESID_F32, a, lda, wt, lda, p, st);
+    int r = launch_gemm(resid_epilogue(kHidden, k), a, lda, wt, lda, p, st);
     if (r != kOk) return r;
     return launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, shift, scale, mod_stride, xn, M, T, st);
   };
@@ -226,7 +237,7 @@ int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, cons
   GemmParams p{};
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
   p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
-  return launch_gemm(EPI_RESID_F32, BF(a), k, BF(w), k, p, ST(stream));
+  return launch_gemm(resid_epilogue(n, k), BF(a), k, BF(w), k, p, ST(stream));
 }
 int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
                                      int64_t gate_stride, float* x, const float* ln_shift, const float* ln_scale,

@@ -36,6 +36,8 @@ enum Epilogue : int {
   EPI_WGRAD_F32 = 8,        // MN-major operands, split contraction: partial[s][i][j] = sum_m P[m,i] Q[m,j]   (weight gradients)
   EPI_RESID_F32 = 9,        // out_f32 += gate[row / tokens] * (acc + bias): the adaLN-Zero gated residual update, in place, fp32
   EPI_BIAS_GELU_GRAD_BF16 = 11,   // training fc1: out_bf16 = gelu_tanh(acc + bias) and out_aux_bf16 = gelu_tanh'(acc + bias)
+  EPI_RESID_TMA_F32 = 12,   // EPI_RESID_F32 with the residual tile moved by TMA: 32x32 fp32 boxes into a per-warp shared-memory
+                            // ring (deep prefetch, no registers), updated in place, TMA-stored back
   EPI_RESID_LN_F32 = 10,    // EPI_RESID_F32 (N == 768) + the NEXT LayerNorm-modulate of the updated rows:
                             // ln_out_bf16 = LN(out_f32) * (1 + ln_scale[sample]) + ln_shift[sample]
 };

@@ -29,7 +29,9 @@ constexpr int kMaxSmem = 227 * 1024;
 constexpr int kStageRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free 16-byte accesses
 constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpose buffer per epilogue warp
 
-template <int BN, int CS, int EW>
+constexpr int kXBoxBytes = 32 * 32 * 4;                   // one residual box: 32 rows x 32 fp32 columns (128-byte swizzled rows)
+
+template <int BN, int CS, int EW, int NB = 0>              // NB > 0: per-warp ring of NB residual boxes instead of the staging tiles
 struct GemmCfg {
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kBRows = BN / CS;                  // W rows this CTA loads
@@ -39,12 +41,13 @@ struct GemmCfg {
   static constexpr int kColsPerWarp = BN / (EW / 4);      // EW/4 warps share a TMEM lane quadrant and split the columns
   static constexpr int kVecWarpBytes = 3 * kColsPerWarp * 4;   // per warp and tile: bias slice + gate slices of <= 2 samples
   static constexpr int kLnStatsBytes = 2 * 2 * BM * 8;    // EPI_RESID_LN_F32: (mean, M2) per row, per column half, 2 M-block parities
-  static constexpr int kFixedBytes = EW * (kStageWarpBytes + kVecWarpBytes) + kLnStatsBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  static constexpr int kStagingBytes = NB > 0 ? EW * NB * kXBoxBytes : EW * kStageWarpBytes;
+  static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + EW * (kStageWarpBytes + kVecWarpBytes) + kLnStatsBytes + kBarBytes + 1024;
+  static constexpr int kBarBytes = (2 * kStages + 4 + EW * NB) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + kBarBytes + 1024;
 };
 
 // ---- cluster helpers -------------------------------------------------------------------------------------------------
@@ -199,23 +202,26 @@ __device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[
   __syncwarp();
 }
 
-template <int BN, int EPI, int CS, int EW>
+template <int BN, int EPI, int CS, int EW, int NB = 0>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CS, EW>;
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_x, const GemmParams p) {
+  using Cfg = GemmCfg<BN, CS, EW, NB>;
+  static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32), "the residual ring belongs to the TMA residual epilogue");
   constexpr int kColsPerWarp = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the shared-space pointer (integer round-trips make the compiler lose the address
   // space and emit generic LD/ST for every staging access)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint8_t* bias_buf = stage_buf + EW * kStageWarpBytes;
+  uint8_t* bias_buf = stage_buf + Cfg::kStagingBytes;     // stage_buf: staging tiles, or (NB > 0) the residual rings, 1024-aligned
   float2* ln_stats = reinterpret_cast<float2*>(bias_buf + EW * Cfg::kVecWarpBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_buf + EW * Cfg::kVecWarpBytes + Cfg::kLnStatsBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready   (own CTA)
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained (leader's is the one waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xfull_bar = tempty_bar + 2;             // [EW * NB] residual box landed (TMA residual epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + EW * NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,6 +236,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int num_kb = WG ? p.split_len / BK : p.K / BK;
   const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
   constexpr bool kLN = (EPI == EPI_RESID_LN_F32);           // residual update + the next LayerNorm of the same rows
+  constexpr bool kXR = (EPI == EPI_RESID_TMA_F32);          // residual tile through the TMA ring
   constexpr bool kResid = (EPI == EPI_RESID_F32) || kLN;
   // s-th work item of this CTA group.  Normally tiles are dealt round robin; the LayerNorm-fused epilogue needs whole rows,
   // so there a group owns M-blocks and walks the N tiles of each one in turn.
@@ -255,6 +262,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS * EW); }
+    for (int i = 0; i < EW * NB; ++i) mbar_init(&xfull_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -354,6 +362,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
     float ln_mean = 0.f, ln_m2 = 0.f;     // kLN: running (mean, sum of squared deviations) of this thread's row over its columns
     int ln_cnt = 0;
+    // kXR: this warp's ring of residual boxes.  Box g (g = s * NC + c, the c-th 32-column chunk of the warp's s-th tile)
+    // lives in slot g % NB; its load is issued NB - 1 chunks ahead, as soon as the TMA store of box g - 1 has read its slot.
+    constexpr int kXNC = kColsPerWarp / 32;
+    uint8_t* xring = stage_buf + (warp - 2) * (NB > 0 ? NB : 1) * kXBoxBytes;
+    uint64_t* xbar = xfull_bar + (warp - 2) * NB;
+    auto x_coords = [&](int g, int& col, int& row) -> bool {
+      int sp, mb, nb;
+      if (!tile_at(g / kXNC, sp, mb, nb)) return false;
+      row = (mb * CS + static_cast<int>(rank)) * BM + quad * 32;
+      col = nb * BN + col_base + (g % kXNC) * 32;
+      return true;
+    };
+    auto x_issue = [&](int g) {            // lane 0 only
+      int col, row;
+      if (x_coords(g, col, row)) {
+        const int slot = g % (NB > 0 ? NB : 1);
+        mbar_expect_tx(&xbar[slot], kXBoxBytes);
+        tma_load_2d(&tma_x, &xbar[slot], xring + slot * kXBoxBytes, col, row);
+      }
+    };
+    if constexpr (kXR) {
+      if (lane == 0) {
+        for (int g = 0; g < NB - 1; ++g) x_issue(g);
+      }
+      __syncwarp();
+    }
     for (int s = 0;; ++s) {
       int split_idx, m_blk, n_blk;
       if (!tile_at(s, split_idx, m_blk, n_blk)) break;
@@ -367,7 +401,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // epilogue math never queues a global load behind the streaming residual prefetch
         for (int i = lane; i < kColsPerWarp / 4; i += 32)
           reinterpret_cast<float4*>(bias_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base) + i);
-        if constexpr (kResid || EPI == EPI_GATE_BF16) {
+        if constexpr (kResid || kXR || EPI == EPI_GATE_BF16) {
           const int last = out_rows - 1;
           const int s_first = (row0 < last ? row0 : last) / p.tokens, s_last = (row0 + 31 < last ? row0 + 31 : last) / p.tokens;
           const float* ga = p.gate + static_cast<long long>(s_first) * p.gate_stride + n_blk * BN + col_base;
@@ -384,7 +418,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t gate_sm = smem_u32(gate_smem);
       const float* gate_gl = nullptr;
       const bool gate_staged = p.tokens >= 32;
-      if constexpr (kResid || EPI == EPI_GATE_BF16) {
+      if constexpr (kResid || kXR || EPI == EPI_GATE_BF16) {
         const int last = out_rows - 1;
         const int s_first = (row0 < last ? row0 : last) / p.tokens;
         const int s_mine = row_ok ? row / p.tokens : s_first;
@@ -505,6 +539,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 __syncwarp();
               }
             }
+          }
+        }
+      } else if constexpr (kXR) {
+        // x[row, n] += gate[row / tokens, n] * (acc + bias[n]): the residual box arrives by TMA (swizzled 128-byte rows, row =
+        // lane), is updated in place by its row's thread and leaves by TMA store - no per-thread global traffic at all
+#pragma unroll
+        for (int c = 0; c < kXNC; ++c) {
+          const int g = s * kXNC + c;
+          const int slot = g % NB;
+          if (lane == 0) {
+            tma_store_wait_read<0>();                        // the store of box g - 1 has released slot (g - 1) % NB ...
+            x_issue(g + NB - 1);                             // ... which is where box g + NB - 1 goes
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + col_base + c * 32, r);
+          tmem_ld_wait();
+          if (c == kXNC - 1) release_tmem();
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_smem + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            const float4 gt = gate4(c * 8 + j);
+            v[4 * j + 0] = gt.x * (__uint_as_float(r[4 * j + 0]) + b.x); v[4 * j + 1] = gt.y * (__uint_as_float(r[4 * j + 1]) + b.y);
+            v[4 * j + 2] = gt.z * (__uint_as_float(r[4 * j + 2]) + b.z); v[4 * j + 3] = gt.w * (__uint_as_float(r[4 * j + 3]) + b.w);
+          }
+          mbar_wait(&xbar[slot], static_cast<uint32_t>((g / NB) & 1));
+          const uint32_t mine = smem_u32(xring + slot * kXBoxBytes) + lane * 128, sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = mine + ((j ^ sw) << 4);
+            float4 q = lds_f4(a);
+            q.x += v[4 * j + 0]; q.y += v[4 * j + 1]; q.z += v[4 * j + 2]; q.w += v[4 * j + 3];
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
+          }
+          fence_proxy_async_smem();                            // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            int col, row;
+            x_coords(g, col, row);
+            tma_store_2d(&tma_x, xring + slot * kXBoxBytes, col, row);
+            tma_store_commit();
           }
         }
       } else if constexpr (kResid) {
@@ -685,6 +761,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   }
 
+  if constexpr (kXR) {
+    if (warp >= 2 && lane == 0) tma_store_wait<0>();          // bulk stores read this CTA's shared memory: drain before exit
+  }
   tc_fence_before();
   if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -729,6 +808,21 @@ int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, lo
   return kOk;
 }
 
+// fp32 [rows, cols] row-major with leading dimension ld (elements); box = {32 cols, 32 rows} = 128-byte swizzled rows.
+static int make_tmap_f32_box32(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(kErrDriver, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(kErrDriver, "cuTensorMapEncodeTiled(fp32 box) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return kOk;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -749,14 +843,14 @@ static int epi_warps() {
   return ew;
 }
 
-template <int BN, int EPI, int EW>
+template <int BN, int EPI, int EW, int NB = 0>
 static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                       cudaStream_t stream) {
   constexpr int CS = 2;
-  using Cfg = GemmCfg<BN, CS, EW>;
+  using Cfg = GemmCfg<BN, CS, EW, NB>;
   static_assert(Cfg::kStages >= 3, "pipeline too shallow");
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, EPI, CS, EW>;
+  auto kern = gemm_kernel<BN, EPI, CS, EW, NB>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return set_error(kErrCuda, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(cudaGetLastError()));
@@ -767,10 +861,15 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   if (rc != kOk) return rc;
   rc = make_tmap_bf16_kmajor(&tb, w, p.N, p.K, ldw, Cfg::kBRows);
   if (rc != kOk) return rc;
+  CUtensorMap tx = ta;                                       // residual-stream boxes (TMA residual epilogue only)
+  if constexpr (NB > 0) {
+    rc = make_tmap_f32_box32(&tx, p.out, p.M, p.N, p.ldo);
+    if (rc != kOk) return rc;
+  }
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, p);
   return check_launch("gemm_kernel");
 }
 
@@ -793,6 +892,15 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
   if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32 || epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
   if ((epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.gate == nullptr) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate");
+  if (epi == EPI_RESID_TMA_F32) {
+    if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");
+    if (p.N % 256 != 0 || (p.ldo % 4) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15))
+      return set_error(kErrBadArg, "gemm: the TMA residual epilogue needs N %% 256 == 0 and a 16-byte aligned residual stream");
+    static int ring = -1;                                     // JPDVT_RESID_RING=2|3: boxes per warp (3 costs a pipeline stage)
+    if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && e[0] == '3') ? 3 : 2; }
+    return ring == 3 ? launch_cfg<256, EPI_RESID_TMA_F32, 8, 3>(a, lda, w, ldw, p, stream)
+                     : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
+  }
   if (epi == EPI_RESID_LN_F32) {
     if (p.N != kHidden || p.ldo != kHidden) return set_error(kErrBadArg, "gemm: the LayerNorm-fused epilogue needs N == ldo == %d", kHidden);
     if (!p.ln_out || !p.ln_shift || !p.ln_scale) return set_error(kErrBadArg, "gemm: LayerNorm-fused epilogue: null pointer");
@@ -872,7 +980,7 @@ static int launch_wgrad_cfg(const __nv_bfloat16* pmat, long long ldp, const __nv
   const int tiles = ((p.wg_rows + 255) / 256) * (p.N / BN) * p.split;
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ta, p);
   return check_launch("gemm_kernel<wgrad>");
 }
 
