@@ -36,15 +36,14 @@ __global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict_
   if (i < n4) reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(in)[i];
 }
 
-// Which gated-residual epilogue.  Short contractions (proj, K = 768) are bound by the residual read-modify-write itself and
-// gain from moving the tile with TMA through a shared-memory ring (58 vs 69 us at M = 36,864); long ones (fc2, K = 3072) hide
-// the register-prefetch RMW under their MMAs and would only lose the pipeline stage the ring costs (144 vs 141 us).
-// JPDVT_RESID_TMA=0 / 1 forces one or the other (A/B timing knob).
+// Which gated-residual epilogue: the residual tile moved by TMA through a per-warp shared-memory ring (default; at
+// M = 36,864 proj 55.8 vs 68.7 us, fc2 135.8 vs 139.1 us), or - JPDVT_RESID_TMA=0, or N not a multiple of 256 - the
+// register-prefetch read-modify-write.
 int resid_epilogue(int n, int k) {
+  (void)k;
   static int mode = -2;
   if (mode == -2) { const char* e = getenv("JPDVT_RESID_TMA"); mode = (e == nullptr) ? -1 : (e[0] == '1' ? 1 : 0); }
-  if (n % 256 != 0 || mode == 0) return EPI_RESID_F32;
-  return (mode == 1 || k <= 1024) ? EPI_RESID_TMA_F32 : EPI_RESID_F32;
+  return (n % 256 != 0 || mode == 0) ? EPI_RESID_F32 : EPI_RESID_TMA_F32;
 }
 
 static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows, int n_mod, cudaStream_t st) {

@@ -39,10 +39,13 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColsPerWarp = BN / (EW / 4);      // EW/4 warps share a TMEM lane quadrant and split the columns
-  static constexpr int kVecWarpBytes = 3 * kColsPerWarp * 4;   // per warp and tile: bias slice + gate slices of <= 2 samples
-  static constexpr int kLnStatsBytes = 2 * 2 * BM * 8;    // EPI_RESID_LN_F32: (mean, M2) per row, per column half, 2 M-block parities
+  // per warp and tile: bias slice + gate slices of <= 2 samples (the residual-ring variant reads them through L1 instead:
+  // its ring needs the room to keep the five pipeline stages)
+  static constexpr int kVecWarpBytes = NB > 0 ? 0 : 3 * kColsPerWarp * 4;
+  static constexpr int kLnStatsBytes = NB > 0 ? 0 : 2 * 2 * BM * 8;   // EPI_RESID_LN_F32: (mean, M2) per row, column half, M-block parity
   static constexpr int kStagingBytes = NB > 0 ? EW * NB * kXBoxBytes : EW * kStageWarpBytes;
-  static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + 2304;   // staging + barriers + align slack + static smem
+  // staging + barriers + align slack (+ the head epilogue's static arrays, absent from the ring variant)
+  static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + (NB > 0 ? 0 : 2304);
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
@@ -396,7 +399,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool row_ok = row < out_rows;
       float* bias_smem = reinterpret_cast<float*>(bias_buf + (warp - 2) * Cfg::kVecWarpBytes);
       float* gate_smem = bias_smem + kColsPerWarp;        // [2][kColsPerWarp]: gate rows of the first / last sample of the warp
-      if constexpr (EPI != EPI_DGELU_BF16 && EPI != EPI_WGRAD_F32 && EPI != EPI_HEAD) {
+      if constexpr (EPI != EPI_DGELU_BF16 && EPI != EPI_WGRAD_F32 && EPI != EPI_HEAD && !kXR) {
         // this warp's bias (and gate) slices -> smem while the MMAs of the tile are still running, so the per-chunk
         // epilogue math never queues a global load behind the streaming residual prefetch
         for (int i = lane; i < kColsPerWarp / 4; i += 32)
@@ -417,7 +420,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // else straight from global memory (kept as two typed pointers so the staged reads stay LDS)
       uint32_t gate_sm = smem_u32(gate_smem);
       const float* gate_gl = nullptr;
-      const bool gate_staged = p.tokens >= 32;
+      const bool gate_staged = !kXR && p.tokens >= 32;
       if constexpr (kResid || kXR || EPI == EPI_GATE_BF16) {
         const int last = out_rows - 1;
         const int s_first = (row0 < last ? row0 : last) / p.tokens;
@@ -557,10 +560,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tmem_ld_wait();
           if (c == kXNC - 1) release_tmem();
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bias_smem + c * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
+            const float4 b = __ldg(b4 + j);
             const float4 gt = gate4(c * 8 + j);
             v[4 * j + 0] = gt.x * (__uint_as_float(r[4 * j + 0]) + b.x); v[4 * j + 1] = gt.y * (__uint_as_float(r[4 * j + 1]) + b.y);
             v[4 * j + 2] = gt.z * (__uint_as_float(r[4 * j + 2]) + b.z); v[4 * j + 3] = gt.w * (__uint_as_float(r[4 * j + 3]) + b.w);
