@@ -46,6 +46,9 @@ int resid_epilogue(int n, int k) {
   return (n % 256 != 0 || mode == 0) ? EPI_RESID_F32 : EPI_RESID_TMA_F32;
 }
 
+// LayerNorm-fused variant: through the TMA ring (default) or the register / ld.global.cg form (JPDVT_RESID_TMA=0)
+int resid_ln_epilogue() { return resid_epilogue(kHidden, kHidden) == EPI_RESID_TMA_F32 ? EPI_RESID_LN_TMA_F32 : EPI_RESID_LN_F32; }
+
 static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows, int n_mod, cudaStream_t st) {
   if (rows <= 8) {
     return launch_adaln_gemv(ws->silu_c, rows, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod, n_mod, st);
@@ -112,7 +115,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     p.bias = bias; p.out = ws->x; p.ldo = kHidden; p.gate = gate; p.gate_stride = mod_stride;
     if (ln_fused) {
       p.ln_out = xn; p.ln_shift = shift; p.ln_scale = scale; p.ln_stride = mod_stride;
-      return launch_gemm(EPI_RESID_LN_F32, a, lda, wt, lda, p, st);
+      return launch_gemm(resid_ln_epilogue(), a, lda, wt, lda, p, st);
     }
     int r = launch_gemm(resid_epilogue(kHidden, k), a, lda, wt, lda, p, st);
     if (r != kOk) return r;
@@ -249,7 +252,7 @@ int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, c
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
   p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
   p.ln_out = BFM(xn); p.ln_shift = ln_shift; p.ln_scale = ln_scale; p.ln_stride = mod_stride;
-  return launch_gemm(EPI_RESID_LN_F32, BF(a), k, BF(w), k, p, ST(stream));
+  return launch_gemm(resid_ln_epilogue(), BF(a), k, BF(w), k, p, ST(stream));
 }
 int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
                            const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {

@@ -38,6 +38,7 @@ enum Epilogue : int {
   EPI_BIAS_GELU_GRAD_BF16 = 11,   // training fc1: out_bf16 = gelu_tanh(acc + bias) and out_aux_bf16 = gelu_tanh'(acc + bias)
   EPI_RESID_TMA_F32 = 12,   // EPI_RESID_F32 with the residual tile moved by TMA: 32x32 fp32 boxes into a per-warp shared-memory
                             // ring (deep prefetch, no registers), updated in place, TMA-stored back
+  EPI_RESID_LN_TMA_F32 = 13,   // EPI_RESID_TMA_F32 + the next LayerNorm-modulate of the same rows (ln_out), boxes re-read by TMA
   EPI_RESID_LN_F32 = 10,    // EPI_RESID_F32 (N == 768) + the NEXT LayerNorm-modulate of the updated rows:
                             // ln_out_bf16 = LN(out_f32) * (1 + ln_scale[sample]) + ln_shift[sample]
 };

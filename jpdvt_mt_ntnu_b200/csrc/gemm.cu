@@ -109,6 +109,10 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+__device__ __forceinline__ void sts_u4_shared(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---- epilogue --------------------------------------------------------------------------------------------------------
 // The thread that owns accumulator row `row` holds fp32 values v[0..NC) for columns [n0, n0 + NC).
 // bf16 outputs are staged 64 columns (128 B per row) at a time, fp32 outputs 32 columns (128 B) at a time.
@@ -208,9 +212,9 @@ __device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[
 template <int BN, int EPI, int CS, int EW, int NB = 0>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_x, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_y, const GemmParams p) {
   using Cfg = GemmCfg<BN, CS, EW, NB>;
-  static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32), "the residual ring belongs to the TMA residual epilogue");
+  static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32 || EPI == EPI_RESID_LN_TMA_F32), "the residual ring belongs to the TMA residual epilogues");
   constexpr int kColsPerWarp = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the shared-space pointer (integer round-trips make the compiler lose the address
@@ -239,12 +243,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int num_kb = WG ? p.split_len / BK : p.K / BK;
   const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
   constexpr bool kLN = (EPI == EPI_RESID_LN_F32);           // residual update + the next LayerNorm of the same rows
+  constexpr bool kLNX = (EPI == EPI_RESID_LN_TMA_F32);      // ... with both the residual tile and the LayerNorm pass through the TMA ring
   constexpr bool kXR = (EPI == EPI_RESID_TMA_F32);          // residual tile through the TMA ring
   constexpr bool kResid = (EPI == EPI_RESID_F32) || kLN;
   // s-th work item of this CTA group.  Normally tiles are dealt round robin; the LayerNorm-fused epilogue needs whole rows,
   // so there a group owns M-blocks and walks the N tiles of each one in turn.
   auto tile_at = [&](int s, int& split_idx, int& m_blk, int& n_blk) -> bool {
-    if constexpr (kLN) {
+    if constexpr (kLN || kLNX) {
       split_idx = 0;
       m_blk = group + (s / num_n) * num_groups;
       n_blk = s % num_n;
@@ -266,6 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CS * EW); }
     for (int i = 0; i < EW * NB; ++i) mbar_init(&xfull_bar[i], 1);
+    if constexpr (kLNX) tma_prefetch_desc(&tma_y);
+    if constexpr (NB > 0) tma_prefetch_desc(&tma_x);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -363,6 +370,188 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
     const uint32_t tempty_remote = (CS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
+    if constexpr (kLNX) {
+      // ============================================================================================================
+      // Gated residual update + the LayerNorm-modulate of the same rows, everything through this warp's TMA ring.
+      // The CTA pair owns whole 256-row blocks (tile_at walks the N tiles of an M-block in turn).  Per M-block the warp
+      // (lane quadrant `quad`, column half `half`) handles 32 rows x 128 columns of each of the kNT N tiles:
+      //   phase R: box b = (tile j, chunk c): TMA-load x, x += gate * (acc + bias) in place, TMA-store; the row's running
+      //            (count, mean, M2) is updated from the registers that hold the new values (Chan's merge per 32 values)
+      //   phase L: statistics of the two column halves meet through shared memory; the same boxes are re-read (L2 hits;
+      //            this warp wrote them itself), normalised + modulated, and leave as bf16 boxes of ln_out.
+      // Boxes are consumed in the fixed order [R 0..kB) [L 0..kB) per M-block; box `pos` sits in ring slot pos % NB and is
+      // requested up to NB - 1 positions ahead, but an L box never before the stores of its M-block have completed.
+      constexpr int kNC = kColsPerWarp / 32;               // 32-column chunks per tile and warp
+      const int kNT = num_n;                               // N tiles per M-block (3 at N = 768)
+      const int kB = kNT * kNC;                            // boxes per phase
+      const int wi = warp - 2, half = wi >> 2;
+      uint8_t* ring = stage_buf + wi * NB * kXBoxBytes;
+      uint64_t* xbar = xfull_bar + wi * NB;
+      const int bar_id = 2 + quad;                         // named barrier of the two warps that share a lane quadrant
+      long long issued = 0, pos = 0;                       // boxes requested / consumed so far (this warp)
+      const int my_blocks = (num_m > group) ? (num_m - group + num_groups - 1) / num_groups : 0;
+      const long long total = static_cast<long long>(my_blocks) * 2 * kB;
+      // coordinates of the box consumed at position q
+      auto box_at = [&](long long q, bool& is_l, int& col, int& row) {
+        const int mb_it = static_cast<int>(q / (2 * kB));
+        int k = static_cast<int>(q - static_cast<long long>(mb_it) * 2 * kB);
+        is_l = k >= kB;
+        if (is_l) k -= kB;
+        const int mb = group + mb_it * num_groups;
+        row = (mb * CS + static_cast<int>(rank)) * BM + quad * 32;
+        col = (k / kNC) * BN + col_base + (k % kNC) * 32;
+      };
+      // lane 0: request boxes up to position `upto` (exclusive); L boxes only when `l_ok` (their M-block's stores are complete)
+      auto issue_to = [&](long long upto, bool l_ok) {
+        if (upto > total) upto = total;
+        while (issued < upto) {
+          bool is_l; int col, row;
+          box_at(issued, is_l, col, row);
+          if (is_l && !l_ok) break;
+          const int slot = static_cast<int>(issued % NB);
+          mbar_expect_tx(&xbar[slot], kXBoxBytes);
+          tma_load_2d_hint(&tma_x, &xbar[slot], ring + slot * kXBoxBytes, col, row, is_l ? kEvictFirst : kEvictNormal);
+          ++issued;
+        }
+      };
+      if (lane == 0) issue_to(NB - 1, false);
+      __syncwarp();
+      for (int mb_it = 0; mb_it < my_blocks; ++mb_it) {
+        const int m_blk = group + mb_it * num_groups;
+        const int row0 = (m_blk * CS + static_cast<int>(rank)) * BM + quad * 32;
+        const int row = row0 + lane;
+        const bool row_ok = row < out_rows;
+        const long long sample = (row_ok ? row : (out_rows - 1)) / p.tokens;
+        const float* gate_row = p.gate + sample * p.gate_stride + col_base;
+        float mean = 0.f, m2 = 0.f, cnt = 0.f;             // this row, this warp's columns
+        // ---------------------------------------------------------------- phase R
+        for (int j = 0; j < kNT; ++j) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll
+          for (int c = 0; c < kNC; ++c, ++pos) {
+            const int slot = static_cast<int>(pos % NB);
+            if (lane == 0) {
+              tma_store_wait_read<0>();                      // the store that used the slot about to be refilled has read it
+              issue_to(pos + NB, false);
+            }
+            const int n0 = j * BN + c * 32;                  // column offset relative to col_base
+            float4 bb[8], gg[8];                             // bias / gate of this chunk: requested before the waits below
+            {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base + n0);
+              const float4* g4 = reinterpret_cast<const float4*>(gate_row + n0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { bb[i] = __ldg(b4 + i); gg[i] = __ldg(g4 + i); }
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + col_base + c * 32, r);
+            tmem_ld_wait();
+            if (c == kNC - 1) {                              // accumulator fully read: hand the TMEM buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CS == 2) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(acc) * 8u);
+                else mbar_arrive(&tempty_bar[acc]);
+              }
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = bb[i], gt = gg[i];
+              v[4 * i + 0] = gt.x * (__uint_as_float(r[4 * i + 0]) + b.x); v[4 * i + 1] = gt.y * (__uint_as_float(r[4 * i + 1]) + b.y);
+              v[4 * i + 2] = gt.z * (__uint_as_float(r[4 * i + 2]) + b.z); v[4 * i + 3] = gt.w * (__uint_as_float(r[4 * i + 3]) + b.w);
+            }
+            mbar_wait(&xbar[slot], static_cast<uint32_t>((pos / NB) & 1));
+            const uint32_t mine = smem_u32(ring + slot * kXBoxBytes) + lane * 128, sw = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t a = mine + ((i ^ sw) << 4);
+              const float4 q = lds_f4(a);
+              v[4 * i + 0] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]),
+                           "f"(v[4 * i + 3]) : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {   // keep the updated rows in L2: phase L of this M-block reads them back
+              tma_store_2d_hint(&tma_x, ring + slot * kXBoxBytes, col_base + n0, row0, kEvictLast);
+              tma_store_commit();
+            }
+            // exact two-pass moments of these 32 new values, merged into the row's running (count, mean, M2)
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) { s0 += v[i]; s1 += v[i + 1]; }
+            const float mc = (s0 + s1) * (1.0f / 32.0f);
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float d0 = v[i] - mc, d1 = v[i + 1] - mc;
+              q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+            }
+            const float delta = mc - mean, n_new = cnt + 32.0f;
+            mean = fmaf(delta, 32.0f / n_new, mean);
+            m2 += (q0 + q1) + delta * delta * (cnt * 32.0f / n_new);
+            cnt = n_new;
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        // ---------------------------------------------------------------- phase L
+        if (lane == 0) tma_store_wait<0>();                  // every box of this M-block is in global memory (and no slot is being read)
+        __syncwarp();
+        float2* xs = reinterpret_cast<float2*>(ring);        // slot 0 doubles as the exchange buffer: (mean, M2) per row
+        xs[lane] = make_float2(mean, m2);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float2 other = reinterpret_cast<const float2*>(stage_buf + (wi ^ 4) * NB * kXBoxBytes)[lane];
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");   // both have read before the ring is refilled
+        const float dm = other.x - mean;
+        const float row_mean = 0.5f * (mean + other.x);      // equal column counts in both halves
+        const float rstd = rsqrtf((m2 + other.y + dm * dm * (0.5f * cnt)) / (2.0f * cnt) + 1e-6f);
+        const float* sh_row = p.ln_shift + sample * p.ln_stride + col_base;
+        const float* sc_row = p.ln_scale + sample * p.ln_stride + col_base;
+        fence_proxy_async_smem();                            // generic reads / writes of slot 0 before the TMA refills it
+        if (lane == 0) issue_to(pos + NB - 1, true);
+        __syncwarp();
+        for (int k = 0; k < kB; ++k, ++pos) {
+          const int slot = static_cast<int>(pos % NB);
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            issue_to(pos + NB, true);                        // further L boxes, then the next M-block's R boxes
+          }
+          const int n0 = (k / kNC) * BN + (k % kNC) * 32;
+          float4 sa[8], sb[8];                               // shift / scale of this box: in flight while the box arrives
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sa[i] = __ldg(reinterpret_cast<const float4*>(sh_row + n0) + i);
+            sb[i] = __ldg(reinterpret_cast<const float4*>(sc_row + n0) + i);
+          }
+          mbar_wait(&xbar[slot], static_cast<uint32_t>((pos / NB) & 1));
+          const uint32_t base = smem_u32(ring + slot * kXBoxBytes);
+          const uint32_t mine = base + lane * 128, sw = lane & 7;
+          float y[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = lds_f4(mine + ((i ^ sw) << 4));
+            const float4 a = sa[i], b = sb[i];
+            y[4 * i + 0] = fmaf((q.x - row_mean) * rstd, 1.0f + b.x, a.x); y[4 * i + 1] = fmaf((q.y - row_mean) * rstd, 1.0f + b.y, a.y);
+            y[4 * i + 2] = fmaf((q.z - row_mean) * rstd, 1.0f + b.z, a.z); y[4 * i + 3] = fmaf((q.w - row_mean) * rstd, 1.0f + b.w, a.w);
+          }
+          __syncwarp();                                      // every lane has read its row before the slot is rewritten
+          // bf16 result: 32 rows x 64 bytes, SWIZZLE_64B (16-byte chunk i of row r at (i ^ ((r >> 1) & 3)))
+          const uint32_t orow = base + lane * 64, osw = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts_u4_shared(orow + ((i ^ osw) << 4), pack_bf16(y[8 * i], y[8 * i + 1]), pack_bf16(y[8 * i + 2], y[8 * i + 3]),
+                          pack_bf16(y[8 * i + 4], y[8 * i + 5]), pack_bf16(y[8 * i + 6], y[8 * i + 7]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_y, ring + slot * kXBoxBytes, col_base + n0, row0);
+            tma_store_commit();
+          }
+        }
+      }
+    } else {
     float ln_mean = 0.f, ln_m2 = 0.f;     // kLN: running (mean, sum of squared deviations) of this thread's row over its columns
     int ln_cnt = 0;
     // kXR: this warp's ring of residual boxes.  Box g (g = s * NC + c, the c-th 32-column chunk of the warp's s-th tile)
@@ -762,9 +951,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }   // !kLNX
   }
 
-  if constexpr (kXR) {
+  if constexpr (kXR || kLNX) {
     if (warp >= 2 && lane == 0) tma_store_wait<0>();          // bulk stores read this CTA's shared memory: drain before exit
   }
   tc_fence_before();
@@ -826,6 +1016,21 @@ static int make_tmap_f32_box32(CUtensorMap* out, const void* base, long long row
   return kOk;
 }
 
+// bf16 [rows, cols] row-major; box = {32 cols, 32 rows} = 64-byte rows, 64B swizzle (the LayerNorm output boxes).
+static int make_tmap_bf16_box32(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(kErrDriver, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(kErrDriver, "cuTensorMapEncodeTiled(bf16 box) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return kOk;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -869,10 +1074,15 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
     rc = make_tmap_f32_box32(&tx, p.out, p.M, p.N, p.ldo);
     if (rc != kOk) return rc;
   }
+  CUtensorMap ty = ta;                                       // LayerNorm output boxes (EPI_RESID_LN_TMA_F32 only)
+  if constexpr (EPI == EPI_RESID_LN_TMA_F32) {
+    rc = make_tmap_bf16_box32(&ty, p.ln_out, p.M, p.N, p.ldo);
+    if (rc != kOk) return rc;
+  }
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, ty, p);
   return check_launch("gemm_kernel");
 }
 
@@ -903,6 +1113,14 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && e[0] == '3') ? 3 : 2; }
     return ring == 3 ? launch_cfg<256, EPI_RESID_TMA_F32, 8, 3>(a, lda, w, ldw, p, stream)
                      : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
+  }
+  if (epi == EPI_RESID_LN_TMA_F32) {
+    if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");
+    if (p.N != kHidden || p.ldo != kHidden) return set_error(kErrBadArg, "gemm: the LayerNorm-fused epilogue needs N == ldo == %d", kHidden);
+    if (!p.ln_out || !p.ln_shift || !p.ln_scale) return set_error(kErrBadArg, "gemm: LayerNorm-fused epilogue: null pointer");
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (reinterpret_cast<uintptr_t>(p.ln_out) & 15))
+      return set_error(kErrBadArg, "gemm: the TMA LayerNorm epilogue needs 16-byte aligned x and xn");
+    return launch_cfg<256, EPI_RESID_LN_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
   }
   if (epi == EPI_RESID_LN_F32) {
     if (p.N != kHidden || p.ldo != kHidden) return set_error(kErrBadArg, "gemm: the LayerNorm-fused epilogue needs N == ldo == %d", kHidden);
@@ -983,7 +1201,7 @@ static int launch_wgrad_cfg(const __nv_bfloat16* pmat, long long ldp, const __nv
   const int tiles = ((p.wg_rows + 255) / 256) * (p.N / BN) * p.split;
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ta, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ta, ta, p);
   return check_launch("gemm_kernel<wgrad>");
 }
 
