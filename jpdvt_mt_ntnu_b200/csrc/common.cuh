@@ -61,6 +61,7 @@ struct GemmParams {
   // EPI_WGRAD_F32: M = contraction length (token rows), N = output columns (in_features), wg_rows = output rows
   int wg_rows, split, split_len;
   // EPI_RESID_LN_F32: the LayerNorm-modulate that consumes the updated residual rows (models.py:120-121, 19-20)
+  int tma_out;                // bf16 epilogues (bias, bias+GELU): leave through TMA store boxes instead of per-thread stores (set by launch_gemm)
   __nv_bfloat16* out_aux;     // EPI_BIAS_GELU_GRAD_BF16: [M, N] bf16, leading dimension ldo
   __nv_bfloat16* ln_out;      // [M, N] bf16
   const float* ln_shift;      // sample b reads ln_shift + b * ln_stride, [N]

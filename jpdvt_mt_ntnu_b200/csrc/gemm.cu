@@ -699,6 +699,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
           bf16_math<EPI>(v, bias_smem + c * 64, gate4, c * 16);
+          if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+            if (p.tma_out) {
+              // 32 rows x 64 bf16 = one 4 KB box of 128-byte swizzled rows, written row-per-thread (conflict free) and
+              // handed to the TMA: no read-back, no per-thread global store, the previous box drains while this one fills
+              const uint32_t sbase = smem_u32(stage);
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+              const uint32_t mine = sbase + lane * 128, sw = ((sbase >> 7) + lane) & 7;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts_u4_shared(mine + ((j ^ sw) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tma_x, stage, n0, row0);
+                tma_store_commit();
+              }
+              continue;
+            }
+          }
           if constexpr (EPI == EPI_BIAS_GELU_GRAD_BF16) {   // activation and its derivative from one tanh; derivative tile first
             uint32_t gp[32];
 #pragma unroll
@@ -954,7 +975,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }   // !kLNX
   }
 
-  if constexpr (kXR || kLNX) {
+  if constexpr (kXR || kLNX || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
     if (warp >= 2 && lane == 0) tma_store_wait<0>();          // bulk stores read this CTA's shared memory: drain before exit
   }
   tc_fence_before();
@@ -1074,6 +1095,16 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
     rc = make_tmap_f32_box32(&tx, p.out, p.M, p.N, p.ldo);
     if (rc != kOk) return rc;
   }
+  GemmParams pp = p;
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+    static int tma_out = -1;                                 // JPDVT_GEMM_TMA_OUT=0: per-thread coalesced stores instead (A/B knob)
+    if (tma_out < 0) { const char* e = getenv("JPDVT_GEMM_TMA_OUT"); tma_out = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    pp.tma_out = (tma_out && (p.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+    if (pp.tma_out) {
+      rc = make_tmap_bf16_kmajor(&tx, p.out, p.M, p.N, p.ldo, 32);   // {64 cols x 32 rows} boxes, 128-byte swizzle
+      if (rc != kOk) return rc;
+    }
+  }
   CUtensorMap ty = ta;                                       // LayerNorm output boxes (EPI_RESID_LN_TMA_F32 only)
   if constexpr (EPI == EPI_RESID_LN_TMA_F32) {
     rc = make_tmap_bf16_box32(&ty, p.ln_out, p.M, p.N, p.ldo);
@@ -1082,7 +1113,7 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, ty, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, ty, pp);
   return check_launch("gemm_kernel");
 }
 
