@@ -172,7 +172,7 @@ def run_reference(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1e_ncu_full_kernels.json")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1g_ncu_full_kernels.json")
 
 
 def ncu_traffic(label):
@@ -208,8 +208,8 @@ def kernel_roofline(model, wl, batch, peaks):
     calls = {
         "gemm_qkv (tcgen05, bias)": (lambda: ops.gemm_bias(xn, W["w_qkv"][0], W["b_qkv"][0]), 2.0 * M * 768 * 2304, "flop"),
         "gemm_fc1 (tcgen05, bias+gelu)": (lambda: ops.gemm_bias_gelu(xn, W["w_fc1"][0], W["b_fc1"][0]), 2.0 * M * 768 * 3072, "flop"),
-        "gemm_fc2 (tcgen05, bias+gate+residual RMW)": (lambda: ops.gemm_bias_gate_residual(x, hid, W["w_fc2"][0], W["b_fc2"][0], gate, T), 2.0 * M * 3072 * 768, "flop"),
-        "gemm_proj (tcgen05, bias+gate+residual RMW)": (lambda: ops.gemm_bias_gate_residual(x, xn, W["w_proj"][0], W["b_proj"][0], gate, T), 2.0 * M * 768 * 768, "flop"),
+        "gemm_fc2 (tcgen05, gated residual via TMA ring)": (lambda: ops.gemm_bias_gate_residual(x, hid, W["w_fc2"][0], W["b_fc2"][0], gate, T), 2.0 * M * 3072 * 768, "flop"),
+        "gemm_proj (tcgen05, gated residual via TMA ring)": (lambda: ops.gemm_bias_gate_residual(x, xn, W["w_proj"][0], W["b_proj"][0], gate, T), 2.0 * M * 768 * 768, "flop"),
         "attention (tcgen05, S/O in TMEM)": (lambda: ops.attention(qkv, batch, T), 4.0 * batch * 12 * T * T * 64, "flop"),
         "ln_modulate (fp32->bf16)": (lambda: ops.ln_modulate(x, shift, scale, T), M * 768 * 6.0, "byte"),
     }
