@@ -107,7 +107,7 @@ struct TcCfg {
 
 // One softmax pass of the thread's S row (TMEM lane = row, columns [0,T)): exact row maximum, then
 // p = 2^((s - max) * log2(e) / 8) written as bf16 into the K-major swizzled P tile; returns sum(p) (fp32, unrounded p).
-template <int T>
+template <int T, int TV = T>     // T columns are read (multiple of 16); columns >= TV are padding and get probability 0
 __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row_addr, uint32_t blk_stride, int sw, bool store,
                                                   float& ms_out) {
   constexpr float sl2 = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
@@ -131,10 +131,16 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
     const int n = (c < kFull) ? 32 : kTail;
 #pragma unroll
     for (int j = 0; j < n; j += 8) {
-      m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
-      m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
-      m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
-      m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+      if (c * 32 + j + 8 <= TV) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c * 32 + j + e < TV) m0 = fmaxf(m0, __uint_as_float(cur[j + e]));
+      }
     }
     if (c + 1 < kChunks) tmem_ld_wait();
   }
@@ -145,7 +151,7 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
   auto emit8 = [&](const uint32_t* r, int chunk) {            // 8 consecutive keys -> one 16-byte chunk of the P row
     float p[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = ex2f(fmaf(__uint_as_float(r[j]), sl2, -ms));
+    for (int j = 0; j < 8; ++j) p[j] = (chunk * 8 + j < TV) ? ex2f(fmaf(__uint_as_float(r[j]), sl2, -ms)) : 0.f;
     sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
     const uint4 u = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
     if (store) sts_u4(p_row_addr + static_cast<uint32_t>(chunk >> 3) * blk_stride + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4), u);
@@ -476,6 +482,180 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Longer sequences (T = 324 @288 px): keys padded to TP = 336 (a multiple of 16, columns >= T masked to probability 0), the
+// score tile is 128 x TP fp32 = TP TMEM columns (two MMAs per k-step, N <= 256 each), so one score tile at a time: the
+// ceil(T / 128) query tiles of a unit run one after the other, O in its own 64 columns, one CTA per SM.
+template <int TP, int TV>
+struct SeqCfg {
+  static_assert(TP % 16 == 0 && TV <= TP && TP - TV < 16 && TP > 256 && TP + 64 <= 512, "padded key count");
+  static constexpr int kTiles = (TV + 127) / 128;
+  static constexpr int kN1 = (TP / 2 + 15) / 16 * 16, kN2 = TP - kN1;     // the two halves of the key range
+  static constexpr int kKBlocks = (TP + 63) / 64;
+  static constexpr int kTileBytes = TP * 128;                  // Q / K / V each (rows >= TV: whatever follows in memory, masked)
+  static constexpr int kBoxRows = TP / 2;                      // TMA boxes are at most 256 rows: two loads per matrix
+  static constexpr int kOffQ = 0, kOffK = kTileBytes, kOffV = 2 * kTileBytes, kOffP = 3 * kTileBytes;
+  static constexpr int kPBytes = kKBlocks * 16384;
+  static constexpr int kBarOff = kOffP + kPBytes;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static_assert(kOffP % 1024 == 0 && kBoxRows <= 256 && kBoxRows % 8 == 0 && kN2 % 16 == 0 && kN1 <= 256, "layout");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+};
+
+template <int TP, int TV>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                        int num_units) {
+  using Cfg = SeqCfg<TP, TV>;
+  constexpr int kTiles = Cfg::kTiles;
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;        // TMA: Q and K landed                     (once per unit)
+  uint64_t* v_full = bars + 1;         // TMA: V landed                           (once per unit)
+  uint64_t* s_full = bars + 2;         // MMA: scores of the current tile ready   (once per tile)
+  uint64_t* p_full = bars + 3;         // softmax warps: P written, S consumed    (once per tile, 4 arrivals)
+  uint64_t* o_full = bars + 4;         // MMA: O of the current tile ready        (once per tile)
+  uint64_t* o_read = bars + 5;         // softmax warps: O read out of TMEM       (once per tile, 4 arrivals)
+  uint64_t* qk_free = bars + 6;        // MMA: every score MMA of the unit has read Q, K   (once per unit - the per-tile barriers
+  uint64_t* v_free = bars + 7;         // MMA: every P V MMA of the unit has read V          cannot tell tile 0 from tile 2 by parity)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_read, 4);
+    mbar_init(qk_free, 1); mbar_init(v_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sP = smem_u32(smem + Cfg::kOffP);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int b = unit / kHeads, h = unit - b * kHeads;
+        if (it > 0) mbar_wait_backoff(qk_free, static_cast<uint32_t>((it - 1) & 1), 100);   // previous unit's score MMAs are done with Q, K
+        mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ + part * Cfg::kBoxRows * 128, h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+          tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK + part * Cfg::kBoxRows * 128, kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+        }
+        if (it > 0) mbar_wait_backoff(v_free, static_cast<uint32_t>((it - 1) & 1), 100);    // ... and its P V MMAs with V
+        mbar_expect_tx(v_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+          tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV + part * Cfg::kBoxRows * 128, 2 * kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s1 = umma_idesc_bf16(128, Cfg::kN1), idesc_s2 = umma_idesc_bf16(128, Cfg::kN2);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), p_lo = desc_lo_k(sP), v_lo = desc_lo_mn(sV);
+      int it = 0;
+      long long tile_no = 0;            // running tile counter: parity of the per-tile barriers
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        mbar_wait(qk_full, static_cast<uint32_t>(it & 1));
+        for (int t = 0; t < kTiles; ++t, ++tile_no) {
+          const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
+          if (tile_no > 0) mbar_wait(p_full, ph ^ 1);            // the previous tile's softmax has consumed the score columns
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {                // S[:, 0:N1) and S[:, N1:TP) of query rows [128 t, 128 t + 128)
+            const uint32_t a = q_lo + t * 128 * 8 + 2 * k;
+            if (k == 0) { umma_lohi<false>(tmem_base, a, k_lo, idesc_s1); umma_lohi<false>(tmem_base + Cfg::kN1, a, k_lo + Cfg::kN1 * 8, idesc_s2); }
+            else { umma_lohi<true>(tmem_base, a, k_lo + 2 * k, idesc_s1); umma_lohi<true>(tmem_base + Cfg::kN1, a, k_lo + Cfg::kN1 * 8 + 2 * k, idesc_s2); }
+          }
+          umma_commit(s_full);
+          if (t == kTiles - 1) umma_commit(qk_free);
+          mbar_wait(p_full, ph);                                   // P of this tile is in shared memory
+          if (t == 0) mbar_wait(v_full, static_cast<uint32_t>(it & 1));
+          if (tile_no > 0) mbar_wait(o_read, ph ^ 1);            // the previous tile's O has left TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < TP / 16; ++j) {
+            const uint32_t a = p_lo + (j >> 2) * 1024 + (j & 3) * 2, bq = v_lo + j * 128;
+            if (j == 0) umma_lohi<false>(tmem_base + TP, a, bq, idesc_o);
+            else umma_lohi<true>(tmem_base + TP, a, bq, idesc_o);
+          }
+          umma_commit(o_full);
+          if (t == kTiles - 1) umma_commit(v_free);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r_tile = warp * 32 + lane;
+    long long tile_no = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int b = unit / kHeads, h = unit - b * kHeads;
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * TV * kHidden + h * kHeadDim;
+      for (int t = 0; t < kTiles; ++t, ++tile_no) {
+        const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
+        mbar_wait(s_full, ph);
+        if (tile_no > 0) mbar_wait(o_full, ph ^ 1);               // the previous tile's P V MMAs have read the P buffer
+        tc_fence_after();
+        float ms;
+        const float sum = softmax_row_to_p<TP, TV>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        const int row = t * 128 + r_tile;
+        if (lse2 != nullptr && row < TV) lse2[(static_cast<long long>(b) * kHeads + h) * TV + row] = ms + log2f(sum);
+        mbar_wait(o_full, ph);
+        tc_fence_after();
+        uint32_t oa[32], ob[32];
+        load_o_row(t_lane + TP, oa, ob);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_read);
+        // staging in the P buffer: idle between this tile's O MMAs and the next tile's softmax stores (this warp's own rows)
+        const int live = TV - (t * 128 + warp * 32);
+        store_o_rows(oa, ob, 1.0f / sum, sP + static_cast<uint32_t>(warp) * 4096u,
+                     obase + static_cast<long long>(t * 128 + warp * 32) * kHidden, live < 0 ? 0 : (live < 32 ? live : 32), lane);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int TP, int TV>
+int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
+  using Cfg = SeqCfg<TP, TV>;
+  static bool configured = false;
+  auto kern = attention_tc_seq_kernel<TP, TV>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_tc_seq: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    configured = true;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_kmajor(&tm, qkv, static_cast<long long>(batch) * TV, kQkvCols, kQkvCols, Cfg::kBoxRows);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  kern<<<units < sms ? units : sms, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units);
+  return check_launch("attention_tc_seq_kernel");
+}
+
 template <int T>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = TcCfg<T>;
@@ -533,7 +713,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
 
 }  // namespace
 
-bool attention_tc_supported(int tokens) { return tokens == 144 || tokens == 256; }
+bool attention_tc_supported(int tokens) { return tokens == 144 || tokens == 256 || tokens == 324; }
 
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0) return kOk;
@@ -542,6 +722,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
   switch (tokens) {
     case 144: return launch_tc<144>(qkv, out, lse2, batch, stream);
     case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
+    case 324: return launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
   }
 }

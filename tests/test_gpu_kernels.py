@@ -112,7 +112,7 @@ def test_ln_modulate(ops, rows, T, ncond):
 
 
 @pytest.mark.parametrize("B,T", [(2, 144), (3, 9), (2, 256), (2, 324), (1, 36), (5, 64), (2, 100), (1, 1), (1, 17),
-                                 (1, 144), (7, 144), (31, 144), (1, 256), (5, 256)])   # T in {144, 256}: tcgen05 kernel
+                                 (1, 144), (7, 144), (31, 144), (1, 256), (5, 256), (13, 324), (40, 324)])   # T in {144, 256, 324}: tcgen05
 def test_attention(ops, B, T):
     torch.manual_seed(T)
     qkv = (torch.randn(B * T, 2304, device="cuda") * 1.5).bfloat16()
