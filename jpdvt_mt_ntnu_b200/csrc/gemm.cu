@@ -936,6 +936,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
             }
           }
+          if constexpr (WG) {
+            if (p.tma_out) {
+              // split contraction: every split ADDS its 32 x 32 fp32 chunk into the gradient through a TMA reduction box -
+              // no partial buffers, no reduction pass (the caller zeroes the gradient first)
+              const uint32_t sbase = smem_u32(stage);
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+              const uint32_t mine = sbase + lane * 128, sw = ((sbase >> 7) + lane) & 7;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mine + ((j ^ sw) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                             "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_reduce_add_2d(&tma_x, stage, n0, row0);
+                tma_store_commit();
+              }
+              continue;
+            }
+          }
           if constexpr (EPI == EPI_PATCH_EMBED_F32) {
             // + x_t[row, :8] . w_in_t[:, n]  (time_emb_in, models.py:280); 8 FMAs per output, weights broadcast from L1
 #pragma unroll
@@ -975,7 +996,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }   // !kLNX
   }
 
-  if constexpr (kXR || kLNX || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+  if constexpr (kXR || kLNX || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_WGRAD_F32) {
     if (warp >= 2 && lane == 0) tma_store_wait<0>();          // bulk stores read this CTA's shared memory: drain before exit
   }
   tc_fence_before();
@@ -1229,10 +1250,15 @@ static int launch_wgrad_cfg(const __nv_bfloat16* pmat, long long ldp, const __nv
   if (rc != kOk) return rc;
   rc = make_tmap_bf16_kmajor(&tb, qmat, p.M, p.N, ldq, 64);
   if (rc != kOk) return rc;
+  CUtensorMap tx = ta;
+  if (p.tma_out) {
+    rc = make_tmap_f32_box32(&tx, p.out, p.wg_rows, p.N, p.ldo);
+    if (rc != kOk) return rc;
+  }
   const int tiles = ((p.wg_rows + 255) / 256) * (p.N / BN) * p.split;
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ta, ta, p);
+  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, ta, p);
   return check_launch("gemm_kernel<wgrad>");
 }
 
@@ -1247,6 +1273,17 @@ int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* 
   p.M = static_cast<int>(m); p.N = n_cols; p.K = BK; p.tokens = 1;
   p.wg_rows = out_rows; p.ldo = n_cols;
   wgrad_plan(m, out_rows, n_cols, &p.split, &p.split_len);
+  static int tma_red = -1;          // JPDVT_WGRAD_TMA_REDUCE=0: split partials to scratch + a reduction pass instead (A/B knob)
+  if (tma_red < 0) { const char* e = getenv("JPDVT_WGRAD_TMA_REDUCE"); tma_red = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (p.split > 1 && tma_red && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (n_cols % 4) == 0) {
+    // splits accumulate straight into the gradient with TMA reduction boxes
+    if (cudaMemsetAsync(out, 0, static_cast<size_t>(out_rows) * n_cols * sizeof(float), stream) != cudaSuccess)
+      return set_error(kErrCuda, "wgrad: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    p.out = out;
+    p.tma_out = 1;
+    return (n_cols % 256 == 0) ? launch_wgrad_cfg<256>(pmat, ldp, qmat, ldq, p, stream)
+                               : launch_wgrad_cfg<128>(pmat, ldp, qmat, ldq, p, stream);
+  }
   if (p.split > 1 && partial == nullptr) return set_error(kErrBadArg, "wgrad: scratch buffer required (split=%d)", p.split);
   p.out = (p.split > 1) ? partial : out;
   int rc = (n_cols % 256 == 0) ? launch_wgrad_cfg<256>(pmat, ldp, qmat, ldq, p, stream)

@@ -114,6 +114,13 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const vo
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "l"(hint)
                : "memory");
 }
+// 2-D tiled reduction shared -> global: global[box] += shared[box] (element type from the tensor map; fp32 here)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
