@@ -292,7 +292,7 @@ class GaussianDiffusion:
         return buf
 
     def p_sample_loop(self, model, condition, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
-                      model_kwargs=None, device=None, progress=False, chain=False, step_noise=None):
+                      model_kwargs=None, device=None, progress=False, chain=False, step_noise=None, graph=False):
         """gaussian_diffusion.py:433-478.  Default behaviour reproduces the reference exactly, including its loop quirk
         (every step is fed the initial `noise`, :518-529); `chain=True` (extra keyword) feeds the running sample."""
         dit = self._fast_path(model, clip_denoised, denoised_fn, cond_fn, model_kwargs)
@@ -303,7 +303,10 @@ class GaussianDiffusion:
             if step_noise is None:
                 step_noise = self._draw_step_noise(noise)
             with th.no_grad():
-                state = dit.engine(dev).sample_loop(self.device_tables(dev), condition, noise, step_noise, chain=chain)
+                eng = dit.engine(dev)
+                # graph=True (extra keyword): replay the whole loop from a CUDA graph - worth it for small, repeated batches
+                run = eng.sample_loop_graphed if graph else eng.sample_loop
+                state = run(self.device_tables(dev), condition, noise, step_noise, chain=chain)
             return state["sample"]
         final = None
         for final in self.p_sample_loop_progressive(model, condition, shape, noise=noise, clip_denoised=clip_denoised,

@@ -70,10 +70,11 @@ class _FakeSolver:
     def draw_indices(self, batch):
         return np.stack([np.roll(np.arange(9), b + 1) for b in range(batch)]).astype(np.int32)
 
-    def solve(self, images, indices=None, want_images=False, prescrambled=False, **kw):
+    def solve(self, images, indices=None, want_images=False, prescrambled=False, graph=False, **kw):
         from jpdvt_mt_ntnu_b200.frontend import SolveResult
         B = images.shape[0]
         self.calls.append((B, prescrambled))
+        self.graph_calls = getattr(self, "graph_calls", 0) + int(graph)
         idx = torch.as_tensor(indices if indices is not None else self.draw_indices(B), dtype=torch.int32)
         pred = idx.clone()
         wrong = images.reshape(B, -1)[:, 0] < 0                 # requests flagged by a negative first pixel are mis-solved
@@ -112,6 +113,12 @@ def test_microbatcher_groups_requests_and_routes_results():
             mb.submit(torch.ones(3, 4, 4)).result(timeout=30)
     with pytest.raises(RuntimeError):
         mb.submit(torch.ones(3, 4, 4))                           # closed
+    # graph mode: every batch padded to max_batch, padding rows never reach a caller
+    fake2 = _FakeSolver()
+    with fe.MicroBatcher(fake2, max_batch=4, max_wait_ms=20.0, graph=True) as mb:
+        outs = [mb.submit(torch.full((3, 4, 4), float(i + 1)), indices=np.roll(np.arange(9), i)).result(timeout=30) for i in range(3)]
+    assert all(b == 4 for b, _ in fake2.calls) and fake2.graph_calls == len(fake2.calls)
+    assert [o["indices"] for o in outs] == [np.roll(np.arange(9), i).tolist() for i in range(3)]
 
 
 # ------------------------------------------------------------------------------------------------------------- GPU
@@ -278,3 +285,9 @@ def test_microbatcher_and_prescrambled_on_device(cuda):
         assert torch.equal(r["scrambled_image"], pre[i]) and tuple(r["solution_image"].shape) == (3, 96, 96)
         assert r["patch_matches"] == int((np.asarray(r["predicted_order"]) == perms[i]).sum())
     assert 2 <= mb.batches_run <= 6
+    # the whole loop replayed from a CUDA graph: bit-identical to the launched loop
+    torch.manual_seed(0)
+    r3 = solver.solve(imgs, indices=perms, graph=True)
+    torch.manual_seed(0)
+    r4 = solver.solve(imgs, indices=perms, graph=True)                                            # replay of the cached graph
+    assert torch.equal(r3.latents, r2.latents) and torch.equal(r4.latents, r2.latents) and torch.equal(r3.pred, r2.pred)
