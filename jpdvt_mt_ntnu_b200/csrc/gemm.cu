@@ -1084,13 +1084,17 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int epi_warps() {
-  static int ew = 0;
-  if (ew == 0) {
-    const char* e = getenv("JPDVT_GEMM_EPI_WARPS");   // tuning knob: 4 or 8 epilogue warps per CTA (default 8)
-    ew = (e != nullptr && e[0] == '4') ? 4 : 8;
+// Epilogue warps per CTA.  The bias / bias+GELU epilogues hand their tiles to TMA store boxes and are best with four
+// (qkv 98 vs 101 us, fc1 140 vs 143 us at M = 36,864); the epilogues that still move data per thread (dGELU, fp32 outputs,
+// weight gradients) want eight.  JPDVT_GEMM_EPI_WARPS=4|8 forces one value for all of them (A/B knob).
+static int epi_warps(int epi) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("JPDVT_GEMM_EPI_WARPS");
+    forced = (e == nullptr) ? 0 : (e[0] == '4' ? 4 : 8);
   }
-  return ew;
+  if (forced) return forced;
+  return (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) ? 4 : 8;
 }
 
 template <int BN, int EPI, int EW, int NB = 0>
@@ -1142,7 +1146,7 @@ template <int BN, int EPI>
 static int launch_cs(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                      cudaStream_t stream) {
   if constexpr (EPI == EPI_HEAD) return launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
-  else return epi_warps() == 8 ? launch_cfg<BN, EPI, 8>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
+  else return epi_warps(EPI) == 8 ? launch_cfg<BN, EPI, 8>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
 }
 
 int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
