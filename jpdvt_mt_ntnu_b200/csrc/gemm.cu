@@ -1166,7 +1166,8 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     if (p.N % 256 != 0 || (p.ldo % 4) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15))
       return set_error(kErrBadArg, "gemm: the TMA residual epilogue needs N %% 256 == 0 and a 16-byte aligned residual stream");
     static int ring = -1;                                     // JPDVT_RESID_RING=2|3: boxes per warp (3 costs a pipeline stage)
-    if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && e[0] == '3') ? 3 : 2; }
+    if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 2; }
+    if (ring == 4) return launch_cfg<256, EPI_RESID_TMA_F32, 4, 4>(a, lda, w, ldw, p, stream);   // four warps, four boxes each
     return ring == 3 ? launch_cfg<256, EPI_RESID_TMA_F32, 8, 3>(a, lda, w, ldw, p, stream)
                      : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
   }
