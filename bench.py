@@ -270,13 +270,12 @@ def run_ours(args, wl):
     cond_h, noise_h, perms = synthetic_inputs(wl, batch, seed=rank)
     cond_pin, noise_pin = cond_h.pin_memory(), noise_h.pin_memory()
     cond, noise = cond_pin.to(dev), noise_pin.to(dev)
-    torch.manual_seed(rank)
-    step_noise = torch.randn(diffusion.num_timesteps, batch, T, 8, device=dev)   # per-step randn (parity-mode noise buffer)
+    torch.manual_seed(rank)        # the loop draws its own randn_like per step inside the timed region, as p_sample does (:424)
     gathered = [torch.empty(batch, G * G, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
 
     def one_step(c, z):
         sample = diffusion.p_sample_loop(model.forward, c, z.shape, z, clip_denoised=False, model_kwargs=None,
-                                         progress=False, device=dev, step_noise=step_noise)
+                                         progress=False, device=dev)
         order, pred = assignment.solve_puzzles(sample, G)
         if world > 1:
             dist.all_gather(gathered, pred)          # the only cross-rank traffic: int32 placements (inference_ddp.py:485-495)
