@@ -31,7 +31,8 @@ constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpos
 
 constexpr int kXBoxBytes = 32 * 32 * 4;                   // one residual box: 32 rows x 32 fp32 columns (128-byte swizzled rows)
 
-template <int BN, int CS, int EW, int NB = 0>              // NB > 0: per-warp ring of NB residual boxes instead of the staging tiles
+// NB > 0: per-warp ring of NB residual boxes instead of the staging tiles; LNS: room for the LayerNorm row statistics
+template <int BN, int CS, int EW, int NB = 0, bool LNS = false>
 struct GemmCfg {
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kBRows = BN / CS;                  // W rows this CTA loads
@@ -42,7 +43,7 @@ struct GemmCfg {
   // per warp and tile: bias slice + gate slices of <= 2 samples (the residual-ring variant reads them through L1 instead:
   // its ring needs the room to keep the five pipeline stages)
   static constexpr int kVecWarpBytes = NB > 0 ? 0 : 3 * kColsPerWarp * 4;
-  static constexpr int kLnStatsBytes = NB > 0 ? 0 : 2 * 2 * BM * 8;   // EPI_RESID_LN_F32: (mean, M2) per row, column half, M-block parity
+  static constexpr int kLnStatsBytes = LNS ? 2 * 2 * BM * 8 : 0;      // EPI_RESID_LN_F32: (mean, M2) per row, column half, M-block parity
   static constexpr int kStagingBytes = NB > 0 ? EW * NB * kXBoxBytes : EW * kStageWarpBytes;
   // staging + barriers + align slack (+ the head epilogue's static arrays, absent from the ring variant)
   static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + (NB > 0 ? 0 : 2304);
@@ -213,7 +214,7 @@ template <int BN, int EPI, int CS, int EW, int NB = 0>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_y, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CS, EW, NB>;
+  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
   static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32 || EPI == EPI_RESID_LN_TMA_F32), "the residual ring belongs to the TMA residual epilogues");
   constexpr int kColsPerWarp = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -1101,7 +1102,7 @@ template <int BN, int EPI, int EW, int NB = 0>
 static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                       cudaStream_t stream) {
   constexpr int CS = 2;
-  using Cfg = GemmCfg<BN, CS, EW, NB>;
+  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
   static_assert(Cfg::kStages >= 3, "pipeline too shallow");
   static bool attr_set = false;
   auto kern = gemm_kernel<BN, EPI, CS, EW, NB>;
