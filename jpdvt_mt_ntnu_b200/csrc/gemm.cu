@@ -1166,11 +1166,15 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");
     if (p.N % 256 != 0 || (p.ldo % 4) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15))
       return set_error(kErrBadArg, "gemm: the TMA residual epilogue needs N %% 256 == 0 and a 16-byte aligned residual stream");
-    static int ring = -1;                                     // JPDVT_RESID_RING=2|3: boxes per warp (3 costs a pipeline stage)
-    if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 2; }
+    static int ring = -1, e_forced = 0;                       // JPDVT_RESID_RING: 2 = eight warps x two boxes for every K, 3/4/5 variants
+    if (ring < 0) { const char* e = getenv("JPDVT_RESID_RING"); ring = (e != nullptr && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 2; e_forced = (e != nullptr) ? 1 : 0; }
     if (ring == 4) return launch_cfg<256, EPI_RESID_TMA_F32, 4, 4>(a, lda, w, ldw, p, stream);   // four warps, four boxes each
-    return ring == 3 ? launch_cfg<256, EPI_RESID_TMA_F32, 8, 3>(a, lda, w, ldw, p, stream)
-                     : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
+    if (ring == 5) return launch_cfg<256, EPI_RESID_TMA_F32, 4, 2>(a, lda, w, ldw, p, stream);   // four warps, two boxes, six stages
+    if (ring == 3) return launch_cfg<256, EPI_RESID_TMA_F32, 8, 3>(a, lda, w, ldw, p, stream);
+    // default: long contractions (fc2) are MMA-bound - four epilogue warps leave room for a sixth pipeline stage (136.5 vs
+    // 139.3 us); short ones (proj) are bound by the residual traffic and want all eight warps moving boxes (56 vs 67 us)
+    return (e_forced == 0 && p.K >= 2048) ? launch_cfg<256, EPI_RESID_TMA_F32, 4, 2>(a, lda, w, ldw, p, stream)
+                                          : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
   }
   if (epi == EPI_RESID_LN_TMA_F32) {
     if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");
