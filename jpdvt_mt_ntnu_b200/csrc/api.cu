@@ -21,6 +21,12 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+bool pdl_enabled() {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("JPDVT_PDL"); pdl = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return pdl != 0;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(kErrCuda, "%s: launch failed: %s", what, cudaGetErrorString(e));

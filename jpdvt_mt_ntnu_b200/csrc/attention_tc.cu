@@ -288,6 +288,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                  // the prologue above may overlap the previous kernel's tail (programmatic dependent launch)
+  griddep_launch_dependents();
   const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
                  sP = smem_u32(smem + Cfg::kOffP), sP1 = smem_u32(smem + Cfg::kOffP1);
   constexpr int kLast = Cfg::kTiles - 1;
@@ -707,7 +709,8 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
       }
     return check_launch("attention_tc_kernel<trace>");
   }
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, nullptr);
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, static_cast<long long*>(nullptr)) != cudaSuccess)
+    return set_error(kErrCuda, "attention_tc_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("attention_tc_kernel");
 }
 

@@ -21,6 +21,21 @@ enum Status : int {
 };
 
 int set_error(int code, const char* fmt, ...);
+
+// Launch with the programmatic-stream-serialization attribute (JPDVT_PDL=0: plain stream order).  Only for kernels that call
+// griddep_wait() before their first global access.
+bool pdl_enabled();
+template <typename... KP, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
+}
 int check_launch(const char* what);
 
 // GEMM epilogues (see gemm.cu)

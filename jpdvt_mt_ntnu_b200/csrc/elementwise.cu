@@ -31,6 +31,8 @@ ln_modulate_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, co
                    const float* __restrict__ gate, long long gate_stride, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_stride, __nv_bfloat16* __restrict__ y, long long rows,
                    int tokens) {
+  griddep_wait();
+  griddep_launch_dependents();
   const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -92,10 +94,14 @@ int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* del
   if (tokens <= 0) return set_error(kErrBadArg, "ln_modulate: tokens must be positive");
   if (delta != nullptr && x_out == nullptr) return set_error(kErrBadArg, "ln_modulate: residual update needs an output buffer");
   const unsigned blocks = static_cast<unsigned>((rows + kLnWarps - 1) / kLnWarps);
+  cudaError_t e;
   if (delta != nullptr)
-    ln_modulate_kernel<true><<<blocks, kLnWarps * 32, 0, stream>>>(x_in, x_out, delta, gate, gate_stride, shift, scale, mod_stride, y, rows, tokens);
+    e = launch_pdl(ln_modulate_kernel<true>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
+                   mod_stride, y, rows, tokens);
   else
-    ln_modulate_kernel<false><<<blocks, kLnWarps * 32, 0, stream>>>(x_in, x_out, delta, gate, gate_stride, shift, scale, mod_stride, y, rows, tokens);
+    e = launch_pdl(ln_modulate_kernel<false>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
+                   mod_stride, y, rows, tokens);
+  if (e != cudaSuccess) return set_error(kErrCuda, "ln_modulate_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("ln_modulate_kernel");
 }
 

@@ -284,6 +284,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if constexpr (CS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                  // everything above overlapped the previous kernel's tail; from here on global memory is touched
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane per CTA)
@@ -1139,7 +1141,8 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
   const int groups = tiles < max_groups ? tiles : max_groups;
-  kern<<<groups * CS, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tx, ty, pp);
+  if (launch_pdl(kern, dim3(groups * CS), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, ta, tb, tx, ty, pp) != cudaSuccess)
+    return set_error(kErrCuda, "gemm_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("gemm_kernel");
 }
 
