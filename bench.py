@@ -16,6 +16,7 @@ oracle port (torch fp32, all host threads) on a bounded sample.  `--impl referen
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -147,12 +148,64 @@ def cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=4):
     return sample_batch / total, cores, f"{sample_batch} puzzles x {sample_steps} of {wl['steps']} diffusion steps + assignment, scaled x{wl['steps']}/{sample_steps}", t_steps + t_assign
 
 
+def stock_torch_gpu_puzzles_per_s(wl, batch, precision="fp32", sample_steps=5):
+    """SURVEY.md 8(d) "same box" comparator: the oracle's stock torch ops (what the reference's fp32 nn.Modules execute)
+    moved to cuda:0 - cuBLAS / ATen kernels, none of this repo's - on the bench batch, `sample_steps` of the 250 steps
+    scaled up + the host assignment loop.  precision: fp32 (inference.py), tf32 (train_JPDVT.py:5-6), bf16 (autocast)."""
+    import torch
+    from oracle import jpdvt_oracle as orc
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = precision == "tf32"
+    S, G = wl["size"], wl["grid"]
+    model = orc.OracleDenoiser(orc.seeded_state(orc.blank_state(S, DEPTH), seed=1234), depth=DEPTH, device=dev)
+    sched = orc.Schedule(str(wl["steps"]))
+    cond, noise, _ = synthetic_inputs(wl, batch)
+    cond, noise = cond.to(dev), noise.to(dev)
+    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if precision == "bf16" else contextlib.nullcontext()
+
+    def step(k):
+        t = torch.full((batch,), sched.num_timesteps - 1 - k, dtype=torch.long, device=dev)
+        return sched.p_step(model, cond, noise, t, torch.randn_like(noise))
+
+    with torch.no_grad(), ctx:
+        for k in range(2):
+            step(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(sample_steps):
+            out = step(k)
+        torch.cuda.synchronize()
+        t_steps = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lat = out["sample"].float().cpu()
+    for b in range(batch):
+        orc.solve(lat[b], G, S // (16 * G))
+    t_assign = time.perf_counter() - t0
+    total = t_steps / sample_steps * wl["steps"] + t_assign
+    return batch / total, 1000.0 * t_steps / sample_steps, 1000.0 * t_assign
+
+
+def run_reference_gpu(args, wl):
+    """`--impl reference --ref-device cuda`: not part of the driver contract (its reference arm is the CPU one below);
+    prints one line per precision for DESIGN.md's comparison table."""
+    batch = args.batch or wl["batch"]
+    for prec in args.ref_precision.split(","):
+        v, ms, ms_assign = stock_torch_gpu_puzzles_per_s(wl, batch, prec, sample_steps=max(1, args.steps))
+        print(json.dumps({"impl": "reference", "device": "cuda:0 (stock torch ops)", "precision": prec,
+                          "metric": "puzzles/sec (3x3 @192px sampling)", "value": v, "unit": "puzzles/s",
+                          "ms_per_diffusion_step": ms, "assignment_ms": ms_assign,
+                          "config": {"workload": wl["name"], "batch": batch, "diffusion_steps": wl["steps"]}}))
+
+
 def run_reference(args, wl):
     """`--impl reference`: the reference path's CPU implementation (oracle port; the Python reference cannot travel to
     the GPU box) on the host cores.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_gpu(args, wl)
     vals, spent = [], 0.0
     for i in range(args.warmup + args.steps):
         v, cores, sample, dt = cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=2)
@@ -481,6 +534,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cuda = stock torch ops on the GPU (same-box comparator, not the contract arm)")
+    ap.add_argument("--ref-precision", default="fp32,tf32,bf16")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="puzzles per GPU (default: the workload's)")
     args = ap.parse_args()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JPDVT_ABI_VERSION 1
+#define JPDVT_ABI_VERSION 2
 #define JPDVT_HIDDEN 768
 #define JPDVT_LATENT 8
 
@@ -82,6 +82,23 @@ int jpdvt_gemm_bias_gate_residual(const jpdvt_bf16* a, const jpdvt_bf16* w, cons
 int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
                                      int64_t gate_stride, float* x, const float* ln_shift, const float* ln_scale,
                                      int64_t mod_stride, jpdvt_bf16* xn, int64_t m, int n, int k, int tokens, void* stream);
+/* The LayerNorm-modulate that FOLLOWS a gated residual update, folded into the GEMM that consumes it (sampling loop: every
+ * puzzle of the batch shares the timestep, gaussian_diffusion.py:509, so shift / scale are one vector per block):
+ *   modulate(LayerNorm(x), shift, scale) . W^T + b  (models.py:19-20,107-121)
+ *     = rstd * (bf16(x) . W'^T) - rstd * mean * u + v,   W' = W (1 + scale), u = rowsum(W'), v = b + W . shift
+ * jpdvt_gemm_bias_gate_residual_copy: jpdvt_gemm_bias_gate_residual that also leaves bf16(x) in x_bf16 [m, n] and the
+ *   rows' (sum, sum of squares) partials in row_stats [m, 2 * n / 256, 2] fp32 (n a multiple of 256).
+ * jpdvt_fold_ln_weights: W', u, v for the qkv (rows 0..2303) and fc1 (rows 2304..5375) matrices of every block from row 0
+ *   of the adaLN table `mod` (jpdvt_adaln_table layout): w_fold [depth, 5376, 768] bf16, fold_u / fold_v [depth, 5376].
+ * jpdvt_gemm_ln_folded: out = [gelu_tanh](rstd * (x_bf16 . w_fold^T) - rstd * mean * fold_u + fold_v), mean / rstd of each
+ *   row from row_stats over the k inputs (eps 1e-6, biased variance). */
+int jpdvt_gemm_bias_gate_residual_copy(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                       int64_t gate_stride, float* x, jpdvt_bf16* x_bf16, float* row_stats, int64_t m, int n,
+                                       int k, int tokens, void* stream);
+int jpdvt_fold_ln_weights(const jpdvt_bf16* w_qkv, const jpdvt_bf16* w_fc1, const float* b_qkv, const float* b_fc1, const float* mod,
+                          jpdvt_bf16* w_fold, float* fold_u, float* fold_v, int depth, void* stream);
+int jpdvt_gemm_ln_folded(int gelu, const jpdvt_bf16* x_bf16, const float* row_stats, int stats_slots, const jpdvt_bf16* w_fold,
+                         const float* fold_u, const float* fold_v, jpdvt_bf16* out, int64_t m, int n, int k, void* stream);
 /* x = cols . w_patch^T + bias + pos_embed[row % tokens] + x_t[row] . w_in_t   (PatchEmbed conv as GEMM + time_emb_in +
  * pos_embed, models.py:280-281).  cols = jpdvt_patchify(img); bias = x_embedder.proj.bias + time_emb_in.bias;
  * w_in_t = time_emb_in.weight^T as [8,768] fp32; pos = pos_embed [tokens,768] fp32. */
@@ -201,6 +218,12 @@ typedef struct jpdvt_workspace {
   float* silu_c;                /* [cond_rows, 768] */
   jpdvt_bf16* silu_c_bf16;      /* [cond_rows, 768] (tensor-core adaLN path, cond_rows > 8) */
   float* mod;                   /* [cond_rows, depth*4608 + 1536] */
+  /* LayerNorm folded into the qkv / fc1 GEMMs (batch-uniform timestep, i.e. the sampling loop - all four NULL = off):
+   * modulate(LayerNorm(x), shift, scale) . W^T + b (models.py:19-20,120-121) = rstd * (x . W'^T) - rstd * mean * u + v */
+  jpdvt_bf16* w_fold;           /* [depth, 2304 + 3072, 768] W' = W * (1 + scale), rebuilt every forward */
+  float* fold_u;                /* [depth, 5376] row sums of W' */
+  float* fold_v;                /* [depth, 5376] b + W . shift */
+  float* row_stats;             /* [rows, 6, 2] per-row (sum, sum of squares) partials of the residual stream */
 } jpdvt_workspace;
 
 /* One DiT.forward (models.py:273-293): (img [B,3,S,S], t, x_t [B,T,8]) -> te_out [B,T,8] and, when img_out != NULL,

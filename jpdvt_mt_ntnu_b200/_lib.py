@@ -30,7 +30,8 @@ class Weights(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cond_rows", C.c_int32), ("reserved", C.c_int32)] + [
-        (n, c_void_p) for n in ("x", "xn", "qkv", "attn", "hid", "y", "y32", "c", "silu_c", "silu_c_bf16", "mod")]
+        (n, c_void_p) for n in ("x", "xn", "qkv", "attn", "hid", "y", "y32", "c", "silu_c", "silu_c_bf16", "mod",
+                                "w_fold", "fold_u", "fold_v", "row_stats")]
 
 
 class Sampler(C.Structure):
@@ -74,6 +75,9 @@ PROTOTYPES = {
     "jpdvt_gemm_bias_gate": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_bias_gate_residual": [P, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
     "jpdvt_gemm_bias_gate_residual_ln": [P, P, P, P, c_int64, P, P, P, c_int64, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_gemm_bias_gate_residual_copy": [P, P, P, P, c_int64, P, P, P, c_int64, c_int, c_int, c_int, P],
+    "jpdvt_fold_ln_weights": [P, P, P, P, P, P, P, P, c_int, P],
+    "jpdvt_gemm_ln_folded": [c_int, P, P, c_int, P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_patch_embed": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "jpdvt_final_head_fwd": [P, P, P, P, P, P, c_int64, P],
     "jpdvt_attention_fwd": [P, P, P, c_int, c_int, P],

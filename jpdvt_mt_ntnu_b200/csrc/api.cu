@@ -114,11 +114,30 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   // epilogue warps are latency-bound on the row read-back), so the default keeps the separate, HBM-rate LN launches.
   static int ln_fused = -1;
   if (ln_fused < 0) { const char* e = getenv("JPDVT_LN_FUSED"); ln_fused = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  // LayerNorm folded into the consuming GEMM (fold.cu): batch-uniform timestep only (one shift / scale vector per block),
+  // i.e. the sampling loop.  The proj / fc2 epilogues then also leave bf16(x) in xn plus the rows' (sum, sum of squares),
+  // qkv / fc1 contract against W (1 + scale) and finish the LayerNorm per row in their epilogue.  Opt-in (JPDVT_LN_FOLD=1):
+  // parity-green, but at M = 36,864 the epilogue additions (qkv +4..7, fc1 +7..13, proj +21, fc2 +15 us) cancel the two
+  // LayerNorm launches they replace (2 x 27 us) - 7.55 vs 7.50 ms per step - so the default keeps the stand-alone kernels.
+  static int ln_fold_env = -1;
+  if (ln_fold_env < 0) { const char* e = getenv("JPDVT_LN_FOLD"); ln_fold_env = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  const bool fold = ln_fold_env && !ln_fused && t == nullptr && ws->w_fold != nullptr && ws->fold_u != nullptr &&
+                    ws->fold_v != nullptr && ws->row_stats != nullptr && resid_epilogue(kHidden, kHidden) == EPI_RESID_TMA_F32;
+  constexpr int kFoldRows = 7 * kHidden, kStatSlots = 2 * (kHidden / 256);
+  float2* row_stats = reinterpret_cast<float2*>(ws->row_stats);
+  if (fold)
+    JP_TRY(launch_fold_ln(reinterpret_cast<bfp>(w->w_qkv), reinterpret_cast<bfp>(w->w_fc1), w->b_qkv, w->b_fc1, ws->mod,
+                          reinterpret_cast<__nv_bfloat16*>(ws->w_fold), ws->fold_u, ws->fold_v, depth, st));
+  // folded = true: the LayerNorm that follows is folded into its consumer, so only bf16(x) and the row sums are produced
   auto resid_gemm = [&](bfp a, long long lda, bfp wt, const float* bias, int k, const float* gate, const float* shift,
-                        const float* scale) -> int {
+                        const float* scale, bool folded) -> int {
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = k; p.tokens = T;
     p.bias = bias; p.out = ws->x; p.ldo = kHidden; p.gate = gate; p.gate_stride = mod_stride;
+    if (folded) {
+      p.ln_out = xn; p.stats_out = row_stats; p.stats_slots = kStatSlots;
+      return launch_gemm(EPI_RESID_TMA_XB_F32, a, lda, wt, lda, p, st);
+    }
     if (ln_fused) {
       p.ln_out = xn; p.ln_shift = shift; p.ln_scale = scale; p.ln_stride = mod_stride;
       return launch_gemm(resid_ln_epilogue(), a, lda, wt, lda, p, st);
@@ -136,22 +155,36 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 3 * kHidden; p.K = kHidden; p.tokens = T;
       p.bias = w->b_qkv + static_cast<long long>(i) * 3 * kHidden; p.out = qkv; p.ldo = 3 * kHidden;
-      JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden, kHidden, p, st));
+      bfp wt = reinterpret_cast<bfp>(w->w_qkv) + static_cast<long long>(i) * 3 * kHidden * kHidden;
+      if (fold && i > 0) {               // block 0 reads the stand-alone LayerNorm of the embedding
+        wt = reinterpret_cast<bfp>(ws->w_fold) + static_cast<long long>(i) * kFoldRows * kHidden;
+        p.bias = ws->fold_v + static_cast<long long>(i) * kFoldRows; p.fold_u = ws->fold_u + static_cast<long long>(i) * kFoldRows;
+        p.stats_in = row_stats; p.stats_slots = kStatSlots;
+      }
+      JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, wt, kHidden, p, st));
     }
     JP_TRY(launch_attention(qkv, att, nullptr, batch, T, st));
     // the gated residual update AND the LayerNorm-modulate of the MLP branch are the proj GEMM's epilogue
     JP_TRY(resid_gemm(att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden,
-                      w->b_proj + static_cast<long long>(i) * kHidden, kHidden, mod + 2 * kHidden, mod + 3 * kHidden, mod + 4 * kHidden));
+                      w->b_proj + static_cast<long long>(i) * kHidden, kHidden, mod + 2 * kHidden, mod + 3 * kHidden, mod + 4 * kHidden, fold));
     // x += gate_mlp * fc2(gelu(fc1(modulate(LN(x), shift_mlp, scale_mlp))))  (models.py:121)
     {
       GemmParams p{};
       p.M = static_cast<int>(M); p.N = 4 * kHidden; p.K = kHidden; p.tokens = T;
       p.bias = w->b_fc1 + static_cast<long long>(i) * 4 * kHidden; p.out = hid; p.ldo = 4 * kHidden;
-      JP_TRY(launch_gemm(EPI_BIAS_GELU_BF16, xn, kHidden, reinterpret_cast<bfp>(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden, kHidden, p, st));
+      bfp wt = reinterpret_cast<bfp>(w->w_fc1) + static_cast<long long>(i) * 4 * kHidden * kHidden;
+      if (fold) {
+        const long long off = static_cast<long long>(i) * kFoldRows + 3 * kHidden;
+        wt = reinterpret_cast<bfp>(ws->w_fold) + off * kHidden;
+        p.bias = ws->fold_v + off; p.fold_u = ws->fold_u + off;
+        p.stats_in = row_stats; p.stats_slots = kStatSlots;
+      }
+      JP_TRY(launch_gemm(EPI_BIAS_GELU_BF16, xn, kHidden, wt, kHidden, p, st));
     }
     // ... and fc2's epilogue also produces the next block's (or the final layer's) modulate(LN(x), shift, scale)
     JP_TRY(resid_gemm(hid, 4 * kHidden, reinterpret_cast<bfp>(w->w_fc2) + static_cast<long long>(i) * 4 * kHidden * kHidden,
-                      w->b_fc2 + static_cast<long long>(i) * kHidden, 4 * kHidden, mod + 5 * kHidden, nxt, nxt + kHidden));
+                      w->b_fc2 + static_cast<long long>(i) * kHidden, 4 * kHidden, mod + 5 * kHidden, nxt, nxt + kHidden,
+                      fold && i + 1 < depth));   // the final layer's LayerNorm stays stand-alone
   }
   // final layer + position head                                            (models.py:287-290)
   {
@@ -259,6 +292,36 @@ int jpdvt_gemm_bias_gate_residual_ln(const jpdvt_bf16* a, const jpdvt_bf16* w, c
   p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
   p.ln_out = BFM(xn); p.ln_shift = ln_shift; p.ln_scale = ln_scale; p.ln_stride = mod_stride;
   return launch_gemm(resid_ln_epilogue(), BF(a), k, BF(w), k, p, ST(stream));
+}
+int jpdvt_gemm_bias_gate_residual_copy(const jpdvt_bf16* a, const jpdvt_bf16* w, const float* bias, const float* gate,
+                                       int64_t gate_stride, float* x, jpdvt_bf16* x_bf16, float* row_stats, int64_t m, int n,
+                                       int k, int tokens, void* stream) {
+  if (m == 0) return kOk;
+  if (!a || !w || !bias || !gate || !x || !x_bf16 || !row_stats) return set_error(kErrBadArg, "gemm_bias_gate_residual_copy: null pointer");
+  if (tokens <= 0) return set_error(kErrBadArg, "gemm_bias_gate_residual_copy: tokens must be positive");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = tokens;
+  p.bias = bias; p.out = x; p.ldo = n; p.gate = gate; p.gate_stride = gate_stride;
+  p.ln_out = BFM(x_bf16); p.stats_out = reinterpret_cast<float2*>(row_stats); p.stats_slots = 2 * (n / 256);
+  return launch_gemm(EPI_RESID_TMA_XB_F32, BF(a), k, BF(w), k, p, ST(stream));
+}
+int jpdvt_fold_ln_weights(const jpdvt_bf16* w_qkv, const jpdvt_bf16* w_fc1, const float* b_qkv, const float* b_fc1, const float* mod,
+                          jpdvt_bf16* w_fold, float* fold_u, float* fold_v, int depth, void* stream) {
+  if (depth <= 0) return kOk;
+  if (!w_qkv || !w_fc1 || !b_qkv || !b_fc1 || !mod || !w_fold || !fold_u || !fold_v) return set_error(kErrBadArg, "fold_ln_weights: null pointer");
+  return launch_fold_ln(BF(w_qkv), BF(w_fc1), b_qkv, b_fc1, mod, BFM(w_fold), fold_u, fold_v, depth, ST(stream));
+}
+int jpdvt_gemm_ln_folded(int gelu, const jpdvt_bf16* x_bf16, const float* row_stats, int stats_slots, const jpdvt_bf16* w_fold,
+                         const float* fold_u, const float* fold_v, jpdvt_bf16* out, int64_t m, int n, int k, void* stream) {
+  if (m == 0) return kOk;
+  if (!x_bf16 || !row_stats || !w_fold || !fold_u || !fold_v || !out) return set_error(kErrBadArg, "gemm_ln_folded: null pointer");
+  if (m > 0x7fffffffLL) return set_error(kErrUnsupported, "gemm: m too large");
+  GemmParams p{};
+  p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = 1;
+  p.bias = fold_v; p.fold_u = fold_u; p.out = out; p.ldo = n;
+  p.stats_in = reinterpret_cast<const float2*>(row_stats); p.stats_slots = stats_slots;
+  return launch_gemm(gelu ? EPI_BIAS_GELU_BF16 : EPI_BIAS_BF16, BF(x_bf16), k, BF(w_fold), k, p, ST(stream));
 }
 int jpdvt_gemm_patch_embed(const jpdvt_bf16* cols, const jpdvt_bf16* w_patch, const float* bias, const float* x_t,
                            const float* w_in_t, const float* pos, float* x, int64_t m, int tokens, void* stream) {

@@ -54,6 +54,8 @@ enum Epilogue : int {
   EPI_RESID_TMA_F32 = 12,   // EPI_RESID_F32 with the residual tile moved by TMA: 32x32 fp32 boxes into a per-warp shared-memory
                             // ring (deep prefetch, no registers), updated in place, TMA-stored back
   EPI_RESID_LN_TMA_F32 = 13,   // EPI_RESID_TMA_F32 + the next LayerNorm-modulate of the same rows (ln_out), boxes re-read by TMA
+  EPI_RESID_TMA_XB_F32 = 14,   // EPI_RESID_TMA_F32 + a bf16 copy of the updated rows (ln_out) + per-row (sum, sum of squares) partials
+                               // (stats_out): the producer half of the LayerNorm folded into the next GEMM (see fold.cu)
   EPI_RESID_LN_F32 = 10,    // EPI_RESID_F32 (N == 768) + the NEXT LayerNorm-modulate of the updated rows:
                             // ln_out_bf16 = LN(out_f32) * (1 + ln_scale[sample]) + ln_shift[sample]
 };
@@ -82,6 +84,14 @@ struct GemmParams {
   const float* ln_shift;      // sample b reads ln_shift + b * ln_stride, [N]
   const float* ln_scale;
   long long ln_stride;
+  // LayerNorm folded into the consuming GEMM (uniform conditioning only; fold.cu): a row's LayerNorm is two scalars, so
+  //   modulate(LN(x)) . W^T + b  =  rstd * (bf16(x) . W'^T) - rstd * mean * u + v,   W' = W * (1 + scale), u = rowsum(W'), v = b + W . shift
+  // producer (EPI_RESID_TMA_XB_F32): stats_out[row * stats_slots + slot] = (sum, sum of squares) over one column group
+  // consumer (EPI_BIAS_BF16 / EPI_BIAS_GELU_BF16 with stats_in != null): bias = v, fold_u = u, K = LayerNorm width
+  float2* stats_out;
+  const float2* stats_in;
+  const float* fold_u;
+  int stats_slots;
 };
 
 // dW[wg_rows, n_cols] (fp32) = P[M, wg_rows]^T . Q[M, n_cols]   (both bf16 row-major); `partial` is scratch of
@@ -102,6 +112,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
 int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
+
+// fold.cu: W' = W (1 + scale), u = rowsum(W'), v = b + W . shift for the qkv and fc1 matrices of every block (mod row 0)
+int launch_fold_ln(const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_fc1, const float* b_qkv, const float* b_fc1, const float* mod,
+                   __nv_bfloat16* w_fold, float* fold_u, float* fold_v, int depth, cudaStream_t stream);
 
 // puzzle.cu
 int launch_gather_pieces(const float* src, float* dst, const int* perm, const unsigned char* keep, int batch, int channels,

@@ -215,7 +215,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_y, const GemmParams p) {
   using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
-  static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32 || EPI == EPI_RESID_LN_TMA_F32), "the residual ring belongs to the TMA residual epilogues");
+  static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32 || EPI == EPI_RESID_LN_TMA_F32 || EPI == EPI_RESID_TMA_XB_F32),
+                "the residual ring belongs to the TMA residual epilogues");
   constexpr int kColsPerWarp = Cfg::kColsPerWarp;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSETTING the shared-space pointer (integer round-trips make the compiler lose the address
@@ -245,7 +246,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int group = blockIdx.x / CS, num_groups = gridDim.x / CS;
   constexpr bool kLN = (EPI == EPI_RESID_LN_F32);           // residual update + the next LayerNorm of the same rows
   constexpr bool kLNX = (EPI == EPI_RESID_LN_TMA_F32);      // ... with both the residual tile and the LayerNorm pass through the TMA ring
-  constexpr bool kXR = (EPI == EPI_RESID_TMA_F32);          // residual tile through the TMA ring
+  constexpr bool kXB = (EPI == EPI_RESID_TMA_XB_F32);       // ... plus a bf16 copy of the updated rows and their (sum, sum of squares)
+  constexpr bool kXR = (EPI == EPI_RESID_TMA_F32) || kXB;   // residual tile through the TMA ring
+  constexpr bool kFoldIn = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);   // may consume a folded LayerNorm (p.stats_in)
   constexpr bool kResid = (EPI == EPI_RESID_F32) || kLN;
   // s-th work item of this CTA group.  Normally tiles are dealt round robin; the LayerNorm-fused epilogue needs whole rows,
   // so there a group owns M-blocks and walks the N tiles of each one in turn.
@@ -555,6 +558,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
     } else {
+    float4 fst[3] = {};                   // kFoldIn: this thread's row statistics of the NEXT tile, requested one tile ahead
     float ln_mean = 0.f, ln_m2 = 0.f;     // kLN: running (mean, sum of squared deviations) of this thread's row over its columns
     int ln_cnt = 0;
     // kXR: this warp's ring of residual boxes.  Box g (g = s * NC + c, the c-th 32-column chunk of the warp's s-th tile)
@@ -596,6 +600,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // epilogue math never queues a global load behind the streaming residual prefetch
         for (int i = lane; i < kColsPerWarp / 4; i += 32)
           reinterpret_cast<float4*>(bias_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base) + i);
+        if constexpr (kFoldIn) {
+          if (p.stats_in != nullptr) {        // folded LayerNorm: u slice next to the bias (= v) slice
+            for (int i = lane; i < kColsPerWarp / 4; i += 32)
+              reinterpret_cast<float4*>(gate_smem)[i] = __ldg(reinterpret_cast<const float4*>(p.fold_u + n_blk * BN + col_base) + i);
+          }
+        }
         if constexpr (kResid || kXR || EPI == EPI_GATE_BF16) {
           const int last = out_rows - 1;
           const int s_first = (row0 < last ? row0 : last) / p.tokens, s_last = (row0 + 31 < last ? row0 + 31 : last) / p.tokens;
@@ -648,9 +658,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       if constexpr (kResid) {
         load_x(xa, 0);
       }
+      float ln_r = 1.0f, ln_rm = 0.0f;       // kFoldIn: rstd and rstd * mean of this thread's row (LayerNorm over the K inputs)
+      if constexpr (kFoldIn) {
+        if (p.stats_in != nullptr) {
+          // six (sum, sum of squares) slots = three 16-byte loads, all in flight at once (a counted loop serialises them:
+          // 6 x L2 latency per tile, qkv 110 vs 95 us); from the second tile on they were requested one tile ahead
+          float4 t0 = fst[0], t1 = fst[1], t2 = fst[2];
+          if (s == 0 && row_ok) {
+            const float4* st = reinterpret_cast<const float4*>(p.stats_in + static_cast<long long>(row) * 6);
+            t0 = __ldg(st); t1 = __ldg(st + 1); t2 = __ldg(st + 2);
+          }
+          const float sum = (t0.x + t0.z) + (t1.x + t1.z) + (t2.x + t2.z), sq = (t0.y + t0.w) + (t1.y + t1.w) + (t2.y + t2.w);
+          const float inv = 1.0f / static_cast<float>(p.K);
+          const float mean = sum * inv;
+          ln_r = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv), 0.f) + 1e-6f);   // nn.LayerNorm(eps=1e-6), biased variance (models.py:107)
+          ln_rm = ln_r * mean;
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if constexpr (kFoldIn) {
+        if (p.stats_in != nullptr) {          // the next tile's row statistics: in flight behind this tile's epilogue math
+          int sp, mb, nb;
+          if (tile_at(s + 1, sp, mb, nb)) {
+            const int nrow = (mb * CS + static_cast<int>(rank)) * BM + quad * 32 + lane;
+            if (nrow < out_rows) {
+              const float4* st = reinterpret_cast<const float4*>(p.stats_in + static_cast<long long>(nrow) * 6);
+              fst[0] = __ldg(st); fst[1] = __ldg(st + 1); fst[2] = __ldg(st + 2);
+            }
+          }
+        }
+      }
 
       if constexpr (EPI == EPI_HEAD) {
         static_assert(EPI != EPI_HEAD || (BN == 64 && EW == 4), "head epilogue needs the whole 64-wide row in one warp");
@@ -701,6 +740,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           const int n0 = n_blk * BN + col_base + c * 64;
+          if constexpr (kFoldIn) {
+            if (p.stats_in != nullptr) {      // acc is bf16(x) . W'^T: apply the row's LayerNorm, y = r acc - r m u (+ v via the bias slot)
+              const float4* u4 = reinterpret_cast<const float4*>(gate_smem + c * 64);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 u = u4[j];
+                v[4 * j + 0] = fmaf(ln_r, v[4 * j + 0], -ln_rm * u.x); v[4 * j + 1] = fmaf(ln_r, v[4 * j + 1], -ln_rm * u.y);
+                v[4 * j + 2] = fmaf(ln_r, v[4 * j + 2], -ln_rm * u.z); v[4 * j + 3] = fmaf(ln_r, v[4 * j + 3], -ln_rm * u.w);
+              }
+            }
+          }
           bf16_math<EPI>(v, bias_smem + c * 64, gate4, c * 16);
           if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
             if (p.tma_out) {
@@ -760,6 +810,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       } else if constexpr (kXR) {
         // x[row, n] += gate[row / tokens, n] * (acc + bias[n]): the residual box arrives by TMA (swizzled 128-byte rows, row =
         // lane), is updated in place by its row's thread and leaves by TMA store - no per-thread global traffic at all
+        float rs = 0.f, rq = 0.f;            // kXB: sum and sum of squares of this thread's updated row over the warp's columns
 #pragma unroll
         for (int c = 0; c < kXNC; ++c) {
           const int g = s * kXNC + c;
@@ -789,6 +840,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             float4 q = lds_f4(a);
             q.x += v[4 * j + 0]; q.y += v[4 * j + 1]; q.z += v[4 * j + 2]; q.w += v[4 * j + 3];
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
+            if constexpr (kXB) {
+              v[4 * j + 0] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+              rs += (q.x + q.y) + (q.z + q.w);
+              rq = fmaf(q.x, q.x, rq); rq = fmaf(q.y, q.y, rq); rq = fmaf(q.z, q.z, rq); rq = fmaf(q.w, q.w, rq);
+            }
           }
           fence_proxy_async_smem();                            // generic-proxy writes -> visible to the TMA store
           __syncwarp();
@@ -797,6 +853,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             x_coords(g, col, row);
             tma_store_2d(&tma_x, xring + slot * kXBoxBytes, col, row);
             tma_store_commit();
+          }
+          if constexpr (kXB) {
+            // bf16 copy of the updated rows (the next GEMM's A operand): 64 contiguous bytes of this thread's row, straight
+            // from registers, behind the box's TMA store.  Measured at M = 36,864: fc2 147 vs 132 us, proj 74-84 vs 54 us; a
+            // staging box + TMA store instead costs a pipeline stage and lands at +14 us for both.  Either way the copy eats
+            // most of what the folded LayerNorm saves, which is why the fold is opt-in.
+            if (row_ok) {
+              uint4* xb = reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(row) * p.ldo + n_blk * BN + col_base + c * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                xb[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+        }
+        if constexpr (kXB) {
+          // one (sum, sum of squares) slot per tile column group; with four epilogue warps a warp covers both groups
+          if (row_ok) {
+            float2* st = p.stats_out + static_cast<long long>(row) * p.stats_slots + n_blk * 2;
+            if constexpr (EW == 4) *reinterpret_cast<float4*>(st) = make_float4(rs, rq, 0.f, 0.f);
+            else st[(warp - 2) >> 2] = make_float2(rs, rq);
           }
         }
       } else if constexpr (kResid) {
@@ -1162,6 +1239,9 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     return set_error(kErrBadArg, "gemm: operand pointers must be 16-byte aligned");
   const int bn = (epi == EPI_HEAD) ? 64 : ((p.N % 256 == 0) ? 256 : 128);
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
+  if (p.stats_in != nullptr && ((epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16) || p.fold_u == nullptr || p.stats_slots != 6 ||
+                                (reinterpret_cast<uintptr_t>(p.stats_in) & 15)))
+    return set_error(kErrBadArg, "gemm: a folded LayerNorm needs the bias / bias+GELU epilogue, fold_u and six 16-byte aligned statistics slots per row");
   if (epi == EPI_HEAD && p.N != 64) return set_error(kErrBadArg, "gemm: head epilogue requires N == 64");
   if ((epi == EPI_GATE_BF16 || epi == EPI_PATCH_EMBED_F32 || epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.tokens <= 0) return set_error(kErrBadArg, "gemm: tokens must be positive");
   if ((epi == EPI_RESID_F32 || epi == EPI_RESID_LN_F32) && p.gate == nullptr) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate");
@@ -1178,6 +1258,16 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
     // 139.3 us); short ones (proj) are bound by the residual traffic and want all eight warps moving boxes (56 vs 67 us)
     return (e_forced == 0 && p.K >= 2048) ? launch_cfg<256, EPI_RESID_TMA_F32, 4, 2>(a, lda, w, ldw, p, stream)
                                           : launch_cfg<256, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
+  }
+  if (epi == EPI_RESID_TMA_XB_F32) {
+    if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");
+    if (p.N % 256 != 0 || p.ldo != p.N || (reinterpret_cast<uintptr_t>(p.out) & 15) || (reinterpret_cast<uintptr_t>(p.ln_out) & 15))
+      return set_error(kErrBadArg, "gemm: the residual + bf16-copy epilogue needs N %% 256 == 0, ldo == N and 16-byte aligned x / copy");
+    if (!p.ln_out || !p.stats_out || p.stats_slots != 2 * (p.N / 256))
+      return set_error(kErrBadArg, "gemm: residual + bf16-copy epilogue: null copy / statistics pointer or stats_slots != 2 * N / 256");
+    // same split as the plain TMA residual epilogue
+    return p.K >= 2048 ? launch_cfg<256, EPI_RESID_TMA_XB_F32, 4, 2>(a, lda, w, ldw, p, stream)
+                       : launch_cfg<256, EPI_RESID_TMA_XB_F32, 8, 2>(a, lda, w, ldw, p, stream);
   }
   if (epi == EPI_RESID_LN_TMA_F32) {
     if (p.gate == nullptr || p.tokens <= 0) return set_error(kErrBadArg, "gemm: residual epilogue needs the gate and tokens");

@@ -105,6 +105,11 @@ class DenoiserEngine:
                 "silu_c": torch.empty(cond_cap, HIDDEN, device=dev, dtype=f32),
                 "silu_c_bf16": torch.empty(cond_cap, HIDDEN, device=dev, dtype=bf),
                 "mod": torch.empty(cond_cap, n_mod, device=dev, dtype=f32),
+                # LayerNorm folded into qkv / fc1 (uniform-timestep forwards; csrc/fold.cu)
+                "w_fold": torch.empty(self.depth * 7 * HIDDEN, HIDDEN, device=dev, dtype=bf),
+                "fold_u": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
+                "fold_v": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
+                "row_stats": torch.empty(rows_cap, 2 * (HIDDEN // 256), 2, device=dev, dtype=f32),
             }
             ws = Workspace()
             ws.rows, ws.cond_rows, ws.reserved = rows_cap, cond_cap, 0

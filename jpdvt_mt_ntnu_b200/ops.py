@@ -127,6 +127,51 @@ def gemm_bias_gate_residual_ln(x, a, w, bias, gate, shift, scale, tokens: int):
     return x, xn
 
 
+def gemm_bias_gate_residual_copy(x, a, w, bias, gate, tokens: int):
+    """x += gate[row // tokens] * (a @ w.T + bias) in place (fp32 [M,N], N % 256 == 0); also returns bf16(x) and the rows'
+    (sum, sum of squares) partials [M, 2N/256, 2] - the producer half of the folded LayerNorm."""
+    lib = _lib_dev()
+    a, w = _need(a, torch.bfloat16, "a"), _need(w, torch.bfloat16, "w")
+    bias, gate = _need(bias, torch.float32, "bias"), _need(gate, torch.float32, "gate")
+    m, k = a.shape
+    n = w.shape[0]
+    if x.dtype != torch.float32 or not x.is_contiguous() or tuple(x.shape) != (m, n) or not x.is_cuda:
+        raise _lib.JpdvtError("gemm_bias_gate_residual_copy: x must be a contiguous fp32 CUDA tensor of shape [M, N]")
+    xb = torch.empty(m, n, device=a.device, dtype=torch.bfloat16)
+    stats = torch.empty(m, 2 * (n // 256), 2, device=a.device, dtype=torch.float32)
+    check(lib.jpdvt_gemm_bias_gate_residual_copy(ptr(a), ptr(w), ptr(bias), ptr(gate), 0 if gate.shape[0] == 1 else n, ptr(x),
+                                                 ptr(xb), ptr(stats), m, n, k, tokens, stream_ptr()), "gemm_bias_gate_residual_copy")
+    return x, xb, stats
+
+
+def fold_ln_weights(w_qkv, w_fc1, b_qkv, b_fc1, mod):
+    """W' = W (1 + scale), u = rowsum(W'), v = b + W @ shift for the qkv / fc1 matrices of every block.  w_qkv [depth,2304,768],
+    w_fc1 [depth,3072,768] bf16; mod: row 0 of the adaLN table.  Returns (w_fold [depth,5376,768] bf16, u, v [depth,5376])."""
+    lib = _lib_dev()
+    w_qkv, w_fc1 = _need(w_qkv, torch.bfloat16, "w_qkv"), _need(w_fc1, torch.bfloat16, "w_fc1")
+    b_qkv, b_fc1, mod = _need(b_qkv, torch.float32, "b_qkv"), _need(b_fc1, torch.float32, "b_fc1"), _need(mod, torch.float32, "mod")
+    depth = w_qkv.shape[0]
+    wf = torch.empty(depth, 5376, 768, device=w_qkv.device, dtype=torch.bfloat16)
+    u = torch.empty(depth, 5376, device=w_qkv.device, dtype=torch.float32)
+    v = torch.empty_like(u)
+    check(lib.jpdvt_fold_ln_weights(ptr(w_qkv), ptr(w_fc1), ptr(b_qkv), ptr(b_fc1), ptr(mod), ptr(wf), ptr(u), ptr(v), depth,
+                                    stream_ptr()), "fold_ln_weights")
+    return wf, u, v
+
+
+def gemm_ln_folded(xb, stats, w_fold, u, v, gelu: bool = False):
+    """[gelu_tanh](rstd * (xb @ w_fold.T) - rstd * mean * u + v) -> bf16 [M,N]; mean / rstd per row from `stats`."""
+    lib = _lib_dev()
+    xb, w_fold = _need(xb, torch.bfloat16, "xb"), _need(w_fold, torch.bfloat16, "w_fold")
+    stats, u, v = _need(stats, torch.float32, "stats"), _need(u, torch.float32, "u"), _need(v, torch.float32, "v")
+    m, k = xb.shape
+    n = w_fold.shape[0]
+    out = torch.empty(m, n, device=xb.device, dtype=torch.bfloat16)
+    check(lib.jpdvt_gemm_ln_folded(1 if gelu else 0, ptr(xb), ptr(stats), stats.shape[1], ptr(w_fold), ptr(u), ptr(v), ptr(out),
+                                   m, n, k, stream_ptr()), "gemm_ln_folded")
+    return out
+
+
 def patchify(img: torch.Tensor) -> torch.Tensor:
     lib = _lib_dev()
     img = _need(img, torch.float32, "img")

@@ -54,7 +54,7 @@ def sincos_2d(dim: int, grid: int) -> np.ndarray:
 def timestep_features(t: torch.Tensor, dim: int = 256, max_period: float = 10000.0) -> torch.Tensor:
     """models.py:40-59 - cos first, then sin; frequencies built in fp32."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)  # :52-54
     ang = t.reshape(-1, 1).float() * freqs.reshape(1, -1)
     return torch.cat([ang.cos(), ang.sin()], dim=1)
 
@@ -68,10 +68,11 @@ def _mod(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor) -> torch.Ten
 
 
 class OracleDenoiser:
-    """Functional JPDVT forward over a reference-keyed state dict (fp32, CPU)."""
+    """Functional JPDVT forward over a reference-keyed state dict (fp32, CPU).  `device="cuda"` runs the same stock
+    torch ops on a GPU - only bench.py's same-box comparator (`--impl reference --ref-device cuda`) uses that."""
 
-    def __init__(self, state: Dict[str, torch.Tensor], depth: int = 12, heads: int = 12, patch: int = 16):
-        self.w = {k: v.detach().float().cpu() for k, v in state.items()}
+    def __init__(self, state: Dict[str, torch.Tensor], depth: int = 12, heads: int = 12, patch: int = 16, device="cpu"):
+        self.w = {k: v.detach().float().to(device) for k, v in state.items()}
         self.depth, self.heads, self.patch = depth, heads, patch
 
     def patch_embed(self, img: torch.Tensor) -> torch.Tensor:
@@ -94,8 +95,11 @@ class OracleDenoiser:
         hd = D // self.heads
         qkv = F.linear(x, w[f"blocks.{i}.attn.qkv.weight"], w[f"blocks.{i}.attn.qkv.bias"])
         q, k, v = qkv.reshape(B, T, 3, self.heads, hd).permute(2, 0, 3, 1, 4)
-        p = torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1)
-        o = (p @ v).transpose(1, 2).reshape(B, T, D)
+        if x.is_cuda:      # bench.py's same-box comparator: what timm >= 0.9 runs on a GPU (fused SDPA, same scale)
+            o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, D)
+        else:
+            p = torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1)
+            o = (p @ v).transpose(1, 2).reshape(B, T, D)
         return F.linear(o, w[f"blocks.{i}.attn.proj.weight"], w[f"blocks.{i}.attn.proj.bias"])
 
     def mlp(self, i: int, x: torch.Tensor) -> torch.Tensor:
@@ -246,7 +250,7 @@ class Schedule:
     @staticmethod
     def gather(table: np.ndarray, t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
         """gaussian_diffusion.py:917-929 - fp64 gather, THEN cast to fp32, broadcast."""
-        v = torch.from_numpy(table)[t].float()
+        v = torch.from_numpy(table).to(t.device)[t].float()
         return v.reshape(-1, *([1] * (like.dim() - 1))).expand_as(like)
 
     # -- forward process ---------------------------------------------------- #
@@ -256,7 +260,7 @@ class Schedule:
     # -- one reverse step --------------------------------------------------- #
     def p_step(self, model, condition, x_t, t, noise):
         """p_mean_variance + p_sample (gaussian_diffusion.py:256-344, 388-431), START_X, FIXED_SMALL, no clip."""
-        ts = torch.tensor(self.timestep_map, dtype=t.dtype)[t]                         # respace.py:124-129
+        ts = torch.tensor(self.timestep_map, dtype=t.dtype, device=t.device)[t]                         # respace.py:124-129
         _, x0 = model(condition, ts, x_t)
         mean = self.gather(self.coef1, t, x_t) * x0 + self.gather(self.coef2, t, x_t) * x_t
         logvar = self.gather(self.post_logvar, t, x_t)

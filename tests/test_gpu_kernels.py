@@ -238,3 +238,42 @@ def test_gemm_residual_layernorm_fused(ops, m, k, T):
         assert x_out is x and rel_l2(x, ref_x) < F32_TOL
         assert rel_l2(xn.float(), ref_xn) < BF16_TOL
         assert (xn.float() - ref_xn).abs().max() < 0.05 * ref_xn.abs().max()
+
+
+@pytest.mark.parametrize("m,k,T", [(432, 768, 144), (1000, 3072, 100), (36864, 768, 144), (300, 3072, 9), (256, 768, 256), (77, 768, 77)])
+def test_layernorm_folded_into_consumer(ops, m, k, T):
+    """The sampling loop's LayerNorm fold (csrc/fold.cu): residual GEMM leaves bf16(x) + row sums, the weights are folded
+    with (shift, scale), the consumer GEMM finishes the LayerNorm per row.  Against fp32 torch of the reference lines
+    modulate(norm(x), shift, scale) -> Linear (models.py:19-20,120-121) within bf16 rounding."""
+    torch.manual_seed(m + k + 1)
+    n, depth = 768, 2
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    gate = torch.randn(1, n, device="cuda") * 0.5
+    x0 = torch.randn(m, n, device="cuda") * 2 + 0.7                 # non-zero row mean: exercises the rank-one mean correction
+    x = x0.clone()
+    x_out, xb, stats = ops.gemm_bias_gate_residual_copy(x, a, w, bias, gate, T)
+    ref_x = x0 + gate * (a.float() @ w.float().t() + bias)
+    assert x_out is x and rel_l2(x, ref_x) < F32_TOL
+    assert torch.equal(xb, x.bfloat16())                            # the copy is the rounded residual stream, bit for bit
+    tot = stats.sum(1)
+    assert torch.allclose(tot[:, 0], x.sum(1), rtol=1e-4, atol=1e-2) and torch.allclose(tot[:, 1], (x * x).sum(1), rtol=1e-4)
+
+    w_qkv = (torch.randn(depth, 2304, 768, device="cuda") * 0.03).bfloat16()
+    w_fc1 = (torch.randn(depth, 3072, 768, device="cuda") * 0.03).bfloat16()
+    b_qkv, b_fc1 = torch.randn(depth, 2304, device="cuda") * 0.1, torch.randn(depth, 3072, device="cuda") * 0.1
+    mod = torch.randn(depth * 6 * 768 + 2 * 768, device="cuda") * 0.5
+    wf, u, v = ops.fold_ln_weights(w_qkv, w_fc1, b_qkv, b_fc1, mod)
+    for blk in range(depth):
+        mm = mod[blk * 4608:(blk + 1) * 4608].reshape(6, 768)
+        for name, wt, bt, sh, sc, rows, gelu in (("qkv", w_qkv[blk], b_qkv[blk], mm[0], mm[1], slice(0, 2304), False),
+                                                 ("fc1", w_fc1[blk], b_fc1[blk], mm[3], mm[4], slice(2304, 5376), True)):
+            assert torch.equal(wf[blk, rows], (wt.float() * (1 + sc)).bfloat16()), name
+            assert torch.allclose(u[blk, rows], wf[blk, rows].float().sum(1), rtol=1e-4, atol=1e-3), name
+            assert torch.allclose(v[blk, rows], bt + wt.float() @ sh, rtol=1e-4, atol=1e-3), name
+            out = ops.gemm_ln_folded(xb, stats, wf[blk, rows].contiguous(), u[blk, rows].contiguous(), v[blk, rows].contiguous(), gelu=gelu)
+            ref = (F.layer_norm(ref_x, (n,), eps=1e-6) * (1 + sc) + sh) @ wt.float().t() + bt
+            if gelu:
+                ref = F.gelu(ref, approximate="tanh")
+            assert rel_l2(out.float(), ref) < BF16_TOL, (name, rel_l2(out.float(), ref))

@@ -5,6 +5,8 @@ Tolerance (bf16 tensor-core operands, fp32 accumulation and fp32 residual stream
 rel-L2 <= 2e-2 on time_emb_out / per-step pred_xstart / mean / sample, max-abs <= 2e-2 * max|ref|.
 Measured: ~3.5e-3.  Placements must be identical.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -12,6 +14,8 @@ import torch
 from conftest import rel_l2
 from oracle import cases
 from oracle import jpdvt_oracle as orc
+
+LN_FOLD = os.environ.get("JPDVT_LN_FOLD", "")[:1] == "1"      # opt-in LayerNorm fold (csrc/fold.cu) reroutes the uniform-timestep path
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-2
@@ -48,7 +52,10 @@ def test_forward_vs_reference_golden(cuda, golden, name):
 
 
 def test_forward_batch_uniform_timestep_path(cuda):
-    """The batch-uniform conditioning path (one adaLN row, mod_stride 0) equals the per-sample path."""
+    """The batch-uniform conditioning path (one adaLN row, mod_stride 0; LayerNorms folded into the qkv / fc1 GEMMs,
+    csrc/fold.cu) against the per-sample path (stand-alone LayerNorm kernels): same function, the two differ by where the
+    bf16 roundings fall - well inside the 2e-2 end-to-end tolerance both paths have against the fp32 oracle.  The fold is
+    opt-in (JPDVT_LN_FOLD=1); without it the two paths run the same kernels."""
     case = cases.FORWARD_CASES["d2_192"]
     m = _model(case)
     img, _, x_t = cases.forward_inputs(case)
@@ -59,7 +66,7 @@ def test_forward_batch_uniform_timestep_path(cuda):
         step = torch.tensor([77], device="cuda", dtype=torch.int32)
         tmap = torch.arange(0, 1000, 4, device="cuda", dtype=torch.int32)
         _, uniform = eng.forward(img.cuda(), None, x_t.cuda(), need_image=False, step_ptr=step, tmap=tmap)
-    assert rel_l2(uniform, per_sample) < 1e-5
+    assert rel_l2(uniform, per_sample) < (5e-3 if LN_FOLD else 1e-5)
 
 
 def test_fresh_init_outputs_exact_zeros(cuda):
@@ -90,11 +97,12 @@ def test_sampling_loop_vs_reference_golden(cuda, golden, name):
     final = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, model_kwargs=None,
                             progress=False, device="cuda", step_noise=step_noise)
     _check(final, g["final"])
-    assert torch.equal(final, outs[-1]["sample"])           # single-call loop == stepwise loop, bit for bit
+    # single-call loop == stepwise loop, bit for bit (unless the opt-in LayerNorm fold reroutes the uniform-timestep loop)
+    assert torch.equal(final, outs[-1]["sample"]) or (LN_FOLD and rel_l2(final, outs[-1]["sample"]) < 5e-3)
     # reference quirk: the result is pred_xstart of ONE forward at t=0 on the initial noise (gaussian_diffusion.py:518-529)
     with torch.no_grad():
         direct = m.forward_latents(cond.cuda(), torch.zeros(case["batch"], dtype=torch.long, device="cuda"), noise.cuda())
-    assert torch.equal(direct, final)
+    assert torch.equal(direct, final) or (LN_FOLD and rel_l2(direct, final) < 5e-3)
     order, pred, scores = assignment.solve_puzzles(final, case["grid"], return_scores=True)
     assert np.abs(scores.cpu().numpy() - g["dist"]).max() < 5e-3
     assert order.cpu().numpy().tolist() == g["order"].tolist()
@@ -116,7 +124,7 @@ def test_generic_callable_path_matches_fast_path(cuda):
     fast = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, step_noise=step_noise)
     slow = d.p_sample_loop(lambda x, t, te: m(x, t, te), cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False,
                            step_noise=step_noise)
-    assert rel_l2(slow, fast) < 1e-5
+    assert rel_l2(slow, fast) < (5e-3 if LN_FOLD else 1e-5)
     chained = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, step_noise=step_noise, chain=True)
     want = orc.Schedule("10").p_sample_loop(orc.OracleDenoiser(cases.state_for(case), depth=case["depth"]), cond, noise,
                                             list(step_noise.cpu()), chain=True)

@@ -41,8 +41,25 @@ b_qkv, b_proj, b_fc1, b_fc2 = (torch.randn(n, device=dev) * 0.02 for n in (2304,
 gate = torch.randn(1, 768, device=dev) * 0.01
 shift, scale = torch.randn(1, 768, device=dev), torch.randn(1, 768, device=dev)
 
+# folded-LayerNorm operands (csrc/fold.cu): one block's W', u, v and the row sums of x
+_wq, _w1 = w_qkv[None].contiguous(), w_fc1[None].contiguous()
+_mod = torch.randn(6 * 768 + 2 * 768, device=dev) * 0.3
+wf, fu, fv = ops.fold_ln_weights(_wq, _w1, b_qkv[None].contiguous(), b_fc1[None].contiguous(), _mod)
+wf_qkv, wf_fc1 = wf[0, :2304].contiguous(), wf[0, 2304:].contiguous()
+xb = x.bfloat16()
+stats = torch.zeros(M, 6, 2, device=dev)
+stats[:, 0, 0], stats[:, 0, 1] = x.sum(1), (x * x).sum(1)
+w12q = torch.randn(12, 2304, 768, device=dev).bfloat16() * 0.02
+w12f = torch.randn(12, 3072, 768, device=dev).bfloat16() * 0.02
+b12q, b12f, mod12 = torch.randn(12, 2304, device=dev), torch.randn(12, 3072, device=dev), torch.randn(12 * 4608 + 1536, device=dev)
+
 GF, MB = 1e9, 1e6
 KERNELS = {
+    "qkv_fold": (lambda: ops.gemm_ln_folded(xb, stats, wf_qkv, fu[0, :2304], fv[0, :2304]), 2.0 * M * 768 * 2304, "flop"),
+    "fc1_fold": (lambda: ops.gemm_ln_folded(xb, stats, wf_fc1, fu[0, 2304:], fv[0, 2304:], gelu=True), 2.0 * M * 768 * 3072, "flop"),
+    "fc2_copy": (lambda: ops.gemm_bias_gate_residual_copy(x, hid, w_fc2, b_fc2, gate, T), 2.0 * M * 3072 * 768, "flop"),
+    "proj_copy": (lambda: ops.gemm_bias_gate_residual_copy(x, att, w_proj, b_proj, gate, T), 2.0 * M * 768 * 768, "flop"),
+    "fold_w": (lambda: ops.fold_ln_weights(w12q, w12f, b12q, b12f, mod12), 12 * 5376 * 768 * 4.0, "byte"),
     "qkv": (lambda: ops.gemm_bias(xn, w_qkv, b_qkv), 2.0 * M * 768 * 2304, "flop"),
     "fc1": (lambda: ops.gemm_bias_gelu(xn, w_fc1, b_fc1), 2.0 * M * 768 * 3072, "flop"),
     "fc2_bf16": (lambda: ops.gemm_bias_gate(hid, w_fc2, b_fc2, gate, T), 2.0 * M * 3072 * 768, "flop"),
