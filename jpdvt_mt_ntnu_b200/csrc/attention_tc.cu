@@ -148,11 +148,25 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
   const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
   ms_out = ms;
   float sum = 0.f;
+  uint64_t sum2 = f2_pack(0.f, 0.f);                           // packed partial row sums (even / odd keys)
+  const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms, -ms);
   auto emit8 = [&](const uint32_t* r, int chunk) {            // 8 consecutive keys -> one 16-byte chunk of the P row
     float p[8];
+    if (chunk * 8 + 8 <= TV) {                                 // all eight keys valid: scale / shift and the sum on packed pairs
+      uint64_t e[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = (chunk * 8 + j < TV) ? ex2f(fmaf(__uint_as_float(r[j]), sl2, -ms)) : 0.f;
-    sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+      for (int j = 0; j < 4; ++j) {
+        float a, b;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), sl2p, nmsp), a, b);
+        p[2 * j] = ex2f(a); p[2 * j + 1] = ex2f(b);
+        e[j] = f2_pack(p[2 * j], p[2 * j + 1]);
+      }
+      sum2 = f2_add(sum2, f2_add(f2_add(e[0], e[1]), f2_add(e[2], e[3])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = (chunk * 8 + j < TV) ? ex2f(fmaf(__uint_as_float(r[j]), sl2, -ms)) : 0.f;
+      sum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    }
     const uint4 u = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
     if (store) sts_u4(p_row_addr + static_cast<uint32_t>(chunk >> 3) * blk_stride + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4), u);
   };
@@ -167,7 +181,9 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
     for (int g = 0; g < n / 8; ++g) emit8(cur + 8 * g, c * 4 + g);
     if (c + 1 < kChunks) tmem_ld_wait();
   }
-  return sum;
+  float s_even, s_odd;
+  f2_unpack(sum2, s_even, s_odd);
+  return sum + (s_even + s_odd);
 }
 
 // Split remainder: this warp's NCJ key columns of the 16 remainder rows (live in lanes 0..15 of the warp's TMEM quadrant).

@@ -120,17 +120,23 @@ __device__ __forceinline__ void sts_u4_shared(uint32_t addr, uint32_t a, uint32_
 
 template <int EPI, typename GateFn>
 __device__ __forceinline__ void bf16_math(float (&v)[64], const float* bias_smem, GateFn gate4, int col4) {
-  if constexpr (EPI != EPI_DGELU_BF16) {
-    const float4* b4 = reinterpret_cast<const float4*>(bias_smem);   // broadcast reads of the staged bias slice
+  if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+    // bias + GELU on packed fp32 pairs: 6 FP32 issue slots + 2 MUFU per two elements instead of 9 + 1 per element
+    const float4* b4 = reinterpret_cast<const float4*>(bias_smem);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float4 b = b4[j];
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      bias_gelu_tanh_x2(v[4 * j + 0], v[4 * j + 1], b.x, b.y);
+      bias_gelu_tanh_x2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
     }
-  }
-  if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+  } else if constexpr (EPI != EPI_DGELU_BF16) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_smem);   // broadcast reads of the staged bias slice
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
+    for (int j = 0; j < 16; ++j) {             // packed pairs: half the issue slots of 64 scalar adds
+      const float4 b = b4[j];
+      f2_unpack(f2_add(f2_pack(v[4 * j + 0], v[4 * j + 1]), f2_pack(b.x, b.y)), v[4 * j + 0], v[4 * j + 1]);
+      f2_unpack(f2_add(f2_pack(v[4 * j + 2], v[4 * j + 3]), f2_pack(b.z, b.w)), v[4 * j + 2], v[4 * j + 3]);
+    }
   }
   if constexpr (EPI == EPI_GATE_BF16) {
 #pragma unroll
@@ -746,8 +752,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float4 u = u4[j];
-                v[4 * j + 0] = fmaf(ln_r, v[4 * j + 0], -ln_rm * u.x); v[4 * j + 1] = fmaf(ln_r, v[4 * j + 1], -ln_rm * u.y);
-                v[4 * j + 2] = fmaf(ln_r, v[4 * j + 2], -ln_rm * u.z); v[4 * j + 3] = fmaf(ln_r, v[4 * j + 3], -ln_rm * u.w);
+                const uint64_t r2 = f2_pack(ln_r, ln_r), nm2 = f2_pack(-ln_rm, -ln_rm);
+                f2_unpack(f2_fma(r2, f2_pack(v[4 * j + 0], v[4 * j + 1]), f2_mul(nm2, f2_pack(u.x, u.y))), v[4 * j + 0], v[4 * j + 1]);
+                f2_unpack(f2_fma(r2, f2_pack(v[4 * j + 2], v[4 * j + 3]), f2_mul(nm2, f2_pack(u.z, u.w))), v[4 * j + 2], v[4 * j + 3]);
               }
             }
           }
@@ -778,8 +785,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
               float y0, d0, y1, d1;
-              gelu_tanh_both(v[j], y0, d0);
-              gelu_tanh_both(v[j + 1], y1, d1);
+              gelu_tanh_both_x2(v[j], v[j + 1], y0, y1, d0, d1);
               v[j] = y0; v[j + 1] = y1;
               gp[j >> 1] = pack_bf16(d0, d1);
             }
@@ -823,14 +829,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tmem_ld_32x32(t_row + col_base + c * 32, r);
           tmem_ld_wait();
           if (c == kXNC - 1) release_tmem();
-          float v[32];
+          [[maybe_unused]] float v[32];
+          uint64_t v2[16];                                    // gate * (acc + bias) as packed fp32 pairs (FADD2 / FMUL2)
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_blk * BN + col_base + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
             const float4 gt = gate4(c * 8 + j);
-            v[4 * j + 0] = gt.x * (__uint_as_float(r[4 * j + 0]) + b.x); v[4 * j + 1] = gt.y * (__uint_as_float(r[4 * j + 1]) + b.y);
-            v[4 * j + 2] = gt.z * (__uint_as_float(r[4 * j + 2]) + b.z); v[4 * j + 3] = gt.w * (__uint_as_float(r[4 * j + 3]) + b.w);
+            v2[2 * j + 0] = f2_mul(f2_pack(gt.x, gt.y), f2_add(f2_pack(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), f2_pack(b.x, b.y)));
+            v2[2 * j + 1] = f2_mul(f2_pack(gt.z, gt.w), f2_add(f2_pack(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), f2_pack(b.z, b.w)));
           }
           mbar_wait(&xbar[slot], static_cast<uint32_t>((g / NB) & 1));
           const uint32_t mine = smem_u32(xring + slot * kXBoxBytes) + lane * 128, sw = lane & 7;
@@ -838,7 +845,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int j = 0; j < 8; ++j) {
             const uint32_t a = mine + ((j ^ sw) << 4);
             float4 q = lds_f4(a);
-            q.x += v[4 * j + 0]; q.y += v[4 * j + 1]; q.z += v[4 * j + 2]; q.w += v[4 * j + 3];
+            f2_unpack(f2_add(f2_pack(q.x, q.y), v2[2 * j + 0]), q.x, q.y);
+            f2_unpack(f2_add(f2_pack(q.z, q.w), v2[2 * j + 1]), q.z, q.w);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(q.x), "f"(q.y), "f"(q.z), "f"(q.w) : "memory");
             if constexpr (kXB) {
               v[4 * j + 0] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;

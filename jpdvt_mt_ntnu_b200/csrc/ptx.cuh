@@ -232,6 +232,57 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float u = k0 * x * fmaf(k1 * x, x, 1.0f);
   return 0.5f * x * (1.0f + tanh_fast(u));
 }
+// ---- packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2: two lanes of fp32 math per issue slot) -------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_tanh of the pair (a + ba, b + bb) in 3 multiplies + 2 fused multiply-adds + 1 add (packed) and two MUFU.TANH:
+//   u = x (k0 + k0 k1 x^2),   y = 0.5 x tanh(u) + 0.5 x        (GELU(approximate="tanh"), models.py:111)
+__device__ __forceinline__ void bias_gelu_tanh_x2(float& a, float& b, float ba, float bb) {
+  const uint64_t x = f2_add(f2_pack(a, b), f2_pack(ba, bb));
+  const uint64_t p = f2_fma(f2_mul(x, x), f2_pack(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f),
+                            f2_pack(0.7978845608028654f, 0.7978845608028654f));
+  float u0, u1;
+  f2_unpack(f2_mul(x, p), u0, u1);
+  const uint64_t h = f2_mul(x, f2_pack(0.5f, 0.5f));
+  f2_unpack(f2_fma(h, f2_pack(tanh_fast(u0), tanh_fast(u1)), h), a, b);
+}
+// gelu_tanh and its derivative for the pair (a, b), packed (10 FP32 issue slots + 2 MUFU per two elements):
+//   u = x (k0 + c1 x^2), t = tanh(u), h = 0.5 + 0.5 t, y = x h, dy = 0.5 x (1 - t^2) (k0 + 3 c1 x^2) + h,   c1 = k0 k1
+__device__ __forceinline__ void gelu_tanh_both_x2(float a, float b, float& ya, float& yb, float& da, float& db) {
+  constexpr float k0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+  const uint64_t x = f2_pack(a, b), k0p = f2_pack(k0, k0), half = f2_pack(0.5f, 0.5f);
+  const uint64_t x2 = f2_mul(x, x);
+  float u0, u1;
+  f2_unpack(f2_mul(x, f2_fma(x2, f2_pack(c1, c1), k0p)), u0, u1);
+  const float t0 = tanh_fast(u0), t1 = tanh_fast(u1);
+  const uint64_t t = f2_pack(t0, t1);
+  const uint64_t h = f2_fma(t, half, half);
+  f2_unpack(f2_mul(x, h), ya, yb);
+  const uint64_t w = f2_fma(f2_pack(-t0, -t1), t, f2_pack(1.0f, 1.0f));          // 1 - t^2
+  const uint64_t q = f2_fma(x2, f2_pack(3.0f * c1, 3.0f * c1), k0p);
+  f2_unpack(f2_fma(f2_mul(f2_mul(x, half), w), q, h), da, db);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // d/dx of gelu_tanh
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
