@@ -225,7 +225,7 @@ def run_reference(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1i_ncu_full_kernels.json")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r1j_ncu_full_kernels.json")
 
 
 def ncu_traffic(label):
