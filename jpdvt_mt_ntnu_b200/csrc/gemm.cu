@@ -1238,6 +1238,22 @@ static int launch_cs(const __nv_bfloat16* a, long long lda, const __nv_bfloat16*
   else return epi_warps(EPI) == 8 ? launch_cfg<BN, EPI, 8>(a, lda, w, ldw, p, stream) : launch_cfg<BN, EPI, 4>(a, lda, w, ldw, p, stream);
 }
 
+// Small problems (serving batches of a few puzzles): a 256x256x64 UMMA step costs the same with 16 valid rows as with 256,
+// and N / 256 tiles leave most CTA pairs idle (batch 1: 3 of 74 for proj / fc2, whose 48 k-steps then run back to back on
+// those three).  Narrower tiles put four (or two) times as many pairs to work on k-steps a quarter (half) as long; the
+// arithmetic per output element - and therefore every result bit - is unchanged.  Returns 0 (keep 256), 128 or 64.
+static int small_tile_width(int epi, const GemmParams& p) {
+  static int enabled = -1;                                     // JPDVT_GEMM_SMALL_TILES=0: always 256-wide tiles (A/B knob)
+  if (enabled < 0) { const char* e = getenv("JPDVT_GEMM_SMALL_TILES"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (!enabled || p.N % 256 != 0) return 0;
+  if (epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16 && epi != EPI_RESID_TMA_F32 && epi != EPI_RESID_F32) return 0;
+  const long long tiles256 = static_cast<long long>((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
+  const int pairs = num_sms() / 2;
+  if (tiles256 * 4 <= pairs) return 64;
+  if (tiles256 * 2 <= pairs) return 128;
+  return 0;
+}
+
 int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                 cudaStream_t stream) {
   if (p.M <= 0) return kOk;
@@ -1245,7 +1261,9 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if ((lda % 8) != 0 || (ldw % 8) != 0) return set_error(kErrBadArg, "gemm: leading dimensions must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
     return set_error(kErrBadArg, "gemm: operand pointers must be 16-byte aligned");
-  const int bn = (epi == EPI_HEAD) ? 64 : ((p.N % 256 == 0) ? 256 : 128);
+  const int bn_small = (p.stats_in == nullptr) ? small_tile_width(epi, p) : 0;
+  if (bn_small != 0 && epi == EPI_RESID_TMA_F32) epi = EPI_RESID_F32;     // the TMA box ring is laid out for 256-wide tiles
+  const int bn = (epi == EPI_HEAD) ? 64 : (bn_small != 0 ? bn_small : ((p.N % 256 == 0) ? 256 : 128));
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (p.stats_in != nullptr && ((epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16) || p.fold_u == nullptr || p.stats_slots != 6 ||
                                 (reinterpret_cast<uintptr_t>(p.stats_in) & 15)))
@@ -1295,6 +1313,11 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
 #define JP_CASE(E)                                                             \
   case E:                                                                      \
     return bn == 256 ? launch_cs<256, E>(a, lda, w, ldw, p, stream) : launch_cs<128, E>(a, lda, w, ldw, p, stream);
+  if (bn == 64 && epi != EPI_HEAD) {                           // 64-wide tiles: one warp per lane quadrant covers all 64 columns
+    if (epi == EPI_BIAS_BF16) return launch_cfg<64, EPI_BIAS_BF16, 4>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_BIAS_GELU_BF16) return launch_cfg<64, EPI_BIAS_GELU_BF16, 4>(a, lda, w, ldw, p, stream);
+    return launch_cfg<64, EPI_RESID_F32, 4>(a, lda, w, ldw, p, stream);
+  }
   switch (epi) {
     JP_CASE(EPI_BIAS_BF16)
     JP_CASE(EPI_BIAS_GELU_BF16)
