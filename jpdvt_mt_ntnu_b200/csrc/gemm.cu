@@ -1246,7 +1246,8 @@ static int small_tile_width(int epi, const GemmParams& p) {
   static int enabled = -1;                                     // JPDVT_GEMM_SMALL_TILES=0: always 256-wide tiles (A/B knob)
   if (enabled < 0) { const char* e = getenv("JPDVT_GEMM_SMALL_TILES"); enabled = (e != nullptr && e[0] == '0') ? 0 : 1; }
   if (!enabled || p.N % 256 != 0) return 0;
-  if (epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16 && epi != EPI_RESID_TMA_F32 && epi != EPI_RESID_F32) return 0;
+  if (epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16 && epi != EPI_RESID_TMA_F32 && epi != EPI_RESID_F32 &&
+      epi != EPI_PATCH_EMBED_F32 && epi != EPI_BIAS_BF16_F32) return 0;
   const long long tiles256 = static_cast<long long>((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 256);
   const int pairs = num_sms() / 2;
   if (tiles256 * 4 <= pairs) return 64;
@@ -1316,6 +1317,8 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if (bn == 64 && epi != EPI_HEAD) {                           // 64-wide tiles: one warp per lane quadrant covers all 64 columns
     if (epi == EPI_BIAS_BF16) return launch_cfg<64, EPI_BIAS_BF16, 4>(a, lda, w, ldw, p, stream);
     if (epi == EPI_BIAS_GELU_BF16) return launch_cfg<64, EPI_BIAS_GELU_BF16, 4>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_PATCH_EMBED_F32) return launch_cfg<64, EPI_PATCH_EMBED_F32, 4>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_BIAS_BF16_F32) return launch_cfg<64, EPI_BIAS_BF16_F32, 4>(a, lda, w, ldw, p, stream);
     return launch_cfg<64, EPI_RESID_F32, 4>(a, lda, w, ldw, p, stream);
   }
   switch (epi) {
