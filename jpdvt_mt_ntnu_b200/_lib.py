@@ -64,6 +64,8 @@ class BwdScratch(C.Structure):
                                         "small_bf16", "wgrad_scratch", "part", "zeros")]
 
 
+ABI_VERSION = 2            # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: jpdvt_workspace grew the LayerNorm-fold buffers)
+
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header
 PROTOTYPES = {
