@@ -376,8 +376,10 @@ def run_ours(args, wl):
             cpu_obj = {"value": cpu_v, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample}
         else:
             cpu_obj = None      # reported at N=1 only (torchrun pins the ranks to one host thread each)
-        fwd_launches = 5 + 7 * DEPTH + 3
-        launches = args.steps * (wl["steps"] * (fwd_launches + 1) + 1)
+        # per diffusion step: patchify, patch-embed, 7 per block, final LN / final / head GEMMs, posterior update; per loop:
+        # the hoisted conditioning (2 timestep kernels + one adaLN GEMV per 8 steps) and the assignment kernel
+        fwd_launches = 2 + 7 * DEPTH + 3
+        launches = args.steps * (wl["steps"] * (fwd_launches + 1) + 2 + (wl["steps"] + 7) // 8 + 1)
         solved = float((pred_host.numpy() == perms).all(axis=1).mean())
         flops = flops_per_forward(T) * wl["steps"] * batch * args.steps
         line = {

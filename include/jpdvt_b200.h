@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JPDVT_ABI_VERSION 2
+#define JPDVT_ABI_VERSION 3
 #define JPDVT_HIDDEN 768
 #define JPDVT_LATENT 8
 
@@ -206,7 +206,7 @@ typedef struct jpdvt_weights {
 typedef struct jpdvt_workspace {
   int64_t rows;                 /* capacity in token rows (>= batch * tokens) */
   int32_t cond_rows;            /* capacity in conditioning rows (>= batch, or 1 for a batch-uniform timestep) */
-  int32_t reserved;
+  int32_t step_rows;            /* capacity of the per-step conditioning tables below, in diffusion steps (0 = none) */
   float* x;                     /* [rows, 768] fp32 residual stream */
   jpdvt_bf16* xn;               /* [rows, 768]  */
   jpdvt_bf16* qkv;              /* [rows, 2304] */
@@ -224,6 +224,10 @@ typedef struct jpdvt_workspace {
   float* fold_u;                /* [depth, 5376] row sums of W' */
   float* fold_v;                /* [depth, 5376] b + W . shift */
   float* row_stats;             /* [rows, 6, 2] per-row (sum, sum of squares) partials of the residual stream */
+  /* jpdvt_sample_loop: conditioning of every step of one call, computed ahead of the loop (all three NULL = per step) */
+  float* c_steps;               /* [step_rows, 768] */
+  float* silu_c_steps;          /* [step_rows, 768] */
+  float* mod_steps;             /* [step_rows, depth*4608 + 1536] */
 } jpdvt_workspace;
 
 /* One DiT.forward (models.py:273-293): (img [B,3,S,S], t, x_t [B,T,8]) -> te_out [B,T,8] and, when img_out != NULL,

@@ -29,9 +29,9 @@ class Weights(C.Structure):
 
 
 class Workspace(C.Structure):
-    _fields_ = [("rows", C.c_int64), ("cond_rows", C.c_int32), ("reserved", C.c_int32)] + [
+    _fields_ = [("rows", C.c_int64), ("cond_rows", C.c_int32), ("step_rows", C.c_int32)] + [
         (n, c_void_p) for n in ("x", "xn", "qkv", "attn", "hid", "y", "y32", "c", "silu_c", "silu_c_bf16", "mod",
-                                "w_fold", "fold_u", "fold_v", "row_stats")]
+                                "w_fold", "fold_u", "fold_v", "row_stats", "c_steps", "silu_c_steps", "mod_steps")]
 
 
 class Sampler(C.Structure):
@@ -64,7 +64,7 @@ class BwdScratch(C.Structure):
                                         "small_bf16", "wgrad_scratch", "part", "zeros")]
 
 
-ABI_VERSION = 2            # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: jpdvt_workspace grew the LayerNorm-fold buffers)
+ABI_VERSION = 3            # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables)
 
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header

@@ -71,9 +71,10 @@ static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows
                      reinterpret_cast<const __nv_bfloat16*>(w->w_ada), kHidden, p, st);
 }
 
+// mod_pre != null: this step's adaLN row was computed ahead of the loop (jpdvt_sample_loop) - no conditioning launches here
 static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const float* img, const int64_t* t,
                         const int32_t* step_ptr, const int32_t* map, const float* x_t, float* te_out, float* img_out,
-                        int batch, cudaStream_t st) {
+                        int batch, cudaStream_t st, const float* mod_pre = nullptr) {
   if (w == nullptr || ws == nullptr) return set_error(kErrBadArg, "forward: null weights/workspace");
   if (batch <= 0) return kOk;
   const int T = w->tokens, depth = w->depth, S = w->image_size;
@@ -101,9 +102,12 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     JP_TRY(launch_gemm(EPI_PATCH_EMBED_F32, cols, kHidden, reinterpret_cast<bfp>(w->w_patch), kHidden, p, st));
   }
   // conditioning: c = t_embedder(t); all 13 adaLN linears at once            (models.py:282-284,119,134)
-  JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), cond_rows, step_ptr, map, w->t_w0, w->t_b0, w->t_w2,
-                               w->t_b2, ws->c, ws->silu_c, nullptr, nullptr, st));
-  JP_TRY(adaln_all(w, ws, cond_rows, n_mod, st));
+  if (mod_pre == nullptr) {
+    JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), cond_rows, step_ptr, map, w->t_w0, w->t_b0, w->t_w2,
+                                 w->t_b2, ws->c, ws->silu_c, nullptr, nullptr, st));
+    JP_TRY(adaln_all(w, ws, cond_rows, n_mod, st));
+  }
+  const float* mod_base = (mod_pre != nullptr) ? mod_pre : ws->mod;
 
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws->xn);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
@@ -126,7 +130,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   constexpr int kFoldRows = 7 * kHidden, kStatSlots = 2 * (kHidden / 256);
   float2* row_stats = reinterpret_cast<float2*>(ws->row_stats);
   if (fold)
-    JP_TRY(launch_fold_ln(reinterpret_cast<bfp>(w->w_qkv), reinterpret_cast<bfp>(w->w_fc1), w->b_qkv, w->b_fc1, ws->mod,
+    JP_TRY(launch_fold_ln(reinterpret_cast<bfp>(w->w_qkv), reinterpret_cast<bfp>(w->w_fc1), w->b_qkv, w->b_fc1, mod_base,
                           reinterpret_cast<__nv_bfloat16*>(ws->w_fold), ws->fold_u, ws->fold_v, depth, st));
   // folded = true: the LayerNorm that follows is folded into its consumer, so only bf16(x) and the row sums are produced
   auto resid_gemm = [&](bfp a, long long lda, bfp wt, const float* bias, int k, const float* gate, const float* shift,
@@ -146,9 +150,9 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     if (r != kOk) return r;
     return launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, shift, scale, mod_stride, xn, M, T, st);
   };
-  JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, ws->mod, ws->mod + kHidden, mod_stride, xn, M, T, st));
+  JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod_base, mod_base + kHidden, mod_stride, xn, M, T, st));
   for (int i = 0; i < depth; ++i) {
-    const float* mod = ws->mod + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
+    const float* mod = mod_base + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
     const float* nxt = mod + 6 * kHidden;                                   // next block's (or the final layer's) shift, scale
     // x += gate_msa * proj(attn(modulate(LN(x), shift_msa, scale_msa)))    (models.py:120); xn holds modulate(LN(x), ...)
     {
@@ -435,12 +439,30 @@ int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const j
   cudaStream_t st = ST(stream);
   const long long per_sample = static_cast<long long>(w->tokens) * kLatent;
   const long long n = per_sample * batch;
+  // The conditioning of step k depends on k alone (every puzzle shares the timestep, gaussian_diffusion.py:509), so the
+  // timestep embeddings and the adaLN rows of ALL steps of this call are computed up front - 2 + ceil(steps / 8) launches
+  // instead of 3 per step, the 87 MB of adaLN weights streamed once per 8 steps instead of once per step.  Row by row the
+  // arithmetic is the per-step kernels' (bit-identical results).  JPDVT_STEP_TABLE=0 keeps the per-step launches.
+  static int step_table = -1;
+  if (step_table < 0) { const char* e = getenv("JPDVT_STEP_TABLE"); step_table = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  const int n_steps = last_step - first_step;
+  const int n_mod = w->depth * 6 * kHidden + 2 * kHidden;
+  const bool pre = step_table && n_steps > 1 && ws->mod_steps != nullptr && ws->c_steps != nullptr && ws->silu_c_steps != nullptr &&
+                   ws->step_rows >= n_steps;
+  if (pre) {
+    int rc = launch_timestep_embed(nullptr, n_steps, s->step_ids + first_step, s->timestep_map, w->t_w0, w->t_b0, w->t_w2, w->t_b2,
+                                   ws->c_steps, ws->silu_c_steps, nullptr, nullptr, st, 1);
+    if (rc != kOk) return rc;
+    rc = launch_adaln_gemv(ws->silu_c_steps, n_steps, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod_steps, n_mod, st);
+    if (rc != kOk) return rc;
+  }
   for (int k = first_step; k < last_step; ++k) {
     // gaussian_diffusion.py:518-527: x_t of EVERY step is the initial noise unless chain mode is requested
     const float* x_t = (s->chain && k > 0) ? s->sample : noise;
     const int32_t* step_ptr = s->step_ids + k;
     float* x0 = s->traj_x0 ? s->traj_x0 + static_cast<long long>(k) * n : s->x0;
-    int rc = forward_impl(w, ws, condition, nullptr, step_ptr, s->timestep_map, x_t, x0, nullptr, batch, st);
+    const float* mod_pre = pre ? ws->mod_steps + static_cast<long long>(k - first_step) * n_mod : nullptr;
+    int rc = forward_impl(w, ws, condition, nullptr, step_ptr, s->timestep_map, x_t, x0, nullptr, batch, st, mod_pre);
     if (rc != kOk) return rc;
     float* smp = s->traj_sample ? s->traj_sample + static_cast<long long>(k) * n : s->sample;
     rc = launch_posterior(x0, x_t, s->step_noise + static_cast<long long>(k) * s->step_noise_stride, s->coef1, s->coef2,

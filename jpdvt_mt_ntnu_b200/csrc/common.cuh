@@ -152,7 +152,7 @@ int launch_patchify(const float* img, __nv_bfloat16* cols, int batch, int size, 
 int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStream_t stream);
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
                           const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
-                          cudaStream_t stream);
+                          cudaStream_t stream, int step_stride = 0);
 int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, const float* bias, float* out, int n_out,
                       cudaStream_t stream);
 int launch_posterior(const float* x0, const float* xt, const float* noise, const float* coef1, const float* coef2,

@@ -164,14 +164,16 @@ int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStrea
 constexpr int kTeRows = 8;
 constexpr int kTeWarps = 8;
 
-__device__ __forceinline__ long long te_timestep(const long long* t, int r, const int* step_ptr, const int* map) {
+// step_stride 0: one device-resident step index for every row; 1: row r reads step_ptr[r] (a whole schedule at once)
+__device__ __forceinline__ long long te_timestep(const long long* t, int r, const int* step_ptr, const int* map, int step_stride) {
   if (t != nullptr) return t[r];
-  return (map != nullptr) ? static_cast<long long>(map[*step_ptr]) : static_cast<long long>(*step_ptr);
+  const int idx = step_ptr[r * step_stride];
+  return (map != nullptr) ? static_cast<long long>(map[idx]) : static_cast<long long>(idx);
 }
 
 __global__ void __launch_bounds__(kTeWarps * 32)
-timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __restrict__ step_ptr, const int* __restrict__ map,
-                       const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ hid,
+timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __restrict__ step_ptr, int step_stride,
+                       const int* __restrict__ map, const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ hid,
                        float* __restrict__ feat_out, float* __restrict__ pre_out) {
   __shared__ float feat[kTeRows][256];
   const int r0 = blockIdx.y * kTeRows;
@@ -180,7 +182,7 @@ timestep_hidden_kernel(const long long* __restrict__ t, int n, const int* __rest
     const int r = i >> 7, k = i & 127;
     float c = 0.f, s = 0.f;
     if (r < nr) {
-      const long long tv = te_timestep(t, r0 + r, step_ptr, map);
+      const long long tv = te_timestep(t, r0 + r, step_ptr, map, step_stride);
       // models.py:52-56: freqs = exp(-ln(10000) * arange(128, fp32) / 128) in fp32, args = t.float() * freqs
       const float f = expf((-9.210340371976184f * static_cast<float>(k)) / 128.0f);
       const float a = static_cast<float>(tv) * f;
@@ -258,11 +260,11 @@ timestep_out_kernel(const float* __restrict__ hid, int n, const float* __restric
 // `silu_c` doubles as the scratch for the hidden activations between the two phases.
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
                           const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int step_stride) {
   if (n <= 0) return kOk;
   if (t == nullptr && step_ptr == nullptr) return set_error(kErrBadArg, "timestep_embed: need t or step_ptr");
   dim3 grid(kHidden / kTeWarps, (n + kTeRows - 1) / kTeRows);
-  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, map, w0, b0, c, feat_out, pre_out);
+  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, step_stride, map, w0, b0, c, feat_out, pre_out);
   int rc = check_launch("timestep_hidden_kernel");
   if (rc != kOk) return rc;
   timestep_out_kernel<<<grid, kTeWarps * 32, 0, stream>>>(c, n, w2, b2, c, silu_c);

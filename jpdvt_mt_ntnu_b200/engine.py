@@ -84,12 +84,13 @@ class DenoiserEngine:
     def load_state(self, state: Dict[str, torch.Tensor]) -> None:
         self.weights = PackedWeights(state, self.depth, self.image_size, self.device)
 
-    def workspace(self, batch: int, cond_rows: int, need_image: bool) -> Workspace:
+    def workspace(self, batch: int, cond_rows: int, need_image: bool, step_rows: int = 0) -> Workspace:
         rows = batch * self.tokens
         key = self._ws_key
-        if key is None or key[0] < rows or key[1] < cond_rows or (need_image and not key[2]):
+        if key is None or key[0] < rows or key[1] < cond_rows or (need_image and not key[2]) or key[3] < step_rows:
             rows_cap = max(rows, key[0] if key else 0)
             cond_cap = max(cond_rows, key[1] if key else 0)
+            step_cap = max(step_rows, key[3] if key else 0)
             img = need_image or bool(key and key[2])
             dev, bf, f32 = self.device, torch.bfloat16, torch.float32
             n_mod = self.depth * 6 * HIDDEN + 2 * HIDDEN
@@ -110,12 +111,17 @@ class DenoiserEngine:
                 "fold_u": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
                 "fold_v": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
                 "row_stats": torch.empty(rows_cap, 2 * (HIDDEN // 256), 2, device=dev, dtype=f32),
+                # conditioning of every step of one sample_loop call, computed ahead of the loop (api.cu: jpdvt_sample_loop)
+                "c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
+                "silu_c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
+                "mod_steps": torch.empty(step_cap, n_mod, device=dev, dtype=f32) if step_cap else None,
             }
             ws = Workspace()
-            ws.rows, ws.cond_rows, ws.reserved = rows_cap, cond_cap, 0
+            ws.rows, ws.cond_rows, ws.step_rows = rows_cap, cond_cap, step_cap
             for k, v in t.items():
                 setattr(ws, k, ptr(v))
-            self._ws_tensors, self._ws, self._ws_key = t, ws, (rows_cap, cond_cap, img)
+            self.__dict__.get("_graphs", {}).clear()           # captured graphs hold the old buffers' addresses
+            self._ws_tensors, self._ws, self._ws_key = t, ws, (rows_cap, cond_cap, img, step_cap)
         return self._ws
 
     # ------------------------------------------------------------------ one forward
@@ -184,7 +190,7 @@ class DenoiserEngine:
         last_step = n_steps if last_step is None else last_step
         condition = condition.to(torch.float32).contiguous()
         noise = noise.to(torch.float32).contiguous()
-        ws = self.workspace(B, 1, False)
+        ws = self.workspace(B, 1, False, step_rows=max(0, last_step - first_step))
         dev = condition.device
         if state is None:
             state = {
