@@ -185,3 +185,79 @@ class Trainer:
     def optimizer_state(self) -> dict:
         return {"step": self.step_count, "exp_avg": self.m_flat, "exp_avg_sq": self.v_flat, "lr": self.lr, "betas": self.betas,
                 "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def _named_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Views of a buffer laid out like the flat parameter buffer, keyed by the module's parameter names."""
+        views = {name: flat[off:off + n].view(shape) for (name, shape), (off, n) in
+                 zip(self.layout, (self.offsets[name] for name, _ in self.layout))}
+        return param_grad_map(self.model, views)
+
+    def optimizer_state_dict(self) -> dict:
+        """The moments in the layout of `torch.optim.AdamW(model.parameters()).state_dict()` - what the reference stores
+        under "opt" and feeds back to `opt.load_state_dict` on resume (train_JPDVT.py:281-284, 413): parameter i of
+        `model.parameters()` -> {step, exp_avg, exp_avg_sq}; frozen parameters (pos_embed) are listed but carry no state."""
+        names = [n for n, _ in self.model.named_parameters()]
+        m, v = self._named_views(self.m_flat), self._named_views(self.v_flat)
+        state = {}
+        if self.step_count > 0:
+            for i, n in enumerate(names):
+                if n in m:
+                    state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m[n].detach().clone(),
+                                "exp_avg_sq": v[n].detach().clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": True, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        names = [n for n, _ in self.model.named_parameters()]
+        m, v = self._named_views(self.m_flat), self._named_views(self.v_flat)
+        self.m_flat.zero_()
+        self.v_flat.zero_()
+        steps = set()
+        for i, st in sd.get("state", {}).items():
+            n = names[int(i)]
+            if n not in m:
+                continue
+            m[n].copy_(st["exp_avg"])
+            v[n].copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"optimizer state carries different step counts per parameter: {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        groups = sd.get("param_groups") or [{}]
+        g = groups[0]
+        self.lr, self.eps, self.weight_decay = g.get("lr", self.lr), g.get("eps", self.eps), g.get("weight_decay", self.weight_decay)
+        self.betas = tuple(g.get("betas", self.betas))
+
+    def checkpoint(self, args=None) -> dict:
+        """The reference trainer's checkpoint dict (train_JPDVT.py:410-416): model, ema, opt, args, train_steps."""
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()}, "ema": self.ema_state_dict(),
+                "opt": self.optimizer_state_dict(), "args": args, "train_steps": self.step_count}
+
+    def save_checkpoint(self, path: str, args=None) -> None:
+        torch.save(self.checkpoint(args), path)
+
+    def load_checkpoint(self, ckpt, strict: bool = False) -> int:
+        """Resume from a checkpoint written by `save_checkpoint` or by the reference trainer (train_JPDVT.py:238-284:
+        model with strict=False, ema, opt, train_steps; missing entries are skipped as the reference does).  Returns
+        train_steps."""
+        if isinstance(ckpt, (str, os.PathLike)):
+            ckpt = torch.load(ckpt, map_location="cpu", weights_only=False)
+        if "model" in ckpt:
+            self.model.load_state_dict(ckpt["model"], strict=strict)        # copies into the flat buffer's slices
+        if "ema" in ckpt:
+            ema = self._named_views(self.ema_flat)
+            for k, val in ckpt["ema"].items():
+                if k in ema:
+                    ema[k].copy_(val)
+        else:
+            self.ema_flat.copy_(self.p_flat)
+        if ckpt.get("opt") is not None:
+            self.load_optimizer_state_dict(ckpt["opt"])
+        if ckpt.get("train_steps") is not None and ckpt.get("opt") is None:
+            self.step_count = int(ckpt["train_steps"])
+        self.pb_flat.copy_(self.p_flat)
+        # (pos_embed: self.pos is a view of the module's frozen buffer, updated in place by load_state_dict)
+        self._refresh_derived()
+        return int(ckpt.get("train_steps") or self.step_count)

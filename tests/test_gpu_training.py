@@ -151,3 +151,56 @@ def test_fused_trainer_matches_stock_adamw_and_ema(cuda):
         a = m2(x.cuda(), t.cuda(), torch.zeros(3, 36, 8, device="cuda"))[1]
         b = m1(x.cuda(), t.cuda(), torch.zeros(3, 36, 8, device="cuda"))[1]
     assert rel_l2(a, b) < 5e-2
+
+
+def test_trainer_checkpoint_resume_in_reference_format(cuda, tmp_path):
+    """save_checkpoint writes the reference trainer's dict (train_JPDVT.py:410-416); a fresh Trainer that loads it
+    continues where the first one stood (same next step: parameters, EMA, moments, step count), and the
+    "opt" entry loads into the reference's own torch.optim.AdamW (train_JPDVT.py:281-284)."""
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT
+    from jpdvt_mt_ntnu_b200.trainer import Trainer
+    case = cases.TRAINING_CASES["tiny96"]
+    x, t, piece = cases.training_inputs(case)
+    kw = dict(block_size=32, patch_size=16, add_mask=False, grid_size=3)
+
+    def fresh(seed_state=True):
+        m = DiT(input_size=96, depth=2, hidden_size=768, patch_size=16, num_heads=12)
+        if seed_state:
+            m.load_state_dict(cases.state_for(case))
+        return m.cuda()
+
+    def step(tr, d):
+        d._draws = cases.training_draws(case)
+        return tr.step(x.cuda(), t.cuda(), piece.cuda(), **kw).item()
+
+    m1, d1 = fresh(), create_diffusion("")
+    tr1 = Trainer(m1, d1, lr=1e-3)
+    for _ in range(2):
+        step(tr1, d1)
+    path = str(tmp_path / "0000002.pt")
+    tr1.save_checkpoint(path, args={"image_size": 96})
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert sorted(ckpt) == ["args", "ema", "model", "opt", "train_steps"] and ckpt["train_steps"] == 2
+    assert list(ckpt["model"]) == list(m1.state_dict()) and list(ckpt["ema"]) == list(m1.state_dict())
+    loss1 = step(tr1, d1)
+
+    m2, d2 = fresh(seed_state=False), create_diffusion("")      # different (fresh-init) weights: everything must come from the file
+    tr2 = Trainer(m2, d2, lr=5e-4)
+    assert tr2.load_checkpoint(path) == 2 and tr2.step_count == 2 and tr2.lr == 1e-3
+    loss2 = step(tr2, d2)
+    # same state, same draws -> same step (weight-gradient splits meet through fp32 reduction boxes whose order is not
+    # fixed, hence a tolerance at rounding level instead of bit equality)
+    assert abs(loss2 - loss1) <= 1e-6 * abs(loss1)
+    for a, b in ((tr2.p_flat, tr1.p_flat), (tr2.ema_flat, tr1.ema_flat), (tr2.m_flat, tr1.m_flat), (tr2.v_flat, tr1.v_flat)):
+        assert rel_l2(a, b) < 1e-4
+
+    # the reference resumes with opt.load_state_dict(checkpoint["opt"]) on AdamW(model.parameters())
+    m3 = fresh()
+    opt = torch.optim.AdamW(m3.parameters(), lr=1e-4, weight_decay=0)
+    opt.load_state_dict(ckpt["opt"])
+    names = [n for n, _ in m3.named_parameters()]
+    i = names.index("blocks.1.mlp.fc1.weight")
+    st = opt.state[opt.param_groups[0]["params"][i]]
+    assert float(st["step"]) == 2.0 and st["exp_avg"].shape == m3.blocks[1].mlp.fc1.weight.shape
+    assert names.index("pos_embed") not in ckpt["opt"]["state"]
