@@ -55,6 +55,10 @@ int resid_epilogue(int n, int k) {
 // LayerNorm-fused variant: through the TMA ring (default) or the register / ld.global.cg form (JPDVT_RESID_TMA=0)
 int resid_ln_epilogue() { return resid_epilogue(kHidden, kHidden) == EPI_RESID_TMA_F32 ? EPI_RESID_LN_TMA_F32 : EPI_RESID_LN_F32; }
 
+static thread_local int g_sweep_reverse = 0;
+int sweep_reverse() { return g_sweep_reverse; }
+void set_sweep_reverse(int reverse) { g_sweep_reverse = reverse; }
+
 static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows, int n_mod, cudaStream_t st) {
   if (rows <= 8) {
     return launch_adaln_gemv(ws->silu_c, rows, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod, n_mod, st);
@@ -109,6 +113,13 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   }
   const float* mod_base = (mod_pre != nullptr) ? mod_pre : ws->mod;
 
+  // alternate the row sweep direction from launch to launch (common.cuh: sweep_reverse) - each consumer starts on the rows
+  // its producer wrote last, which are the ones still in L2
+  static int sweep_env = -1;
+  if (sweep_env < 0) { const char* e = getenv("JPDVT_SWEEP"); sweep_env = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  struct SweepGuard { ~SweepGuard() { set_sweep_reverse(0); } } sweep_guard;
+  int sweep_dir = 0;
+  auto flip = [&]() { sweep_dir ^= sweep_env; set_sweep_reverse(sweep_dir); };
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws->xn);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws->qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws->attn);
@@ -138,6 +149,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = k; p.tokens = T;
     p.bias = bias; p.out = ws->x; p.ldo = kHidden; p.gate = gate; p.gate_stride = mod_stride;
+    flip();
     if (folded) {
       p.ln_out = xn; p.stats_out = row_stats; p.stats_slots = kStatSlots;
       return launch_gemm(EPI_RESID_TMA_XB_F32, a, lda, wt, lda, p, st);
@@ -148,8 +160,10 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     }
     int r = launch_gemm(resid_epilogue(kHidden, k), a, lda, wt, lda, p, st);
     if (r != kOk) return r;
+    flip();
     return launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, shift, scale, mod_stride, xn, M, T, st);
   };
+  flip();
   JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod_base, mod_base + kHidden, mod_stride, xn, M, T, st));
   for (int i = 0; i < depth; ++i) {
     const float* mod = mod_base + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
@@ -165,8 +179,10 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
         p.bias = ws->fold_v + static_cast<long long>(i) * kFoldRows; p.fold_u = ws->fold_u + static_cast<long long>(i) * kFoldRows;
         p.stats_in = row_stats; p.stats_slots = kStatSlots;
       }
+      flip();
       JP_TRY(launch_gemm(EPI_BIAS_BF16, xn, kHidden, wt, kHidden, p, st));
     }
+    flip();
     JP_TRY(launch_attention(qkv, att, nullptr, batch, T, st));
     // the gated residual update AND the LayerNorm-modulate of the MLP branch are the proj GEMM's epilogue
     JP_TRY(resid_gemm(att, kHidden, reinterpret_cast<bfp>(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden,
@@ -183,6 +199,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
         p.bias = ws->fold_v + off; p.fold_u = ws->fold_u + off;
         p.stats_in = row_stats; p.stats_slots = kStatSlots;
       }
+      flip();
       JP_TRY(launch_gemm(EPI_BIAS_GELU_BF16, xn, kHidden, wt, kHidden, p, st));
     }
     // ... and fc2's epilogue also produces the next block's (or the final layer's) modulate(LN(x), shift, scale)
@@ -196,10 +213,12 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_final; p.out = ws->y; p.ldo = kHidden;
     p.out2 = (img_out != nullptr) ? ws->y32 : nullptr;
+    flip();
     JP_TRY(launch_gemm(EPI_BIAS_BF16_F32, xn, kHidden, reinterpret_cast<bfp>(w->w_final), kHidden, p, st));
     GemmParams h{};
     h.M = static_cast<int>(M); h.N = 64; h.K = kHidden; h.tokens = T;
     h.bias = w->b_head1; h.out = te_out; h.ldo = kLatent; h.w2 = w->w_head2; h.b2 = w->b_head2;
+    flip();
     JP_TRY(launch_gemm(EPI_HEAD, reinterpret_cast<bfp>(ws->y), kHidden, reinterpret_cast<bfp>(w->w_head1), kHidden, h, st));
     if (img_out != nullptr) JP_TRY(launch_unpatchify(ws->y32, img_out, batch, S, st));   // models.py:291
   }

@@ -271,7 +271,7 @@ constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: M
 template <int T, bool TRACE>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                    int num_units, long long* __restrict__ trace) {
+                    int num_units, int reverse, long long* __restrict__ trace) {
   using Cfg = TcCfg<T>;
   auto mark = [&](int role, int it, int ev) {
     if constexpr (TRACE) {
@@ -315,7 +315,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-        const int b = unit / kHeads, h = unit - b * kHeads;
+        const int uu = reverse ? num_units - 1 - unit : unit;   // sweep direction: see sweep_reverse() in common.cuh
+        const int b = uu / kHeads, h = uu - b * kHeads;
         const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
         mark(3, it, 0);
         if (it > 0) mbar_wait(&s_full[kLast], prev);          // every score MMA of the previous unit has read Q, K
@@ -419,7 +420,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     int it = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const uint32_t ph = static_cast<uint32_t>(it & 1);
-      const int b = unit / kHeads, h = unit - b * kHeads;
+      const int uu = reverse ? num_units - 1 - unit : unit;
+      const int b = uu / kHeads, h = uu - b * kHeads;
       __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
       const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
       // ---- tile 0
@@ -523,7 +525,7 @@ struct SeqCfg {
 template <int TP, int TV>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                        int num_units) {
+                        int num_units, int reverse) {
   using Cfg = SeqCfg<TP, TV>;
   constexpr int kTiles = Cfg::kTiles;
   extern __shared__ uint8_t att_tc_smem[];
@@ -557,7 +559,8 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-        const int b = unit / kHeads, h = unit - b * kHeads;
+        const int uu = reverse ? num_units - 1 - unit : unit;   // sweep direction: see sweep_reverse() in common.cuh
+        const int b = uu / kHeads, h = uu - b * kHeads;
         if (it > 0) mbar_wait_backoff(qk_free, static_cast<uint32_t>((it - 1) & 1), 100);   // previous unit's score MMAs are done with Q, K
         mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
 #pragma unroll
@@ -615,7 +618,8 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
     const int r_tile = warp * 32 + lane;
     long long tile_no = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int b = unit / kHeads, h = unit - b * kHeads;
+      const int uu = reverse ? num_units - 1 - unit : unit;
+      const int b = uu / kHeads, h = uu - b * kHeads;
       __nv_bfloat16* obase = out + static_cast<long long>(b) * TV * kHidden + h * kHeadDim;
       for (int t = 0; t < kTiles; ++t, ++tile_no) {
         const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
@@ -670,7 +674,7 @@ int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = batch * kHeads;
-  kern<<<units < sms ? units : sms, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units);
+  kern<<<units < sms ? units : sms, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, sweep_reverse());
   return check_launch("attention_tc_seq_kernel");
 }
 
@@ -706,7 +710,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
     long long* d = nullptr;
     cudaMalloc(&d, n * sizeof(long long));
     cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
-    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, d);
+    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d);
     long long h[n];
     cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -725,7 +729,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
       }
     return check_launch("attention_tc_kernel<trace>");
   }
-  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, static_cast<long long*>(nullptr)) != cudaSuccess)
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(), static_cast<long long*>(nullptr)) != cudaSuccess)
     return set_error(kErrCuda, "attention_tc_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("attention_tc_kernel");
 }

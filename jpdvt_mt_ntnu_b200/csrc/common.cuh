@@ -92,7 +92,16 @@ struct GemmParams {
   const float2* stats_in;
   const float* fold_u;
   int stats_slots;
+  int reverse_m;              // walk the row blocks from the last to the first (set by launch_gemm from sweep_reverse())
 };
+
+// Sweep direction of the next row-streaming launch (LayerNorm, GEMMs, attention).  Every activation of a forward is larger
+// than what L2 keeps of it (M = 36,864: x 113 MB, qkv 170 MB, hidden 226 MB against a 126 MB L2), so a consumer that walks
+// the rows in its producer's order finds the head of its input evicted and re-reads all of it from HBM; walking them the
+// other way round it starts on the rows written last, which are still resident.  forward_impl therefore flips the
+// direction with every launch (JPDVT_SWEEP=0: always upwards).  Single-op C-ABI calls leave it at 0.
+int sweep_reverse();
+void set_sweep_reverse(int reverse);
 
 // dW[wg_rows, n_cols] (fp32) = P[M, wg_rows]^T . Q[M, n_cols]   (both bf16 row-major); `partial` is scratch of
 // split * wg_rows * n_cols floats (see wgrad_scratch_floats)

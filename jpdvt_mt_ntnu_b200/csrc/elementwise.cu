@@ -30,10 +30,12 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_modulate_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, const __nv_bfloat16* __restrict__ delta,
                    const float* __restrict__ gate, long long gate_stride, const float* __restrict__ shift,
                    const float* __restrict__ scale, long long mod_stride, __nv_bfloat16* __restrict__ y, long long rows,
-                   int tokens) {
+                   int tokens, int reverse) {
   griddep_wait();
   griddep_launch_dependents();
-  const long long row = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  // blocks are dispatched in index order: `reverse` makes the kernel walk the rows downwards (sweep_reverse(), common.cuh)
+  const long long blk = reverse ? static_cast<long long>(gridDim.x) - 1 - blockIdx.x : blockIdx.x;
+  const long long row = blk * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const long long sample = row / tokens;
@@ -97,10 +99,10 @@ int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* del
   cudaError_t e;
   if (delta != nullptr)
     e = launch_pdl(ln_modulate_kernel<true>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
-                   mod_stride, y, rows, tokens);
+                   mod_stride, y, rows, tokens, sweep_reverse());
   else
     e = launch_pdl(ln_modulate_kernel<false>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
-                   mod_stride, y, rows, tokens);
+                   mod_stride, y, rows, tokens, sweep_reverse());
   if (e != cudaSuccess) return set_error(kErrCuda, "ln_modulate_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("ln_modulate_kernel");
 }

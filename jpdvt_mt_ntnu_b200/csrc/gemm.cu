@@ -271,6 +271,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int rem = tile - split_idx * tiles_mn;
       m_blk = rem / num_n;
       n_blk = rem % num_n;
+      if (p.reverse_m) m_blk = num_m - 1 - m_blk;            // walk the row blocks downwards (sweep_reverse(), common.cuh)
       return true;
     }
   };
@@ -1209,6 +1210,7 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
     if (rc != kOk) return rc;
   }
   GemmParams pp = p;
+  pp.reverse_m = sweep_reverse();
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
     static int tma_out = -1;                                 // JPDVT_GEMM_TMA_OUT=0: per-thread coalesced stores instead (A/B knob)
     if (tma_out < 0) { const char* e = getenv("JPDVT_GEMM_TMA_OUT"); tma_out = (e != nullptr && e[0] == '0') ? 0 : 1; }
