@@ -6,6 +6,7 @@ side only sees raw pointers and the current CUDA stream (SURVEY.md 8b "Ownership
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -94,6 +95,7 @@ class DenoiserEngine:
             img = need_image or bool(key and key[2])
             dev, bf, f32 = self.device, torch.bfloat16, torch.float32
             n_mod = self.depth * 6 * HIDDEN + 2 * HIDDEN
+            fold = os.environ.get("JPDVT_LN_FOLD", "")[:1] == "1"      # opt-in path: its 100 MB of buffers only when asked for
             t = {
                 "x": torch.empty(rows_cap, HIDDEN, device=dev, dtype=f32),
                 "xn": torch.empty(rows_cap, HIDDEN, device=dev, dtype=bf),
@@ -107,10 +109,10 @@ class DenoiserEngine:
                 "silu_c_bf16": torch.empty(cond_cap, HIDDEN, device=dev, dtype=bf),
                 "mod": torch.empty(cond_cap, n_mod, device=dev, dtype=f32),
                 # LayerNorm folded into qkv / fc1 (uniform-timestep forwards; csrc/fold.cu)
-                "w_fold": torch.empty(self.depth * 7 * HIDDEN, HIDDEN, device=dev, dtype=bf),
-                "fold_u": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
-                "fold_v": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32),
-                "row_stats": torch.empty(rows_cap, 2 * (HIDDEN // 256), 2, device=dev, dtype=f32),
+                "w_fold": torch.empty(self.depth * 7 * HIDDEN, HIDDEN, device=dev, dtype=bf) if fold else None,
+                "fold_u": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32) if fold else None,
+                "fold_v": torch.empty(self.depth * 7 * HIDDEN, device=dev, dtype=f32) if fold else None,
+                "row_stats": torch.empty(rows_cap, 2 * (HIDDEN // 256), 2, device=dev, dtype=f32) if fold else None,
                 # conditioning of every step of one sample_loop call, computed ahead of the loop (api.cu: jpdvt_sample_loop)
                 "c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
                 "silu_c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
