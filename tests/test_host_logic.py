@@ -149,3 +149,24 @@ def test_block_and_strided_shards():
     items = list(range(11))
     got = sorted(sum((parallel.strided_shard(items, r, 4) for r in range(4)), []))
     assert got == items
+
+
+def test_documented_knobs_exist_in_the_sources():
+    """Every JPDVT_* environment knob DESIGN.md's table names is read somewhere in the package (and vice versa for the
+    knobs the C sources read), so the A/B documentation cannot drift from the code."""
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    table = design[design.index("## 9. A/B knobs"):design.index("## 10.")]
+    documented = set(re.findall(r"`(JPDVT_[A-Z0-9_]+)", table))
+    src = ""
+    pkg = os.path.join(ROOT, "jpdvt_mt_ntnu_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".py")):
+                src += open(os.path.join(base, f), errors="ignore").read()
+    read_in_c = set(re.findall(r'getenv\("(JPDVT_[A-Z0-9_]+)"\)', src))
+    read_in_py = set(re.findall(r'environ(?:\.get)?[\(\[]\s*"(JPDVT_[A-Z0-9_]+)"', src))
+    missing = {k for k in documented if k not in src}
+    assert not missing, f"documented but not read anywhere: {sorted(missing)}"
+    internal = {"JPDVT_FORCE_BUILD", "JPDVT_KEEP_NCCL_DEBUG"}          # build / bench plumbing, not A/B knobs
+    undocumented = (read_in_c | read_in_py) - documented - internal
+    assert not undocumented, f"read by the code but missing from DESIGN.md section 9: {sorted(undocumented)}"
