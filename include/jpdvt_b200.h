@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JPDVT_ABI_VERSION 3
+#define JPDVT_ABI_VERSION 4
 #define JPDVT_HIDDEN 768
 #define JPDVT_LATENT 8
 
@@ -119,9 +119,11 @@ int jpdvt_patchify(const float* img, jpdvt_bf16* cols, int batch, int image_size
 int jpdvt_unpatchify(const float* y, float* img, int batch, int image_size, void* stream);
 
 /* c = Linear(SiLU(Linear(sinusoid_256(t)))) and silu(c)   (TimestepEmbedder, models.py:27-64).
- * t: int64[n] model timesteps, or NULL: then every row uses map[*step_ptr] (or *step_ptr when map is NULL). */
+ * t: int64[n] model timesteps, or NULL: then every row uses map[*step_ptr] (or *step_ptr when map is NULL).
+ * hid_scratch: [n, 768] fp32 of its own (the hidden activations between the two grid-wide phases; must not alias c / silu_c). */
 int jpdvt_timestep_embed(const int64_t* t, int n, const int32_t* step_ptr, const int32_t* map, const float* w0,
-                         const float* b0, const float* w2, const float* b2, float* c, float* silu_c, void* stream);
+                         const float* b0, const float* w2, const float* b2, float* c, float* silu_c, float* hid_scratch,
+                         void* stream);
 /* mod[r, :] = W_all . silu_c[r] + b_all for all adaLN linears at once (models.py:113-116,133-136);
  * W_all bf16 [n_out, 768] = concat(blocks[i].adaLN_modulation[1].weight ..., final_layer.adaLN_modulation[1].weight). */
 int jpdvt_adaln_table(const float* silu_c, int rows, const jpdvt_bf16* w_all, const float* b_all, float* mod, int n_out,
@@ -133,6 +135,13 @@ int jpdvt_adaln_table(const float* silu_c, int rows, const jpdvt_bf16* w_all, co
 int jpdvt_posterior_step(const float* x0, const float* x_t, const float* noise, const float* coef1, const float* coef2,
                          const float* logvar, const int64_t* t, const int32_t* step_ptr, float* mean_or_null,
                          float* sample_or_null, int64_t n, int64_t per_sample, void* stream);
+/* The generator behind noise_key (jpdvt_sampler) on its own: out[i] (fp32, n % 4 == 0) = the normals the posterior kernel
+ * draws for loop position `step`; raw (nullable, uint32[n]) = the underlying Philox4x32-10 words (counter = {i/4 lo, i/4 hi,
+ * step, key[1]}, key = key[0]).  jpdvt_posterior_step_philox = jpdvt_posterior_step with that noise drawn in the kernel. */
+int jpdvt_philox_normal(float* out_or_null, uint32_t* raw_or_null, int64_t n, int step, const int64_t* key, void* stream);
+int jpdvt_posterior_step_philox(const float* x0, const float* x_t, const int64_t* noise_key, int noise_step, const float* coef1,
+                                const float* coef2, const float* logvar, const int64_t* t, const int32_t* step_ptr,
+                                float* sample, int64_t n, int64_t per_sample, void* stream);
 /* DDIM update (gaussian_diffusion.py:559-578, with the `condition` argument the reference call at :547 forgot):
  * eps = (recip[t]*x_t - x0)/recipm1[t]; sample = sqrt_abp[t]*x0 + dir[t]*eps + [t != 0]*sigma[t]*noise.  Pinned against
  * the reference's own DDIM code run with that argument supplied (tests/golden/ddim_*.npz). */
@@ -228,6 +237,8 @@ typedef struct jpdvt_workspace {
   float* c_steps;               /* [step_rows, 768] */
   float* silu_c_steps;          /* [step_rows, 768] */
   float* mod_steps;             /* [step_rows, depth*4608 + 1536] */
+  float* te_hid;                /* [max(cond_rows, step_rows), 768] hidden activations of the timestep MLP (scratch of its own) */
+  float* x_embed;               /* [rows, 768] fp32 or NULL: jpdvt_sample_loop keeps the loop-invariant embedding here (NULL = per step) */
 } jpdvt_workspace;
 
 /* One DiT.forward (models.py:273-293): (img [B,3,S,S], t, x_t [B,T,8]) -> te_out [B,T,8] and, when img_out != NULL,
@@ -245,12 +256,14 @@ typedef struct jpdvt_sampler {
   const float* coef1;           /* [num_steps] posterior_mean_coef1 (fp32) */
   const float* coef2;           /* [num_steps] */
   const float* logvar;          /* [num_steps] posterior_log_variance_clipped */
-  const float* step_noise;      /* [num_steps or 1, B, T, 8] noise drawn per step (torch-generated in parity mode) */
+  const float* step_noise;      /* [num_steps or 1, B, T, 8] noise drawn per step (torch-generated in parity mode), or NULL */
   int64_t step_noise_stride;    /* elements between consecutive steps' noise (0 = reuse one tensor) */
   float* x0;                    /* [B, T, 8] scratch: pred_xstart of the current step */
   float* sample;                /* [B, T, 8] scratch / result: sample of the current step */
   float* traj_x0;               /* optional [num_steps, B, T, 8] record of every pred_xstart, or NULL */
   float* traj_sample;           /* optional [num_steps, B, T, 8] record of every sample, or NULL */
+  const int64_t* noise_key;     /* device int64[2] {seed, call counter}: with step_noise == NULL the per-step noise of p_sample
+                                   (gaussian_diffusion.py:424) is drawn inside the posterior kernel (Philox4x32-10 + Box-Muller) */
 } jpdvt_sampler;
 
 /* SpacedDiffusion.p_sample_loop (gaussian_diffusion.py:433-529 through respace.py:89-129): runs steps
@@ -323,6 +336,7 @@ typedef struct jpdvt_tape {        /* activations kept by the training forward f
   float* silu_c;                /* [batch, 768] */
   jpdvt_bf16* silu_c_bf16;      /* [batch, 768] */
   float* mod;                   /* [batch, depth*4608 + 1536] */
+  float* thid;                  /* [batch, 768] SiLU(tpre): scratch between the two phases of the timestep MLP */
 } jpdvt_tape;
 
 typedef struct jpdvt_grads {       /* fp32 gradients in the parameters' own layouts; zero-filled by the caller before a backward */
@@ -365,6 +379,19 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
                                const jpdvt_bwd_scratch* s, const jpdvt_grads* g, int block, void* stream);
 int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt, const jpdvt_tape* tape,
                                const jpdvt_bwd_scratch* s, const jpdvt_grads* g, const float* x_t, void* stream);
+
+/* The loss terms of training_losses (diffusion/gaussian_diffusion.py:835-838 with mean_flat, :18-22):
+ *   loss[b] = mean((te_tgt - te_out)^2)  [+ mean((img_tgt - img_out)^2 * (1 - keep[b, slot]))  when img_out != NULL]
+ * te_*: [batch, per_te] fp32 (per_te = T*8); img_*: [batch, 3, S, S] fp32; keep: [batch, grid*grid] fp32 slot mask (the
+ * reference's `masks`, 1 = slot shown clean, carries no image loss); part: jpdvt_mse_part_floats(batch) floats of scratch.
+ * _bwd: d_te = dloss[b] * 2 (te_out - te_tgt) / per_te, d_img = dloss[b] * 2 (img_out - img_tgt)(1 - keep) / (3 S S). */
+int64_t jpdvt_mse_part_floats(int batch);
+int jpdvt_mse_loss_fwd(const float* te_out, const float* te_tgt, int64_t per_te, const float* img_out_or_null,
+                       const float* img_tgt_or_null, const float* keep_or_null, int image_size, int grid, float* part,
+                       float* loss, int batch, void* stream);
+int jpdvt_mse_loss_bwd(const float* te_out, const float* te_tgt, int64_t per_te, const float* img_out_or_null,
+                       const float* img_tgt_or_null, const float* keep_or_null, int image_size, int grid, const float* dloss,
+                       float* d_te, float* d_img_or_null, int batch, void* stream);
 
 /* One fused pass of torch.optim.AdamW.step() + update_ema() over a flat fp32 parameter buffer (train_JPDVT.py:281,371-372,
  * 36-46): g is scaled by grad_scale first (1/world_size after a SUM all-reduce), `step` counts from 1; optionally refreshes

@@ -31,13 +31,14 @@ class Weights(C.Structure):
 class Workspace(C.Structure):
     _fields_ = [("rows", C.c_int64), ("cond_rows", C.c_int32), ("step_rows", C.c_int32)] + [
         (n, c_void_p) for n in ("x", "xn", "qkv", "attn", "hid", "y", "y32", "c", "silu_c", "silu_c_bf16", "mod",
-                                "w_fold", "fold_u", "fold_v", "row_stats", "c_steps", "silu_c_steps", "mod_steps")]
+                                "w_fold", "fold_u", "fold_v", "row_stats", "c_steps", "silu_c_steps", "mod_steps", "te_hid",
+                                "x_embed")]
 
 
 class Sampler(C.Structure):
     _fields_ = [("num_steps", C.c_int32), ("chain", C.c_int32)] + [
         (n, c_void_p) for n in ("step_ids", "timestep_map", "coef1", "coef2", "logvar", "step_noise")] + [
-        ("step_noise_stride", C.c_int64)] + [(n, c_void_p) for n in ("x0", "sample", "traj_x0", "traj_sample")]
+        ("step_noise_stride", C.c_int64)] + [(n, c_void_p) for n in ("x0", "sample", "traj_x0", "traj_sample", "noise_key")]
 
 
 class WeightsT(C.Structure):
@@ -47,7 +48,7 @@ class WeightsT(C.Structure):
 class Tape(C.Structure):
     _fields_ = [("rows", C.c_int64), ("batch", C.c_int32), ("reserved", C.c_int32)] + [
         (n, c_void_p) for n in ("cols", "x", "xn1", "qkv", "lse2", "att", "y1", "xn2", "hpre", "h", "y2", "xnf", "yfin", "yfin32",
-                                "headpre", "feat", "tpre", "c", "silu_c", "silu_c_bf16", "mod")]
+                                "headpre", "feat", "tpre", "c", "silu_c", "silu_c_bf16", "mod", "thid")]
 
 
 GRAD_FIELDS = ("w_patch", "b_patch", "w_in", "b_in", "t_w0", "t_b0", "t_w2", "t_b2", "w_ada", "b_ada", "w_qkv", "b_qkv",
@@ -64,7 +65,9 @@ class BwdScratch(C.Structure):
                                         "small_bf16", "wgrad_scratch", "part", "zeros")]
 
 
-ABI_VERSION = 3            # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables)
+# JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables, 4: timestep-MLP
+# scratch of its own, hoisted embedding, in-kernel Philox noise, loss kernels, tcgen05 attention backward)
+ABI_VERSION = 4
 
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header
@@ -85,7 +88,11 @@ PROTOTYPES = {
     "jpdvt_attention_fwd": [P, P, P, c_int, c_int, P],
     "jpdvt_patchify": [P, P, c_int, c_int, P],
     "jpdvt_unpatchify": [P, P, c_int, c_int, P],
-    "jpdvt_timestep_embed": [P, c_int, P, P, P, P, P, P, P, P, P],
+    "jpdvt_timestep_embed": [P, c_int, P, P, P, P, P, P, P, P, P, P],
+    "jpdvt_philox_normal": [P, P, c_int64, c_int, P, P],
+    "jpdvt_posterior_step_philox": [P, P, P, c_int, P, P, P, P, P, P, c_int64, c_int64, P],
+    "jpdvt_mse_loss_fwd": [P, P, c_int64, P, P, P, c_int, c_int, P, P, c_int, P],
+    "jpdvt_mse_loss_bwd": [P, P, c_int64, P, P, P, c_int, c_int, P, P, P, c_int, P],
     "jpdvt_adaln_table": [P, c_int, P, P, P, c_int, P],
     "jpdvt_posterior_step": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, P],
     "jpdvt_ddim_step": [P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int64, P],
@@ -114,7 +121,8 @@ PROTOTYPES = {
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
 }
-OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats", "jpdvt_bwd_part_floats"]
+OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats",
+                 "jpdvt_bwd_part_floats", "jpdvt_mse_part_floats"]
 
 _lock = threading.Lock()
 _lib = None
@@ -153,8 +161,14 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         lib.jpdvt_train_wgrad_scratch_floats.restype = c_int64
         lib.jpdvt_bwd_part_floats.argtypes = [c_int, c_int]
         lib.jpdvt_bwd_part_floats.restype = c_int64
+        lib.jpdvt_mse_part_floats.argtypes = [c_int]
+        lib.jpdvt_mse_part_floats.restype = c_int64
         lib.jpdvt_abi_version.restype = c_int
         lib.jpdvt_last_error_string.restype = C.c_char_p
+        got = lib.jpdvt_abi_version()
+        if got != ABI_VERSION:       # a stale prebuilt library would be driven with mismatched ctypes structs
+            raise JpdvtError(f"{override or LIB_PATH} has ABI version {got}, this package binds version {ABI_VERSION}: "
+                             "rebuild it with `python -m jpdvt_mt_ntnu_b200.build --force`")
         _lib = lib
         return lib
 
@@ -192,6 +206,52 @@ def ptr(t) -> int:
     return t.data_ptr()
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the thread's current device).  Launch sites wrap
+    themselves in `on_device(...)` so that the current device IS the tensors' device: a kernel launched while another
+    device is current would run there, on a stream that does not order it against the torch ops of the tensors' device."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """`with on_device(dev):` - make `dev` the thread's current CUDA device for the launches inside (no-op when it already
+    is; new threads, e.g. frontend.MicroBatcher's worker, start on device 0 whatever the model's device)."""
+
+    def __init__(self, device):
+        import torch
+        self.idx = device.index if hasattr(device, "index") else int(device)
+        if self.idx is None:
+            self.idx = torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def on_tensor_device(fn):
+    """Decorator for the per-kernel wrappers: run `fn` with the first CUDA tensor argument's device current."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(*args, **kw):
+        import torch
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with on_device(a.device):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+    return inner

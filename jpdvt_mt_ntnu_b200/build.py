@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpdvt_sm100.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "train_api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "assign.cu", "puzzle.cu", "fold.cu", "backward.cu", "optim.cu"]
+SOURCES = ["api.cu", "train_api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "assign.cu", "puzzle.cu", "fold.cu", "backward.cu", "optim.cu", "loss.cu", "attention_bwd_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -53,6 +53,18 @@ def needs_build() -> bool:
     return open(STAMP).read().strip() != _digest()
 
 
+def _unit_digest(src: str) -> str:
+    """Digest of one translation unit: its own text, every shared header and the flags."""
+    h = hashlib.sha256()
+    h.update(open(os.path.join(CSRC, src), "rb").read())
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cuh", ".h")):
+            h.update(open(os.path.join(CSRC, name), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "jpdvt_b200.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -61,8 +73,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(CSRC, src[:-3] + ".o")
+        tag = obj + ".sha"
+        dig = _unit_digest(src)
+        if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read().strip() == dig:
+            return src, obj, subprocess.CompletedProcess([], 0, "", "(up to date)")
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            with open(tag, "w") as f:
+                f.write(dig)
         return src, obj, r
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

@@ -78,7 +78,8 @@ static int adaln_all(const jpdvt_weights* w, const jpdvt_workspace* ws, int rows
 // mod_pre != null: this step's adaLN row was computed ahead of the loop (jpdvt_sample_loop) - no conditioning launches here
 static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const float* img, const int64_t* t,
                         const int32_t* step_ptr, const int32_t* map, const float* x_t, float* te_out, float* img_out,
-                        int batch, cudaStream_t st, const float* mod_pre = nullptr) {
+                        int batch, cudaStream_t st, const float* mod_pre = nullptr, const float* embed_pre = nullptr,
+                        const __nv_bfloat16* cols_pre = nullptr) {
   if (w == nullptr || ws == nullptr) return set_error(kErrBadArg, "forward: null weights/workspace");
   if (batch <= 0) return kOk;
   const int T = w->tokens, depth = w->depth, S = w->image_size;
@@ -88,6 +89,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   if (M > 0x7fffffffLL) return set_error(kErrUnsupported, "forward: %lld token rows exceed the 32-bit tile index", M);
   const int cond_rows = (t != nullptr) ? batch : 1;
   if (cond_rows > ws->cond_rows) return set_error(kErrBadArg, "forward: workspace holds %d conditioning rows, need %d", ws->cond_rows, cond_rows);
+  if (ws->te_hid == nullptr) return set_error(kErrBadArg, "forward: workspace.te_hid is null");
   if (img_out != nullptr && ws->y32 == nullptr) return set_error(kErrBadArg, "forward: image output requested but workspace.y32 is null");
   const int n_mod = depth * 6 * kHidden + 2 * kHidden;
   const long long mod_stride = (t != nullptr) ? n_mod : 0;
@@ -96,9 +98,15 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
 #define JP_TRY(expr) do { rc = (expr); if (rc != kOk) return rc; } while (0)
 
   // embeddings: x = patch_embed(img) + time_emb_in(x_t) + pos_embed       (models.py:280-281)
-  __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(ws->hid);
-  JP_TRY(launch_patchify(img, cols, batch, S, st));
-  {
+  // embed_pre: the whole embedding was computed ahead of the loop (it enters x on the first LayerNorm pass below);
+  // cols_pre: only the im2col tile was (chain mode: x_t changes from step to step)
+  const __nv_bfloat16* cols = cols_pre;
+  if (embed_pre == nullptr && cols_pre == nullptr) {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+    JP_TRY(launch_patchify(img, c, batch, S, st));
+    cols = c;
+  }
+  if (embed_pre == nullptr) {
     GemmParams p{};
     p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
     p.bias = w->b_embed; p.out = ws->x; p.ldo = kHidden;
@@ -108,7 +116,7 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
   // conditioning: c = t_embedder(t); all 13 adaLN linears at once            (models.py:282-284,119,134)
   if (mod_pre == nullptr) {
     JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), cond_rows, step_ptr, map, w->t_w0, w->t_b0, w->t_w2,
-                                 w->t_b2, ws->c, ws->silu_c, nullptr, nullptr, st));
+                                 w->t_b2, ws->c, ws->silu_c, ws->te_hid, nullptr, nullptr, st));
     JP_TRY(adaln_all(w, ws, cond_rows, n_mod, st));
   }
   const float* mod_base = (mod_pre != nullptr) ? mod_pre : ws->mod;
@@ -164,7 +172,8 @@ static int forward_impl(const jpdvt_weights* w, const jpdvt_workspace* ws, const
     return launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, shift, scale, mod_stride, xn, M, T, st);
   };
   flip();
-  JP_TRY(launch_ln_modulate(ws->x, nullptr, nullptr, nullptr, 0, mod_base, mod_base + kHidden, mod_stride, xn, M, T, st));
+  JP_TRY(launch_ln_modulate(embed_pre != nullptr ? embed_pre : ws->x, embed_pre != nullptr ? ws->x : nullptr, nullptr, nullptr, 0,
+                            mod_base, mod_base + kHidden, mod_stride, xn, M, T, st));
   for (int i = 0; i < depth; ++i) {
     const float* mod = mod_base + static_cast<long long>(i) * 6 * kHidden;   // shift_msa scale_msa gate_msa shift_mlp scale_mlp gate_mlp
     const float* nxt = mod + 6 * kHidden;                                   // next block's (or the final layer's) shift, scale
@@ -380,9 +389,11 @@ int jpdvt_unpatchify(const float* y, float* img, int batch, int image_size, void
   return launch_unpatchify(y, img, batch, image_size, ST(stream));
 }
 int jpdvt_timestep_embed(const int64_t* t, int n, const int32_t* step_ptr, const int32_t* map, const float* w0,
-                         const float* b0, const float* w2, const float* b2, float* c, float* silu_c, void* stream) {
-  if (!w0 || !b0 || !w2 || !b2 || !c || !silu_c) return set_error(kErrBadArg, "timestep_embed: null pointer");
-  return launch_timestep_embed(reinterpret_cast<const long long*>(t), n, step_ptr, map, w0, b0, w2, b2, c, silu_c, nullptr, nullptr, ST(stream));
+                         const float* b0, const float* w2, const float* b2, float* c, float* silu_c, float* hid_scratch,
+                         void* stream) {
+  if (!w0 || !b0 || !w2 || !b2 || !c || !silu_c || !hid_scratch) return set_error(kErrBadArg, "timestep_embed: null pointer");
+  return launch_timestep_embed(reinterpret_cast<const long long*>(t), n, step_ptr, map, w0, b0, w2, b2, c, silu_c, hid_scratch,
+                               nullptr, nullptr, ST(stream));
 }
 int jpdvt_adaln_table(const float* silu_c, int rows, const jpdvt_bf16* w_all, const float* b_all, float* mod, int n_out,
                       void* stream) {
@@ -409,6 +420,33 @@ int jpdvt_q_sample(const float* x0, const float* noise, const float* sqrt_ac, co
                    const float* keep_or_null, float* out, int64_t n, int64_t per_sample, void* stream) {
   if (!x0 || !noise || !sqrt_ac || !sqrt_1mac || !t || !out) return set_error(kErrBadArg, "q_sample: null pointer");
   return launch_q_sample(x0, noise, sqrt_ac, sqrt_1mac, reinterpret_cast<const long long*>(t), keep_or_null, out, n, per_sample, ST(stream));
+}
+int jpdvt_philox_normal(float* out_or_null, uint32_t* raw_or_null, int64_t n, int step, const int64_t* key, void* stream) {
+  return launch_philox_normal(out_or_null, raw_or_null, n, step, reinterpret_cast<const long long*>(key), ST(stream));
+}
+int jpdvt_posterior_step_philox(const float* x0, const float* x_t, const int64_t* noise_key, int noise_step, const float* coef1,
+                                const float* coef2, const float* logvar, const int64_t* t, const int32_t* step_ptr,
+                                float* sample, int64_t n, int64_t per_sample, void* stream) {
+  if (!x0 || !x_t || !noise_key || !coef1 || !coef2 || !logvar || !sample) return set_error(kErrBadArg, "posterior_step_philox: null pointer");
+  return launch_posterior(x0, x_t, nullptr, coef1, coef2, logvar, reinterpret_cast<const long long*>(t), step_ptr, nullptr, sample, n,
+                          per_sample, ST(stream), reinterpret_cast<const long long*>(noise_key), noise_step);
+}
+int64_t jpdvt_mse_part_floats(int batch) { return mse_part_floats(batch); }
+int jpdvt_mse_loss_fwd(const float* te_out, const float* te_tgt, int64_t per_te, const float* img_out_or_null,
+                       const float* img_tgt_or_null, const float* keep_or_null, int image_size, int grid, float* part,
+                       float* loss, int batch, void* stream) {
+  if (batch == 0) return kOk;
+  if (!te_out || !te_tgt || !part || !loss) return set_error(kErrBadArg, "mse_loss_fwd: null pointer");
+  return launch_mse_loss_fwd(te_out, te_tgt, per_te, img_out_or_null, img_tgt_or_null, keep_or_null, image_size, grid, part, loss,
+                             batch, ST(stream));
+}
+int jpdvt_mse_loss_bwd(const float* te_out, const float* te_tgt, int64_t per_te, const float* img_out_or_null,
+                       const float* img_tgt_or_null, const float* keep_or_null, int image_size, int grid, const float* dloss,
+                       float* d_te, float* d_img_or_null, int batch, void* stream) {
+  if (batch == 0) return kOk;
+  if (!te_out || !te_tgt || !dloss || !d_te) return set_error(kErrBadArg, "mse_loss_bwd: null pointer");
+  return launch_mse_loss_bwd(te_out, te_tgt, per_te, img_out_or_null, img_tgt_or_null, keep_or_null, image_size, grid, dloss, d_te,
+                             d_img_or_null, batch, ST(stream));
 }
 int jpdvt_assign_from_scores(const double* scores, int batch, int n, double sentinel, int32_t* order, int32_t* pred,
                              void* stream) {
@@ -451,8 +489,9 @@ int jpdvt_denoiser_forward(const jpdvt_weights* w_host, const jpdvt_workspace* w
 int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const jpdvt_sampler* s, const float* condition,
                       const float* noise, int batch, int first_step, int last_step, void* stream) {
   if (!w || !ws || !s || !condition || !noise) return set_error(kErrBadArg, "sample_loop: null pointer");
-  if (!s->step_ids || !s->timestep_map || !s->coef1 || !s->coef2 || !s->logvar || !s->x0 || !s->sample || !s->step_noise)
+  if (!s->step_ids || !s->timestep_map || !s->coef1 || !s->coef2 || !s->logvar || !s->x0 || !s->sample)
     return set_error(kErrBadArg, "sample_loop: sampler struct has null members");
+  if (!s->step_noise && !s->noise_key) return set_error(kErrBadArg, "sample_loop: need step_noise or a Philox noise_key");
   if (first_step < 0 || last_step > s->num_steps || first_step > last_step)
     return set_error(kErrBadArg, "sample_loop: bad step range [%d, %d) of %d", first_step, last_step, s->num_steps);
   cudaStream_t st = ST(stream);
@@ -470,10 +509,40 @@ int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const j
                    ws->step_rows >= n_steps;
   if (pre) {
     int rc = launch_timestep_embed(nullptr, n_steps, s->step_ids + first_step, s->timestep_map, w->t_w0, w->t_b0, w->t_w2, w->t_b2,
-                                   ws->c_steps, ws->silu_c_steps, nullptr, nullptr, st, 1);
+                                   ws->c_steps, ws->silu_c_steps, ws->te_hid, nullptr, nullptr, st, 1);
     if (rc != kOk) return rc;
     rc = launch_adaln_gemv(ws->silu_c_steps, n_steps, reinterpret_cast<const __nv_bfloat16*>(w->w_ada), w->b_ada, ws->mod_steps, n_mod, st);
     if (rc != kOk) return rc;
+  }
+  // Loop-invariant embedding work, once per call instead of once per step (JPDVT_HOIST_EMBED=0 restores the per-step launches):
+  // the condition image never changes, so its im2col tile is built once; and with the reference's loop quirk every step is fed
+  // the same x_t (gaussian_diffusion.py:518-527), so the whole x = patch_embed(cond) + time_emb_in(x_t) + pos_embed
+  // (models.py:280-281) is the same tensor in every step - it is computed once and enters the residual stream on the first
+  // LayerNorm pass of each forward.  Every step still runs all its blocks; results are bit-identical.
+  static int hoist = -1;
+  if (hoist < 0) { const char* e = getenv("JPDVT_HOIST_EMBED"); hoist = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  const float* embed_pre = nullptr;
+  const __nv_bfloat16* cols_pre = nullptr;
+  if (hoist && n_steps > 1 && ws->x_embed != nullptr && batch > 0) {
+    const int T = w->tokens;
+    const long long M = static_cast<long long>(batch) * T;
+    if (M > ws->rows) return set_error(kErrBadArg, "sample_loop: workspace holds %lld rows, need %lld", (long long)ws->rows, M);
+    if (!s->chain) {
+      __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(ws->hid);
+      int rc = launch_patchify(condition, cols, batch, w->image_size, st);
+      if (rc != kOk) return rc;
+      GemmParams p{};
+      p.M = static_cast<int>(M); p.N = kHidden; p.K = kHidden; p.tokens = T;
+      p.bias = w->b_embed; p.out = ws->x_embed; p.ldo = kHidden; p.xt = noise; p.w_in_t = w->w_in_t; p.pos = w->pos;
+      rc = launch_gemm(EPI_PATCH_EMBED_F32, cols, kHidden, reinterpret_cast<const __nv_bfloat16*>(w->w_patch), kHidden, p, st);
+      if (rc != kOk) return rc;
+      embed_pre = ws->x_embed;
+    } else {
+      __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(ws->x_embed);      // bf16 [M, 768] fits the fp32 buffer
+      int rc = launch_patchify(condition, cols, batch, w->image_size, st);
+      if (rc != kOk) return rc;
+      cols_pre = cols;
+    }
   }
   for (int k = first_step; k < last_step; ++k) {
     // gaussian_diffusion.py:518-527: x_t of EVERY step is the initial noise unless chain mode is requested
@@ -481,11 +550,13 @@ int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const j
     const int32_t* step_ptr = s->step_ids + k;
     float* x0 = s->traj_x0 ? s->traj_x0 + static_cast<long long>(k) * n : s->x0;
     const float* mod_pre = pre ? ws->mod_steps + static_cast<long long>(k - first_step) * n_mod : nullptr;
-    int rc = forward_impl(w, ws, condition, nullptr, step_ptr, s->timestep_map, x_t, x0, nullptr, batch, st, mod_pre);
+    int rc = forward_impl(w, ws, condition, nullptr, step_ptr, s->timestep_map, x_t, x0, nullptr, batch, st, mod_pre, embed_pre, cols_pre);
     if (rc != kOk) return rc;
     float* smp = s->traj_sample ? s->traj_sample + static_cast<long long>(k) * n : s->sample;
-    rc = launch_posterior(x0, x_t, s->step_noise + static_cast<long long>(k) * s->step_noise_stride, s->coef1, s->coef2,
-                          s->logvar, nullptr, step_ptr, nullptr, smp, n, per_sample, st);
+    // per-step noise: the caller's tensor (parity with torch-drawn noise) or Philox normals drawn inside the kernel
+    const float* eps = s->step_noise ? s->step_noise + static_cast<long long>(k) * s->step_noise_stride : nullptr;
+    rc = launch_posterior(x0, x_t, eps, s->coef1, s->coef2, s->logvar, nullptr, step_ptr, nullptr, smp, n, per_sample, st,
+                          reinterpret_cast<const long long*>(s->noise_key), k);
     if (rc != kOk) return rc;
     if (s->traj_sample) {   // keep sampler->sample current (chain mode reads it; callers read the final result there)
       copy_f32_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(smp, s->sample, n / 4);

@@ -160,13 +160,22 @@ int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* del
 int launch_patchify(const float* img, __nv_bfloat16* cols, int batch, int size, cudaStream_t stream);
 int launch_unpatchify(const float* y, float* img, int batch, int size, cudaStream_t stream);
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
-                          const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
-                          cudaStream_t stream, int step_stride = 0);
+                          const float* w2, const float* b2, float* c, float* silu_c, float* hid_scratch, float* feat_out,
+                          float* pre_out, cudaStream_t stream, int step_stride = 0);
 int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, const float* bias, float* out, int n_out,
                       cudaStream_t stream);
 int launch_posterior(const float* x0, const float* xt, const float* noise, const float* coef1, const float* coef2,
                      const float* logvar, const long long* t, const int* step_ptr, float* mean, float* sample, long long n,
-                     long long per_sample, cudaStream_t stream);
+                     long long per_sample, cudaStream_t stream, const long long* noise_key = nullptr, int noise_step = 0);
+// Philox4x32-10 normals (the generator posterior_kernel uses when no noise tensor is given); raw (nullable): the 32-bit stream
+int launch_philox_normal(float* out, unsigned* raw, long long n, int step, const long long* key, cudaStream_t stream);
+// loss.cu: per-sample MSE terms of training_losses and their gradient
+long long mse_part_floats(int batch);
+int launch_mse_loss_fwd(const float* te_out, const float* te_tgt, long long per_te, const float* img_out, const float* img_tgt,
+                        const float* keep, int size, int grid, float* part, float* loss, int batch, cudaStream_t stream);
+int launch_mse_loss_bwd(const float* te_out, const float* te_tgt, long long per_te, const float* img_out, const float* img_tgt,
+                        const float* keep, int size, int grid, const float* dloss, float* d_te, float* d_img, int batch,
+                        cudaStream_t stream);
 int launch_ddim(const float* x0, const float* xt, const float* noise, const float* recip, const float* recipm1,
                 const float* sqrt_abp, const float* dir, const float* sigma, const long long* t, const int* step_ptr,
                 float* sample, long long n, long long per_sample, cudaStream_t stream);

@@ -25,7 +25,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Algorithmic traffic per row: 3072 B read + 1536 B written (+ 1536 B read + 3072 B written with delta).
 constexpr int kLnWarps = 8;
 
-template <bool HAS_DELTA>
+template <bool HAS_DELTA, bool COPY_X = false>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_modulate_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, const __nv_bfloat16* __restrict__ delta,
                    const float* __restrict__ gate, long long gate_stride, const float* __restrict__ shift,
@@ -58,6 +58,12 @@ ln_modulate_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, co
       v[j].z = fmaf(g.z, __uint_as_float(d[j].y << 16), v[j].z); v[j].w = fmaf(g.w, __uint_as_float(d[j].y & 0xffff0000u), v[j].w);
       xo[lane + 32 * j] = v[j];
     }
+  }
+  if constexpr (COPY_X) {
+    // x_out = x_in: the sampling loop's hoisted embedding enters the residual stream on this pass (api.cu: jpdvt_sample_loop)
+    float4* xo = reinterpret_cast<float4*>(x_out + row * kHidden);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xo[lane + 32 * j] = v[j];
   }
   float s = 0.f;
 #pragma unroll
@@ -100,6 +106,9 @@ int launch_ln_modulate(const float* x_in, float* x_out, const __nv_bfloat16* del
   if (delta != nullptr)
     e = launch_pdl(ln_modulate_kernel<true>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
                    mod_stride, y, rows, tokens, sweep_reverse());
+  else if (x_out != nullptr && x_out != x_in)
+    e = launch_pdl(ln_modulate_kernel<false, true>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift,
+                   scale, mod_stride, y, rows, tokens, sweep_reverse());
   else
     e = launch_pdl(ln_modulate_kernel<false>, dim3(blocks), dim3(kLnWarps * 32), 0, stream, x_in, x_out, delta, gate, gate_stride, shift, scale,
                    mod_stride, y, rows, tokens, sweep_reverse());
@@ -259,17 +268,20 @@ timestep_out_kernel(const float* __restrict__ hid, int n, const float* __restric
   }
 }
 
-// `silu_c` doubles as the scratch for the hidden activations between the two phases.
+// `hid` ([n, 768] fp32, caller-provided scratch distinct from c and silu_c) carries the hidden activations between the two
+// phases: several CTAs (blockIdx.x) of one row group read all 768 hidden features while others already write their outputs,
+// so the scratch must not alias either output.
 int launch_timestep_embed(const long long* t, int n, const int* step_ptr, const int* map, const float* w0, const float* b0,
-                          const float* w2, const float* b2, float* c, float* silu_c, float* feat_out, float* pre_out,
+                          const float* w2, const float* b2, float* c, float* silu_c, float* hid, float* feat_out, float* pre_out,
                           cudaStream_t stream, int step_stride) {
   if (n <= 0) return kOk;
   if (t == nullptr && step_ptr == nullptr) return set_error(kErrBadArg, "timestep_embed: need t or step_ptr");
+  if (hid == nullptr || hid == c || hid == silu_c) return set_error(kErrBadArg, "timestep_embed: hidden scratch must be a buffer of its own");
   dim3 grid(kHidden / kTeWarps, (n + kTeRows - 1) / kTeRows);
-  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, step_stride, map, w0, b0, c, feat_out, pre_out);
+  timestep_hidden_kernel<<<grid, kTeWarps * 32, 0, stream>>>(t, n, step_ptr, step_stride, map, w0, b0, hid, feat_out, pre_out);
   int rc = check_launch("timestep_hidden_kernel");
   if (rc != kOk) return rc;
-  timestep_out_kernel<<<grid, kTeWarps * 32, 0, stream>>>(c, n, w2, b2, c, silu_c);
+  timestep_out_kernel<<<grid, kTeWarps * 32, 0, stream>>>(hid, n, w2, b2, c, silu_c);
   return check_launch("timestep_out_kernel");
 }
 
@@ -344,13 +356,67 @@ int launch_adaln_gemv(const float* silu_c, int rows, const __nv_bfloat16* w, con
 }
 
 // ---------------------------------------------------------------------------------------------- diffusion elementwise
+// Counter-based normals for the per-step noise of p_sample (gaussian_diffusion.py:424 `th.randn_like(x)`): Philox4x32-10
+// keyed by (seed), counter = (element group, diffusion step, call counter) -> 4 uniforms -> 2 Box-Muller pairs, so a
+// sampling step needs no noise buffer and no generator launch.  philox_normal_kernel fills a buffer with exactly the same
+// numbers (tests compare the two bit for bit; the raw 32-bit stream is checked against a numpy Philox in tests/).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(long long group, int step, const long long* __restrict__ key) {
+  const unsigned long long seed = static_cast<unsigned long long>(key[0]), call = static_cast<unsigned long long>(key[1]);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<unsigned>(group), static_cast<unsigned>(static_cast<unsigned long long>(group) >> 32),
+                                           static_cast<unsigned>(step), static_cast<unsigned>(call)),
+                                make_uint2(static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32)));
+  // uniforms strictly inside (0, 1): 24 random bits + half an ulp
+  const float u0 = static_cast<float>(r.x >> 8) * 5.9604645e-8f + 2.9802322e-8f;
+  const float u1 = static_cast<float>(r.y >> 8) * 5.9604645e-8f + 2.9802322e-8f;
+  const float u2 = static_cast<float>(r.z >> 8) * 5.9604645e-8f + 2.9802322e-8f;
+  const float u3 = static_cast<float>(r.w >> 8) * 5.9604645e-8f + 2.9802322e-8f;
+  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  float sa, ca, sb, cb;
+  sincosf(6.2831853071795865f * u1, &sa, &ca);
+  sincosf(6.2831853071795865f * u3, &sb, &cb);
+  return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
+}
+
+__global__ void philox_normal_kernel(float* __restrict__ out, long long n4, int step, const long long* __restrict__ key,
+                                     unsigned* __restrict__ raw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  if (out != nullptr) reinterpret_cast<float4*>(out)[i] = philox_normal4(i, step, key);
+  if (raw != nullptr) {
+    const unsigned long long seed = static_cast<unsigned long long>(key[0]), call = static_cast<unsigned long long>(key[1]);
+    reinterpret_cast<uint4*>(raw)[i] = philox4x32_10(
+        make_uint4(static_cast<unsigned>(i), static_cast<unsigned>(static_cast<unsigned long long>(i) >> 32), static_cast<unsigned>(step),
+                   static_cast<unsigned>(call)), make_uint2(static_cast<unsigned>(seed), static_cast<unsigned>(seed >> 32)));
+  }
+}
+
+int launch_philox_normal(float* out, unsigned* raw, long long n, int step, const long long* key, cudaStream_t stream) {
+  if (n <= 0) return kOk;
+  if (n & 3) return set_error(kErrBadArg, "philox_normal: element count must be a multiple of 4");
+  if (key == nullptr || (out == nullptr && raw == nullptr)) return set_error(kErrBadArg, "philox_normal: null pointer");
+  const long long n4 = n / 4;
+  philox_normal_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(out, n4, step, key, raw);
+  return check_launch("philox_normal_kernel");
+}
+
 // mean = coef1[t] * x0 + coef2[t] * x_t ; sample = mean + [t != 0] * exp(0.5 * logvar[t]) * noise
 // t is per-sample (`t` != null) or one device-resident step index for the whole batch (`step_ptr`).
+// noise == null: drawn in place from Philox (noise_key = {seed, call counter} on the device, noise_step = loop position).
 __global__ void posterior_kernel(const float* __restrict__ x0, const float* __restrict__ xt, const float* __restrict__ noise,
                                  const float* __restrict__ coef1, const float* __restrict__ coef2,
                                  const float* __restrict__ logvar, const long long* __restrict__ t,
                                  const int* __restrict__ step_ptr, float* __restrict__ mean, float* __restrict__ sample,
-                                 long long n4, long long per_sample4) {
+                                 long long n4, long long per_sample4, const long long* __restrict__ noise_key, int noise_step) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const long long ti = (t != nullptr) ? t[i / per_sample4] : static_cast<long long>(*step_ptr);
@@ -368,7 +434,7 @@ __global__ void posterior_kernel(const float* __restrict__ x0, const float* __re
   if (sample != nullptr) {
     float4 s = m;
     if (ti != 0) {
-      const float4 e = reinterpret_cast<const float4*>(noise)[i];
+      const float4 e = (noise != nullptr) ? reinterpret_cast<const float4*>(noise)[i] : philox_normal4(i, noise_step, noise_key);
       s.x = __fadd_rn(m.x, __fmul_rn(sigma, e.x));
       s.y = __fadd_rn(m.y, __fmul_rn(sigma, e.y));
       s.z = __fadd_rn(m.z, __fmul_rn(sigma, e.z));
@@ -380,13 +446,15 @@ __global__ void posterior_kernel(const float* __restrict__ x0, const float* __re
 
 int launch_posterior(const float* x0, const float* xt, const float* noise, const float* coef1, const float* coef2,
                      const float* logvar, const long long* t, const int* step_ptr, float* mean, float* sample, long long n,
-                     long long per_sample, cudaStream_t stream) {
+                     long long per_sample, cudaStream_t stream, const long long* noise_key, int noise_step) {
   if (n <= 0) return kOk;
   if ((n & 3) || (per_sample & 3)) return set_error(kErrBadArg, "posterior: element counts must be multiples of 4");
   if (t == nullptr && step_ptr == nullptr) return set_error(kErrBadArg, "posterior: need t or step_ptr");
+  if (sample != nullptr && noise == nullptr && noise_key == nullptr) return set_error(kErrBadArg, "posterior: sample requested without noise or a Philox key");
   const long long n4 = n / 4;
   posterior_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(x0, xt, noise, coef1, coef2, logvar, t,
-                                                                                step_ptr, mean, sample, n4, per_sample / 4);
+                                                                                step_ptr, mean, sample, n4, per_sample / 4,
+                                                                                noise_key, noise_step);
   return check_launch("posterior_kernel");
 }
 

@@ -106,7 +106,7 @@ int jpdvt_train_forward(const jpdvt_weights* w, const jpdvt_tape* tp, const floa
   }
   // conditioning (models.py:282-284,119,134): per-sample timesteps -> tensor-core adaLN over bf16 silu(c) (GEMV for <= 8 rows)
   JP_TRY(launch_timestep_embed(reinterpret_cast<const long long*>(t), batch, nullptr, nullptr, w->t_w0, w->t_b0, w->t_w2, w->t_b2,
-                               tp->c, tp->silu_c, tp->feat, tp->tpre, st));
+                               tp->c, tp->silu_c, tp->thid, tp->feat, tp->tpre, st));
   JP_TRY(launch_cast_bf16(tp->silu_c, BFM(tp->silu_c_bf16), static_cast<long long>(batch) * kHidden, st));
   if (batch <= 8) {
     JP_TRY(launch_adaln_gemv(tp->silu_c, batch, BF(w->w_ada), w->b_ada, tp->mod, static_cast<int>(n_mod), st));

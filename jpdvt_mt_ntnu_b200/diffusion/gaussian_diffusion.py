@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import enum
 import math
+import os
 import random
 from typing import Dict, Iterator, Optional
 
@@ -24,8 +25,29 @@ from .. import _lib, ops
 
 
 def mean_flat(tensor: th.Tensor) -> th.Tensor:
-    """Mean over all non-batch dimensions (gaussian_diffusion.py:18-22)."""
+    """Mean over all non-batch dimensions (gaussian_diffusion.py:18-22).  Utility for callers; `training_losses` computes
+    its MSE terms (and their gradient) in the fused loss kernels below instead."""
     return tensor.mean(dim=list(range(1, tensor.dim())))
+
+
+class _MseLossFn(th.autograd.Function):
+    """terms["mse"] of training_losses (gaussian_diffusion.py:835-838) as one kernel pair: per-sample
+    mean((te_tgt - te_out)^2) [+ mean((x_tgt - x_out)^2 * (1 - masks))], gradient w.r.t. the two model outputs."""
+
+    @staticmethod
+    def forward(ctx, te_out, x_out, te_tgt, x_tgt, keep_slots, grid):
+        te_out, te_tgt = te_out.detach().float().contiguous(), te_tgt.detach().float().contiguous()
+        if x_out is not None:
+            x_out, x_tgt = x_out.detach().float().contiguous(), x_tgt.detach().float().contiguous()
+            keep_slots = keep_slots.detach().float().contiguous()
+        ctx.saved = (te_out, te_tgt, x_out, x_tgt, keep_slots, grid)
+        return ops.mse_loss_fwd(te_out, te_tgt, x_out, x_tgt, keep_slots, grid)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        te_out, te_tgt, x_out, x_tgt, keep_slots, grid = ctx.saved
+        d_te, d_img = ops.mse_loss_bwd(dloss.float().contiguous(), te_out, te_tgt, x_out, x_tgt, keep_slots, grid)
+        return d_te, d_img, None, None, None, None
 
 
 class ModelMeanType(enum.Enum):
@@ -284,8 +306,13 @@ class GaussianDiffusion:
             return None
         return _resolve_denoiser(model)
 
-    def _draw_step_noise(self, noise: th.Tensor) -> th.Tensor:
-        """One randn_like per step, in loop order, exactly like gaussian_diffusion.py:424 consumes the generator."""
+    def _draw_step_noise(self, noise: th.Tensor) -> Optional[th.Tensor]:
+        """The per-step noise of p_sample (gaussian_diffusion.py:424 `th.randn_like(x)`).  Default: None - the posterior
+        kernel draws it in place (Philox4x32-10 keyed by a seed taken from torch's default generator, so `torch.manual_seed`
+        still makes runs repeatable; no noise buffer, no generator launches).  JPDVT_TORCH_NOISE=1: one torch `normal_()`
+        per step in loop order, which consumes the device generator exactly like the reference's loop does."""
+        if os.environ.get("JPDVT_TORCH_NOISE", "")[:1] != "1":
+            return None
         buf = th.empty((self.num_timesteps,) + tuple(noise.shape), device=noise.device, dtype=th.float32)
         for k in range(self.num_timesteps):
             buf[k].normal_()
@@ -399,11 +426,13 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ training
     @staticmethod
     def _scramble(x, perm, grid, block):
-        """[B,C,(g h),(g w)] -> pieces permuted so that slot i holds original piece perm[i] (:757-775)."""
-        B, Cc = x.shape[:2]
-        pieces = x.reshape(B, Cc, grid, block, grid, block).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, grid * grid, block, block)
-        pieces = pieces[:, :, th.as_tensor(np.asarray(perm), device=x.device, dtype=th.long)]
-        return pieces.reshape(B, Cc, grid, grid, block, block).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, grid * block, grid * block)
+        """[B,C,(g h),(g w)] -> pieces permuted so that slot i holds original piece perm[i] (:757-775): the rearrange /
+        index / rearrange of the reference as one device gather (jpdvt_gather_pieces)."""
+        B = x.shape[0]
+        if x.shape[-1] != grid * block or x.shape[-2] != grid * block:
+            raise AssertionError(f"{tuple(x.shape)} images do not tile a {grid}x{grid} puzzle of {block}-pixel pieces")
+        idx = th.as_tensor(np.asarray(perm), dtype=th.int32).to(x.device).unsqueeze(0).expand(B, grid * grid).contiguous()
+        return ops.gather_pieces(x.float().contiguous(), idx, grid)
 
     def training_losses(self, model, x_start, t, time_emb_start, model_kwargs=None, noise=None, block_size=96,
                         patch_size=16, add_mask=False, grid_size=3):
@@ -429,7 +458,7 @@ class GaussianDiffusion:
                 for i in range(B):
                     r = np.random.randint(0, G)
                     keep_slots[i, random.sample(range(n), r)] = 0
-        x0 = self._scramble(x_start.float(), perm, G, block_size).contiguous()
+        x0 = self._scramble(x_start, perm, G, block_size)
         tok = block_size // patch_size
         te = time_emb_start.to(x_start.device).float().expand(B, -1, -1)[:, th.as_tensor(perm, device=x_start.device, dtype=th.long)]
         te0 = te.reshape(B, G, 1, G, 1, -1).expand(B, G, tok, G, tok, te.shape[-1]).reshape(B, n * tok * tok, -1).contiguous()
@@ -454,8 +483,9 @@ class GaussianDiffusion:
             raise NotImplementedError(self.model_mean_type)
         if x_out.shape != x0.shape:
             raise AssertionError("model image output must match x_start")
-        terms = {"mse": mean_flat((target_te - te_out) ** 2)}
+        # mean_flat((target_te - te_out)**2) [+ mean_flat((target_x - x_out)**2 * (1 - masks))] (:835-838), fused
         if add_mask:
-            terms["mse"] = terms["mse"] + mean_flat((target_x - x_out) ** 2 * (1 - keep))
-        terms["loss"] = terms["mse"]
-        return terms
+            mse = _MseLossFn.apply(te_out, x_out, target_te, target_x, keep_slots.to(x0.device), G)
+        else:
+            mse = _MseLossFn.apply(te_out, None, target_te, None, None, G)
+        return {"mse": mse, "loss": mse}

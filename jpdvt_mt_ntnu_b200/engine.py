@@ -29,6 +29,8 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """Reference-keyed fp32 state dict -> the layouts the kernels read (include/jpdvt_b200.h: jpdvt_weights)."""
 
+    _generation = 0
+
     def __init__(self, state: Dict[str, torch.Tensor], depth: int, image_size: int, device: torch.device):
         self.depth, self.image_size = depth, image_size
         self.tokens = (image_size // 16) ** 2
@@ -62,6 +64,8 @@ class PackedWeights:
         t["w_head1"], t["b_head1"] = _bf16(g("time_emb_out1.weight")), _f32(g("time_emb_out1.bias"))
         t["w_head2"], t["b_head2"] = _f32(g("time_emb_out2.weight")), _f32(g("time_emb_out2.bias"))
         self.tensors = t
+        PackedWeights._generation += 1
+        self.generation = PackedWeights._generation        # monotonically increasing: CUDA-graph cache key (ids get reused)
         self.n_mod = depth * 6 * HIDDEN + 2 * HIDDEN
         s = Weights()
         s.depth, s.tokens, s.image_size, s.reserved = depth, self.tokens, image_size, 0
@@ -80,6 +84,8 @@ class DenoiserEngine:
         self._ws_key = None
         self._ws_tensors: Dict[str, torch.Tensor] = {}
         self._ws = None
+        self._noise_key: Optional[torch.Tensor] = None       # device int64[2] {seed, call counter} of the in-kernel step noise
+        self._noise_calls = 0
 
     # ------------------------------------------------------------------ weights / workspace
     def load_state(self, state: Dict[str, torch.Tensor]) -> None:
@@ -117,6 +123,10 @@ class DenoiserEngine:
                 "c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
                 "silu_c_steps": torch.empty(step_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
                 "mod_steps": torch.empty(step_cap, n_mod, device=dev, dtype=f32) if step_cap else None,
+                # hidden activations of the timestep MLP between its two phases (a buffer of its own: csrc/elementwise.cu)
+                "te_hid": torch.empty(max(cond_cap, step_cap, 1), HIDDEN, device=dev, dtype=f32),
+                # loop-invariant embedding of one sample_loop call (api.cu: jpdvt_sample_loop; JPDVT_HOIST_EMBED=0 = per step)
+                "x_embed": torch.empty(rows_cap, HIDDEN, device=dev, dtype=f32) if step_cap else None,
             }
             ws = Workspace()
             ws.rows, ws.cond_rows, ws.step_rows = rows_cap, cond_cap, step_cap
@@ -142,56 +152,99 @@ class DenoiserEngine:
             t = t.to(device=img.device, dtype=torch.int64).contiguous()
             if t.shape != (B,):
                 raise _lib.JpdvtError(f"t {tuple(t.shape)} must be [{B}]")
-        ws = self.workspace(B, B if t is not None else 1, need_image)
-        te = torch.empty(B, self.tokens, LATENT, device=img.device, dtype=torch.float32)
-        out_img = torch.empty(B, 3, self.image_size, self.image_size, device=img.device, dtype=torch.float32) if need_image else None
-        check(self.lib.jpdvt_denoiser_forward(C.byref(self.weights.struct), C.byref(ws), ptr(img), ptr(t), ptr(step_ptr),
-                                              ptr(tmap), ptr(x_t), ptr(te), ptr(out_img), B, _lib.stream_ptr()),
-              "jpdvt_denoiser_forward")
+        with _lib.on_device(self.device):
+            ws = self.workspace(B, B if t is not None else 1, need_image)
+            te = torch.empty(B, self.tokens, LATENT, device=img.device, dtype=torch.float32)
+            out_img = torch.empty(B, 3, self.image_size, self.image_size, device=img.device, dtype=torch.float32) if need_image else None
+            check(self.lib.jpdvt_denoiser_forward(C.byref(self.weights.struct), C.byref(ws), ptr(img), ptr(t), ptr(step_ptr),
+                                                  ptr(tmap), ptr(x_t), ptr(te), ptr(out_img), B, _lib.stream_ptr(self.device)),
+                  "jpdvt_denoiser_forward")
         return out_img, te
 
+    # ------------------------------------------------------------------ per-step noise drawn inside the posterior kernel
+    def next_noise_key(self) -> torch.Tensor:
+        """Device int64[2] {seed, call counter} for one sample_loop call.  The seed is drawn once per engine from torch's
+        default CPU generator (so `torch.manual_seed` makes runs repeatable); the counter advances on the device, in stream
+        order, so a replayed CUDA graph draws fresh noise on every replay too."""
+        if self._noise_key is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._noise_key = torch.tensor([seed, 0], dtype=torch.int64, device=self.device)
+            self._noise_inc = torch.tensor([0, 1], dtype=torch.int64, device=self.device)
+        else:
+            self._noise_key.add_(self._noise_inc)
+        self._noise_calls += 1
+        return self._noise_key
+
     # ------------------------------------------------------------------ whole reverse loop
-    def sample_loop_graphed(self, tables: dict, condition: torch.Tensor, noise: torch.Tensor, step_noise: torch.Tensor,
-                            chain: bool = False) -> dict:
+    def sample_loop_graphed(self, tables: dict, condition: torch.Tensor, noise: torch.Tensor,
+                            step_noise: Optional[torch.Tensor], chain: bool = False) -> dict:
         """`sample_loop` replayed from a CUDA graph (captured once per batch size / step count / weights): for small
         batches the ~23,000 launches of a 250-step loop are launch- and gap-bound, the graph removes the host from the loop.
         Inputs are copied into graph-owned buffers; the returned tensors are copies."""
         n_steps = tables["num_steps"]
-        strided = step_noise.dim() == noise.dim() + 1 and step_noise.shape[0] > 1
-        key = (tuple(condition.shape), n_steps, bool(chain), bool(strided), id(self.weights))
+        strided = step_noise is not None and step_noise.dim() == noise.dim() + 1 and step_noise.shape[0] > 1
+        # The graph bakes in raw pointers to the packed weights and the schedule tables: key on the weights' generation
+        # counter (ids are reused after a re-pack) and on the tables' storage, and pin both objects in the entry.
+        key = (tuple(condition.shape), n_steps, bool(chain), bool(strided), step_noise is None, self.weights.generation,
+               tables["coef1"].data_ptr(), tables["timestep_map"].data_ptr())
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
-        if ent is None:
-            cache.clear()                                        # one graph at a time: they pin workspaces and inputs
-            ent = {"cond": torch.empty_like(condition, dtype=torch.float32), "noise": torch.empty_like(noise, dtype=torch.float32),
-                   "step_noise": torch.empty_like(step_noise, dtype=torch.float32), "state": None}
-            for k, src in (("cond", condition), ("noise", noise), ("step_noise", step_noise)):
+        inputs = [("cond", condition), ("noise", noise)] + ([("step_noise", step_noise)] if step_noise is not None else [])
+        with _lib.on_device(self.device):
+            if ent is None:
+                cache.clear()                                        # one graph at a time: they pin workspaces and inputs
+                ent = {k: torch.empty_like(src, dtype=torch.float32).contiguous() for k, src in inputs}
+                ent.update(step_noise=ent.get("step_noise"), state=None, weights=self.weights, tables=tables)
+                for k, src in inputs:
+                    ent[k].copy_(src)
+                if step_noise is None:
+                    self.next_noise_key()
+                side = torch.cuda.Stream(device=condition.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):                        # warm-up outside capture (function attributes, workspaces)
+                    ent["state"] = self.sample_loop(tables, ent["cond"], ent["noise"], ent["step_noise"], chain=chain, _advance_key=False)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.sample_loop(tables, ent["cond"], ent["noise"], ent["step_noise"], chain=chain, state=ent["state"], _advance_key=False)
+                ent["graph"] = g
+                cache[key] = ent
+            for k, src in inputs:
                 ent[k].copy_(src)
-            side = torch.cuda.Stream(device=condition.device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                        # warm-up outside capture (function attributes, workspaces)
-                ent["state"] = self.sample_loop(tables, ent["cond"], ent["noise"], ent["step_noise"], chain=chain)
-            torch.cuda.current_stream().wait_stream(side)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.sample_loop(tables, ent["cond"], ent["noise"], ent["step_noise"], chain=chain, state=ent["state"])
-            ent["graph"] = g
-            cache[key] = ent
-        for k, src in (("cond", condition), ("noise", noise), ("step_noise", step_noise)):
-            ent[k].copy_(src)
-        ent["graph"].replay()
-        return {k: (v.clone() if v is not None else None) for k, v in ent["state"].items()}
+            if step_noise is None:
+                self.next_noise_key()                                # advances the device-side call counter before the replay
+            ent["graph"].replay()
+            return {k: (v.clone() if v is not None else None) for k, v in ent["state"].items()}
 
-    def sample_loop(self, tables: dict, condition: torch.Tensor, noise: torch.Tensor, step_noise: torch.Tensor,
+    def sample_loop(self, tables: dict, condition: torch.Tensor, noise: torch.Tensor, step_noise: Optional[torch.Tensor],
                     chain: bool = False, record: bool = False, first_step: int = 0, last_step: Optional[int] = None,
-                    state: Optional[dict] = None) -> dict:
-        """SpacedDiffusion.p_sample_loop on the device (diffusion/gaussian_diffusion.py:433-529)."""
+                    state: Optional[dict] = None, _advance_key: bool = True) -> dict:
+        """SpacedDiffusion.p_sample_loop on the device (diffusion/gaussian_diffusion.py:433-529).  step_noise: the per-step
+        noise tensors ([steps, B, T, 8] or one [B, T, 8] reused), or None = drawn inside the posterior kernel (Philox)."""
         assert self.weights is not None
+        with _lib.on_device(self.device):
+            return self._sample_loop(tables, condition, noise, step_noise, chain, record, first_step, last_step, state, _advance_key)
+
+    def _sample_loop(self, tables, condition, noise, step_noise, chain, record, first_step, last_step, state, advance_key):
         B = condition.shape[0]
         n_steps = tables["num_steps"]
         last_step = n_steps if last_step is None else last_step
-        condition = condition.to(torch.float32).contiguous()
-        noise = noise.to(torch.float32).contiguous()
+        condition = condition.to(device=self.device, dtype=torch.float32).contiguous()
+        noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(condition.shape[1:]) != (3, self.image_size, self.image_size) or tuple(noise.shape) != (B, self.tokens, LATENT):
+            raise _lib.JpdvtError(f"sample_loop: condition {tuple(condition.shape)} / noise {tuple(noise.shape)} do not fit "
+                                  f"input_size {self.image_size}")
+        noise_key = None
+        if step_noise is None:
+            noise_key = self.next_noise_key() if (advance_key or self._noise_key is None) else self._noise_key
+        else:
+            step_noise = step_noise.to(device=self.device, dtype=torch.float32).contiguous()
+            ok = tuple(step_noise.shape) == tuple(noise.shape) or (step_noise.dim() == noise.dim() + 1
+                                                                  and tuple(step_noise.shape[1:]) == tuple(noise.shape)
+                                                                  and step_noise.shape[0] in (1, n_steps))
+            if not ok:
+                raise _lib.JpdvtError(f"sample_loop: step_noise {tuple(step_noise.shape)} must be {tuple(noise.shape)} or "
+                                      f"[{n_steps}, ...] of it")
         ws = self.workspace(B, 1, False, step_rows=max(0, last_step - first_step))
         dev = condition.device
         if state is None:
@@ -206,9 +259,11 @@ class DenoiserEngine:
         s.step_ids, s.timestep_map = ptr(tables["step_ids"]), ptr(tables["timestep_map"])
         s.coef1, s.coef2, s.logvar = ptr(tables["coef1"]), ptr(tables["coef2"]), ptr(tables["logvar"])
         s.step_noise = ptr(step_noise)
-        s.step_noise_stride = step_noise.stride(0) if step_noise.dim() == noise.dim() + 1 and step_noise.shape[0] > 1 else 0
+        s.noise_key = ptr(noise_key)
+        s.step_noise_stride = step_noise.stride(0) if (step_noise is not None and step_noise.dim() == noise.dim() + 1
+                                                       and step_noise.shape[0] > 1) else 0
         s.x0, s.sample = ptr(state["x0"]), ptr(state["sample"])
         s.traj_x0, s.traj_sample = ptr(state["traj_x0"]), ptr(state["traj_sample"])
         check(self.lib.jpdvt_sample_loop(C.byref(self.weights.struct), C.byref(ws), C.byref(s), ptr(condition), ptr(noise),
-                                         B, first_step, last_step, _lib.stream_ptr()), "jpdvt_sample_loop")
+                                         B, first_step, last_step, _lib.stream_ptr(self.device)), "jpdvt_sample_loop")
         return state

@@ -146,12 +146,19 @@ class PuzzleSolver:
 
     @torch.no_grad()
     def solve(self, images: torch.Tensor, indices=None, keep=None, step_noise: Optional[torch.Tensor] = None,
-              want_images: bool = False, prescrambled: bool = False, graph: bool = False) -> SolveResult:
+              want_images: bool = False, prescrambled: bool = False, graph: bool = False,
+              count_rows: Optional[int] = None) -> SolveResult:
         """images [B,3,S,S] fp32 in [-1,1] (host - pinned or not - or device).  indices [B,G*G] (default: drawn), keep
         [B,G*G] 0/1 (default: drawn from `missing_per_puzzle`, None = nothing missing).  prescrambled=True: the images
         ARE the puzzles (api/app.py:350-451 receives them that way); `indices` is then only the ground truth to score
         against (required).  graph=True replays the sampling loop from a CUDA graph (small, repeated batch shapes: -13 % at
-        batch 1, -16 % at batch 16)."""
+        batch 1, -16 % at batch 16).  count_rows: only the first `count_rows` puzzles enter the running totals (the rest
+        are shape padding of a graph-replayed batch)."""
+        from . import _lib
+        with _lib.on_device(self.device):
+            return self._solve(images, indices, keep, step_noise, want_images, prescrambled, graph, count_rows)
+
+    def _solve(self, images, indices, keep, step_noise, want_images, prescrambled, graph, count_rows):
         B = images.shape[0]
         n = self.grid * self.grid
         if tuple(images.shape[1:]) != (3, self.size, self.size):
@@ -171,7 +178,12 @@ class PuzzleSolver:
                                                model_kwargs=None, progress=False, device=self.device, step_noise=step_noise,
                                                graph=graph)
         order, pred = assignment.solve_puzzles(latents, self.grid, self.sentinel)
-        correct, matches = ops.score_placements(pred, idx, totals=self.totals)
+        if count_rows is None or count_rows >= B:
+            correct, matches = ops.score_placements(pred, idx, totals=self.totals)
+        else:
+            correct, matches = ops.score_placements(pred, idx)
+            if count_rows > 0:
+                ops.score_placements(pred[:count_rows].contiguous(), idx[:count_rows].contiguous(), totals=self.totals)
         res = SolveResult(indices=idx, pred=pred, order=order, puzzle_correct=correct, patch_matches=matches, latents=latents)
         if want_images:
             res.scrambled = scrambled
@@ -306,7 +318,8 @@ class MicroBatcher:
                     if pad > 0:
                         images = torch.cat([images, images[-1:].expand(pad, -1, -1, -1)])
                         idx = np.concatenate([idx, np.repeat(idx[-1:], pad, axis=0)])
-                    res = self.solver.solve(images, indices=idx, want_images=True, prescrambled=kind, graph=True)
+                    res = self.solver.solve(images, indices=idx, want_images=True, prescrambled=kind, graph=True,
+                                            **({"count_rows": len(group)} if pad > 0 else {}))   # padding stays out of the totals
                 else:
                     res = self.solver.solve(images, indices=idx, want_images=True, prescrambled=kind)
                 ok, matches = res.puzzle_correct.tolist(), res.patch_matches.tolist()
@@ -322,6 +335,9 @@ class MicroBatcher:
         self.batches_run += 1
 
     def _loop(self) -> None:
+        dev = getattr(self.solver, "device", None)
+        if dev is not None and dev.type == "cuda":
+            torch.cuda.set_device(dev)          # a new thread starts on device 0 whatever the model's device
         while not self._stop.is_set():
             items = self._collect()
             if items is None:

@@ -225,9 +225,10 @@ def timestep_embed(t: torch.Tensor, w0, b0, w2, b2) -> Tuple[torch.Tensor, torch
     n = t.shape[0]
     c = torch.empty(n, HIDDEN, device=t.device, dtype=torch.float32)
     sc = torch.empty_like(c)
+    hid = torch.empty_like(c)          # scratch of its own between the two grid-wide phases (must not alias c / sc)
     check(lib.jpdvt_timestep_embed(ptr(t), n, None, None, ptr(_need(w0, torch.float32, "w0")), ptr(_need(b0, torch.float32, "b0")),
                                    ptr(_need(w2, torch.float32, "w2")), ptr(_need(b2, torch.float32, "b2")), ptr(c), ptr(sc),
-                                   stream_ptr()), "timestep_embed")
+                                   ptr(hid), stream_ptr()), "timestep_embed")
     return c, sc
 
 
@@ -250,6 +251,68 @@ def posterior_step(x0, x_t, noise, coef1, coef2, logvar, t: torch.Tensor):
                                    ptr(_need(t, torch.int64, "t")), None, ptr(mean), ptr(sample), n, per, stream_ptr()),
           "posterior_step")
     return mean, sample
+
+
+def philox_key(seed: int, call: int, device) -> torch.Tensor:
+    """Device int64[2] {seed, call counter}: the key of the in-kernel per-step noise (jpdvt_sampler.noise_key)."""
+    return torch.tensor([int(seed) & 0x7fffffffffffffff, int(call)], dtype=torch.int64, device=device)
+
+
+def philox_normal(key: torch.Tensor, n: int, step: int = 0, return_raw: bool = False):
+    """The normals posterior_step_philox draws for loop position `step` (n % 4 == 0); optionally the raw Philox4x32-10 words."""
+    lib = _lib_dev()
+    key = _need(key, torch.int64, "key")
+    out = torch.empty(n, device=key.device, dtype=torch.float32)
+    raw = torch.empty(n, device=key.device, dtype=torch.int32) if return_raw else None
+    check(lib.jpdvt_philox_normal(ptr(out), ptr(raw), n, int(step), ptr(key), stream_ptr()), "philox_normal")
+    return (out, raw) if return_raw else out
+
+
+def posterior_step_philox(x0, x_t, key: torch.Tensor, step: int, coef1, coef2, logvar, t: torch.Tensor) -> torch.Tensor:
+    """posterior_step whose noise is drawn inside the kernel from Philox (key, loop position `step`) -> sample."""
+    lib = _lib_dev()
+    x0, x_t = _need(x0, torch.float32, "x0"), _need(x_t, torch.float32, "x_t")
+    sample = torch.empty_like(x0)
+    n, per = x0.numel(), x0.numel() // x0.shape[0]
+    check(lib.jpdvt_posterior_step_philox(ptr(x0), ptr(x_t), ptr(_need(key, torch.int64, "key")), int(step), ptr(coef1), ptr(coef2),
+                                          ptr(logvar), ptr(_need(t, torch.int64, "t")), None, ptr(sample), n, per, stream_ptr()),
+          "posterior_step_philox")
+    return sample
+
+
+def mse_loss_fwd(te_out, te_tgt, img_out=None, img_tgt=None, keep_slots=None, grid: int = 0) -> torch.Tensor:
+    """Per-sample loss terms of training_losses (gaussian_diffusion.py:835-838): mean((te_tgt - te_out)^2)
+    [+ mean((img_tgt - img_out)^2 * (1 - keep))]; keep_slots fp32 [B, grid*grid]."""
+    lib = _lib_dev()
+    te_out, te_tgt = _need(te_out, torch.float32, "te_out"), _need(te_tgt, torch.float32, "te_tgt")
+    b = te_out.shape[0]
+    per = te_out.numel() // max(b, 1)
+    loss = torch.empty(b, device=te_out.device, dtype=torch.float32)
+    part = torch.empty(max(int(lib.jpdvt_mse_part_floats(b)), 1), device=te_out.device, dtype=torch.float32)
+    size = 0
+    if img_out is not None:
+        img_out, img_tgt = _need(img_out, torch.float32, "img_out"), _need(img_tgt, torch.float32, "img_tgt")
+        keep_slots = _need(keep_slots, torch.float32, "keep_slots")
+        size = img_out.shape[-1]
+        if img_out.shape != img_tgt.shape or tuple(keep_slots.shape) != (b, grid * grid) or img_out.shape[1] != 3:
+            raise _lib.JpdvtError("mse_loss: image / mask shapes do not fit")
+    check(lib.jpdvt_mse_loss_fwd(ptr(te_out), ptr(te_tgt), per, ptr(img_out), ptr(img_tgt), ptr(keep_slots), size, grid, ptr(part),
+                                 ptr(loss), b, stream_ptr()), "mse_loss_fwd")
+    return loss
+
+
+def mse_loss_bwd(dloss, te_out, te_tgt, img_out=None, img_tgt=None, keep_slots=None, grid: int = 0):
+    """-> (d_te, d_img or None) for upstream per-sample gradients dloss [B]."""
+    lib = _lib_dev()
+    dloss = _need(dloss, torch.float32, "dloss")
+    b = te_out.shape[0]
+    per = te_out.numel() // max(b, 1)
+    d_te = torch.empty_like(te_out)
+    d_img = torch.empty_like(img_out) if img_out is not None else None
+    size = img_out.shape[-1] if img_out is not None else 0
+    check(lib.jpdvt_mse_loss_bwd(ptr(te_out), ptr(te_tgt), per, ptr(img_out), ptr(img_tgt), ptr(keep_slots), size, grid, ptr(dloss),
+                                 ptr(d_te), ptr(d_img), b, stream_ptr()), "mse_loss_bwd")
+    return d_te, d_img
 
 
 def ddim_step(x0, x_t, noise, tabs: dict, t: torch.Tensor) -> torch.Tensor:
@@ -430,3 +493,14 @@ def colsum(src: torch.Tensor) -> torch.Tensor:
     fn = lib.jpdvt_colsum_bf16 if src.dtype == torch.bfloat16 else lib.jpdvt_colsum_f32
     check(fn(ptr(src.contiguous()), rows, cols, ptr(out), stream_ptr()), "colsum")
     return out
+
+
+def _wrap_all():
+    """Every public wrapper runs with its first CUDA tensor argument's device current (see _lib.on_tensor_device)."""
+    import types
+    for name, fn in list(globals().items()):
+        if isinstance(fn, types.FunctionType) and not name.startswith("_") and fn.__module__ == __name__:
+            globals()[name] = _lib.on_tensor_device(fn)
+
+
+_wrap_all()

@@ -109,12 +109,31 @@ class Trainer:
         model.__dict__["_train_engine"] = self.engine
         model.__dict__["_train_engine_key"] = "adopted"
         model.__dict__["_adopted_by_trainer"] = True
+        self._sync_replicas()
         self._refresh_derived()
         self._works: List = []
 
+    # ------------------------------------------------------------------ replica alignment (DDP's constructor broadcast)
+    def _sync_replicas(self) -> None:
+        """Every rank adopts the group's rank-0 state.  The reference seeds each rank differently before building the model
+        (train_JPDVT.py:115-116) and relies on DistributedDataParallel's constructor to broadcast rank 0's parameters
+        (:231); the same holds after a checkpoint load (every rank reads the file, rank 0's copy is authoritative)."""
+        if self.world <= 1:
+            return
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        steps = torch.tensor([self.step_count], dtype=torch.int64, device=self.device)
+        for buf in (self.p_flat, self.ema_flat, self.m_flat, self.v_flat, steps):
+            dist.broadcast(buf, src=src, group=self.group)
+        self.step_count = int(steps.item())
+        self.pb_flat.copy_(self.p_flat)
+
     # ------------------------------------------------------------------ derived operand copies
     def _refresh_derived(self) -> None:
-        st = _lib.stream_ptr()
+        with _lib.on_device(self.device):
+            self._refresh_derived_impl()
+
+    def _refresh_derived_impl(self) -> None:
+        st = _lib.stream_ptr(self.device)
         torch.add(self.p_views["b_patch"], self.p_views["b_in"], out=self.b_embed)
         self.w_in_t.copy_(self.p_views["w_in"].t())
         self.t_w2_bf16.copy_(self.p_views["t_w2"])
@@ -161,10 +180,11 @@ class Trainer:
             wk.wait()
         self._works = []
         self.step_count += 1
-        check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
-                                       ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
-                                       self.betas[1], self.eps, self.weight_decay, self.ema_decay, _lib.stream_ptr()),
-              "jpdvt_adamw_ema")
+        with _lib.on_device(self.device):
+            check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
+                                           ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
+                                           self.betas[1], self.eps, self.weight_decay, self.ema_decay,
+                                           _lib.stream_ptr(self.device)), "jpdvt_adamw_ema")
         self._refresh_derived()
         for p in model.parameters():
             p.grad = None
@@ -259,5 +279,6 @@ class Trainer:
             self.step_count = int(ckpt["train_steps"])
         self.pb_flat.copy_(self.p_flat)
         # (pos_embed: self.pos is a view of the module's frozen buffer, updated in place by load_state_dict)
+        self._sync_replicas()
         self._refresh_derived()
         return int(ckpt.get("train_steps") or self.step_count)

@@ -96,6 +96,7 @@ class TrainEngine:
             "yfin": e(M, HIDDEN), "yfin32": e(M, HIDDEN, dtype=f32), "headpre": e(M, 64, dtype=f32),
             "feat": e(batch, 256, dtype=f32), "tpre": e(batch, HIDDEN, dtype=f32), "c": e(batch, HIDDEN, dtype=f32),
             "silu_c": e(batch, HIDDEN, dtype=f32), "silu_c_bf16": e(batch, HIDDEN), "mod": e(batch, self.n_mod, dtype=f32),
+            "thid": e(batch, HIDDEN, dtype=f32),
         }
         tape = Tape()
         tape.rows, tape.batch, tape.reserved = M, batch, 0
@@ -133,21 +134,26 @@ class TrainEngine:
         B = img.shape[0]
         if tuple(img.shape[1:]) != (3, self.image_size, self.image_size) or tuple(x_t.shape) != (B, self.tokens, LATENT) or t.shape != (B,):
             raise _lib.JpdvtError(f"bad training input shapes: img {tuple(img.shape)}, t {tuple(t.shape)}, time_emb {tuple(x_t.shape)}")
-        self._ensure(B)
-        self.ticket += 1
-        te = torch.empty(B, self.tokens, LATENT, device=self.device, dtype=torch.float32)
-        out_img = torch.empty(B, 3, self.image_size, self.image_size, device=self.device, dtype=torch.float32)
-        check(self.lib.jpdvt_train_forward(C.byref(self.w_struct), C.byref(self.tape), ptr(img), ptr(t), ptr(x_t), ptr(te),
-                                           ptr(out_img), B, _lib.stream_ptr()), "jpdvt_train_forward")
+        with _lib.on_device(self.device):
+            self._ensure(B)
+            self.ticket += 1
+            te = torch.empty(B, self.tokens, LATENT, device=self.device, dtype=torch.float32)
+            out_img = torch.empty(B, 3, self.image_size, self.image_size, device=self.device, dtype=torch.float32)
+            check(self.lib.jpdvt_train_forward(C.byref(self.w_struct), C.byref(self.tape), ptr(img), ptr(t), ptr(x_t), ptr(te),
+                                               ptr(out_img), B, _lib.stream_ptr(self.device)), "jpdvt_train_forward")
         return out_img, te
 
     def backward(self, d_te: torch.Tensor, d_img: Optional[torch.Tensor], x_t: torch.Tensor,
                  stage_done: Optional[Callable[[str, Dict[str, torch.Tensor]], None]] = None):
         """Runs the backward stages; `stage_done(name, views)` is called after each stage (head, block<i>, embed) so a
         data-parallel trainer can start reducing that stage's gradients while the next stage computes."""
+        with _lib.on_device(self.device):
+            return self._backward(d_te, d_img, x_t, stage_done)
+
+    def _backward(self, d_te, d_img, x_t, stage_done):
         flat, g, views = self.new_grads()
         self.scr_t["dmod"].zero_()
-        st = _lib.stream_ptr()
+        st = _lib.stream_ptr(self.device)
         args = (C.byref(self.w_struct), C.byref(self.wt), C.byref(self.tape), C.byref(self.scratch), C.byref(g))
         check(self.lib.jpdvt_train_backward_head(*args, ptr(d_te), ptr(d_img) if d_img is not None else None, st),
               "jpdvt_train_backward_head")
