@@ -62,6 +62,27 @@ def gather_placements(pred: torch.Tensor, counts: Sequence[int] | None = None, g
     return torch.cat([b[:c] for b, c in zip(bufs, counts)])
 
 
+def broadcast_state(buffers: Sequence[torch.Tensor], group=None, src: int = 0) -> None:
+    """Every rank adopts rank `src`'s copy of each buffer, in place - what DistributedDataParallel's constructor does for the
+    module's parameters and buffers (train_JPDVT.py:231; the ranks seed differently at :115-116, so without it the replicas
+    start from different weights)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    root = dist.get_global_rank(group, src) if group is not None else src
+    for b in buffers:
+        dist.broadcast(b, src=root, group=group)
+
+
+def sum_gradients(flat: torch.Tensor, group=None, async_op: bool = False):
+    """SUM all-reduce of a flat gradient buffer over the data-parallel group; returns (work or None, scale) where
+    `scale` = 1 / world_size is what turns the sum into DDP's average (train_JPDVT.py:231,370) - the B200 trainer folds it
+    into the optimizer kernel instead of spending a pass on it."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None, 1.0
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return (work if async_op else None), 1.0 / dist.get_world_size(group)
+
+
 def reduce_stats(puzzle_correct: float, piece_correct: float, count: float, seconds: float, device, group=None):
     """inference_ddp.py:485-495: SUM of the three counters, MAX of the elapsed time."""
     stats = torch.tensor([puzzle_correct, piece_correct, count], device=device, dtype=torch.float32)

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, parallel
 from ._lib import Weights, WeightsT, check, ptr
 from .engine import HIDDEN, LATENT
 from .training import TrainEngine, _grad_layout, param_grad_map
@@ -120,10 +120,8 @@ class Trainer:
         (:231); the same holds after a checkpoint load (every rank reads the file, rank 0's copy is authoritative)."""
         if self.world <= 1:
             return
-        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
         steps = torch.tensor([self.step_count], dtype=torch.int64, device=self.device)
-        for buf in (self.p_flat, self.ema_flat, self.m_flat, self.v_flat, steps):
-            dist.broadcast(buf, src=src, group=self.group)
+        parallel.broadcast_state((self.p_flat, self.ema_flat, self.m_flat, self.v_flat, steps), self.group)
         self.step_count = int(steps.item())
         self.pb_flat.copy_(self.p_flat)
 
@@ -175,7 +173,7 @@ class Trainer:
         loss.backward()
         flat = self.engine.last_flat
         if self.world > 1 and self.allreduce == "end":
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            parallel.sum_gradients(flat, self.group)
         for wk in self._works:
             wk.wait()
         self._works = []

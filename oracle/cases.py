@@ -30,6 +30,11 @@ SAMPLING_CASES = {
     "d2_192_s250":  dict(size=192, depth=2,  batch=2, grid=3, wseed=22,   seed=202, respacing="250", loop_seed=6),
     "d2_256g4_s25": dict(size=256, depth=2,  batch=2, grid=4, wseed=23,   seed=203, respacing="25",  loop_seed=7),
     "full192_s250": dict(size=192, depth=12, batch=2, grid=3, wseed=1234, seed=204, respacing="250", loop_seed=8),
+    # BASELINE configs[3] (C4): 4x4 @256 px, all 12 blocks, all 250 steps
+    "c4_256g4_s250": dict(size=256, depth=12, batch=2, grid=4, wseed=1234, seed=205, respacing="250", loop_seed=12),
+    # BASELINE configs[4] (C5): 3x3 @288 px with 1-2 missing pieces per puzzle = slots of the scrambled condition image set to
+    # zero (inference_visualize_missing_patches.ipynb cell 9), all 12 blocks, all 250 steps
+    "c5_288_miss_s250": dict(size=288, depth=12, batch=2, grid=3, wseed=1234, seed=206, respacing="250", loop_seed=13, missing=(1, 2)),
 }
 
 # DDIM: the reference's ddim_sample calls p_mean_variance without `condition` (gaussian_diffusion.py:546-553, TypeError);
@@ -82,8 +87,29 @@ def sampling_inputs(case):
     rs = np.random.RandomState(case["seed"])
     perms = [rs.permutation(G * G) for _ in range(B)]
     cond = torch.cat([orc.scramble(img[b:b + 1], perms[b], G) for b in range(B)], 0)
+    if case.get("missing"):
+        cond = zero_slots(cond, missing_slots(case), G)
     noise = torch.randn(1, T, 8, generator=g).repeat(B, 1, 1)
     return cond, noise
+
+
+def missing_slots(case):
+    """Per puzzle: the slots of the scrambled image that are blanked (r in [lo, hi] of them, seeded)."""
+    lo, hi = case["missing"]
+    rs = np.random.RandomState(case["seed"] + 7919)
+    n = case["grid"] ** 2
+    return [sorted(rs.choice(n, size=int(rs.randint(lo, hi + 1)), replace=False).tolist()) for _ in range(case["batch"])]
+
+
+def zero_slots(cond, slots, grid):
+    """Masked-puzzle inference: the selected slots of the (already scrambled) condition image become zeros."""
+    cond = cond.clone()
+    p = cond.shape[-1] // grid
+    for b, ss in enumerate(slots):
+        for s in ss:
+            r, c = divmod(int(s), grid)
+            cond[b, :, r * p:(r + 1) * p, c * p:(c + 1) * p] = 0
+    return cond
 
 
 def sampling_perms(case):

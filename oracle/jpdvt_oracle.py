@@ -404,3 +404,35 @@ def solve(latent: torch.Tensor, grid: int, tok: int, sentinel: float = 1e9) -> T
     sc = l1_scores(feat, canon)
     order = greedy_order(sc, sentinel)
     return order, placements(order), sc
+
+
+# ---------------------------------------------------------------------------------------------- Philox4x32-10 (per-step noise)
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the generator family behind
+    torch's CUDA `randn_like`, which the reference's p_sample calls at gaussian_diffusion.py:424).  counter: uint32 [n, 4],
+    key: (k0, k1).  Returns uint32 [n, 4].  Checks the raw stream of csrc/elementwise.cu: philox4x32_10."""
+    c = np.asarray(counter, dtype=np.uint64).copy()
+    k0, k1 = np.uint64(key[0] & 0xFFFFFFFF), np.uint64(key[1] & 0xFFFFFFFF)
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[:, 0], m1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def philox_normals(n, seed, call, step):
+    """The normals the B200 posterior kernel draws for loop position `step`: counter = (group lo, group hi, step, call),
+    key = seed; 24-bit uniforms strictly inside (0, 1), two Box-Muller pairs per counter (fp64 here; the kernel's fp32
+    logf / sincosf agree to rounding)."""
+    groups = np.arange(n // 4, dtype=np.uint64)
+    ctr = np.stack([groups & np.uint64(0xFFFFFFFF), groups >> np.uint64(32), np.full_like(groups, step), np.full_like(groups, call)], 1)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).astype(np.float64)
+    u = np.floor(r / 256.0) * 2.0 ** -24 + 2.0 ** -25
+    ra, rb = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
+    out = np.stack([ra * np.cos(2 * np.pi * u[:, 1]), ra * np.sin(2 * np.pi * u[:, 1]),
+                    rb * np.cos(2 * np.pi * u[:, 3]), rb * np.sin(2 * np.pi * u[:, 3])], 1)
+    return out.reshape(-1)

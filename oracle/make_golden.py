@@ -102,8 +102,10 @@ def golden_forward():
         np.savez_compressed(os.path.join(OUT, f"forward_{name}.npz"), **out)
 
 
-def golden_sampling():
+def golden_sampling(only=None):
     for name, case in cases.SAMPLING_CASES.items():
+        if only and name not in only:
+            continue
         m, st = build_ref(case)
         d = create_diffusion(case["respacing"])
         cond, noise = cases.sampling_inputs(case)
@@ -264,4 +266,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or ["static", "assignment", "forward", "training", "sampling", "ddim"]
     for w in which:
-        globals()["golden_" + w]()
+        if ":" in w:                                   # e.g. sampling:c4_256g4_s250,c5_288_miss_s250 - regenerate named cases only
+            fn, names = w.split(":", 1)
+            globals()["golden_" + fn](set(names.split(",")))
+        else:
+            globals()["golden_" + w]()

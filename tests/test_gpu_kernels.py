@@ -277,3 +277,77 @@ def test_layernorm_folded_into_consumer(ops, m, k, T):
             if gelu:
                 ref = F.gelu(ref, approximate="tanh")
             assert rel_l2(out.float(), ref) < BF16_TOL, (name, rel_l2(out.float(), ref))
+
+
+def test_timestep_embed_many_row_groups(ops):
+    """More row groups than one wave of CTAs (the per-step table of a 250-step loop, training batches > 96): the hidden
+    activations live in a scratch of their own, so CTAs that finish early cannot overwrite what later ones still read."""
+    torch.manual_seed(9)
+    n = 2048
+    t = torch.randint(0, 1000, (n,), device="cuda")
+    w0, b0 = torch.randn(768, 256, device="cuda") * 0.05, torch.randn(768, device="cuda") * 0.1
+    w2, b2 = torch.randn(768, 768, device="cuda") * 0.05, torch.randn(768, device="cuda") * 0.1
+    half = 128
+    freqs = torch.exp(-np.log(10000.0) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    args = t[:, None].float() * freqs[None]
+    feat = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    cref = F.silu(feat @ w0.t() + b0) @ w2.t() + b2
+    for _ in range(3):
+        c, sc = ops.timestep_embed(t, w0, b0, w2, b2)
+        assert rel_l2(c, cref) < 1e-5 and rel_l2(sc, F.silu(cref)) < 1e-5
+
+
+def test_mse_loss_kernels_vs_torch(ops):
+    """jpdvt_mse_loss_{fwd,bwd} against mean_flat((target - out)**2 [* (1 - masks)]) and its autograd
+    (gaussian_diffusion.py:18-22, 835-838)."""
+    torch.manual_seed(11)
+    for B, S, G in ((3, 96, 3), (2, 128, 4), (5, 192, 3)):
+        T = (S // 16) ** 2
+        te_out = torch.randn(B, T, 8, device="cuda", requires_grad=True)
+        te_tgt = torch.randn(B, T, 8, device="cuda")
+        x_out = torch.randn(B, 3, S, S, device="cuda", requires_grad=True)
+        x_tgt = torch.randn(B, 3, S, S, device="cuda")
+        keep = (torch.rand(B, G * G, device="cuda") > 0.4).float()
+        p = S // G
+        full = keep.view(B, 1, G, 1, G, 1).expand(B, 3, G, p, G, p).reshape(B, 3, S, S)
+        mf = lambda v: v.mean(dim=list(range(1, v.dim())))
+        ref = mf((te_tgt - te_out) ** 2) + mf((x_tgt - x_out) ** 2 * (1 - full))
+        dl = torch.randn(B, device="cuda")
+        ref.backward(dl)
+        got = ops.mse_loss_fwd(te_out.detach(), te_tgt, x_out.detach(), x_tgt, keep, G)
+        assert rel_l2(got, ref.detach()) < 1e-6
+        d_te, d_img = ops.mse_loss_bwd(dl, te_out.detach(), te_tgt, x_out.detach(), x_tgt, keep, G)
+        assert rel_l2(d_te, te_out.grad) < 1e-6 and rel_l2(d_img, x_out.grad) < 1e-6
+        only = ops.mse_loss_fwd(te_out.detach(), te_tgt)
+        assert rel_l2(only, mf((te_tgt - te_out.detach()) ** 2)) < 1e-6
+        d_te2, none = ops.mse_loss_bwd(dl, te_out.detach(), te_tgt)
+        assert none is None and rel_l2(d_te2, 2 * (te_out.detach() - te_tgt) * dl.view(-1, 1, 1) / (T * 8)) < 1e-6
+
+
+def test_philox_step_noise(ops):
+    """The in-kernel per-step noise: raw words bit-exact against the numpy Philox4x32-10 restatement, normals against its
+    fp64 Box-Muller, unit moments, and posterior_step_philox == posterior_step fed the same numbers."""
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from oracle import jpdvt_oracle as orc
+    seed, call, step, n = 0x1234567ABCDEF, 5, 17, 4096
+    key = ops.philox_key(seed, call, "cuda")
+    z, raw = ops.philox_normal(key, n, step, return_raw=True)
+    groups = np.arange(n // 4, dtype=np.uint64)
+    ctr = np.stack([groups, np.zeros_like(groups), np.full_like(groups, step), np.full_like(groups, call)], 1)
+    want_raw = orc.philox4x32_10(ctr, (seed & 0xFFFFFFFF, seed >> 32)).reshape(-1)
+    assert np.array_equal(raw.cpu().numpy().view(np.uint32), want_raw)
+    want = orc.philox_normals(n, seed, call, step)
+    assert np.abs(z.cpu().numpy().astype(np.float64) - want).max() < 2e-5
+    big = ops.philox_normal(key, 1 << 22, 0)
+    assert abs(big.mean().item()) < 3e-3 and abs(big.std().item() - 1.0) < 3e-3
+    assert abs((big ** 4).mean().item() - 3.0) < 5e-2                                   # Gaussian kurtosis
+    assert not torch.equal(ops.philox_normal(key, n, step + 1), z)                       # another step, other numbers
+    assert torch.equal(ops.philox_normal(key, n, step), z)                               # counter-based: repeatable
+    d = create_diffusion("250")
+    tabs = d.device_tables(torch.device("cuda"))
+    x0, xt = torch.randn(4, 144, 8, device="cuda"), torch.randn(4, 144, 8, device="cuda")
+    tt = torch.tensor([0, 1, 100, 249], device="cuda")
+    eps = ops.philox_normal(key, x0.numel(), step).view_as(x0)
+    _, want_s = ops.posterior_step(x0, xt, eps, tabs["coef1"], tabs["coef2"], tabs["logvar"], tt)
+    got_s = ops.posterior_step_philox(x0, xt, key, step, tabs["coef1"], tabs["coef2"], tabs["logvar"], tt)
+    assert torch.equal(got_s, want_s)

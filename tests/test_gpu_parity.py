@@ -77,7 +77,7 @@ def test_fresh_init_outputs_exact_zeros(cuda):
     assert img.abs().max() == 0 and te.abs().max() == 0     # adaLN-Zero + zero final layer (models.py:216-225)
 
 
-@pytest.mark.parametrize("name", ["tiny48_s10", "d2_256g4_s25", "d2_192_s250", "full192_s250"])
+@pytest.mark.parametrize("name", ["tiny48_s10", "d2_256g4_s25", "d2_192_s250", "full192_s250", "c4_256g4_s250", "c5_288_miss_s250"])
 def test_sampling_loop_vs_reference_golden(cuda, golden, name):
     from jpdvt_mt_ntnu_b200 import assignment
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
@@ -197,3 +197,61 @@ def test_full_size_properties_c2(cuda):
     _check(final[:1], want)
     order, pred = assignment.solve_puzzles(final, 3)
     assert torch.equal(pred, pred[:1].expand_as(pred))
+
+
+@pytest.mark.parametrize("cfg", ["c4", "c5"])
+def test_full_size_properties_c4_c5(cuda, cfg):
+    """BASELINE configs[3] / [4] at full size - C4: 4x4 @256 px, batch 128 (T = 256); C5: 3x3 @288 px with one or two blanked
+    slots, batch 128 (T = 324, the padded / masked tcgen05 attention) - through the same size-independent properties as C2:
+    the loop equals one t=0 forward, identical puzzles give identical rows, row 0 matches the fp32 CPU oracle, and (C5) a
+    blanked slot changes the answer (the mask reaches the network)."""
+    from jpdvt_mt_ntnu_b200 import assignment
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    size, grid = (256, 4) if cfg == "c4" else (288, 3)
+    B, T = 128, (size // 16) ** 2
+    case = dict(size=size, depth=12, batch=B, grid=grid, wseed=1234, seed=0)
+    m = _model(case)
+    d = create_diffusion("250")
+    g = torch.Generator().manual_seed(1)
+    one = torch.rand(1, 3, size, size, generator=g) * 2 - 1
+    if cfg == "c5":
+        one = cases.zero_slots(one, [[2, 7]], grid)
+    cond = one.repeat(B, 1, 1, 1).cuda()
+    noise = torch.randn(1, T, 8, generator=g).repeat(B, 1, 1).cuda()
+    final = d.p_sample_loop(m.forward, cond, noise.shape, noise, clip_denoised=False)      # per-step noise drawn in-kernel
+    with torch.no_grad():
+        tabs = d.device_tables(torch.device("cuda"))
+        _, direct = m.engine().forward(cond, None, noise, need_image=False, step_ptr=tabs["step_ids"][-1:].clone(), tmap=tabs["timestep_map"])
+    assert torch.equal(final, direct)
+    assert torch.equal(final, final[:1].expand_as(final))
+    want = orc.OracleDenoiser(cases.state_for(case), depth=12)(one, torch.zeros(1, dtype=torch.long), noise[:1].cpu())[1]
+    _check(final[:1], want)
+    order, pred = assignment.solve_puzzles(final, grid)
+    assert torch.equal(pred, pred[:1].expand_as(pred))
+    o, p, _ = orc.solve(final[0].cpu(), grid, size // (16 * grid))
+    assert order[0].cpu().tolist() == [int(v) for v in o] and pred[0].cpu().tolist() == [int(v) for v in p]
+    if cfg == "c5":
+        g2 = torch.Generator().manual_seed(1)
+        full = (torch.rand(1, 3, size, size, generator=g2) * 2 - 1).repeat(2, 1, 1, 1).cuda()
+        other = d.p_sample_loop(m.forward, full, noise[:2].shape, noise[:2], clip_denoised=False)
+        assert rel_l2(other[:1], final[:1]) > 1e-3
+
+
+def test_in_kernel_step_noise_chain_mode_statistics(cuda):
+    """chain=True feeds the running sample back, so the per-step noise matters: with the noise drawn inside the posterior
+    kernel (Philox) the chained result must differ from run to run (fresh call counter), stay finite, and agree with the
+    explicit-noise path when that path is given the very numbers the kernel draws."""
+    from jpdvt_mt_ntnu_b200 import ops
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    case = cases.SAMPLING_CASES["tiny48_s10"]
+    m = _model(case)
+    d = create_diffusion("10")
+    cond, noise = cases.sampling_inputs(case)
+    a = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, chain=True)
+    eng = m.engine()
+    key = eng._noise_key.clone()
+    same = torch.stack([ops.philox_normal(key, noise.numel(), k).view_as(noise) for k in range(10)])
+    a2 = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, chain=True, step_noise=same)
+    assert torch.equal(a, a2)
+    b = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, chain=True)
+    assert torch.isfinite(b).all() and not torch.equal(a, b)

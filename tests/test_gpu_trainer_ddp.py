@@ -1,0 +1,180 @@
+"""Data-parallel training on a B200 box: two ranks of `Trainer` against one rank on the concatenated batch.
+
+The reference wraps the model in DistributedDataParallel (image_model/train_JPDVT.py:231): the constructor broadcasts rank
+0's parameters (the ranks seed differently, :115-116) and the backward averages the gradients over the ranks before
+`opt.step()` / `update_ema` (:368-372).  `Trainer` does the same with one SUM all-reduce of its flat gradient buffer and
+a 1/world scale inside the fused AdamW + EMA kernel.  Asserted here, through real process groups:
+  * replicas built under different torch seeds hold identical parameters after construction and after a step;
+  * a 2-rank step on two half-batches == a 1-rank step on the whole batch: first moment (= the averaged gradient), second
+    moment, parameters, EMA - to rounding (the weight-gradient splits meet through fp32 reduction boxes in no fixed
+    order, and Adam's first step is sign-like, so a handful of near-zero gradients may flip: compared in aggregate).
+Backend: NCCL with one GPU per rank when the box has two, else gloo with both ranks on cuda:0 (NCCL refuses two ranks on
+one device); the trainer code path is the same.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CASE = dict(size=96, depth=2, batch=4, grid=3, wseed=31, seed=311, add_mask=True)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _draws(case):
+    from oracle import cases
+    d = cases.training_draws(case)
+    return d
+
+
+def _slice(draws, lo, hi):
+    return dict(noise_x=draws["noise_x"][lo:hi], perm=draws["perm"], masks=None if draws["masks"] is None else draws["masks"][lo:hi],
+                noise_te=draws["noise_te"][lo:hi])
+
+
+def _build(seed, dev, load_state):
+    from jpdvt_mt_ntnu_b200.models import DiT
+    from oracle import cases
+    torch.manual_seed(seed)
+    m = DiT(input_size=CASE["size"], depth=CASE["depth"], hidden_size=768, patch_size=16, num_heads=12)
+    if load_state:
+        m.load_state_dict(cases.state_for(CASE))
+    return m.to(dev)
+
+
+def _one_step(trainer, diffusion, x, t, piece, draws, steps=1):
+    kw = dict(block_size=CASE["size"] // CASE["grid"], patch_size=16, add_mask=CASE["add_mask"], grid_size=CASE["grid"])
+    loss = None
+    for _ in range(steps):
+        diffusion._draws = draws
+        loss = trainer.step(x, t, piece, **kw)
+    return loss
+
+
+def _worker(rank, world, port, backend, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.trainer import Trainer
+    from oracle import cases
+    dev = torch.device("cuda", rank if backend == "nccl" else 0)
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0 carries the case's weights, rank 1 a fresh init under another seed: only the broadcast can align them
+        model = _build(1000 + rank, dev, load_state=(rank == 0))
+        d = create_diffusion("")
+        tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999)
+        def gather(buf):          # gloo has no CUDA all_gather: stage through the host there
+            src = buf if backend == "nccl" else buf.detach().cpu()
+            outs = [torch.empty_like(src) for _ in range(world)]
+            dist.all_gather(outs, src.contiguous())
+            return outs
+
+        got = gather(tr.p_flat)
+        assert torch.equal(got[0], got[1]), "replicas differ after Trainer construction"
+        x, t, piece = cases.training_inputs(CASE)
+        draws = _draws(CASE)
+        half = CASE["batch"] // world
+        lo, hi = rank * half, (rank + 1) * half
+        loss = _one_step(tr, d, x[lo:hi].to(dev), t[lo:hi].to(dev), piece.to(dev), _slice(draws, lo, hi), steps=2)
+        for buf in (tr.p_flat, tr.ema_flat, tr.m_flat, tr.v_flat):
+            got = gather(buf)
+            assert torch.equal(got[0], got[1]), "replicas diverged after two data-parallel steps"
+        losses = gather(loss.reshape(1))
+        if rank == 0:
+            torch.save({"p": tr.p_flat.cpu(), "ema": tr.ema_flat.cpu(), "m": tr.m_flat.cpu(), "v": tr.v_flat.cpu(),
+                        "loss": torch.cat([l.cpu() for l in losses]).mean(), "step": tr.step_count}, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path):
+    from conftest import rel_l2
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.trainer import Trainer
+    from oracle import cases
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    out = str(tmp_path / "two_rank.pt")
+    mp.spawn(_worker, args=(2, _free_port(), backend, out), nprocs=2, join=True)
+    two = torch.load(out, map_location="cpu")
+
+    dev = torch.device("cuda", 0)
+    model = _build(1000, dev, load_state=True)
+    p0 = None
+    d = create_diffusion("")
+    tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999)
+    p0 = tr.p_flat.clone().cpu()
+    x, t, piece = cases.training_inputs(CASE)
+    loss = _one_step(tr, d, x.to(dev), t.to(dev), piece.to(dev), _draws(CASE), steps=2)
+    assert two["step"] == tr.step_count == 2
+    # loss of the second step: mean over the whole batch == mean of the two half-batch means
+    assert abs(two["loss"].item() - loss.item()) <= 2e-3 * abs(loss.item())
+    # first / second moments after two steps are linear / quadratic in the averaged gradients
+    assert rel_l2(two["m"], tr.m_flat.cpu()) < 2e-2
+    assert rel_l2(two["v"], tr.v_flat.cpu()) < 4e-2
+    # parameters: Adam's early steps are sign-like, so compare the update in aggregate and the parameters tightly
+    assert rel_l2(two["p"], tr.p_flat.cpu()) < 2e-3
+    assert rel_l2(two["p"] - p0, tr.p_flat.cpu() - p0) < 0.15
+    assert rel_l2(two["ema"], tr.ema_flat.cpu()) < 1e-4
+
+
+def test_load_reference_checkpoint(cuda, tmp_path):
+    """weights.load_reference_checkpoint follows the reference's inference loader (inference.py:207-211): the file is the
+    trainer's dict (train_JPDVT.py:410-416), keys present in the model are loaded with strict=False, the rest reported;
+    `use_ema` picks the EMA weights (what valwhiletrain-style evaluation uses).  The loaded model then produces the same
+    latents as a model given the state dict directly."""
+    from jpdvt_mt_ntnu_b200.models import DiT
+    from jpdvt_mt_ntnu_b200.weights import load_reference_checkpoint
+    from oracle import cases
+    case = cases.FORWARD_CASES["tiny48"]
+    state = cases.state_for(case)
+    ema = {k: (v * 0.5 if k != "pos_embed" else v.clone()) for k, v in state.items()}
+    extra = dict(state)
+    extra["y_embedder.embedding_table.weight"] = torch.zeros(3, 768)         # a key the JPDVT model does not have
+    shape_clash = dict(ema)
+    shape_clash["time_emb_out2.bias"] = torch.zeros(16)                      # wrong shape: skipped, not loaded
+    path = str(tmp_path / "0010000.pt")
+    torch.save({"model": extra, "ema": shape_clash, "opt": {"state": {}, "param_groups": []}, "args": None, "train_steps": 10000}, path)
+
+    def fresh():
+        return DiT(input_size=case["size"], depth=case["depth"], hidden_size=768, patch_size=16, num_heads=12)
+
+    img, t, x_t = cases.forward_inputs(case)
+    want_m = fresh()
+    want_m.load_state_dict(state)
+    want_m.cuda()
+    with torch.no_grad():
+        want = want_m(img.cuda(), t.cuda(), x_t.cuda())[1]
+
+    m = fresh()
+    rep = load_reference_checkpoint(m, path)
+    assert rep["train_steps"] == 10000 and rep["loaded"] == len(state)
+    assert rep["skipped"] == ["y_embedder.embedding_table.weight"] and rep["missing"] == []
+    m.cuda()
+    with torch.no_grad():
+        got = m(img.cuda(), t.cuda(), x_t.cuda())[1]
+    assert torch.equal(got, want)
+
+    m2 = fresh()
+    rep2 = load_reference_checkpoint(m2, path, use_ema=True)
+    assert rep2["skipped"] == ["time_emb_out2.bias"] and rep2["missing"] == ["time_emb_out2.bias"]
+    assert torch.equal(m2.blocks[0].attn.qkv.weight, ema["blocks.0.attn.qkv.weight"])
+    # a bare state dict (no trainer wrapper) loads too
+    bare = str(tmp_path / "bare.pt")
+    torch.save(state, bare)
+    m3 = fresh()
+    assert load_reference_checkpoint(m3, bare)["loaded"] == len(state)
+    assert all(torch.equal(a, b) for a, b in zip(m3.state_dict().values(), want_m.cpu().state_dict().values()))

@@ -158,3 +158,19 @@ def test_ddim_loop_matches_reference(golden, name):
                 _close(o["sample"].numpy(), g[f"step{k}_sample"], 5e-5)
                 _close(o["pred_xstart"].numpy(), g[f"step{k}_x0"], 5e-5)
     _close(x.numpy(), g["final"], 5e-5)
+
+
+def test_philox_restatement_known_answers():
+    """oracle.philox4x32_10 against the published Random123 known-answer vectors for philox4x32-10 (kat_vectors: all-zero
+    counter/key, all-ones counter/key, and the pi-digits vector), so the GPU test that compares the in-kernel step-noise
+    stream with it is anchored outside this repo."""
+    import numpy as np
+    from oracle import jpdvt_oracle as orc
+    z = orc.philox4x32_10(np.zeros((1, 4), dtype=np.uint32), (0, 0))[0]
+    assert [int(v) for v in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    o = orc.philox4x32_10(np.full((1, 4), 0xffffffff, dtype=np.uint64), (0xffffffff, 0xffffffff))[0]
+    assert [int(v) for v in o] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    p = orc.philox4x32_10(np.array([[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint64), (0xa4093822, 0x299f31d0))[0]
+    assert [int(v) for v in p] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    n = orc.philox_normals(1 << 16, seed=12345, call=0, step=3)
+    assert abs(n.mean()) < 2e-2 and abs(n.std() - 1) < 2e-2

@@ -35,6 +35,40 @@ def _worker(rank, world, port, total):
         dist.destroy_process_group()
 
 
+def _train_worker(rank, world, port):
+    """Host logic of the data-parallel trainer (jpdvt_mt_ntnu_b200/trainer.py) on gloo: replicas seeded differently agree
+    after broadcast_state; sum_gradients + the 1/world scale equals the gradient of the concatenated batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from jpdvt_mt_ntnu_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                      # train_JPDVT.py:115-116: a different seed on every rank
+        p, ema, m = torch.randn(1000), torch.randn(1000), torch.randn(1000)
+        steps = torch.tensor([7 * (rank + 1)])
+        parallel.broadcast_state((p, ema, m, steps))
+        torch.manual_seed(100)
+        want = torch.randn(1000)
+        assert torch.equal(p, want) and int(steps) == 7
+        # a linear model y = w.x: mean-loss gradient over the whole batch == average of the two half-batch gradients
+        g = torch.Generator().manual_seed(5)
+        x, y, w = torch.randn(8, 16, generator=g), torch.randn(8, generator=g), torch.randn(16, generator=g)
+        full = (2 * (x @ w - y)[:, None] * x).mean(0)
+        half = slice(rank * 4, rank * 4 + 4)
+        mine = (2 * (x[half] @ w - y[half])[:, None] * x[half]).mean(0)
+        work, scale = parallel.sum_gradients(mine)
+        assert work is None and scale == 0.5
+        assert torch.allclose(mine * scale, full, atol=1e-6)
+        work, scale = parallel.sum_gradients(torch.ones(4), async_op=True)
+        work.wait()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_trainer_host_logic():
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port), nprocs=2, join=True)
+
+
 def test_two_rank_sharding_and_gather():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 11), nprocs=2, join=True)
