@@ -116,7 +116,19 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
-def cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=4):
+def sampling_config(wl, batch):
+    """`config` of the sampling line - one dict for both arms, so the driver's same-config check compares like with like."""
+    S = wl["size"]
+    T = (S // 16) ** 2
+    return {"workload": wl["name"], "batch_per_gpu": batch, "diffusion_steps": wl["steps"], "grid": wl["grid"],
+            "image_size": S, "tokens": T, "weights": "random N(0,0.02), seed 1234 (fresh init outputs zeros)",
+            "l2": f"activations per launch (>= {batch * T * 768 * 2 / 1e6:.0f} MB bf16 / {batch * T * 768 * 4 / 1e6:.0f} MB fp32) exceed "
+                  "or rival L2; no flush needed",
+            "denoiser_forwards_per_step": wl["steps"], "sharding": "independent puzzle batches per rank, no data-path collective",
+            "precision": "ours: bf16 tensor-core operands, fp32 accumulation and residual stream; reference arm: fp32 on the host cores"}
+
+
+def cpu_port_puzzles_per_s(wl, sample_batch=16, sample_steps=2):
     """The oracle port (torch fp32 CPU restatement of the reference path) on a BOUNDED sample: `sample_batch` puzzles x
     `sample_steps` of the 250 diffusion steps (every step is identical work - the reference feeds the same
     (condition, noise) to all of them) + the assignment, scaled to the full step count."""
@@ -208,7 +220,7 @@ def run_reference(args, wl):
         return run_reference_gpu(args, wl)
     vals, spent = [], 0.0
     for i in range(args.warmup + args.steps):
-        v, cores, sample, dt = cpu_port_puzzles_per_s(wl, sample_batch=4, sample_steps=2)
+        v, cores, sample, dt = cpu_port_puzzles_per_s(wl, sample_batch=16, sample_steps=2)
         if i >= args.warmup:
             vals.append(v); spent += dt
     value = statistics.mean(vals)
@@ -216,7 +228,7 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "puzzles/sec (3x3 @192px sampling)", "value": value, "unit": "puzzles/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * spent / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "diffusion_steps": wl["steps"], "grid": wl["grid"], "image_size": wl["size"]},
+        "config": sampling_config(wl, args.batch or wl["batch"]),
         "cpu_baseline": {"value": value, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "puzzles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -281,29 +293,76 @@ def kernel_roofline(model, wl, batch, peaks):
         ms = e0.elapsed_time(e1) / n
         if kind == "flop":
             ach = work / (ms * 1e-3) / 1e12
-            out[name] = {"ms": ms, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"]}
+            out[name] = {"ms": ms, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["bf16"]}
         else:
             ach = work / (ms * 1e-3) / 1e9
             out[name] = {"ms": ms, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
     top = "gemm_fc1 (tcgen05, bias+gelu)"
     traffic, traffic_src = ncu_traffic("fc1")
-    roof = {"bound": "tensor", "kernel": top, "achieved": out[top]["achieved"], "peak": peaks["bf16_sustained"],
+    roof = {"bound": "tensor", "kernel": top, "achieved": out[top]["achieved"], "peak": peaks["bf16"],
             "unit": "TFLOP/s", "frac": out[top]["frac"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read + write)",
             "traffic_source": traffic_src, "algorithmic_bytes": M * 768 * 2.0 + 3072 * 768 * 2.0 + M * 3072 * 2.0,
-            "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+            "peak_source": f"{peaks['source']} bf16 burst (the kernel is timed alone, 10 back-to-back launches; every entry of "
+                           "`kernels` uses the same burst / HBM peaks)",
+            "frac_of_sustained": out[top]["achieved"] / peaks["bf16_sustained"],
             "how": "CUDA events on the launching stream over 10 back-to-back launches at the bench shape "
                    f"(M={M}, activations > L2); algorithmic FLOPs 2*M*768*3072"}
     return roof, out
+
+
+def build_sampler(wl, batch, rank, dev):
+    """Model (random seeded weights), diffusion and the synthetic puzzle batch of one rank; inputs pinned on the host."""
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT_models
+    from jpdvt_mt_ntnu_b200.weights import seeded_state
+    model = DiT_models["JPDVT"](input_size=wl["size"])
+    model.load_state_dict(seeded_state(model.state_dict(), seed=1234))
+    model.to(dev)
+    diffusion = create_diffusion(str(wl["steps"]))
+    cond_h, noise_h, perms = synthetic_inputs(wl, batch, seed=rank)
+    return model, diffusion, cond_h.pin_memory(), noise_h.pin_memory(), perms
+
+
+def measure_strong(wl, total, world, rank, dev, steps, model=None, diffusion=None):
+    """The sharded-batch form of a sampling config (SURVEY.md 8d/8e; reference: image_paths[rank::world_size],
+    inference_ddp.py:325): `total` puzzles split over the ranks, each rank solving total / world of them with the loop
+    replayed from a CUDA graph (small per-GPU batches are launch-bound), one all_gather of the placements per pass."""
+    import torch
+    import torch.distributed as dist
+    from jpdvt_mt_ntnu_b200 import _lib, assignment
+    per = total // world
+    G = wl["grid"]
+    if model is None:
+        model, diffusion, cond_pin, noise_pin, _ = build_sampler(wl, per, rank, dev)
+    else:
+        cond_h, noise_h, _ = synthetic_inputs(wl, per, seed=100 + rank)
+        cond_pin, noise_pin = cond_h.pin_memory(), noise_h.pin_memory()
+    cond, noise = cond_pin.to(dev), noise_pin.to(dev)
+    gathered = [torch.empty(per, G * G, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    graph = per <= 64
+
+    def one(c, z):
+        sample = diffusion.p_sample_loop(model.forward, c, z.shape, z, clip_denoised=False, model_kwargs=None, progress=False,
+                                         device=dev, graph=graph)
+        order, pred = assignment.solve_puzzles(sample, G)
+        if world > 1:
+            dist.all_gather(gathered, pred)
+        return pred
+
+    for _ in range(2):
+        one(cond, noise)
+    ms, _ = _timed(lambda: one(cond, noise), steps, world, dev)
+    ms_e2e, _ = _timed(lambda: one(cond_pin.to(dev, non_blocking=True), noise_pin.to(dev, non_blocking=True)).cpu(), steps, world, dev)
+    return {"workload": wl["name"].split(",")[0], "total_puzzles": per * world, "batch_per_gpu": per, "graph_replay": graph,
+            "value": per * world * steps / (ms * 1e-3), "unit": "puzzles/s", "ms_per_pass": ms / steps,
+            "e2e": {"value": per * world * steps / (ms_e2e * 1e-3), "unit": "puzzles/s", "ms_per_pass": ms_e2e / steps}}
 
 
 def run_ours(args, wl):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jpdvt_mt_ntnu_b200 import assignment
-    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
-    from jpdvt_mt_ntnu_b200.models import DiT_models
-    from jpdvt_mt_ntnu_b200.weights import seeded_state
+    from jpdvt_mt_ntnu_b200 import _lib, assignment
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -316,14 +375,9 @@ def run_ours(args, wl):
     S, G = wl["size"], wl["grid"]
     T = (S // 16) ** 2
 
-    model = DiT_models["JPDVT"](input_size=S)
-    model.load_state_dict(seeded_state(model.state_dict(), seed=1234))
-    model.to(dev)
-    diffusion = create_diffusion(str(wl["steps"]))
-    cond_h, noise_h, perms = synthetic_inputs(wl, batch, seed=rank)
-    cond_pin, noise_pin = cond_h.pin_memory(), noise_h.pin_memory()
+    model, diffusion, cond_pin, noise_pin, perms = build_sampler(wl, batch, rank, dev)
     cond, noise = cond_pin.to(dev), noise_pin.to(dev)
-    torch.manual_seed(rank)        # the loop draws its own randn_like per step inside the timed region, as p_sample does (:424)
+    torch.manual_seed(rank)        # seeds the per-step noise p_sample draws inside the loop (gaussian_diffusion.py:424)
     gathered = [torch.empty(batch, G * G, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
 
     def one_step(c, z):
@@ -334,28 +388,13 @@ def run_ours(args, wl):
             dist.all_gather(gathered, pred)          # the only cross-rank traffic: int32 placements (inference_ddp.py:485-495)
         return pred
 
-    def timed(fn, k):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = None
-        for _ in range(k):
-            out = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), out
-
     for _ in range(args.warmup):
         one_step(cond, noise)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, pred = timed(lambda: one_step(cond, noise), args.steps)
+    n0 = _lib.launch_count()
+    ms, pred = _timed(lambda: one_step(cond, noise), args.steps, world, dev)
+    launches = _lib.launch_count() - n0
     value = batch * world * args.steps / (ms * 1e-3)
 
     def e2e_step():
@@ -364,22 +403,46 @@ def run_ours(args, wl):
         return one_step(c, z).cpu()
 
     e2e_step()
-    ms_e2e, pred_host = timed(e2e_step, args.steps)
+    ms_e2e, pred_host = _timed(e2e_step, args.steps, world, dev)
     clock_info = clocks.stop()
     e2e_value = batch * world * args.steps / (ms_e2e * 1e-3)
 
+    # ---- the sharded-batch (strong-scaling) form: the config's puzzle count is the WHOLE job's, split over the ranks
+    strong = None
+    if not args.no_extras and wl is WORKLOADS["c2"]:
+        strong = {"c2": measure_strong(wl, 256, world, rank, dev, max(2, args.steps), model, diffusion)}
+        del model
+        torch.cuda.empty_cache()
+        model = None
+        c5 = WORKLOADS["c5"]
+        strong["c5"] = measure_strong(c5, 128, world, rank, dev, 2)
+        torch.cuda.empty_cache()
+    # ---- BASELINE.json's other metric: train img/s (configs[2]) with the NCCL gradient all-reduce at this N
+    train = None
+    if not args.no_extras and wl is WORKLOADS["c2"]:
+        tclocks = ClockSampler(local)
+        tclocks.start()
+        train = measure_training(WORKLOADS["c3"], WORKLOADS["c3"]["batch"], 10, 3, world, rank, dev)
+        train["clocks"] = tclocks.stop()
+
     if rank == 0:
         peaks = measured_peaks()
+        if model is None:
+            model = build_sampler(wl, batch, rank, dev)[0]
         roof, breakdown = kernel_roofline(model, wl, batch, peaks)
-        if world == 1:
+        cpu_obj, stock = None, None
+        if world == 1:           # reported at N=1 only (torchrun pins the ranks to one host thread each)
             cpu_v, cores, sample, _ = cpu_port_puzzles_per_s(wl)
             cpu_obj = {"value": cpu_v, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample}
-        else:
-            cpu_obj = None      # reported at N=1 only (torchrun pins the ranks to one host thread each)
-        # per diffusion step: patchify, patch-embed, 7 per block, final LN / final / head GEMMs, posterior update; per loop:
-        # the hoisted conditioning (2 timestep kernels + one adaLN GEMV per 8 steps) and the assignment kernel
-        fwd_launches = 2 + 7 * DEPTH + 3
-        launches = args.steps * (wl["steps"] * (fwd_launches + 1) + 2 + (wl["steps"] + 7) // 8 + 1)
+            if not args.no_extras:
+                del model
+                torch.cuda.empty_cache()
+                stock = {"what": "the reference path's stock torch ops (cuBLAS / ATen / fused SDPA - none of this repo's kernels) on "
+                                 "the same B200 and batch, a few of the 250 steps scaled up + the host assignment loop",
+                         "unit": "puzzles/s"}
+                for prec in ("fp32", "tf32", "bf16"):
+                    v, ms_step, _ = stock_torch_gpu_puzzles_per_s(wl, batch, prec, sample_steps=3)
+                    stock[prec] = {"value": v, "ms_per_diffusion_step": ms_step}
         solved = float((pred_host.numpy() == perms).all(axis=1).mean())
         flops = flops_per_forward(T) * wl["steps"] * batch * args.steps
         line = {
@@ -387,19 +450,20 @@ def run_ours(args, wl):
             "value": value, "unit": "puzzles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": batch, "diffusion_steps": wl["steps"], "grid": G,
-                       "image_size": S, "tokens": T, "weights": "random N(0,0.02), seed 1234 (fresh init outputs zeros)",
-                       "l2": "activations per launch (>= 57 MB bf16 / 113 MB fp32 at M=36864) exceed L2; no flush needed",
-                       "denoiser_forwards_per_step": wl["steps"], "sharding": "independent puzzle batches per rank, no data-path collective"},
+            "config": sampling_config(wl, batch),
             "e2e": {"value": e2e_value, "unit": "puzzles/s", "h2d_bytes_per_step": int(cond_pin.numel() * 4 + noise_pin.numel() * 4),
                     "d2h_bytes_per_step": int(batch * G * G * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
+            "gpu_launches_how": "jpdvt_launch_count() before / after the timed region (every launch site of the library counts itself)",
             "clocks": clock_info,
             "roofline": roof,
             "kernels": breakdown,
             "model_tflops": flops / (ms * 1e-3) / 1e12,
-            "model_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "model_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"] / world,
             "cpu_baseline": cpu_obj,
+            "gpu_stock_baseline": stock,
+            "strong": strong,
+            "train": train,
             "puzzles_solved_frac_random_weights": solved,
         }
         print(json.dumps(line))
@@ -439,22 +503,35 @@ def cpu_port_train_img_per_s(wl, sample_batch=2):
     return sample_batch / times[-1], cores, f"{sample_batch} images, one fwd+bwd+AdamW step (second of two)", sum(times)
 
 
-def run_train(args, wl):
+def _timed(fn, k, world, dev):
+    """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks."""
     import torch
     import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(k):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), out
+
+
+def measure_training(wl, batch, steps, warmup, world, rank, dev):
+    """BASELINE.json configs[2]: data-parallel training steps (training_losses -> backward -> NCCL gradient all-reduce ->
+    fused AdamW + EMA, train_JPDVT.py:357-372) through `Trainer`; returns the numbers of the `train` object."""
+    import torch
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from jpdvt_mt_ntnu_b200.models import DiT_models, get_2d_sincos_pos_embed
     from jpdvt_mt_ntnu_b200.trainer import Trainer
     from jpdvt_mt_ntnu_b200.weights import seeded_state
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    batch = args.batch or wl["batch"]
     S, G = wl["size"], wl["grid"]
     T = (S // 16) ** 2
     model = DiT_models["JPDVT"](input_size=S)
@@ -473,56 +550,67 @@ def run_train(args, wl):
         t = torch.randint(0, diffusion.num_timesteps, (batch,), device=dev)          # train_JPDVT.py:354
         return trainer.step(xin, t, piece, **kw)
 
-    def timed(fn, k):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = None
-        for _ in range(k):
-            out = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), out
-
-    steps = max(args.steps, 10)
-    for _ in range(max(args.warmup, 3)):
+    from jpdvt_mt_ntnu_b200 import _lib
+    for _ in range(max(warmup, 3)):
         one_step(x)
+    n0 = _lib.launch_count()
+    ms, loss = _timed(lambda: one_step(x), steps, world, dev)
+    launches = _lib.launch_count() - n0
+    ms_e2e, loss_h = _timed(lambda: one_step(x_pin.to(dev, non_blocking=True)).cpu(), steps, world, dev)
+    flops = 3.0 * flops_per_forward(T) * batch * steps
+    mode = "none (1 GPU)"
+    if world > 1:
+        mode = trainer.allreduce_description()
+    out = {"value": batch * world * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "steps": steps,
+           "batch_per_gpu": batch, "workload": wl["name"], "params": trainer.total, "allreduce": mode,
+           "e2e": {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+           "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "final_loss": float(loss_h),
+           "gpu_launches": launches}
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch or wl["batch"]
+    S, G = wl["size"], wl["grid"]
+    T = (S // 16) ** 2
+    steps = max(args.steps, 10)
     clocks = ClockSampler(local)
     clocks.start()
-    ms, loss = timed(lambda: one_step(x), steps)
-    value = batch * world * steps / (ms * 1e-3)
-    ms_e2e, loss_h = timed(lambda: one_step(x_pin.to(dev, non_blocking=True)).cpu(), steps)
+    tr = measure_training(wl, batch, steps, args.warmup, world, rank, dev)
     clock_info = clocks.stop()
     if rank == 0:
         peaks = measured_peaks()
-        flops = 3.0 * flops_per_forward(T) * batch * steps
         cpu_obj = None
         if world == 1:
             v, cores, sample, _ = cpu_port_train_img_per_s(wl)
             cpu_obj = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample}
-        n_params = trainer.total
         line = {
-            "metric": "train img/s", "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "metric": "train img/s", "value": tr["value"], "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "image_size": S, "grid": G, "tokens": T,
-                       "optimizer": "AdamW lr 1e-4 wd 0 + EMA 0.9999 (fused, fp32 state)", "params": n_params,
-                       "allreduce": ("NCCL SUM per backward stage, overlapped with the remaining backward" if trainer.allreduce == "stage" else "one NCCL SUM of the flat fp32 gradient buffer (523 MB) after the backward") if world > 1 else "none (1 GPU)",
-                       "l2": "activations per launch exceed L2; no flush needed"},
-            "e2e": {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
-            "gpu_launches": steps * (12 * 8 + 8 + 12 * 21 + 40), "clocks": clock_info,
-            "model_tflops": flops / (ms * 1e-3) / 1e12, "model_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                       "optimizer": "AdamW lr 1e-4 wd 0 + EMA 0.9999 (fused, fp32 state)", "params": tr["params"],
+                       "allreduce": tr["allreduce"], "l2": "activations per launch exceed L2; no flush needed"},
+            "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "clocks": clock_info,
+            "model_tflops": tr["model_tflops_per_gpu"] * world,
+            "model_frac_of_bf16_sustained": tr["model_tflops_per_gpu"] / peaks["bf16_sustained"],
             "roofline": {"bound": "tensor", "kernel": "whole training step (3 x forward FLOPs: fwd + dgrad + wgrad)",
-                         "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None},
-            "cpu_baseline": cpu_obj, "final_loss": float(loss_h),
+                         "achieved": tr["model_tflops_per_gpu"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tr["model_tflops_per_gpu"] / peaks["bf16_sustained"], "traffic": None},
+            "cpu_baseline": cpu_obj, "final_loss": tr["final_loss"],
         }
         print(json.dumps(line))
     if world > 1:
@@ -541,6 +629,8 @@ def main():
     ap.add_argument("--ref-precision", default="fp32,tf32,bf16")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="puzzles per GPU (default: the workload's)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the headline sampling measurement (skip the strong-scaling, training and stock-torch legs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3            # timing rule: at least 3 warm-up steps
@@ -551,8 +641,10 @@ def main():
     if args.impl == "reference" or world == 1:
         for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
             os.environ[var] = str(os.cpu_count() or 1)
-    if not os.environ.get("JPDVT_KEEP_NCCL_DEBUG"):
-        os.environ.pop("NCCL_DEBUG", None)     # NCCL prints its version banner on stdout; keep stdout to the one JSON line
+    # NCCL logs to stdout by default; stdout carries the one JSON line, so its log (whatever NCCL_DEBUG level the caller
+    # set - the driver reads the communicator's rank count from it) goes to stderr instead of being switched off
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     if args.impl == "reference":
         run_reference(args, wl)
     elif wl.get("train"):

@@ -40,6 +40,8 @@ typedef uint16_t jpdvt_bf16;
 
 int jpdvt_abi_version(void);
 const char* jpdvt_last_error_string(void);
+/* Kernels this library has launched in the calling process so far (every launch site counts itself). */
+int64_t jpdvt_launch_count(void);
 /* Checks that the current device is sm_100 (B200); returns JPDVT_ERR_UNSUPPORTED otherwise.  No CPU fallback exists. */
 int jpdvt_device_check(void);
 

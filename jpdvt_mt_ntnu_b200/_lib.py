@@ -122,7 +122,7 @@ PROTOTYPES = {
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],
 }
 OTHER_SYMBOLS = ["jpdvt_abi_version", "jpdvt_last_error_string", "jpdvt_wgrad_scratch_floats", "jpdvt_train_wgrad_scratch_floats",
-                 "jpdvt_bwd_part_floats", "jpdvt_mse_part_floats"]
+                 "jpdvt_bwd_part_floats", "jpdvt_mse_part_floats", "jpdvt_launch_count"]
 
 _lock = threading.Lock()
 _lib = None
@@ -163,6 +163,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         lib.jpdvt_bwd_part_floats.restype = c_int64
         lib.jpdvt_mse_part_floats.argtypes = [c_int]
         lib.jpdvt_mse_part_floats.restype = c_int64
+        lib.jpdvt_launch_count.argtypes = []
+        lib.jpdvt_launch_count.restype = c_int64
         lib.jpdvt_abi_version.restype = c_int
         lib.jpdvt_last_error_string.restype = C.c_char_p
         got = lib.jpdvt_abi_version()
@@ -171,6 +173,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                              "rebuild it with `python -m jpdvt_mt_ntnu_b200.build --force`")
         _lib = lib
         return lib
+
+
+def launch_count() -> int:
+    """Kernels launched by libjpdvt_sm100.so in this process so far."""
+    return int(load().jpdvt_launch_count())
 
 
 def last_error() -> str:

@@ -1,5 +1,6 @@
 // C ABI of libjpdvt_sm100.so (see include/jpdvt_b200.h) + the launch sequences for one denoiser forward and for the
 // whole reverse-diffusion loop.  Host code here only validates arguments and enqueues kernels on the caller's stream.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +28,13 @@ bool pdl_enabled() {
   return pdl != 0;
 }
 
+// every kernel launch site of the library calls check_launch exactly once after its launch: the running count is what
+// jpdvt_launch_count() reports (bench.py's `gpu_launches` is a difference of two readings, not an estimate)
+static std::atomic<long long> g_launches{0};
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(kErrCuda, "%s: launch failed: %s", what, cudaGetErrorString(e));
   return kOk;
@@ -246,6 +253,7 @@ using namespace jp;
 extern "C" {
 
 int jpdvt_abi_version(void) { return JPDVT_ABI_VERSION; }
+int64_t jpdvt_launch_count(void) { return launch_count(); }
 const char* jpdvt_last_error_string(void) { return g_err; }
 
 int jpdvt_device_check(void) {

@@ -37,6 +37,7 @@ inline cudaError_t launch_pdl(void (*kern)(KP...), dim3 grid, dim3 block, size_t
   return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
 }
 int check_launch(const char* what);
+long long launch_count();
 
 // GEMM epilogues (see gemm.cu)
 enum Epilogue : int {

@@ -189,6 +189,14 @@ class Trainer:
         self.engine.last_flat = None
         return loss.detach()
 
+    def allreduce_description(self) -> str:
+        if self.world == 1:
+            return "none (1 GPU)"
+        mb = self.total * 4 / 1e6
+        if self.allreduce == "stage":
+            return f"NCCL SUM per backward stage ({mb:.0f} MB in {self.model.depth + 2} pieces), overlapped with the remaining backward"
+        return f"one NCCL SUM of the flat fp32 gradient buffer ({mb:.0f} MB) after the backward, 1/world folded into the optimizer kernel"
+
     # ------------------------------------------------------------------ checkpoint views (train_JPDVT.py:410-416)
     def ema_state_dict(self) -> Dict[str, torch.Tensor]:
         views, off = {}, 0

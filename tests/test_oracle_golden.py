@@ -86,7 +86,7 @@ def test_sampling_loop_matches_reference(golden, name):
         assert list(order) == g["order"][b].tolist() and list(pred) == g["pred"][b].tolist()
 
 
-@pytest.mark.parametrize("name", ["d2_192_s250", "full192_s250"])
+@pytest.mark.parametrize("name", ["d2_192_s250", "full192_s250", "c4_256g4_s250", "c5_288_miss_s250"])
 def test_loop_quirk_one_forward_equals_loop(golden, name):
     """the reference loop result is ONE forward at t=0 on the initial noise (gaussian_diffusion.py:518-529)."""
     case = cases.SAMPLING_CASES[name]
