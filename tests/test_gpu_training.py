@@ -2,8 +2,10 @@
 unmodified reference (fp32 autograd on CPU).
 
 Tolerances (bf16 tensor-core operands, fp32 accumulation): per-sample mse rel-err <= 1e-2; per-parameter gradient
-cosine >= 0.995 and norm rel-err <= 3e-2 on the stored 64-element heads / norms (SURVEY.md 8c asks cosine >= 0.999 for
-tensors with a healthy signal; the smallest gradients here sit at bf16 noise level, hence the looser common bound).
+cosine >= 0.999 (SURVEY.md 8c's contract) on the stored 64-element heads and norm rel-err <= 1e-2 against the reference
+fixtures; against fp32 autograd through the oracle EVERY trainable tensor of all four cases must reach cosine >= 0.9995 and
+rel-L2 <= 1e-2.  Measured per tensor (tools/grad_parity.py -> profiles/r2a_grad_parity_table.json, 36 tensors x 4 cases):
+worst cosine 0.99999, worst rel-L2 4.6e-3, smallest reference norm 2.4e-4 - no tensor needs a looser bound.
 """
 import numpy as np
 import pytest
@@ -47,9 +49,9 @@ def test_training_losses_and_grads_vs_reference(cuda, golden, name):
         want_norm = float(g["grad_norm/" + key])
         want_head = torch.from_numpy(g["grad_head/" + key])
         got_head = grad.reshape(-1)[:64].cpu()
-        assert abs(grad.norm().item() - want_norm) <= 3e-2 * want_norm, (key, grad.norm().item(), want_norm)
+        assert abs(grad.norm().item() - want_norm) <= 1e-2 * want_norm, (key, grad.norm().item(), want_norm)
         cos = torch.nn.functional.cosine_similarity(got_head.double(), want_head.double(), dim=0).item()
-        assert cos > 0.995, (key, cos)
+        assert cos > 0.999, (key, cos)
 
 
 def test_every_trainable_parameter_gets_a_gradient(cuda):
@@ -61,29 +63,28 @@ def test_every_trainable_parameter_gets_a_gradient(cuda):
             assert p.grad.abs().max() > 0, name
 
 
-def test_gradients_match_oracle_autograd_fullcheck(cuda):
-    """Every parameter's gradient against fp32 autograd through the CPU oracle on the same draws."""
+@pytest.mark.parametrize("name", list(cases.TRAINING_CASES))
+def test_gradients_match_oracle_autograd_fullcheck(cuda, name):
+    """Every parameter's gradient against fp32 autograd through the CPU oracle on the same draws (the oracle's loss is
+    pinned to the reference at 1e-5 when the fixtures are generated, oracle/make_golden.py: golden_training)."""
     from oracle import jpdvt_oracle as orc
-    case = cases.TRAINING_CASES["tiny96"]
-    m, terms = _run(case, False)
+    case = cases.TRAINING_CASES[name]
+    m, terms = _run(case, case["add_mask"])
     st = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in cases.state_for(case).items()}
     x, t, piece = cases.training_inputs(case)
     d = cases.training_draws(case)
     model = orc.OracleDenoiser.__new__(orc.OracleDenoiser)
     model.w, model.depth, model.heads, model.patch = st, case["depth"], 12, 16
     o = orc.training_losses(orc.Schedule(""), model, x, t, piece, d["perm"], d["noise_x"], d["noise_te"],
-                            block_size=case["size"] // case["grid"], grid=case["grid"], masks=None)
+                            block_size=case["size"] // case["grid"], grid=case["grid"], masks=d["masks"])
     o["loss"].mean().backward()
-    worst = 1.0
-    for name, p in m.named_parameters():
+    for pname, p in m.named_parameters():
         if not p.requires_grad:
             continue
-        ref = st[name].grad
+        ref = st[pname].grad
         cos = torch.nn.functional.cosine_similarity(p.grad.cpu().double().flatten(), ref.double().flatten(), dim=0).item()
-        worst = min(worst, cos)
-        assert cos > 0.99, (name, cos)
-        assert rel_l2(p.grad.cpu(), ref) < 0.15, (name, rel_l2(p.grad.cpu(), ref))
-    assert worst > 0.99
+        assert cos > 0.9995, (pname, cos)
+        assert rel_l2(p.grad.cpu(), ref) < 1e-2, (pname, rel_l2(p.grad.cpu(), ref))
 
 
 def test_adamw_step_changes_outputs_and_engines_refresh(cuda):
