@@ -443,6 +443,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
+  if (attention_bwd_tc_supported(tokens)) return launch_attention_bwd_tc(qkv, o, d_o, lse2, dqkv, batch, tokens, stream);
   if (batch > 65535) return set_error(kErrBadArg, "attention_bwd: batch %d exceeds gridDim.y limit", batch);
   const int mt = (tokens + 15) / 16;
   int nw = (mt % 3 == 0) ? 3 : 4;

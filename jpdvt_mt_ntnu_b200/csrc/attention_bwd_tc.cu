@@ -1,0 +1,451 @@
+// tcgen05 attention backward for the JPDVT piece tokens (training): dQ, dK, dV of softmax(Q K^T / 8) V per (sample, head),
+// all five contractions on the 5th-generation tensor cores with the score-sized tiles living in TMEM.
+//
+// Replaces the autograd of timm Attention.forward's F.scaled_dot_product_attention (image_model/models.py:108,120, reached
+// from loss.backward() in train_JPDVT.py:369) for T = 144 (192 px, BASELINE configs[2]); the mma.sync kernel in attention.cu
+// keeps the other sizes.  Flash-attention style: the probabilities are recomputed from the forward's log-sum-exp.
+//
+//   S^T  = K Q^T          P^T  = exp2(S^T * log2(e)/8 - lse2[q])            (rows = keys, columns = queries)
+//   dP^T = V dO^T         dS^T = P^T * (dP^T - D[q]) / 8,   D[q] = sum_d dO[q,d] O[q,d]
+//   dV   = P^T dO         dK   = dS^T Q          dQ = dS K
+//
+// Everything is kept in the TRANSPOSED orientation (TMEM lane = key): P^T and dS^T then sit in shared memory as K-major
+// [key][query] tiles, which is what dV and dK want as their A operand, and dQ reads the same dS^T tile MN-major - no
+// transposition anywhere.  One CTA per SM walks (sample, head) units:
+//   warps 0-3 : D and lse2 of the unit, then thread = key row: S^T / dP^T out of TMEM -> P^T, dS^T (bf16) into shared memory;
+//               later the epilogue: dV / dK / dQ accumulators -> bf16 -> coalesced rows of dqkv [B*T, 2304]
+//   warp 4    : TMA producer - Q, K, V of the head out of the fused QKV activation, dO and O out of [B*T, 768]
+//   warp 5    : MMA issuer
+// T = 144 = 128 + 16.  Rows (keys) 128..143 are NOT given a second 128-row pass in the transposed orientation (one warp would
+// do all its softmax work): their scores come from two small MMAs in the UNtransposed orientation, S[q, 128:144] = Q K_tail^T
+// (query rows 0..127, and again with the query rows shifted by 16 so that lanes 112..127 hold queries 128..143), so every
+// thread handles one query row x 16 keys and writes its 16 probabilities transposed (2-byte stores, contiguous per warp).
+// The 16-row remainder of each OUTPUT is a second MMA pass over the A operand shifted by 16 rows (dV, dK: K-major rows
+// [16,144), valid lanes 112..127) or over query blocks 2,3 of the MN-major dS^T tile (dQ: valid lanes 0..15).
+// TMEM (512 columns): phase 1  S^T [0,144) dP^T [144,288) tails [288,352);  phase 2 (aliases phase 1, consumed by then)
+// dV0 dV1 dK0 dK1 dQ0 dQ1, 64 columns each.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jp {
+
+namespace {
+
+constexpr int kBtThreads = 192;
+constexpr int kQkvCols = 3 * kHidden;
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// tcgen05.mma from split descriptor words (see attention_tc.cu): low word = start address (+ LBO), high word shared
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);        // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi)
+      : "memory");
+}
+
+template <int T>
+struct BtCfg {
+  static_assert(T == 144, "the tcgen05 attention backward is laid out for 128 + 16 tokens");
+  static constexpr int kTile = T * 128;                      // one of Q / K / V / dO / O: T rows x 64 bf16, 128-byte swizzled
+  static constexpr int kQBlocks = (T + 63) / 64;             // 64-query blocks of the P^T / dS^T tiles
+  static constexpr int kBlk = T * 128;                       // one block: T key rows x 128 B
+  static constexpr int kOffQ = 0, kOffK = kTile, kOffV = 2 * kTile, kOffdO = 3 * kTile, kOffO = 4 * kTile;
+  static constexpr int kOffdS = 5 * kTile;                   // dS^T first: dQ's second pass reads "blocks 2, 3" of it, block 3
+  static constexpr int kOffP = kOffdS + kQBlocks * kBlk;     // being the first block of P^T (finite garbage in discarded rows)
+  static constexpr int kOffStage = kOffP + kQBlocks * kBlk;  // 4 x 4 KB epilogue staging
+  static constexpr int kOffL = kOffStage + 4 * 4096;         // lse2[T], D[T] fp32
+  static constexpr int kBarOff = kOffL + 2 * ((T * 4 + 127) / 128 * 128);
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;    // + alignment slack
+  static constexpr int kInBytes = 5 * kTile;
+  static_assert(kTile % 1024 == 0 && kBlk % 1024 == 0 && kOffP % 1024 == 0 && kOffStage % 1024 == 0, "swizzle atoms");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+  // TMEM columns
+  static constexpr int kColS = 0, kColdP = T, kColSt0 = 2 * T, kColSt1 = 2 * T + 16, kColdPt0 = 2 * T + 32, kColdPt1 = 2 * T + 48;
+  static constexpr int kColdV0 = 0, kColdV1 = 64, kColdK0 = 128, kColdK1 = 192, kColdQ0 = 256, kColdQ1 = 320;
+  static_assert(2 * T + 64 <= 512, "TMEM columns");
+};
+
+// 32 accumulator rows of this warp (TMEM lane = row, 64 fp32 columns) -> bf16 -> global rows of `ld` elements.  The 32 x 128 B
+// tile is transposed through a 4 KB staging tile (XOR-swizzled 16-byte chunks) so that every store instruction writes four
+// full 128-byte rows.  Rows r with lo <= r < hi are live.
+__device__ __forceinline__ void store_acc_rows(uint32_t t_row, uint32_t stage, __nv_bfloat16* dst_row0, long long ld, int lo, int hi,
+                                               int lane) {
+  uint32_t a[32], b[32];
+  tmem_ld_32x32(t_row, a);
+  tmem_ld_32x32(t_row + 32, b);
+  tmem_ld_wait();
+  const uint32_t mine = stage + lane * 128, sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sts_u4(mine + ((j ^ sw) << 4),
+           make_uint4(pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
+                      pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
+                      pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
+                      pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7]))));
+    sts_u4(mine + (((4 + j) ^ sw) << 4),
+           make_uint4(pack_bf16(__uint_as_float(b[8 * j]), __uint_as_float(b[8 * j + 1])),
+                      pack_bf16(__uint_as_float(b[8 * j + 2]), __uint_as_float(b[8 * j + 3])),
+                      pack_bf16(__uint_as_float(b[8 * j + 4]), __uint_as_float(b[8 * j + 5])),
+                      pack_bf16(__uint_as_float(b[8 * j + 6]), __uint_as_float(b[8 * j + 7]))));
+  }
+  __syncwarp();
+  const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub;
+    const uint4 u = lds_u4(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+    if (r >= lo && r < hi) *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(r) * ld + ch * 8) = u;
+  }
+  __syncwarp();
+}
+
+template <int T>
+__global__ void __launch_bounds__(kBtThreads, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_o, const float* __restrict__ lse2, __nv_bfloat16* __restrict__ dqkv,
+                        int num_units) {
+  using Cfg = BtCfg<T>;
+  extern __shared__ uint8_t att_bt_smem[];
+  uint8_t* smem = att_bt_smem + ((1024u - (smem_u32(att_bt_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* in_full = bars + 0;        // TMA: Q, K, V, dO, O of the unit landed
+  uint64_t* s_full = bars + 1;         // MMA: S^T, dP^T and the tails are in TMEM
+  uint64_t* p_full = bars + 2;         // math warps: P^T, dS^T are in shared memory, phase-1 TMEM columns consumed (4 arrivals)
+  uint64_t* o_full = bars + 3;         // MMA: dV, dK, dQ are in TMEM; every operand tile of the unit has been read
+  uint64_t* epi_done = bars + 4;       // math warps: accumulators have left TMEM (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sL = reinterpret_cast<float*>(smem + Cfg::kOffL);
+  float* sD = sL + (T * 4 + 127) / 128 * 32;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(in_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(epi_done, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sdO = smem_u32(smem + Cfg::kOffdO), sO = smem_u32(smem + Cfg::kOffO), sdS = smem_u32(smem + Cfg::kOffdS),
+                 sP = smem_u32(smem + Cfg::kOffP);
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int b = unit / kHeads, h = unit - b * kHeads;
+        if (it > 0) mbar_wait_backoff(o_full, static_cast<uint32_t>((it - 1) & 1), 64);   // the previous unit's MMAs have read every tile
+        mbar_expect_tx(in_full, Cfg::kInBytes);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+        tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO, h * kHeadDim, b * T);
+        tma_load_2d(&tm_o, in_full, smem + Cfg::kOffO, h * kHeadDim, b * T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);                 // S^T / dP^T: M = 128 keys, N = T queries
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 16);                // tails: M = 128 queries, N = 16 keys
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHeadDim, 0, 1);   // dV, dK: A K-major, B (dO / Q) MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHeadDim, 1, 1);    // dQ: A (dS^T) and B (K) both MN-major
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), v_lo = desc_lo_k(sV), do_lo = desc_lo_k(sdO);
+      const uint32_t p_lo = desc_lo_k(sP), ds_lo = desc_lo_k(sdS);
+      const uint32_t do_mn = desc_lo_mn(sdO, 8192), q_mn = desc_lo_mn(sQ, 8192), k_mn = desc_lo_mn(sK, 8192);
+      const uint32_t ds_mn = desc_lo_mn(sdS, Cfg::kBlk);                    // next 64 queries: one block further
+      constexpr uint32_t kBlkW = Cfg::kBlk / 16;                            // block stride in descriptor units (16 B)
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        mbar_wait(in_full, ph);
+        if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // the previous unit's accumulators have left TMEM
+        tc_fence_after();
+        // ---- phase 1: scores and their gradient
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColS, k_lo, q_lo, idesc_s);
+          else umma_lohi<true>(tmem_base + Cfg::kColS, k_lo + 2 * k, q_lo + 2 * k, idesc_s);
+        }
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColdP, v_lo, do_lo, idesc_s);
+          else umma_lohi<true>(tmem_base + Cfg::kColdP, v_lo + 2 * k, do_lo + 2 * k, idesc_s);
+        }
+        // tails, untransposed: [query rows] x keys 128..143; pass 0 = queries 0..127, pass 1 = queries 16..143 (row shift 16)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const uint32_t sh = pass * 16 * 8;                                // 16 rows x 128 B in descriptor units
+          const uint32_t cs = pass ? Cfg::kColSt1 : Cfg::kColSt0, cp = pass ? Cfg::kColdPt1 : Cfg::kColdPt0;
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + cs, q_lo + sh, k_lo + 128 * 8, idesc_t);
+            else umma_lohi<true>(tmem_base + cs, q_lo + sh + 2 * k, k_lo + 128 * 8 + 2 * k, idesc_t);
+          }
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + cp, do_lo + sh, v_lo + 128 * 8, idesc_t);
+            else umma_lohi<true>(tmem_base + cp, do_lo + sh + 2 * k, v_lo + 128 * 8 + 2 * k, idesc_t);
+          }
+        }
+        umma_commit(s_full);
+        // ---- phase 2: the three gradients (contraction over all T queries / keys: T / 16 k-steps)
+        mbar_wait(p_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {                              // pass 1: A rows shifted by 16 -> keys 16..143
+          const uint32_t sh = pass * 16 * 8;
+#pragma unroll
+          for (int j = 0; j < T / 16; ++j) {
+            const uint32_t a = p_lo + sh + (j >> 2) * kBlkW + (j & 3) * 2, bq = do_mn + j * 128;
+            if (j == 0) umma_lohi<false>(tmem_base + (pass ? Cfg::kColdV1 : Cfg::kColdV0), a, bq, idesc_kv);
+            else umma_lohi<true>(tmem_base + (pass ? Cfg::kColdV1 : Cfg::kColdV0), a, bq, idesc_kv);
+          }
+#pragma unroll
+          for (int j = 0; j < T / 16; ++j) {
+            const uint32_t a = ds_lo + sh + (j >> 2) * kBlkW + (j & 3) * 2, bq = q_mn + j * 128;
+            if (j == 0) umma_lohi<false>(tmem_base + (pass ? Cfg::kColdK1 : Cfg::kColdK0), a, bq, idesc_kv);
+            else umma_lohi<true>(tmem_base + (pass ? Cfg::kColdK1 : Cfg::kColdK0), a, bq, idesc_kv);
+          }
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {                              // pass 1: query blocks 2, 3 (queries 128..)
+#pragma unroll
+          for (int j = 0; j < T / 16; ++j) {
+            const uint32_t a = ds_mn + pass * 2 * kBlkW + j * 128, bq = k_mn + j * 128;
+            if (j == 0) umma_lohi<false>(tmem_base + (pass ? Cfg::kColdQ1 : Cfg::kColdQ0), a, bq, idesc_q);
+            else umma_lohi<true>(tmem_base + (pass ? Cfg::kColdQ1 : Cfg::kColdQ0), a, bq, idesc_q);
+          }
+        }
+        umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- math + epilogue warps
+    constexpr float sl2 = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
+    const int tid = threadIdx.x;                              // 0..127 = TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t stage = smem_u32(smem + Cfg::kOffStage) + static_cast<uint32_t>(warp) * 4096u;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      const int b = unit / kHeads, h = unit - b * kHeads;
+      const float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+      mbar_wait(in_full, ph);
+      // ---- D[q] = sum_d dO[q, d] O[q, d] and lse2[q] for the unit's T queries (thread = query row; 16 threads take two)
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {
+        const int q = tid + rep * 128;
+        if (q < T) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t off = static_cast<uint32_t>(q) * 128u + static_cast<uint32_t>((j ^ (q & 7)) << 4);
+            const uint4 a = lds_u4(sdO + off), c = lds_u4(sO + off);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(cw[e] << 16), acc);
+              acc = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(cw[e] & 0xffff0000u), acc);
+            }
+          }
+          sD[q] = acc;
+          sL[q] = __ldg(lrow + q);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // ---- main tile: thread = key row `tid`, columns = queries; 16 columns per step, the next step's loads in flight
+      {
+        uint32_t sa[16], da[16], sb[16], db[16];
+        tmem_ld_32x16(t_lane + Cfg::kColS, sa);
+        tmem_ld_32x16(t_lane + Cfg::kColdP, da);
+        tmem_ld_wait();
+        const uint32_t prow = sP + static_cast<uint32_t>(tid) * 128u, dsrow = sdS + static_cast<uint32_t>(tid) * 128u;
+        const int sw = tid & 7;
+#pragma unroll
+        for (int c = 0; c < T / 16; ++c) {
+          uint32_t (&s_cur)[16] = (c & 1) ? sb : sa;
+          uint32_t (&d_cur)[16] = (c & 1) ? db : da;
+          uint32_t (&s_nxt)[16] = (c & 1) ? sa : sb;
+          uint32_t (&d_nxt)[16] = (c & 1) ? da : db;
+          if (c + 1 < T / 16) {
+            tmem_ld_32x16(t_lane + Cfg::kColS + 16 * (c + 1), s_nxt);
+            tmem_ld_32x16(t_lane + Cfg::kColdP + 16 * (c + 1), d_nxt);
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {                        // 8 queries -> one 16-byte chunk of the row
+            const int q0 = 16 * c + 8 * g;
+            const float4 l0 = *reinterpret_cast<const float4*>(sL + q0), l1 = *reinterpret_cast<const float4*>(sL + q0 + 4);
+            const float4 e0 = *reinterpret_cast<const float4*>(sD + q0), e1 = *reinterpret_cast<const float4*>(sD + q0 + 4);
+            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const float dv[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            float p[8], ds[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              p[e] = ex2f(fmaf(__uint_as_float(s_cur[8 * g + e]), sl2, -lv[e]));
+              ds[e] = p[e] * (__uint_as_float(d_cur[8 * g + e]) - dv[e]) * 0.125f;
+            }
+            const int chunk = q0 >> 3;                          // 16-byte chunk index along the row of T queries
+            const uint32_t off = static_cast<uint32_t>(chunk >> 3) * Cfg::kBlk + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4);
+            sts_u4(prow + off, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+            sts_u4(dsrow + off, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7])));
+          }
+          if (c + 1 < T / 16) tmem_ld_wait();
+        }
+      }
+      // ---- tails: thread = query row, 16 keys (128..143); written transposed into rows 128..143 of P^T / dS^T
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int q = pass ? tid + 16 : tid;                    // pass 1 (rows shifted by 16): lanes 112..127 hold queries 128..143
+        if (pass == 0 || warp == 3) {                            // warp-uniform: tcgen05.ld is a .sync.aligned instruction
+          uint32_t st[16], dt[16];
+          tmem_ld_32x16(t_lane + (pass ? Cfg::kColSt1 : Cfg::kColSt0), st);
+          tmem_ld_32x16(t_lane + (pass ? Cfg::kColdPt1 : Cfg::kColdPt0), dt);
+          tmem_ld_wait();
+          if (pass == 0 || lane >= 16) {                         // pass 1: only lanes 112..127 hold new rows (queries 128..143)
+            const float lq = sL[q], dq = sD[q];
+            const uint32_t col = static_cast<uint32_t>(q >> 6) * Cfg::kBlk + static_cast<uint32_t>((q & 7) * 2);
+            const int qc = (q & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p = ex2f(fmaf(__uint_as_float(st[j]), sl2, -lq));
+              const float ds = p * (__uint_as_float(dt[j]) - dq) * 0.125f;
+              const uint32_t off = static_cast<uint32_t>(128 + j) * 128u + static_cast<uint32_t>((qc ^ (j & 7)) << 4) + col;
+              sts_u16(sP + off, bf16_bits(p));
+              sts_u16(sdS + off, bf16_bits(ds));
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();                                 // generic-proxy stores -> visible to the tensor core's reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- epilogue: accumulators -> bf16 rows of dqkv (dQ | dK | dV column groups of the head)
+      __nv_bfloat16* base = dqkv + static_cast<long long>(b) * T * kQkvCols + h * kHeadDim;
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      __nv_bfloat16* row0 = base + static_cast<long long>(warp * 32) * kQkvCols;
+      store_acc_rows(t_lane + Cfg::kColdV0, stage, row0 + 2 * kHidden, kQkvCols, 0, 32, lane);
+      store_acc_rows(t_lane + Cfg::kColdK0, stage, row0 + kHidden, kQkvCols, 0, 32, lane);
+      store_acc_rows(t_lane + Cfg::kColdQ0, stage, row0, kQkvCols, 0, 32, lane);
+      if (warp == 3) {        // shifted pass: lane 112 + i holds key 128 + i, i.e. row (96 + 16) + r for this warp's lane r >= 16
+        __nv_bfloat16* r16 = base + static_cast<long long>(112) * kQkvCols;
+        store_acc_rows(t_lane + Cfg::kColdV1, stage, r16 + 2 * kHidden, kQkvCols, 16, 32, lane);
+        store_acc_rows(t_lane + Cfg::kColdK1, stage, r16 + kHidden, kQkvCols, 16, 32, lane);
+      }
+      if (warp == 0) {        // query blocks 2, 3: lane i holds query 128 + i
+        store_acc_rows(t_lane + Cfg::kColdQ1, stage, base + static_cast<long long>(128) * kQkvCols, kQkvCols, 0, 16, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int T>
+int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
+              int batch, cudaStream_t stream) {
+  using Cfg = BtCfg<T>;
+  static bool configured = false;
+  auto kern = attention_bwd_tc_kernel<T>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_bwd_tc: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    configured = true;
+  }
+  CUtensorMap tm_qkv, tm_do, tm_o;
+  const long long rows = static_cast<long long>(batch) * T;
+  int rc = make_tmap_bf16_kmajor(&tm_qkv, qkv, rows, kQkvCols, kQkvCols, T);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tm_do, d_o, rows, kHidden, kHidden, T);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tm_o, o, rows, kHidden, kHidden, T);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  kern<<<units < sms ? units : sms, kBtThreads, Cfg::kSmemBytes, stream>>>(tm_qkv, tm_do, tm_o, lse2, dqkv, units);
+  return check_launch("attention_bwd_tc_kernel");
+}
+
+}  // namespace
+
+bool attention_bwd_tc_supported(int tokens) {
+  static int legacy = -1;      // JPDVT_ATTN_BWD_LEGACY=1: the mma.sync backward for every size (A/B knob)
+  if (legacy < 0) { const char* e = getenv("JPDVT_ATTN_BWD_LEGACY"); legacy = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return !legacy && tokens == 144;
+}
+
+int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                            __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream) {
+  if (batch <= 0) return kOk;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(o) & 15) || (reinterpret_cast<uintptr_t>(d_o) & 15) ||
+      (reinterpret_cast<uintptr_t>(dqkv) & 15))
+    return set_error(kErrBadArg, "attention_bwd_tc: pointers must be 16-byte aligned");
+  switch (tokens) {
+    case 144: return launch_bt<144>(qkv, o, d_o, lse2, dqkv, batch, stream);
+    default: return set_error(kErrUnsupported, "attention_bwd_tc: %d tokens not instantiated", tokens);
+  }
+}
+
+}  // namespace jp

@@ -122,6 +122,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
 int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
                          __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
+// attention_bwd_tc.cu: tcgen05 / TMEM backward for the sizes attention_bwd_tc_supported() names
+bool attention_bwd_tc_supported(int tokens);
+int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
+                            __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
 
 // fold.cu: W' = W (1 + scale), u = rowsum(W'), v = b + W . shift for the qkv and fc1 matrices of every block (mod row 0)
 int launch_fold_ln(const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_fc1, const float* b_qkv, const float* b_fc1, const float* mod,

@@ -52,7 +52,7 @@ def test_dgelu_gate_ln_colsum(ops):
     assert rel_l2(ops.colsum(gp), gp.float().sum(0)) < 1e-5 and rel_l2(ops.colsum(dx), dx.sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("B,T", [(2, 144), (3, 9), (2, 256), (1, 324), (2, 100), (1, 36)])
+@pytest.mark.parametrize("B,T", [(2, 144), (1, 144), (13, 144), (40, 144), (3, 9), (2, 256), (1, 324), (2, 100), (1, 36)])
 def test_attention_backward(ops, B, T):
     torch.manual_seed(T)
     qkv = (torch.randn(B * T, 2304, device="cuda") * 1.2).bfloat16()
