@@ -10,3 +10,7 @@ if _root not in _sys.path:
 from jpdvt_mt_ntnu_b200.diffusion import create_diffusion, SpacedDiffusion, space_timesteps  # noqa: F401,E402
 from jpdvt_mt_ntnu_b200.diffusion import gaussian_diffusion, respace  # noqa: F401,E402
 from jpdvt_mt_ntnu_b200.diffusion import gaussian_diffusion as gd  # noqa: F401,E402
+
+if _os.environ.get("JPDVT_DROPIN_VERBOSE"):
+    import jpdvt_mt_ntnu_b200.diffusion as _d
+    print(f"[jpdvt-dropin] diffusion -> {_d.__file__}", file=_sys.stderr, flush=True)

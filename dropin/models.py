@@ -13,3 +13,7 @@ if _root not in _sys.path:
 
 from jpdvt_mt_ntnu_b200.models import *  # noqa: F401,F403,E402
 from jpdvt_mt_ntnu_b200.models import DiT, DiT_models, get_2d_sincos_pos_embed  # noqa: F401,E402
+
+if _os.environ.get("JPDVT_DROPIN_VERBOSE"):
+    import jpdvt_mt_ntnu_b200.models as _m
+    print(f"[jpdvt-dropin] models -> {_m.__file__}", file=_sys.stderr, flush=True)
