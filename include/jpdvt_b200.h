@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JPDVT_ABI_VERSION 4
+#define JPDVT_ABI_VERSION 5
 #define JPDVT_HIDDEN 768
 #define JPDVT_LATENT 8
 
@@ -401,6 +401,41 @@ int jpdvt_mse_loss_bwd(const float* te_out, const float* te_tgt, int64_t per_te,
 int jpdvt_adamw_ema(float* p, const float* g, float* m, float* v, float* ema_or_null, jpdvt_bf16* p_bf16_or_null, int64_t n,
                     int64_t step, float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
                     float ema_decay, void* stream);
+/* ---- data-parallel optimizer step over NVLink / NVSwitch peer memory (world > 1) ----------------------------------------
+ * Replaces DistributedDataParallel's gradient all-reduce followed by AdamW.step() and update_ema() (train_JPDVT.py:231,
+ * 370-372, 36-46) with ONE kernel per rank: reduce-scatter of the fp32 gradients (multimem.ld_reduce through the NVSwitch
+ * multicast object, or plain peer loads), AdamW + EMA on the rank's own contiguous slice of the flat parameter space, and
+ * all-gather of the refreshed bf16 operand copy (multimem.st, or peer stores).  The caller maps every rank's buffers into
+ * this process (CUDA VMM / symmetric memory) and passes the addresses AS SEEN FROM THIS PROCESS. */
+#define JPDVT_MAX_PEERS 8
+#define JPDVT_MAX_F32_RANGES 16
+typedef struct jpdvt_peer_step {
+  int32_t world;                 /* ranks on this NVLink domain, 2..JPDVT_MAX_PEERS */
+  int32_t rank;
+  int64_t shard_begin;           /* this rank's slice [shard_begin, shard_end) of the flat parameter index space; */
+  int64_t shard_end;             /*   multiples of 8; every parameter belongs to exactly one rank */
+  uint32_t epoch;                /* barrier token: strictly increasing from call to call, identical on every rank */
+  uint32_t timeout_ms;           /* a barrier gives up after this long and sets *status (1: gradients, 2: weights) */
+  const float* grads[JPDVT_MAX_PEERS];         /* rank q's flat fp32 gradient buffer (grads[rank] is the local one) */
+  jpdvt_bf16* weights_bf16[JPDVT_MAX_PEERS];   /* rank q's flat bf16 operand buffer */
+  float* params[JPDVT_MAX_PEERS];              /* rank q's flat fp32 parameter buffer (written only inside f32_ranges) */
+  void* signals[JPDVT_MAX_PEERS];              /* rank q's flag pad: uint32[2 * JPDVT_MAX_PEERS], zero before the first call */
+  const float* grads_mc;         /* multicast address of the gradient buffers (NULL: plain peer loads / stores) */
+  jpdvt_bf16* weights_mc;        /* multicast address of the bf16 operand buffers */
+  float* params_mc;              /* multicast address of the fp32 parameter buffers */
+  int32_t n_f32_ranges;          /* parameters the kernels read in fp32 (biases, timestep MLP, head): index ranges */
+  int32_t reserved;              /*   [f32_ranges[2k], f32_ranges[2k+1]) whose fp32 values are replicated to every rank too */
+  int64_t f32_ranges[2 * JPDVT_MAX_F32_RANGES];
+  uint32_t* local_sync;          /* device uint32, zero before the first call (CTA counter of this rank) */
+  int32_t* status;               /* device int32, stays zero unless a barrier timed out */
+} jpdvt_peer_step;
+/* p, m, v, ema: this rank's full-length flat fp32 buffers - only [shard_begin, shard_end) is read and written (the fp32
+ * master state of a parameter lives on its owner, except the f32_ranges, which every rank receives; gather the rest for
+ * checkpoints).  `step` counts from 1; grad_scale is applied
+ * to the summed gradient (1 / world for DDP's mean).  Every rank must call this once per step on its own stream. */
+int jpdvt_adamw_ema_peer(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, int64_t step,
+                         float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
+                         void* stream);
 /* out[b][c][r] = in[b][r][c]: refreshes the [in, out] weight copies of jpdvt_weights_t after an optimizer step. */
 int jpdvt_transpose_bf16(const jpdvt_bf16* in, jpdvt_bf16* out, int batch, int rows, int cols, void* stream);
 

@@ -65,9 +65,23 @@ class BwdScratch(C.Structure):
                                         "small_bf16", "wgrad_scratch", "part", "zeros")]
 
 
+MAX_PEERS = 8
+MAX_F32_RANGES = 16
+
+
+class PeerStep(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("shard_begin", C.c_int64), ("shard_end", C.c_int64),
+                ("epoch", C.c_uint32), ("timeout_ms", C.c_uint32), ("grads", c_void_p * MAX_PEERS),
+                ("weights_bf16", c_void_p * MAX_PEERS), ("params", c_void_p * MAX_PEERS), ("signals", c_void_p * MAX_PEERS),
+                ("grads_mc", c_void_p), ("weights_mc", c_void_p), ("params_mc", c_void_p), ("n_f32_ranges", C.c_int32),
+                ("reserved", C.c_int32), ("f32_ranges", C.c_int64 * (2 * MAX_F32_RANGES)), ("local_sync", c_void_p),
+                ("status", c_void_p)]
+
+
 # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables, 4: timestep-MLP
-# scratch of its own, hoisted embedding, in-kernel Philox noise, loss kernels, tcgen05 attention backward)
-ABI_VERSION = 4
+# scratch of its own, hoisted embedding, in-kernel Philox noise, loss kernels, tcgen05 attention backward, 5: peer-memory
+# optimizer step)
+ABI_VERSION = 5
 
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header
@@ -117,6 +131,7 @@ PROTOTYPES = {
     "jpdvt_train_backward_embed": [C.POINTER(Weights), C.POINTER(WeightsT), C.POINTER(Tape), C.POINTER(BwdScratch),
                                    C.POINTER(Grads), P, P],
     "jpdvt_adamw_ema": [P, P, P, P, P, P, c_int64, c_int64] + [C.c_float] * 7 + [P],
+    "jpdvt_adamw_ema_peer": [C.POINTER(PeerStep), P, P, P, P, c_int64] + [C.c_float] * 7 + [P],
     "jpdvt_transpose_bf16": [P, P, c_int, c_int, c_int, P],
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpdvt_sm100.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "train_api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "assign.cu", "puzzle.cu", "fold.cu", "backward.cu", "optim.cu", "loss.cu", "attention_bwd_tc.cu"]
+SOURCES = ["api.cu", "train_api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "assign.cu", "puzzle.cu", "fold.cu", "backward.cu", "optim.cu", "loss.cu", "attention_bwd_tc.cu", "peer_optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -49,7 +49,9 @@ struct GemmCfg {
   static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + (NB > 0 ? 0 : 2304);
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers; power of two for BN in {64,128,256}
+  // two accumulator buffers in a power-of-two allocation; BN = 192 takes 512 columns with the buffers 256 apart
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kAccStride = kTmemCols / 2;
   static constexpr int kBarBytes = (2 * kStages + 4 + EW * NB) * 8 + 16;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + kBarBytes + 1024;
 };
@@ -347,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (!tile_at(s, split_idx, m_blk, n_blk)) break;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::kAccStride);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -441,7 +443,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int j = 0; j < kNT; ++j) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
-          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * Cfg::kAccStride);
 #pragma unroll
           for (int c = 0; c < kNC; ++c, ++pos) {
             const int slot = static_cast<int>(pos % NB);
@@ -684,7 +686,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * Cfg::kAccStride);
       if constexpr (kFoldIn) {
         if (p.stats_in != nullptr) {          // the next tile's row statistics: in flight behind this tile's epilogue math
           int sp, mb, nb;
@@ -1254,6 +1256,17 @@ static int small_tile_width(int epi, const GemmParams& p) {
   const int pairs = num_sms() / 2;
   if (tiles256 * 4 <= pairs) return 64;
   if (tiles256 * 2 <= pairs) return 128;
+  // Mid-size batches (a few waves of tiles): the time of a launch is waves x tile width.  192-wide tiles (a 256 x 192 x 16
+  // UMMA, 512 TMEM columns) fill the last wave where 256-wide ones leave a third of the pairs idle - e.g. 32 puzzles,
+  // M = 4,608: proj / fc2 54 -> 72 tiles on 74 pairs, qkv 162 tiles in 3 waves -> 216 tiles in 3 shorter waves.  A tile
+  // carries a fixed cost (pipeline fill, epilogue tail), hence the +16; ties go to the wide tile (M = 36,864 keeps 256).
+  if (p.N % 192 == 0 && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_RESID_TMA_F32)) {
+    static int wide192 = -1;                                   // JPDVT_GEMM_TILE192=0: never (A/B knob)
+    if (wide192 < 0) { const char* e = getenv("JPDVT_GEMM_TILE192"); wide192 = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    const long long tiles192 = static_cast<long long>((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / 192);
+    const long long cost256 = ((tiles256 + pairs - 1) / pairs) * (256 + 16), cost192 = ((tiles192 + pairs - 1) / pairs) * (192 + 16);
+    if (wide192 && cost192 < cost256) return 192;
+  }
   return 0;
 }
 
@@ -1265,7 +1278,15 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
     return set_error(kErrBadArg, "gemm: operand pointers must be 16-byte aligned");
   const int bn_small = (p.stats_in == nullptr) ? small_tile_width(epi, p) : 0;
-  if (bn_small != 0 && epi == EPI_RESID_TMA_F32) epi = EPI_RESID_F32;     // the TMA box ring is laid out for 256-wide tiles
+  if (bn_small == 192) {                                       // 192-wide tiles: the TMA-store and TMA-ring epilogues as they are
+    if (epi == EPI_BIAS_BF16) return launch_cfg<192, EPI_BIAS_BF16, 4>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_BIAS_GELU_BF16) return launch_cfg<192, EPI_BIAS_GELU_BF16, 4>(a, lda, w, ldw, p, stream);
+    if (p.gate == nullptr || p.tokens <= 0 || (p.ldo % 4) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15))
+      return set_error(kErrBadArg, "gemm: the TMA residual epilogue needs the gate, tokens and a 16-byte aligned residual stream");
+    return p.K >= 2048 ? launch_cfg<192, EPI_RESID_TMA_F32, 4, 2>(a, lda, w, ldw, p, stream)
+                       : launch_cfg<192, EPI_RESID_TMA_F32, 8, 2>(a, lda, w, ldw, p, stream);
+  }
+  if (bn_small != 0 && epi == EPI_RESID_TMA_F32) epi = EPI_RESID_F32;     // narrow tiles: register read-modify-write epilogue
   const int bn = (epi == EPI_HEAD) ? 64 : (bn_small != 0 ? bn_small : ((p.N % 256 == 0) ? 256 : 128));
   if (p.N % bn != 0) return set_error(kErrBadArg, "gemm: N=%d is not a multiple of the %d-wide tile", p.N, bn);
   if (p.stats_in != nullptr && ((epi != EPI_BIAS_BF16 && epi != EPI_BIAS_GELU_BF16) || p.fold_u == nullptr || p.stats_slots != 6 ||

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib, parallel
+from . import _lib, parallel, peer
 from ._lib import Weights, WeightsT, check, ptr
 from .engine import HIDDEN, LATENT
 from .training import TrainEngine, _grad_layout, param_grad_map
@@ -43,10 +43,22 @@ class Trainer:
         # "stage": all-reduce each backward stage's gradients as soon as they exist (overlaps the rest of the backward, but
         # the NCCL kernels then compete for SMs with the persistent one-CTA-per-SM GEMMs); "end": one all-reduce of the flat
         # gradient buffer after the backward (exposed, ~1.5 ms for 523 MB over NVSwitch, no contention)
-        self.allreduce = allreduce or os.environ.get("JPDVT_TRAIN_ALLREDUCE", "end")
-        if self.allreduce not in ("stage", "end"):
-            raise ValueError(f"allreduce must be 'stage' or 'end', got {self.allreduce!r}")
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # "peer" (default when the ranks share an NVLink domain): no collective at all - reduce-scatter, AdamW/EMA on the
+        # rank's own slice and the all-gather of the bf16 operands are ONE kernel over peer memory (csrc/peer_optim.cu).
+        # "end": one NCCL all-reduce of the flat gradient buffer after the backward (exposed, ~1.5 ms for 523 MB), then the
+        # full optimizer pass on every rank.  "stage": one all-reduce per backward stage (overlaps the rest of the backward,
+        # but the NCCL kernels then compete for SMs with the persistent one-CTA-per-SM GEMMs - measured slower).
+        mode = allreduce or os.environ.get("JPDVT_TRAIN_ALLREDUCE")
+        if mode is None:
+            mode = "peer" if (self.world > 1 and peer.available(process_group)[0]) else "end"
+        if mode not in ("stage", "end", "peer"):
+            raise ValueError(f"allreduce must be 'peer', 'end' or 'stage', got {mode!r}")
+        if mode == "peer" and self.world > 1:
+            ok, why = peer.available(process_group)
+            if not ok:
+                raise _lib.JpdvtError(f"allreduce='peer' is not possible here: {why}")
+        self.allreduce = mode
         self.step_count = 0
         dev = next(model.parameters()).device
         if dev.type != "cuda":
@@ -58,10 +70,19 @@ class Trainer:
         sizes = [int(torch.Size(s).numel()) for _, s in self.layout]
         self.total = sum(sizes)
         f32 = dict(device=dev, dtype=torch.float32)
-        self.p_flat = torch.zeros(self.total, **f32)
-        self.m_flat = torch.zeros(self.total, **f32)
-        self.v_flat = torch.zeros(self.total, **f32)
-        self.pb_flat = torch.zeros(self.total, device=dev, dtype=torch.bfloat16)
+        self.px: Optional[peer.PeerExchange] = None
+        if self.allreduce == "peer" and self.world > 1:
+            # every flat buffer lives in this rank's symmetric block: the peers read the gradients, write the bf16 operands
+            # (and the few fp32 values the kernels read directly) and can read the owner's slice of the fp32 state
+            self.px = peer.PeerExchange(self.total, dev, process_group)
+            self.p_flat, self.m_flat, self.v_flat = self.px.p, self.px.m, self.px.v
+            self.pb_flat = self.px.weights_bf16
+        else:
+            self.p_flat = torch.zeros(self.total, **f32)
+            self.m_flat = torch.zeros(self.total, **f32)
+            self.v_flat = torch.zeros(self.total, **f32)
+            self.pb_flat = torch.zeros(self.total, device=dev, dtype=torch.bfloat16)
+        self._stale = set()          # peer mode: fp32 state buffers whose non-owned slices are behind the owners'
         self.p_views, self.pb_views, self.offsets = {}, {}, {}
         off = 0
         for (name, shape), n in zip(self.layout, sizes):
@@ -76,7 +97,11 @@ class Trainer:
                 if name in by_name:
                     by_name[name].copy_(p.data)
                     p.data = by_name[name]
-        self.ema_flat = self.p_flat.clone()
+        if self.px is not None:
+            self.ema_flat = self.px.ema
+            self.ema_flat.copy_(self.p_flat)
+        else:
+            self.ema_flat = self.p_flat.clone()
         self.pb_flat.copy_(self.p_flat)
         self.pos = model.pos_embed.data[0].contiguous()
         # small derived tensors + transposed copies
@@ -106,6 +131,10 @@ class Trainer:
         for k, v in self.wt_t.items():
             setattr(wt, k, ptr(v))
         self.engine.adopt(w, wt, keepalive=(self,))
+        if self.px is not None:
+            self.engine.grad_buffer = self.px.grads
+            self.px.set_f32_ranges([(off, off + n) for name, (off, n) in self.offsets.items() if name not in _BF16_FIELDS])
+            self._install_state_hook()
         model.__dict__["_train_engine"] = self.engine
         model.__dict__["_train_engine_key"] = "adopted"
         model.__dict__["_adopted_by_trainer"] = True
@@ -172,26 +201,65 @@ class Trainer:
         loss = terms["loss"].mean()
         loss.backward()
         flat = self.engine.last_flat
-        if self.world > 1 and self.allreduce == "end":
-            parallel.sum_gradients(flat, self.group)
-        for wk in self._works:
-            wk.wait()
-        self._works = []
         self.step_count += 1
-        with _lib.on_device(self.device):
-            check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
-                                           ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
-                                           self.betas[1], self.eps, self.weight_decay, self.ema_decay,
-                                           _lib.stream_ptr(self.device)), "jpdvt_adamw_ema")
+        if self.px is not None:
+            # one kernel: sum of every rank's gradients for my slice (peer memory), AdamW + EMA on the slice, bf16 operands
+            # (+ the fp32 biases) written to every rank; its two in-kernel barriers are the only synchronisation
+            with _lib.on_device(self.device):
+                check(self.lib.jpdvt_adamw_ema_peer(C.byref(self.px.next_epoch()), ptr(self.p_flat), ptr(self.m_flat), ptr(self.v_flat),
+                                                    ptr(self.ema_flat), self.step_count, 1.0 / self.world, self.lr, self.betas[0],
+                                                    self.betas[1], self.eps, self.weight_decay, self.ema_decay,
+                                                    _lib.stream_ptr(self.device)), "jpdvt_adamw_ema_peer")
+            self._stale = {"p", "m", "v", "ema"}
+        else:
+            if self.world > 1 and self.allreduce == "end":
+                parallel.sum_gradients(flat, self.group)
+            for wk in self._works:
+                wk.wait()
+            self._works = []
+            with _lib.on_device(self.device):
+                check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
+                                               ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
+                                               self.betas[1], self.eps, self.weight_decay, self.ema_decay,
+                                               _lib.stream_ptr(self.device)), "jpdvt_adamw_ema")
         self._refresh_derived()
         for p in model.parameters():
             p.grad = None
         self.engine.last_flat = None
         return loss.detach()
 
+    # ------------------------------------------------------------------ peer mode: the fp32 state is owned slice by slice
+    def sync_state(self, names=("p", "m", "v", "ema")) -> None:
+        """Bring this rank's copy of the named fp32 buffers up to date with their owners (one-sided peer reads; a no-op
+        outside peer mode or when nothing changed since the last call).  Called by `state_dict()` of the adopted model and
+        by the checkpoint methods, so a rank-0-only `save_checkpoint` works as it does under DDP."""
+        if self.px is None:
+            return
+        need = [n for n in names if n in self._stale]
+        if need:
+            self.px.pull(need)
+            self._stale -= set(need)
+
+    def _install_state_hook(self) -> None:
+        import weakref
+        ref = weakref.ref(self)
+
+        def hook(module, prefix, keep_vars):      # a plain function: copy.deepcopy(model) must not drag the Trainer along
+            tr = ref()
+            if tr is not None:
+                tr.sync_state(("p",))
+        self.model.register_state_dict_pre_hook(hook)
+
+    def check_peers(self) -> None:
+        """Raise if an in-kernel barrier of the peer-memory step ever timed out (one 4-byte device->host read)."""
+        if self.px is not None:
+            self.px.check()
+
     def allreduce_description(self) -> str:
         if self.world == 1:
             return "none (1 GPU)"
+        if self.px is not None:
+            return self.px.describe()
         mb = self.total * 4 / 1e6
         if self.allreduce == "stage":
             return f"NCCL SUM per backward stage ({mb:.0f} MB in {self.model.depth + 2} pieces), overlapped with the remaining backward"
@@ -199,6 +267,7 @@ class Trainer:
 
     # ------------------------------------------------------------------ checkpoint views (train_JPDVT.py:410-416)
     def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+        self.sync_state(("ema",))
         views, off = {}, 0
         for (name, shape) in self.layout:
             n = int(torch.Size(shape).numel())
@@ -222,6 +291,7 @@ class Trainer:
         """The moments in the layout of `torch.optim.AdamW(model.parameters()).state_dict()` - what the reference stores
         under "opt" and feeds back to `opt.load_state_dict` on resume (train_JPDVT.py:281-284, 413): parameter i of
         `model.parameters()` -> {step, exp_avg, exp_avg_sq}; frozen parameters (pos_embed) are listed but carry no state."""
+        self.sync_state(("m", "v"))
         names = [n for n, _ in self.model.named_parameters()]
         m, v = self._named_views(self.m_flat), self._named_views(self.v_flat)
         state = {}
@@ -284,6 +354,7 @@ class Trainer:
         if ckpt.get("train_steps") is not None and ckpt.get("opt") is None:
             self.step_count = int(ckpt["train_steps"])
         self.pb_flat.copy_(self.p_flat)
+        self._stale = set()           # every rank has just loaded the whole state
         # (pos_embed: self.pos is a view of the module's frozen buffer, updated in place by load_state_dict)
         self._sync_replicas()
         self._refresh_derived()

@@ -55,6 +55,7 @@ class TrainEngine:
         self.zeros = torch.zeros(max(self.n_mod, 4 * HIDDEN), device=device, dtype=torch.float32)
         self.w_struct = None
         self.last_flat = None
+        self.grad_buffer: Optional[torch.Tensor] = None    # persistent flat gradient buffer owned by the Trainer (peer-mapped)
         self._keepalive = None
         self.ticket = 0      # forward counter: a backward must match the forward whose activations are on the tape
 
@@ -120,7 +121,11 @@ class TrainEngine:
         """Fresh zero-filled flat fp32 gradient buffer + the struct of pointers into it + per-field views."""
         layout = _grad_layout(self.depth)
         sizes = [int(torch.Size(shape).numel()) for _, shape in layout]
-        flat = torch.zeros(sum(sizes), device=self.device, dtype=torch.float32)
+        if self.grad_buffer is not None:            # the peers read this very buffer: same address every step
+            flat = self.grad_buffer[:sum(sizes)]
+            self.grad_buffer.zero_()
+        else:
+            flat = torch.zeros(sum(sizes), device=self.device, dtype=torch.float32)
         g, views, off = Grads(), {}, 0
         for (name, shape), n in zip(layout, sizes):
             v = flat[off:off + n].view(shape)

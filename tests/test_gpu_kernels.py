@@ -72,6 +72,33 @@ def test_gemm_epilogues(ops):
         assert rel_l2(x - x0, g * lin) < 1e-4          # the update itself, not hidden behind |x0|
 
 
+def test_gemm_192_wide_tiles(ops):
+    """M = 4,608 (32 puzzles of 144 tokens - the per-GPU shard of C2 on 8 GPUs): the launcher picks 256 x 192 tiles for qkv,
+    proj and fc2 there (gemm.cu: small_tile_width - 72 / 216 tiles on 74 CTA pairs instead of 54 / 162) and keeps 256-wide
+    ones for fc1.  Same epilogues, same arithmetic per element; checked against fp32 torch like the wide tiles."""
+    torch.manual_seed(5)
+    m, T = 4608, 144
+    a = torch.randn(m, 768, device="cuda").bfloat16()
+    for n in (2304, 3072):
+        w = (torch.randn(n, 768, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(n, device="cuda")
+        lin = a.float() @ w.float().t() + b
+        assert rel_l2(ops.gemm_bias(a, w, b).float(), lin) < BF16_TOL
+        assert rel_l2(ops.gemm_bias_gelu(a, w, b).float(), F.gelu(lin, approximate="tanh")) < BF16_TOL
+    for k in (768, 3072):                                       # proj (eight epilogue warps) and fc2 (four, six stages)
+        a2 = torch.randn(m, k, device="cuda").bfloat16()
+        w = (torch.randn(768, k, device="cuda") * 0.03).bfloat16()
+        b = torch.randn(768, device="cuda")
+        lin = a2.float() @ w.float().t() + b
+        for ncond in (32, 1):
+            gate = torch.randn(ncond, 768, device="cuda")
+            g = gate.repeat_interleave(T, 0) if ncond > 1 else gate
+            x0 = torch.randn(m, 768, device="cuda")
+            x = x0.clone()
+            ops.gemm_bias_gate_residual(x, a2, w, b, gate, T)
+            assert rel_l2(x - x0, g * lin) < 1e-4
+
+
 def test_patch_embed_head_and_patchify(ops):
     torch.manual_seed(1)
     img = torch.rand(3, 3, 192, 192, device="cuda") * 2 - 1

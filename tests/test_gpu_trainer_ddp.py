@@ -61,7 +61,7 @@ def _one_step(trainer, diffusion, x, t, piece, draws, steps=1):
     return loss
 
 
-def _worker(rank, world, port, backend, out_path):
+def _worker(rank, world, port, backend, out_path, mode="end"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from jpdvt_mt_ntnu_b200.trainer import Trainer
@@ -76,9 +76,14 @@ def _worker(rank, world, port, backend, out_path):
         # rank 0 carries the case's weights, rank 1 a fresh init under another seed: only the broadcast can align them
         model = _build(1000 + rank, dev, load_state=(rank == 0))
         d = create_diffusion("")
-        tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999)
+        if mode == "peer-nomc":
+            os.environ["JPDVT_PEER_MULTICAST"] = "0"
+        tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999, allreduce=mode.split("-")[0])
+        assert (tr.px is not None) == mode.startswith("peer")
+        n = tr.total                # peer mode pads the flat buffers to world x slice
         def gather(buf):          # gloo has no CUDA all_gather: stage through the host there
-            src = buf if backend == "nccl" else buf.detach().cpu()
+            src = (buf if backend == "nccl" else buf.detach().cpu())[:n] if buf.dim() == 1 and buf.numel() >= n else \
+                (buf if backend == "nccl" else buf.detach().cpu())
             outs = [torch.empty_like(src) for _ in range(world)]
             dist.all_gather(outs, src.contiguous())
             return outs
@@ -90,25 +95,51 @@ def _worker(rank, world, port, backend, out_path):
         half = CASE["batch"] // world
         lo, hi = rank * half, (rank + 1) * half
         loss = _one_step(tr, d, x[lo:hi].to(dev), t[lo:hi].to(dev), piece.to(dev), _slice(draws, lo, hi), steps=2)
+        tr.check_peers()
+        if tr.px is not None:
+            # the fp32 state is owned slice by slice; rank 0 alone assembles a checkpoint (one-sided peer reads), as the
+            # reference's rank-0-only torch.save does under DDP (train_JPDVT.py:409-417)
+            own = slice(tr.px.begin, min(tr.px.end, n))
+            other = slice(tr.px.chunk * (1 - rank), min(tr.px.chunk * (2 - rank), n))
+            mine_before = tr.m_flat[own].clone()
+            ck = tr.checkpoint() if rank == 0 else None
+            dist.barrier()
+            tr.sync_state()
+            assert torch.equal(tr.m_flat[own], mine_before)
+            if rank == 0:
+                flat_names = [k for k, _ in tr.model.named_parameters() if k in tr._named_views(tr.p_flat)]
+                for k in flat_names[:6] + flat_names[-6:]:
+                    assert torch.equal(ck["model"][k], tr._named_views(tr.p_flat)[k]), k
+                    assert torch.equal(ck["ema"][k], tr._named_views(tr.ema_flat)[k]), k
+            assert float(tr.m_flat[other].abs().sum()) > 0
         for buf in (tr.p_flat, tr.ema_flat, tr.m_flat, tr.v_flat):
             got = gather(buf)
             assert torch.equal(got[0], got[1]), "replicas diverged after two data-parallel steps"
         losses = gather(loss.reshape(1))
         if rank == 0:
-            torch.save({"p": tr.p_flat.cpu(), "ema": tr.ema_flat.cpu(), "m": tr.m_flat.cpu(), "v": tr.v_flat.cpu(),
+            torch.save({"p": tr.p_flat[:n].cpu(), "ema": tr.ema_flat[:n].cpu(), "m": tr.m_flat[:n].cpu(), "v": tr.v_flat[:n].cpu(),
                         "loss": torch.cat([l.cpu() for l in losses]).mean(), "step": tr.step_count}, out_path)
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path):
+MODES = ["end", "peer", "peer-nomc"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path, mode):
+    """`end`: NCCL SUM all-reduce + the full optimizer pass on every rank.  `peer` / `peer-nomc`: the fused reduce-scatter +
+    AdamW/EMA + all-gather kernel over NVLink peer memory (csrc/peer_optim.cu), with multimem instructions or plain peer
+    loads / stores - needs two GPUs with symmetric memory, skipped on a one-GPU box."""
     from conftest import rel_l2
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from jpdvt_mt_ntnu_b200.trainer import Trainer
     from oracle import cases
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    if mode.startswith("peer") and backend != "nccl":
+        pytest.skip("the peer-memory step needs two GPUs on one NVLink domain")
     out = str(tmp_path / "two_rank.pt")
-    mp.spawn(_worker, args=(2, _free_port(), backend, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), backend, out, mode), nprocs=2, join=True)
     two = torch.load(out, map_location="cpu")
 
     dev = torch.device("cuda", 0)

@@ -123,7 +123,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/jpdvt_b200.h but not exported"
     assert set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS) == declared
-    assert lib.jpdvt_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.jpdvt_abi_version() == _lib.ABI_VERSION == 5
     assert isinstance(lib.jpdvt_last_error_string(), bytes)
 
 
@@ -134,9 +134,11 @@ def test_cabi_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.Sampler) == 8 + 6 * 8 + 8 + 5 * 8
     header = open(os.path.join(ROOT, "include", "jpdvt_b200.h")).read()
     for struct, cls in (("jpdvt_weights", _lib.Weights), ("jpdvt_workspace", _lib.Workspace), ("jpdvt_sampler", _lib.Sampler),
-                        ("jpdvt_tape", _lib.Tape), ("jpdvt_bwd_scratch", _lib.BwdScratch), ("jpdvt_weights_t", _lib.WeightsT)):
+                        ("jpdvt_tape", _lib.Tape), ("jpdvt_bwd_scratch", _lib.BwdScratch), ("jpdvt_weights_t", _lib.WeightsT),
+                        ("jpdvt_peer_step", _lib.PeerStep)):
         body = header[header.index(f"typedef struct {struct} {{"):header.index(f"}} {struct};")]
-        names = re.findall(r"\b([a-z_0-9]+);", body)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = re.findall(r"\b([a-z_0-9]+)(?:\[[^\]]+\])?;", body)
         assert names == [f[0] for f in cls._fields_], struct
 
 
