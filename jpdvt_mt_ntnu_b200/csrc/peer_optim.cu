@@ -19,6 +19,8 @@
 //
 // so the step costs one pass over 1/world of the optimizer state plus (world-1)/world of 4 + 2 bytes per parameter over
 // the links, instead of an all-reduce (2 x 4 bytes per parameter over the links) followed by the full 38 B/param pass.
+#include <cstdlib>
+
 #include "../../include/jpdvt_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -195,6 +197,169 @@ peer_adamw_ema_kernel(const jpdvt_peer_step px, float* __restrict__ p, float* __
   }
 }
 
+// ---- bulk variant -----------------------------------------------------------------------------------------------------
+// Per-thread peer loads keep at most ~16 KB per SM in flight (the LSU's outstanding-miss budget), which at the ~10 us loaded
+// latency of an NVLink read caps the kernel near 230 GB/s of gradient traffic (measured, 2 GPUs: 1.15 ms).  Here the remote
+// gradient tiles are pulled by the bulk-copy engine instead (cp.async.bulk global -> shared, mbarrier completion): a CTA
+// keeps kStages x (world - 1) x 8 KB in flight, the threads only ever read shared memory, and the bf16 results leave the
+// same way (cp.async.bulk shared -> every rank's operand buffer), so no thread waits on a link.
+constexpr int kTile = 2048;                      // parameters per tile: 256 threads x 8
+constexpr int kTileBytes = kTile * 4;
+constexpr int kBulkStages = 4;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+peer_adamw_ema_bulk_kernel(const jpdvt_peer_step px, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                           float* __restrict__ ema, const AdamHyper h, const int stages) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int world = px.world, rank = px.rank, nrem = world - 1;
+  const unsigned long long timeout_ns = static_cast<unsigned long long>(px.timeout_ms) * 1000000ull;
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(px.signals[rank]);
+  // [stages][nrem][kTileBytes] remote gradient tiles | [2][kTile * 2] bf16 output tiles | full barriers
+  uint8_t* in_buf = smem;
+  uint8_t* out_buf = smem + static_cast<size_t>(stages) * nrem * kTileBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(out_buf + 2 * kTile * 2);
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  // ---- barrier A ---------------------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && tid < world && tid != rank) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + rank, px.epoch);
+  }
+  if (!wait_flags(my_flags, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 1);
+  __syncthreads();
+
+  const long long t0 = px.shard_begin / kTile, t1 = px.shard_end / kTile;   // tiles of my slice
+  const long long first = t0 + blockIdx.x, stride = gridDim.x;
+  auto issue = [&](long long tile, int stage) {                              // thread 0: pull the remote tiles of `tile`
+    mbar_expect_tx(&full[stage], static_cast<uint32_t>(nrem * kTileBytes));
+    int slot = 0;
+    for (int q = 0; q < world; ++q) {
+      if (q == rank) continue;
+      bulk_load(in_buf + (static_cast<size_t>(stage) * nrem + slot) * kTileBytes, px.grads[q] + tile * kTile, kTileBytes, &full[stage]);
+      ++slot;
+    }
+  };
+  if (tid == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");       // the acquire above orders generic accesses; the bulk engine is another proxy
+    for (int k = 0; k < stages - 1; ++k)
+      if (first + k * stride < t1) issue(first + k * stride, k);
+  }
+  const float wd_mul = 1.0f - h.lr * h.weight_decay;
+  long long it = 0;
+  for (long long tile = first; tile < t1; tile += stride, ++it) {
+    const int stage = static_cast<int>(it % stages);
+    if (tid == 0) {                                                          // refill the stage consumed in the previous iteration
+      const long long nxt = tile + static_cast<long long>(stages - 1) * stride;
+      if (nxt < t1) issue(nxt, static_cast<int>((it + stages - 1) % stages));
+    }
+    const long long i = tile * kTile + tid * 8;
+    // local operands first: their latency overlaps the wait for the remote tile
+    const float4 ga = __ldcs(reinterpret_cast<const float4*>(px.grads[rank] + i)), gb = __ldcs(reinterpret_cast<const float4*>(px.grads[rank] + i) + 1);
+    const float4 p0 = reinterpret_cast<const float4*>(p + i)[0], p1 = reinterpret_cast<const float4*>(p + i)[1];
+    const float4 m0 = reinterpret_cast<const float4*>(m + i)[0], m1 = reinterpret_cast<const float4*>(m + i)[1];
+    const float4 v0 = reinterpret_cast<const float4*>(v + i)[0], v1 = reinterpret_cast<const float4*>(v + i)[1];
+    float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+    if (ema != nullptr) { e0 = reinterpret_cast<const float4*>(ema + i)[0]; e1 = reinterpret_cast<const float4*>(ema + i)[1]; }
+    mbar_wait(&full[stage], static_cast<uint32_t>((it / stages) & 1));
+    // sum in rank order (the local contribution takes its place in the sequence), so every owner adds identically
+    float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int slot = 0;
+    for (int q = 0; q < world; ++q) {
+      float4 a, b;
+      if (q == rank) { a = ga; b = gb; }
+      else {
+        const float4* src = reinterpret_cast<const float4*>(in_buf + (static_cast<size_t>(stage) * nrem + slot) * kTileBytes) + tid * 2;
+        a = src[0]; b = src[1];
+        ++slot;
+      }
+      gr[0] += a.x; gr[1] += a.y; gr[2] += a.z; gr[3] += a.w; gr[4] += b.x; gr[5] += b.y; gr[6] += b.z; gr[7] += b.w;
+    }
+    float pa[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float ma[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float va[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {                                            // identical arithmetic to adamw_ema_kernel (optim.cu)
+      const float gk = gr[k] * h.grad_scale;
+      pa[k] *= wd_mul;
+      ma[k] = h.beta1 * ma[k] + (1.0f - h.beta1) * gk;
+      va[k] = h.beta2 * va[k] + (1.0f - h.beta2) * gk * gk;
+      const float denom = sqrtf(va[k]) * h.inv_sqrt_bc2 + h.eps;
+      pa[k] -= h.step_size * (ma[k] / denom);
+    }
+    reinterpret_cast<float4*>(p + i)[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(p + i)[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
+    reinterpret_cast<float4*>(m + i)[0] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(m + i)[1] = make_float4(ma[4], ma[5], ma[6], ma[7]);
+    reinterpret_cast<float4*>(v + i)[0] = make_float4(va[0], va[1], va[2], va[3]);
+    reinterpret_cast<float4*>(v + i)[1] = make_float4(va[4], va[5], va[6], va[7]);
+    if (ema != nullptr) {
+      const float d = h.ema_decay, c = 1.0f - h.ema_decay;
+      e0.x = d * e0.x + c * pa[0]; e0.y = d * e0.y + c * pa[1]; e0.z = d * e0.z + c * pa[2]; e0.w = d * e0.w + c * pa[3];
+      e1.x = d * e1.x + c * pa[4]; e1.y = d * e1.y + c * pa[5]; e1.z = d * e1.z + c * pa[6]; e1.w = d * e1.w + c * pa[7];
+      reinterpret_cast<float4*>(ema + i)[0] = e0;
+      reinterpret_cast<float4*>(ema + i)[1] = e1;
+    }
+    bool rep = false;
+    for (int k = 0; k < px.n_f32_ranges; ++k) rep = rep || (i < px.f32_ranges[2 * k + 1] && i + 8 > px.f32_ranges[2 * k]);
+    if (rep) {                                                               // rare (biases, timestep MLP, head): direct peer stores
+      const float4 q0 = make_float4(pa[0], pa[1], pa[2], pa[3]), q1 = make_float4(pa[4], pa[5], pa[6], pa[7]);
+      for (int q = 0; q < world; ++q) {
+        if (q != rank) {
+          reinterpret_cast<float4*>(px.params[q] + i)[0] = q0;
+          reinterpret_cast<float4*>(px.params[q] + i)[1] = q1;
+        }
+      }
+    }
+    // bf16 tile -> shared -> every rank's operand buffer by bulk stores (two output tiles: the stores of tile it - 2 must
+    // have READ their buffer before it is refilled)
+    uint8_t* ob = out_buf + (it & 1) * (kTile * 2);
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    uint4 w;
+    w.x = pack_bf16(pa[0], pa[1]); w.y = pack_bf16(pa[2], pa[3]); w.z = pack_bf16(pa[4], pa[5]); w.w = pack_bf16(pa[6], pa[7]);
+    reinterpret_cast<uint4*>(ob)[tid] = w;
+    fence_proxy_async_smem();
+    __syncthreads();               // also: every thread is done reading in_buf[stage], so iteration it + 1 may refill it
+    if (tid == 0) {
+      for (int q = 0; q < world; ++q) bulk_store(px.weights_bf16[q] + tile * kTile, ob, kTile * 2);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my bulk stores are complete (visible) ...
+
+  // ---- barrier B -----------------------------------------------------------------------------------------------------
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(px.local_sync, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    __threadfence();
+  }
+  __syncthreads();
+  if (s_last) {
+    if (tid == 0) *px.local_sync = 0u;
+    if (tid < world && tid != rank) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + JPDVT_MAX_PEERS + rank, px.epoch);
+    }
+    if (!wait_flags(my_flags + JPDVT_MAX_PEERS, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 2);
+  }
+}
+
 }  // namespace jp
 
 using namespace jp;
@@ -234,6 +399,29 @@ int jpdvt_adamw_ema_peer(const jpdvt_peer_step* px, float* p, float* m, float* v
   if (blocks > 8LL * sms) blocks = 8LL * sms;
   if (blocks < 1) blocks = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static int variant = -1;          // JPDVT_PEER_VARIANT=thread: per-thread peer loads / stores instead of bulk copies (A/B knob)
+  if (variant < 0) { const char* e = getenv("JPDVT_PEER_VARIANT"); variant = (e != nullptr && e[0] == 't') ? 0 : 1; }
+  if (!mc && variant == 1 && (px->shard_begin % kTile) == 0 && (px->shard_end % kTile) == 0) {
+    const int nrem = px->world - 1;
+    int stages = kBulkStages;
+    auto smem_for = [&](int s) { return static_cast<size_t>(s) * nrem * kTileBytes + 2 * kTile * 2 + 8 * kBulkStages + 128; };
+    while (stages > 2 && smem_for(stages) > 200 * 1024) --stages;
+    const size_t smem = smem_for(stages);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      if (cudaFuncSetAttribute(peer_adamw_ema_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        return set_error(kErrCuda, "adamw_ema_peer: cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(cudaGetLastError()));
+      smem_set = smem;
+    }
+    int per_sm = static_cast<int>((220 * 1024) / smem);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const long long tiles = (px->shard_end - px->shard_begin) / kTile;
+    long long grid = static_cast<long long>(sms) * per_sm;
+    if (grid > tiles) grid = tiles > 0 ? tiles : 1;
+    peer_adamw_ema_bulk_kernel<<<static_cast<unsigned>(grid), 256, smem, st>>>(*px, p, m, v, ema_or_null, h, stages);
+    return check_launch("peer_adamw_ema_bulk_kernel");
+  }
   if (mc) peer_adamw_ema_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(*px, p, m, v, ema_or_null, h);
   else peer_adamw_ema_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(*px, p, m, v, ema_or_null, h);
   return check_launch("peer_adamw_ema_kernel");

@@ -24,9 +24,10 @@ from ._lib import MAX_F32_RANGES, MAX_PEERS, PeerStep
 
 
 def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int, int]:
-    """(chunk, begin, end): equal contiguous slices of the flat parameter space, a multiple of 8 parameters each (one
-    16-byte bf16 store / two 16-byte fp32 loads per group); buffers are padded to world * chunk."""
-    chunk = -(-total // (world * 8)) * 8
+    """(chunk, begin, end): equal contiguous slices of the flat parameter space, a multiple of 2048 parameters each (the
+    tile the bulk-copy kernel moves: 8 KB of fp32 gradients per peer, 4 KB of bf16 results); buffers are padded to
+    world * chunk."""
+    chunk = -(-total // (world * 2048)) * 2048
     return chunk, rank * chunk, (rank + 1) * chunk
 
 
@@ -81,8 +82,8 @@ class PeerExchange:
             raise _lib.JpdvtError("symmetric-memory rendezvous returned an unexpected address table")
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         env = os.environ.get("JPDVT_PEER_MULTICAST")
-        if multicast is None:
-            multicast = (env != "0") if env is not None else True
+        if multicast is None:           # measured slower than bulk peer copies on 2 GPUs: opt-in
+            multicast = env == "1"
         self.multicast = bool(multicast and mc)
         s = PeerStep()
         s.world, s.rank, s.shard_begin, s.shard_end = self.world, self.rank, self.begin, self.end
@@ -146,6 +147,7 @@ class PeerExchange:
 
     def describe(self) -> str:
         how = ("multimem.ld_reduce / multimem.st through the NVSwitch multicast object" if self.multicast
-               else "peer loads / stores over NVLink")
+               else "per-thread peer loads / stores over NVLink" if os.environ.get("JPDVT_PEER_VARIANT", "")[:1] == "t"
+               else "cp.async.bulk pulls of the peers' gradient tiles and pushes of the bf16 tiles over NVLink")
         return (f"fused reduce-scatter + AdamW/EMA on 1/{self.world} of the state + bf16 all-gather in one kernel per rank "
                 f"({how}; {self.total * 4 / 1e6:.0f} MB of fp32 gradients, no NCCL call on the data path)")

@@ -76,8 +76,10 @@ def _worker(rank, world, port, backend, out_path, mode="end"):
         # rank 0 carries the case's weights, rank 1 a fresh init under another seed: only the broadcast can align them
         model = _build(1000 + rank, dev, load_state=(rank == 0))
         d = create_diffusion("")
-        if mode == "peer-nomc":
-            os.environ["JPDVT_PEER_MULTICAST"] = "0"
+        if mode == "peer-mc":
+            os.environ["JPDVT_PEER_MULTICAST"] = "1"
+        if mode == "peer-thread":
+            os.environ["JPDVT_PEER_VARIANT"] = "thread"
         tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999, allreduce=mode.split("-")[0])
         assert (tr.px is not None) == mode.startswith("peer")
         n = tr.total                # peer mode pads the flat buffers to world x slice
@@ -123,14 +125,14 @@ def _worker(rank, world, port, backend, out_path, mode="end"):
         dist.destroy_process_group()
 
 
-MODES = ["end", "peer", "peer-nomc"]
+MODES = ["end", "peer", "peer-mc", "peer-thread"]
 
 
 @pytest.mark.parametrize("mode", MODES)
 def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path, mode):
-    """`end`: NCCL SUM all-reduce + the full optimizer pass on every rank.  `peer` / `peer-nomc`: the fused reduce-scatter +
-    AdamW/EMA + all-gather kernel over NVLink peer memory (csrc/peer_optim.cu), with multimem instructions or plain peer
-    loads / stores - needs two GPUs with symmetric memory, skipped on a one-GPU box."""
+    """`end`: NCCL SUM all-reduce + the full optimizer pass on every rank.  `peer*`: the fused reduce-scatter + AdamW/EMA +
+    all-gather kernel over NVLink peer memory (csrc/peer_optim.cu) - bulk async copies (default), multimem instructions,
+    per-thread peer loads / stores.  Needs two GPUs with symmetric memory, skipped on a one-GPU box."""
     from conftest import rel_l2
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from jpdvt_mt_ntnu_b200.trainer import Trainer

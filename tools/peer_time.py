@@ -42,7 +42,7 @@ def timed(fn, label, nbytes_link):
 
 
 step = [0]
-for mc in (True, False):
+for mc in ((True, False) if os.environ.get("JPDVT_PEER_VARIANT", "")[:1] != "t" else (False,)):
     px = peer.PeerExchange(total, dev, None, multicast=mc)
     px.grads.normal_()
     px.p.normal_()
@@ -55,7 +55,8 @@ for mc in (True, False):
         check(lib.jpdvt_adamw_ema_peer(C.byref(px.next_epoch()), ptr(px.p), ptr(px.m), ptr(px.v), ptr(px.ema), step[0], 1.0 / world,
                                        1e-4, 0.9, 0.999, 1e-8, 0.0, 0.9999, st()), "peer")
     link = (world - 1) / world * total * (4 + 2)             # gradients in + bf16 operands out, per GPU
-    timed(fused, f"fused peer step, {'multimem' if px.multicast else 'peer ld/st'} ({world} GPUs)", link)
+    how = "multimem" if px.multicast else ("peer ld/st per thread" if os.environ.get("JPDVT_PEER_VARIANT", "")[:1] == "t" else "bulk async copies")
+    timed(fused, f"fused peer step, {how} ({world} GPUs)", link)
     px.check()
     del px
 
