@@ -556,7 +556,16 @@ def measure_training(wl, batch, steps, warmup, world, rank, dev):
     n0 = _lib.launch_count()
     ms, loss = _timed(lambda: one_step(x), steps, world, dev)
     launches = _lib.launch_count() - n0
-    ms_e2e, loss_h = _timed(lambda: one_step(x_pin.to(dev, non_blocking=True)).cpu(), steps, world, dev)
+    # end to end through the trainer's own host-side pieces: every step's batch comes from pinned host memory (copied one
+    # step ahead on a copy stream - BatchPrefetcher), every step's loss goes back to the host (pinned ring - LossLog)
+    from jpdvt_mt_ntnu_b200.trainer import BatchPrefetcher, LossLog
+    log = LossLog()
+
+    def e2e_steps():
+        for xin in BatchPrefetcher((x_pin for _ in range(steps)), dev):
+            log.push(one_step(xin))
+        return log.values(dev)[-1]
+    ms_e2e, loss_h = _timed(e2e_steps, 1, world, dev)
     flops = 3.0 * flops_per_forward(T) * batch * steps
     mode = "none (1 GPU)"
     if world > 1:

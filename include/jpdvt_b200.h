@@ -298,6 +298,14 @@ int64_t jpdvt_bwd_part_floats(int batch, int tokens);
 int jpdvt_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
                           float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, float* part, int batch,
                           int tokens, void* stream);
+/* jpdvt_ln_modulate_bwd fused with the jpdvt_gate_bwd that consumes its dx (models.py:120-121 read upwards: every
+ * LayerNorm backward is followed by the gate backward of the residual branch below it): the rows of dx are finished, gated
+ * (dy = gate[b] * dx, bf16) and folded into dgate[b] / dbias in one pass.  y_or_null == NULL: LayerNorm backward only.
+ * dshift, dscale, dgate and dbias are ACCUMULATED into with atomics (zero them once per backward pass); no scratch. */
+int jpdvt_ln_gate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
+                      float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, const jpdvt_bf16* y_or_null,
+                      const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate, int64_t dgate_stride,
+                      float* dbias_or_null, int batch, int tokens, void* stream);
 /* out[c] += sum_rows src[row, c]  (bias gradients) */
 int jpdvt_colsum_bf16(const jpdvt_bf16* src, int64_t rows, int cols, float* out, void* stream);
 int jpdvt_colsum_f32(const float* src, int64_t rows, int cols, float* out, void* stream);

@@ -121,6 +121,7 @@ PROTOTYPES = {
     "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],
     "jpdvt_gate_bwd": [P, P, P, c_int64, P, P, c_int64, P, P, c_int, c_int, P],
     "jpdvt_ln_modulate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, c_int, c_int, P],
+    "jpdvt_ln_gate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, P, c_int64, P, P, c_int64, P, c_int, c_int, P],
     "jpdvt_colsum_bf16": [P, c_int64, c_int, P, P],
     "jpdvt_colsum_f32": [P, c_int64, c_int, P, P],
     "jpdvt_train_forward": [C.POINTER(Weights), C.POINTER(Tape), P, P, P, P, P, c_int, P],

@@ -205,6 +205,161 @@ long long bwd_part_floats(int batch, int tokens) {
   return a > b ? a : b;
 }
 
+// ---------------------------------------------------------------------------------------------- LN backward + the next gate backward
+// In the backward pass every LayerNorm-modulate backward is followed by the gate backward of the residual branch below it
+// (models.py:120-121 read upwards): the second kernel re-reads the dx rows the first has just written.  Fused here: the
+// warp that finishes a row of dx also emits dy = gate[b] * dx (bf16) and folds the row into dgate[b] / dbias.  A CTA of
+// eight warps owns a slice of ONE sample's tokens, so the per-sample sums (dshift, dscale, dgate) leave through a
+// cross-warp reduction in shared memory and one atomicAdd per column and CTA - no partial buffers, no sum_parts /
+// colsum launches (ten launches per block become two).
+constexpr int kLgWarps = 8;
+
+template <bool GATE>
+__global__ void __launch_bounds__(kLgWarps * 32, 2)
+ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, const float* __restrict__ scale,
+                   long long mod_stride, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
+                   float* __restrict__ dscale, long long dmod_stride, __nv_bfloat16* __restrict__ dx_bf16,
+                   const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate, long long gate_stride,
+                   __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dgate_stride,
+                   float* __restrict__ dbias, int tokens, int rows_per_cta) {
+  extern __shared__ __align__(16) float lg_smem[];     // [kLgWarps][768] x (dshift, dscale[, dgate, dbias])
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.y * rows_per_cta, t1 = min(tokens, t0 + rows_per_cta);
+  float4* acc_g = reinterpret_cast<float4*>(lg_smem + (2 * kLgWarps + warp) * kHidden);     // this warp's dgate sums
+  float4* acc_b = reinterpret_cast<float4*>(lg_smem + (3 * kLgWarps + warp) * kHidden);     // this warp's dbias sums
+  if constexpr (GATE) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { acc_g[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f); acc_b[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  }
+  // the sample's scale (and gate) row: staged in shared memory and re-read per token row through volatile LDS, so the
+  // compiler cannot hoist 48 loop-invariant registers out of the row loop (it did: 128 registers + spills)
+  float* row_sc = lg_smem + (GATE ? 4 : 2) * kLgWarps * kHidden;
+  float* row_gt = row_sc + kHidden;
+  for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
+    row_sc[c] = __ldg(scale + b * mod_stride + c) + 1.0f;
+    if constexpr (GATE) row_gt[c] = __ldg(gate + b * gate_stride + c);
+  }
+  __syncthreads();
+  const uint32_t sc_s = smem_u32(row_sc), gt_s = smem_u32(row_gt);
+  float4 ssh[6], ssc[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { ssh[j] = make_float4(0.f, 0.f, 0.f, 0.f); ssc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (int t = t0 + warp; t < t1; t += kLgWarps) {
+    const long long row = static_cast<long long>(b) * tokens + t;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * kHidden);
+    const float4* gr = reinterpret_cast<const float4*>(dxn + row * kHidden);
+    float4 v[6], g[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { v[j] = __ldcs(xr + lane + 32 * j); g[j] = __ldcs(gr + lane + 32 * j); }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum_b(s) * (1.0f / kHidden);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float rstd = rsqrtf(warp_sum_b(q) * (1.0f / kHidden) + 1e-6f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {        // same arithmetic, in the same order, as ln_modulate_bwd_kernel
+      const float4 sc = lds_f4(sc_s + 16u * static_cast<uint32_t>(lane + 32 * j));      // 1 + scale
+      v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;
+      ssh[j].x += g[j].x; ssh[j].y += g[j].y; ssh[j].z += g[j].z; ssh[j].w += g[j].w;
+      ssc[j].x = fmaf(g[j].x, v[j].x, ssc[j].x); ssc[j].y = fmaf(g[j].y, v[j].y, ssc[j].y);
+      ssc[j].z = fmaf(g[j].z, v[j].z, ssc[j].z); ssc[j].w = fmaf(g[j].w, v[j].w, ssc[j].w);
+      g[j].x *= sc.x; g[j].y *= sc.y; g[j].z *= sc.z; g[j].w *= sc.w;
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * v[j].x + g[j].y * v[j].y) + (g[j].z * v[j].z + g[j].w * v[j].w);
+    }
+    const float c1 = warp_sum_b(s1) * (1.0f / kHidden), c2 = warp_sum_b(s2) * (1.0f / kHidden);
+    float4* dr = reinterpret_cast<float4*>(dx + row * kHidden);
+    uint2* db = dx_bf16 != nullptr ? reinterpret_cast<uint2*>(dx_bf16 + row * kHidden) : nullptr;
+    const uint2* yr = GATE ? reinterpret_cast<const uint2*>(y + row * kHidden) : nullptr;
+    uint2* dyr = GATE ? reinterpret_cast<uint2*>(dy + row * kHidden) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float4 o;
+      o.x = rstd * (g[j].x - c1 - v[j].x * c2); o.y = rstd * (g[j].y - c1 - v[j].y * c2);
+      o.z = rstd * (g[j].z - c1 - v[j].z * c2); o.w = rstd * (g[j].w - c1 - v[j].w * c2);
+      if (accumulate) {
+        const float4 prev = dr[lane + 32 * j];
+        o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+      }
+      dr[lane + 32 * j] = o;
+      if (db != nullptr) { uint2 u; u.x = pack_bf16(o.x, o.y); u.y = pack_bf16(o.z, o.w); db[lane + 32 * j] = u; }
+      if constexpr (GATE) {              // gate_bwd_kernel's arithmetic on the finished row
+        const float4 gt = lds_f4(gt_s + 16u * static_cast<uint32_t>(lane + 32 * j));
+        const uint2 yv = __ldcs(yr + lane + 32 * j);
+        const float y0 = __uint_as_float(yv.x << 16), y1 = __uint_as_float(yv.x & 0xffff0000u);
+        const float y2 = __uint_as_float(yv.y << 16), y3 = __uint_as_float(yv.y & 0xffff0000u);
+        float4 ag = acc_g[lane + 32 * j], ab = acc_b[lane + 32 * j];
+        ag.x = fmaf(o.x, y0, ag.x); ag.y = fmaf(o.y, y1, ag.y); ag.z = fmaf(o.z, y2, ag.z); ag.w = fmaf(o.w, y3, ag.w);
+        const float o0 = gt.x * o.x, o1 = gt.y * o.y, o2 = gt.z * o.z, o3 = gt.w * o.w;
+        ab.x += o0; ab.y += o1; ab.z += o2; ab.w += o3;
+        acc_g[lane + 32 * j] = ag; acc_b[lane + 32 * j] = ab;
+        uint2 u; u.x = pack_bf16(o0, o1); u.y = pack_bf16(o2, o3);
+        dyr[lane + 32 * j] = u;
+      }
+    }
+  }
+  float4* red_sh = reinterpret_cast<float4*>(lg_smem + warp * kHidden);
+  float4* red_sc = reinterpret_cast<float4*>(lg_smem + (kLgWarps + warp) * kHidden);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { red_sh[lane + 32 * j] = ssh[j]; red_sc[lane + 32 * j] = ssc[j]; }
+  __syncthreads();
+  // cross-warp sums: thread -> 3 columns of each quantity; one atomicAdd per column, quantity and CTA
+  for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLgWarps; ++w) {
+      a0 += lg_smem[w * kHidden + c];
+      a1 += lg_smem[(kLgWarps + w) * kHidden + c];
+      if constexpr (GATE) { a2 += lg_smem[(2 * kLgWarps + w) * kHidden + c]; a3 += lg_smem[(3 * kLgWarps + w) * kHidden + c]; }
+    }
+    atomicAdd(dshift + b * dmod_stride + c, a0);
+    atomicAdd(dscale + b * dmod_stride + c, a1);
+    if constexpr (GATE) {
+      atomicAdd(dgate + b * dgate_stride + c, a2);
+      if (dbias != nullptr) atomicAdd(dbias + c, a3);
+    }
+  }
+}
+
+// dshift / dscale / dgate / dbias are ACCUMULATED into (atomicAdd): the caller zeroes them once per backward pass.
+int launch_ln_gate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx, int accumulate,
+                       float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16, const __nv_bfloat16* y,
+                       const float* gate, long long gate_stride, __nv_bfloat16* dy, float* dgate, long long dgate_stride,
+                       float* dbias, int batch, int tokens, cudaStream_t stream) {
+  if (batch <= 0 || tokens <= 0) return kOk;
+  const bool with_gate = y != nullptr;
+  if (with_gate && (!gate || !dy || !dgate)) return set_error(kErrBadArg, "ln_gate_bwd: the gate half needs gate, dy and dgate");
+  int slices = (2 * 148 + batch - 1) / batch;                  // ~2 CTAs per SM
+  const int max_slices = (tokens + kLgWarps - 1) / kLgWarps;   // at least one row per warp
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  const int rows = (tokens + slices - 1) / slices;
+  slices = (tokens + rows - 1) / rows;
+  const size_t smem = (static_cast<size_t>(with_gate ? 4 : 2) * kLgWarps + 2) * kHidden * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(ln_gate_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * kLgWarps + 2) * kHidden * 4) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_gate_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kLgWarps + 2) * kHidden * 4) != cudaSuccess)
+      return set_error(kErrCuda, "ln_gate_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  dim3 grid(batch, slices);
+  if (with_gate)
+    ln_gate_bwd_kernel<true><<<grid, kLgWarps * 32, smem, stream>>>(x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride,
+                                                                    dx_bf16, y, gate, gate_stride, dy, dgate, dgate_stride, dbias, tokens, rows);
+  else
+    ln_gate_bwd_kernel<false><<<grid, kLgWarps * 32, smem, stream>>>(x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride,
+                                                                     dx_bf16, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, tokens, rows);
+  return check_launch("ln_gate_bwd_kernel");
+}
+
 // ---------------------------------------------------------------------------------------------- column sums (bias grads)
 template <typename T>
 __device__ __forceinline__ float2 load2(const T* p);

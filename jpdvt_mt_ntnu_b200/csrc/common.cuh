@@ -144,6 +144,10 @@ int launch_score_placements(const int* pred, const int* truth, int batch, int n,
 long long bwd_part_floats(int batch, int tokens);
 int launch_gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, long long gate_stride, __nv_bfloat16* dy,
                     float* dgate, long long dgate_stride, float* dbias, float* part, int batch, int tokens, cudaStream_t stream);
+int launch_ln_gate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx, int accumulate,
+                       float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16, const __nv_bfloat16* y,
+                       const float* gate, long long gate_stride, __nv_bfloat16* dy, float* dgate, long long dgate_stride,
+                       float* dbias, int batch, int tokens, cudaStream_t stream);
 int launch_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, long long mod_stride, float* dx,
                            int accumulate, float* dshift, float* dscale, long long dmod_stride, __nv_bfloat16* dx_bf16,
                            float* part, int batch, int tokens, cudaStream_t stream);

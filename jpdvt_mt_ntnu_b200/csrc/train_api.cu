@@ -1,6 +1,8 @@
 // Training step on the device: the denoiser forward that keeps its activations (tape) and the three-stage backward.
 // Mirrors what autograd does for the reference's `loss.backward()` through DiT.forward (image_model/models.py:273-293,
 // called from diffusion/gaussian_diffusion.py:817 inside train_JPDVT.py:357-370), as explicit kernel launches.
+#include <cstdlib>
+
 #include "../../include/jpdvt_b200.h"
 #include "common.cuh"
 
@@ -24,6 +26,14 @@ int gemm(int epi, bfp a, long long lda, bfp w, long long ldw, const float* bias,
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = 1;
   p.bias = bias; p.out = out; p.ldo = ldo; p.out2 = out2; p.aux = aux; p.w2 = w2; p.b2 = b2;
   return launch_gemm(epi, a, lda, w, ldw, p, st);
+}
+
+// JPDVT_BWD_FUSED=0: separate LayerNorm-backward / gate-backward / partial-sum launches (A/B knob); default: each
+// LayerNorm backward also runs the gate backward of the residual branch below it (backward.cu: ln_gate_bwd_kernel)
+bool bwd_fused() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JPDVT_BWD_FUSED"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 }  // namespace
@@ -61,6 +71,14 @@ int jpdvt_ln_modulate_bwd(const float* x, const float* dxn, const float* scale, 
   if (!x || !dxn || !scale || !dx || !dshift || !dscale || !part) return set_error(kErrBadArg, "ln_modulate_bwd: null pointer");
   return launch_ln_modulate_bwd(x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride, BFM(dx_bf16_or_null),
                                 part, batch, tokens, ST(stream));
+}
+int jpdvt_ln_gate_bwd(const float* x, const float* dxn, const float* scale, int64_t mod_stride, float* dx, int accumulate,
+                      float* dshift, float* dscale, int64_t dmod_stride, jpdvt_bf16* dx_bf16_or_null, const jpdvt_bf16* y_or_null,
+                      const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate, int64_t dgate_stride,
+                      float* dbias_or_null, int batch, int tokens, void* stream) {
+  if (!x || !dxn || !scale || !dx || !dshift || !dscale) return set_error(kErrBadArg, "ln_gate_bwd: null pointer");
+  return launch_ln_gate_bwd(x, dxn, scale, mod_stride, dx, accumulate, dshift, dscale, dmod_stride, BFM(dx_bf16_or_null), BF(y_or_null),
+                            gate, gate_stride, BFM(dy), dgate, dgate_stride, dbias_or_null, batch, tokens, ST(stream));
 }
 int jpdvt_colsum_bf16(const jpdvt_bf16* src, int64_t rows, int cols, float* out, void* stream) {
   if (rows == 0) return kOk;
@@ -188,6 +206,18 @@ int jpdvt_train_backward_head(const jpdvt_weights* w, const jpdvt_weights_t* wt,
   JP_TRY(gemm(EPI_BIAS_F32, BF(s->dy), kHidden, BF(wt->w_final_t), kHidden, s->zeros, s->dxn, kHidden, M, kHidden, kHidden, st));
   const float* mod = tp->mod + static_cast<long long>(depth) * 6 * kHidden;
   float* dmod = s->dmod + static_cast<long long>(depth) * 6 * kHidden;
+  if (bwd_fused()) {
+    if (depth == 0)
+      return launch_ln_gate_bwd(tp->x, s->dxn, mod + kHidden, n_mod, s->dx, 0, dmod, dmod + kHidden, n_mod, BFM(s->dy), nullptr,
+                                nullptr, 0, nullptr, nullptr, 0, nullptr, batch, T, st);
+    // ... and the gate backward of the last block's MLP branch (models.py:121), whose dy the block stage starts from
+    const int l = depth - 1;
+    const float* mod_l = tp->mod + static_cast<long long>(l) * 6 * kHidden;
+    float* dmod_l = s->dmod + static_cast<long long>(l) * 6 * kHidden;
+    return launch_ln_gate_bwd(tp->x + static_cast<long long>(2 * depth) * X, s->dxn, mod + kHidden, n_mod, s->dx, 0, dmod,
+                              dmod + kHidden, n_mod, nullptr, BF(tp->y2) + l * X, mod_l + 5 * kHidden, n_mod, BFM(s->dy),
+                              dmod_l + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(l) * kHidden, batch, T, st);
+  }
   JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * depth) * X, s->dxn, mod + kHidden, n_mod, s->dx, 0, dmod,
                                 dmod + kHidden, n_mod, depth == 0 ? BFM(s->dy) : nullptr, s->part, batch, T, st));
   return kOk;
@@ -209,7 +239,8 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   bfm dy = BFM(s->dy), dh = BFM(s->dh), dqkv = BFM(s->dqkv), datt = BFM(s->datt);
 
   // ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(xn2)))            (models.py:121)
-  JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
+  const bool fused = bwd_fused();      // then dy = gate_mlp * dx came with the LayerNorm backward of the stage before
+  if (!fused) JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   JP_TRY(launch_wgrad(dy, kHidden, h, H4, g->w_fc2 + static_cast<long long>(i) * kHidden * H4, s->wgrad_scratch, M, kHidden, static_cast<int>(H4), st));
   JP_TRY(gemm(EPI_DGELU_BF16, dy, kHidden, BF(wt->w_fc2_t) + static_cast<long long>(i) * H4 * kHidden, kHidden, nullptr, dh, H4, M,
               static_cast<int>(H4), kHidden, st, nullptr, hpre));
@@ -217,11 +248,16 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   JP_TRY(launch_wgrad(dh, H4, xn2, kHidden, g->w_fc1 + static_cast<long long>(i) * H4 * kHidden, s->wgrad_scratch, M, static_cast<int>(H4), kHidden, st));
   JP_TRY(gemm(EPI_BIAS_F32, dh, H4, BF(wt->w_fc1_t) + static_cast<long long>(i) * kHidden * H4, H4, s->zeros, s->dxn, kHidden, M,
               kHidden, static_cast<int>(H4), st));
-  JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * i + 1) * X, s->dxn, mod + 4 * kHidden, n_mod, s->dx, 1,
-                                dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, s->part, batch, T, st));
-
   // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(xn1)))     (models.py:120)
-  JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
+  if (fused) {
+    JP_TRY(launch_ln_gate_bwd(tp->x + static_cast<long long>(2 * i + 1) * X, s->dxn, mod + 4 * kHidden, n_mod, s->dx, 1,
+                              dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, y1, mod + 2 * kHidden, n_mod, dy,
+                              dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, batch, T, st));
+  } else {
+    JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * i + 1) * X, s->dxn, mod + 4 * kHidden, n_mod, s->dx, 1,
+                                  dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, s->part, batch, T, st));
+    JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
+  }
   JP_TRY(launch_wgrad(dy, kHidden, att, kHidden, g->w_proj + static_cast<long long>(i) * kHidden * kHidden, s->wgrad_scratch, M, kHidden, kHidden, st));
   JP_TRY(gemm(EPI_BIAS_BF16, dy, kHidden, BF(wt->w_proj_t) + static_cast<long long>(i) * kHidden * kHidden, kHidden, s->zeros, datt,
               kHidden, M, kHidden, kHidden, st));
@@ -230,6 +266,17 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   JP_TRY(launch_wgrad(dqkv, H3, xn1, kHidden, g->w_qkv + static_cast<long long>(i) * H3 * kHidden, s->wgrad_scratch, M, static_cast<int>(H3), kHidden, st));
   JP_TRY(gemm(EPI_BIAS_F32, dqkv, H3, BF(wt->w_qkv_t) + static_cast<long long>(i) * kHidden * H3, H3, s->zeros, s->dxn, kHidden, M,
               kHidden, static_cast<int>(H3), st));
+  if (fused) {
+    if (i == 0)     // bf16(dx0) for the patch-embedding weight gradient
+      return launch_ln_gate_bwd(tp->x, s->dxn, mod + kHidden, n_mod, s->dx, 1, dmod, dmod + kHidden, n_mod, dy, nullptr, nullptr, 0,
+                                nullptr, nullptr, 0, nullptr, batch, T, st);
+    // ... and the gate backward of block i - 1's MLP branch
+    const float* mod_l = mod - 6 * kHidden;
+    float* dmod_l = dmod - 6 * kHidden;
+    return launch_ln_gate_bwd(tp->x + static_cast<long long>(2 * i) * X, s->dxn, mod + kHidden, n_mod, s->dx, 1, dmod, dmod + kHidden,
+                              n_mod, nullptr, BF(tp->y2) + (i - 1) * X, mod_l + 5 * kHidden, n_mod, dy, dmod_l + 5 * kHidden, n_mod,
+                              g->b_fc2 + static_cast<long long>(i - 1) * kHidden, batch, T, st);
+  }
   JP_TRY(launch_ln_modulate_bwd(tp->x + static_cast<long long>(2 * i) * X, s->dxn, mod + kHidden, n_mod, s->dx, 1, dmod,
                                 dmod + kHidden, n_mod, i == 0 ? dy : nullptr, s->part, batch, T, st));
   return kOk;

@@ -486,6 +486,28 @@ def ln_modulate_bwd(x, dxn, scale, tokens: int, dx: Optional[torch.Tensor] = Non
     return dx, dshift, dscale, dxb
 
 
+def ln_gate_bwd(x, dxn, scale, tokens: int, dx: Optional[torch.Tensor] = None, y=None, gate=None):
+    """Fused LayerNorm-modulate backward + the gate backward that consumes its dx.
+    -> (dx fp32, dshift, dscale, dx_bf16, dy bf16 | None, dgate | None, dbias | None)."""
+    lib = _lib_dev()
+    batch = x.shape[0] // tokens
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty_like(x)
+    dshift = torch.zeros(batch, HIDDEN, device=x.device, dtype=torch.float32)
+    dscale = torch.zeros_like(dshift)
+    dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    dy = dgate = dbias = None
+    if y is not None:
+        dy = torch.empty_like(_need(y, torch.bfloat16, "y"))
+        dgate, dbias = torch.zeros_like(dshift), torch.zeros(HIDDEN, device=x.device, dtype=torch.float32)
+    check(lib.jpdvt_ln_gate_bwd(ptr(_need(x, torch.float32, "x")), ptr(_need(dxn, torch.float32, "dxn")),
+                                ptr(_need(scale, torch.float32, "scale")), HIDDEN, ptr(dx), int(acc), ptr(dshift), ptr(dscale), HIDDEN,
+                                ptr(dxb), ptr(y), ptr(_need(gate, torch.float32, "gate")) if gate is not None else None, HIDDEN,
+                                ptr(dy), ptr(dgate), HIDDEN, ptr(dbias), batch, tokens, stream_ptr()), "ln_gate_bwd")
+    return dx, dshift, dscale, dxb, dy, dgate, dbias
+
+
 def colsum(src: torch.Tensor) -> torch.Tensor:
     lib = _lib_dev()
     rows, cols = src.shape

@@ -359,3 +359,68 @@ class Trainer:
         self._sync_replicas()
         self._refresh_derived()
         return int(ckpt.get("train_steps") or self.step_count)
+
+
+class BatchPrefetcher:
+    """Pinned host batches -> device batches, copied one step ahead on a copy stream while the current step computes - the
+    job `DataLoader(pin_memory=True)` + `x.to(device)` do at the top of the reference loop (train_JPDVT.py:303-311, 351),
+    without the copy sitting in front of every step.  Two device slots; a slot is overwritten only after the compute
+    stream has passed the work that read it."""
+
+    def __init__(self, batches, device: torch.device):
+        self.batches, self.device = batches, device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots: List[Optional[torch.Tensor]] = [None, None]
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._used = [False, False]
+
+    def _start(self, host: torch.Tensor, k: int) -> None:
+        if self.slots[k] is None or self.slots[k].shape != host.shape or self.slots[k].dtype != host.dtype:
+            self.slots[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        if self._used[k]:
+            self.copy_stream.wait_event(self.consumed[k])
+        with torch.cuda.stream(self.copy_stream):
+            self.slots[k].copy_(host, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        k = 0
+        self._start(first, k)
+        pending = True
+        while pending:
+            try:
+                nxt = next(it)
+                self._start(nxt, 1 - k)
+            except StopIteration:
+                pending = False
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self.copied[k])
+            yield self.slots[k]
+            self.consumed[k].record(torch.cuda.current_stream(self.device))    # everything enqueued for this batch so far
+            self._used[k] = True
+            k = 1 - k
+
+
+class LossLog:
+    """Per-step losses read back without stalling the step: each device scalar is copied into a pinned ring (non-blocking);
+    `values()` synchronises once - the logging cadence of the reference loop (train_JPDVT.py:374-397) instead of its
+    per-step `loss.item()`."""
+
+    def __init__(self, capacity: int = 4096):
+        self.ring = torch.empty(capacity, dtype=torch.float32).pin_memory()
+        self.n = 0
+
+    def push(self, loss: torch.Tensor) -> None:
+        self.ring[self.n % self.ring.numel()].copy_(loss.detach().reshape(()), non_blocking=True)
+        self.n += 1
+
+    def values(self, device: Optional[torch.device] = None) -> List[float]:
+        torch.cuda.current_stream(device).synchronize()
+        k = min(self.n, self.ring.numel())
+        return self.ring[:k].tolist()

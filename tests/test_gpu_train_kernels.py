@@ -52,6 +52,36 @@ def test_dgelu_gate_ln_colsum(ops):
     assert rel_l2(ops.colsum(gp), gp.float().sum(0)) < 1e-5 and rel_l2(ops.colsum(dx), dx.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("B,T", [(3, 144), (128, 144), (1, 9), (5, 324), (40, 36)])
+def test_ln_gate_bwd_fused(ops, B, T):
+    """The fused kernel of the training backward (LayerNorm-modulate backward + the gate backward below it, models.py:19-20,
+    120-121) against torch autograd of both ops, with and without the gate half / the accumulate flag."""
+    torch.manual_seed(B * 1000 + T)
+    m = B * T
+    xx = (torch.randn(m, 768, device="cuda") * 2 + 0.3).requires_grad_(True)
+    shift = torch.randn(B, 768, device="cuda", requires_grad=True)
+    scale = (torch.randn(B, 768, device="cuda") * 0.5).requires_grad_(True)
+    idx = torch.arange(m, device="cuda") // T
+    dxn = torch.randn(m, 768, device="cuda")
+    (F.layer_norm(xx, (768,), eps=1e-6) * (1 + scale[idx]) + shift[idx]).backward(dxn)
+    base = torch.randn(m, 768, device="cuda")
+    y = torch.randn(m, 768, device="cuda").bfloat16()
+    gate = torch.randn(B, 768, device="cuda")
+    dx, dsh, dsc, dxb, dy, dgate, dbias = ops.ln_gate_bwd(xx.detach(), dxn, scale.detach(), T, dx=base.clone(), y=y, gate=gate)
+    want = base + xx.grad
+    assert rel_l2(dx, want) < 1e-5 and rel_l2(dsh, shift.grad) < 1e-5 and rel_l2(dsc, scale.grad) < 1e-5
+    assert rel_l2(dxb.float(), want) < 5e-3
+    assert rel_l2(dy.float(), gate[idx] * want) < 5e-3
+    assert rel_l2(dgate, (want * y.float()).reshape(B, T, 768).sum(1)) < 1e-5
+    assert rel_l2(dbias, (gate[idx] * want).sum(0)) < 1e-5
+    # the two halves run separately give the same numbers (same arithmetic per element)
+    ref_dx, ref_dsh, ref_dsc, _ = ops.ln_modulate_bwd(xx.detach(), dxn, scale.detach(), T, dx=base.clone())
+    assert torch.equal(dx, ref_dx)
+    assert torch.equal(dy, ops.gate_bwd(ref_dx, y, gate, T)[0])
+    only = ops.ln_gate_bwd(xx.detach(), dxn, scale.detach(), T)
+    assert rel_l2(only[0], xx.grad) < 1e-5 and only[4] is None
+
+
 @pytest.mark.parametrize("B,T", [(2, 144), (1, 144), (13, 144), (40, 144), (3, 9), (2, 256), (1, 324), (2, 100), (1, 36)])
 def test_attention_backward(ops, B, T):
     torch.manual_seed(T)

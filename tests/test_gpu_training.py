@@ -205,3 +205,21 @@ def test_trainer_checkpoint_resume_in_reference_format(cuda, tmp_path):
     st = opt.state[opt.param_groups[0]["params"][i]]
     assert float(st["step"]) == 2.0 and st["exp_avg"].shape == m3.blocks[1].mlp.fc1.weight.shape
     assert names.index("pos_embed") not in ckpt["opt"]["state"]
+
+
+def test_batch_prefetcher_and_loss_log(cuda):
+    """The trainer's host-side pieces: pinned batches arrive on the device one step ahead, in order and unmodified, while
+    a slot is never overwritten before the work that read it has run; per-step scalars come back through the pinned ring."""
+    from jpdvt_mt_ntnu_b200.trainer import BatchPrefetcher, LossLog
+    dev = torch.device("cuda", 0)
+    host = [torch.full((8, 3, 96, 96), float(i)).pin_memory() for i in range(7)]
+    log, seen = LossLog(capacity=4), []
+    big = torch.randn(4096, 4096, device=dev)
+    for i, x in enumerate(BatchPrefetcher(iter(host), dev)):
+        for _ in range(3):
+            big = big @ big * 1e-4                      # keep the compute stream busy so that the copies do run ahead
+        seen.append(x.mean())                           # consumed late on the compute stream
+        log.push(x.sum() / x.numel())
+    assert [float(v) for v in seen] == [float(i) for i in range(7)]
+    assert log.values(dev) == [4.0, 5.0, 6.0, 3.0]      # ring of 4: slots overwritten in order
+    assert list(BatchPrefetcher(iter([]), dev)) == []
