@@ -286,9 +286,18 @@ int64_t jpdvt_wgrad_scratch_floats(int64_t m, int out_rows, int n_cols);
  * fused with the GELU derivative (timm Mlp, models.py:110-112) */
 int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16* gprime, jpdvt_bf16* out, int64_t m, int n, int k,
                      void* stream);
-/* dQ, dK, dV of softmax(q k^T / 8) v into dqkv [batch*tokens, 2304]; o / d_o: [batch*tokens, 768]; lse2 from the forward. */
+/* Data gradient of a Linear layer from the layer's own weight: dX[m, n_in] = dY[m, k_out] . W with W [k_out, n_in] as nn.Linear
+ * stores it (autograd of models.py:108-112's Linear calls).  W is read as an MN-major tensor-core operand, so no transposed
+ * copy of the weights exists.  Output fp32 or bf16 (exactly one), optionally multiplied by gprime (the dGELU form), whose
+ * epilogue can also accumulate the column sums of its bf16 output into colsum_or_null [n_in] (the bias gradient of the
+ * layer below: db_fc1 = column sums of dh) so that no pass re-reads the output.  n_in must be a multiple of 256, k_out of 64. */
+int jpdvt_gemm_dgrad(const jpdvt_bf16* dy, const jpdvt_bf16* w, const jpdvt_bf16* gprime_or_null, jpdvt_bf16* out_bf16_or_null,
+                     float* out_f32_or_null, float* colsum_or_null, int64_t m, int n_in, int k_out, void* stream);
+/* dQ, dK, dV of softmax(q k^T / 8) v into dqkv [batch*tokens, 2304]; o / d_o: [batch*tokens, 768]; lse2 from the forward.
+ * dbias_or_null: the qkv Linear's bias gradient [2304], dbias[c] += sum_rows dqkv[row, c] (column sums of the bf16 values
+ * just written, folded into the kernel's epilogue; accumulated with atomics - zero it once per backward pass). */
 int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_bf16* d_o, const float* lse2, jpdvt_bf16* dqkv,
-                        int batch, int tokens, void* stream);
+                        float* dbias_or_null, int batch, int tokens, void* stream);
 /* x_out = x_in + gate[b]*y  =>  dy = gate[b]*dx (bf16); dgate[b] += sum_t dx*y; dbias += sum_rows dy */
 int jpdvt_gate_bwd(const float* dx, const jpdvt_bf16* y, const float* gate, int64_t gate_stride, jpdvt_bf16* dy, float* dgate,
                    int64_t dgate_stride, float* dbias_or_null, float* part, int batch, int tokens, void* stream);

@@ -118,7 +118,8 @@ PROTOTYPES = {
     "jpdvt_crop_pieces": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "jpdvt_gemm_wgrad": [P, P, P, P, c_int64, c_int, c_int, P],
     "jpdvt_gemm_dgelu": [P, P, P, P, c_int64, c_int, c_int, P],
-    "jpdvt_attention_bwd": [P, P, P, P, P, c_int, c_int, P],
+    "jpdvt_gemm_dgrad": [P, P, P, P, P, P, c_int64, c_int, c_int, P],
+    "jpdvt_attention_bwd": [P, P, P, P, P, P, c_int, c_int, P],
     "jpdvt_gate_bwd": [P, P, P, c_int64, P, P, c_int64, P, P, c_int, c_int, P],
     "jpdvt_ln_modulate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, c_int, c_int, P],
     "jpdvt_ln_gate_bwd": [P, P, P, c_int64, P, c_int, P, P, c_int64, P, P, P, c_int64, P, P, c_int64, P, c_int, c_int, P],

@@ -441,9 +441,9 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 }
 
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
-                         __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream) {
+                         __nv_bfloat16* dqkv, float* dbias, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0 || tokens <= 0) return kOk;
-  if (attention_bwd_tc_supported(tokens)) return launch_attention_bwd_tc(qkv, o, d_o, lse2, dqkv, batch, tokens, stream);
+  if (attention_bwd_tc_supported(tokens)) return launch_attention_bwd_tc(qkv, o, d_o, lse2, dqkv, dbias, batch, tokens, stream);
   if (batch > 65535) return set_error(kErrBadArg, "attention_bwd: batch %d exceeds gridDim.y limit", batch);
   const int mt = (tokens + 15) / 16;
   int nw = (mt % 3 == 0) ? 3 : 4;
@@ -460,7 +460,10 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const
   }
   dim3 grid(kHeads, batch);
   attention_bwd_kernel<<<grid, nw * 32, smem, stream>>>(qkv, o, d_o, lse2, dqkv, tokens, Tp);
-  return check_launch("attention_bwd_kernel");
+  const int rc = check_launch("attention_bwd_kernel");
+  if (rc != kOk || dbias == nullptr) return rc;
+  // the mma.sync kernel has no fused column sums: one pass over dqkv for the qkv bias gradient
+  return launch_colsum_bf16(dqkv, 3 * kHidden, static_cast<long long>(batch) * tokens, 3 * kHidden, dbias, stream);
 }
 
 }  // namespace jp

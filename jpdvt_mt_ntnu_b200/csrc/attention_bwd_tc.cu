@@ -96,10 +96,10 @@ struct BtCfg {
   static constexpr int kOffStage = kOffP + kQBlocks * kBlk;  // 4 x 4 KB epilogue staging
   static constexpr int kOffL = kOffStage + 4 * 4096;         // lse2[T], D[T] fp32
   static constexpr int kBarOff = kOffL + 2 * ((T * 4 + 127) / 128 * 128);
-  static constexpr int kSmemBytes = kBarOff + 128 + 1024;    // + alignment slack
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;    // + alignment slack (the kernel adds 768 B of static shared memory)
   static constexpr int kInBytes = 5 * kTile;
   static_assert(kTile % 1024 == 0 && kBlk % 1024 == 0 && kOffP % 1024 == 0 && kOffStage % 1024 == 0, "swizzle atoms");
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+  static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory");
   // TMEM columns
   static constexpr int kColS = 0, kColdP = T, kColSt0 = 2 * T, kColSt1 = 2 * T + 16, kColdPt0 = 2 * T + 32, kColdPt1 = 2 * T + 48;
   static constexpr int kColdV0 = 0, kColdV1 = 64, kColdK0 = 128, kColdK1 = 192, kColdQ0 = 256, kColdQ1 = 320;
@@ -109,8 +109,10 @@ struct BtCfg {
 // 32 accumulator rows of this warp (TMEM lane = row, 64 fp32 columns) -> bf16 -> global rows of `ld` elements.  The 32 x 128 B
 // tile is transposed through a 4 KB staging tile (XOR-swizzled 16-byte chunks) so that every store instruction writes four
 // full 128-byte rows.  Rows r with lo <= r < hi are live.
+// colsum_s != 0: the live rows' bf16 values are also added, column by column, into 64 floats of shared memory (the bias
+// gradient of the qkv Linear is the column sum of dqkv; folding it here saves a pass over the 85 MB the kernel has just written).
 __device__ __forceinline__ void store_acc_rows(uint32_t t_row, uint32_t stage, __nv_bfloat16* dst_row0, long long ld, int lo, int hi,
-                                               int lane) {
+                                               int lane, uint32_t colsum_s = 0) {
   uint32_t a[32], b[32];
   tmem_ld_32x32(t_row, a);
   tmem_ld_32x32(t_row + 32, b);
@@ -131,11 +133,29 @@ __device__ __forceinline__ void store_acc_rows(uint32_t t_row, uint32_t stage, _
   }
   __syncwarp();
   const int sub = lane >> 3, ch = lane & 7;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + sub;
     const uint4 u = lds_u4(stage + r * 128 + ((ch ^ (r & 7)) << 4));
-    if (r >= lo && r < hi) *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(r) * ld + ch * 8) = u;
+    if (r >= lo && r < hi) {
+      *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(r) * ld + ch * 8) = u;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { cs[2 * e] += __uint_as_float(w[e] << 16); cs[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
+    }
+  }
+  if (colsum_s != 0) {                   // lanes (sub, ch) -> sum over sub (4 lanes), then one shared-memory add per column
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+      cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(colsum_s + static_cast<uint32_t>(ch * 8 + e) * 4u), "f"(cs[e]) : "memory");
+    }
   }
   __syncwarp();
 }
@@ -144,7 +164,7 @@ template <int T>
 __global__ void __launch_bounds__(kBtThreads, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_o, const float* __restrict__ lse2, __nv_bfloat16* __restrict__ dqkv,
-                        int num_units) {
+                        float* __restrict__ dbias, int num_units) {
   using Cfg = BtCfg<T>;
   extern __shared__ uint8_t att_bt_smem[];
   uint8_t* smem = att_bt_smem + ((1024u - (smem_u32(att_bt_smem) & 1023u)) & 1023u);
@@ -157,6 +177,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* sL = reinterpret_cast<float*>(smem + Cfg::kOffL);
   float* sD = sL + (T * 4 + 127) / 128 * 32;
+  __shared__ float s_colsum[3 * kHeadDim];     // dQ | dK | dV column sums of the current unit (dbias != null)
+  if (threadIdx.x < 3 * kHeadDim) s_colsum[threadIdx.x] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -375,20 +397,35 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_wait(o_full, ph);
       tc_fence_after();
       __nv_bfloat16* row0 = base + static_cast<long long>(warp * 32) * kQkvCols;
-      store_acc_rows(t_lane + Cfg::kColdV0, stage, row0 + 2 * kHidden, kQkvCols, 0, 32, lane);
-      store_acc_rows(t_lane + Cfg::kColdK0, stage, row0 + kHidden, kQkvCols, 0, 32, lane);
-      store_acc_rows(t_lane + Cfg::kColdQ0, stage, row0, kQkvCols, 0, 32, lane);
+      const uint32_t csq = dbias != nullptr ? smem_u32(s_colsum) : 0u;
+      const uint32_t csk = csq ? csq + kHeadDim * 4 : 0u, csv = csq ? csq + 2 * kHeadDim * 4 : 0u;
+      store_acc_rows(t_lane + Cfg::kColdV0, stage, row0 + 2 * kHidden, kQkvCols, 0, 32, lane, csv);
+      store_acc_rows(t_lane + Cfg::kColdK0, stage, row0 + kHidden, kQkvCols, 0, 32, lane, csk);
+      store_acc_rows(t_lane + Cfg::kColdQ0, stage, row0, kQkvCols, 0, 32, lane, csq);
       if (warp == 3) {        // shifted pass: lane 112 + i holds key 128 + i, i.e. row (96 + 16) + r for this warp's lane r >= 16
         __nv_bfloat16* r16 = base + static_cast<long long>(112) * kQkvCols;
-        store_acc_rows(t_lane + Cfg::kColdV1, stage, r16 + 2 * kHidden, kQkvCols, 16, 32, lane);
-        store_acc_rows(t_lane + Cfg::kColdK1, stage, r16 + kHidden, kQkvCols, 16, 32, lane);
+        store_acc_rows(t_lane + Cfg::kColdV1, stage, r16 + 2 * kHidden, kQkvCols, 16, 32, lane, csv);
+        store_acc_rows(t_lane + Cfg::kColdK1, stage, r16 + kHidden, kQkvCols, 16, 32, lane, csk);
       }
       if (warp == 0) {        // query blocks 2, 3: lane i holds query 128 + i
-        store_acc_rows(t_lane + Cfg::kColdQ1, stage, base + static_cast<long long>(128) * kQkvCols, kQkvCols, 0, 16, lane);
+        store_acc_rows(t_lane + Cfg::kColdQ1, stage, base + static_cast<long long>(128) * kQkvCols, kQkvCols, 0, 16, lane, csq);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(epi_done);
+      if (dbias != nullptr) {
+        // the unit's 3 x 64 column sums -> dbias[{q,k,v} * 768 + h * 64 + c]: six coalesced red.adds by warp 0, which also
+        // re-zeroes the accumulators (the bar.sync at the top of the next unit orders that against the next adds)
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int idx = k * 32 + lane;
+            atomicAdd(dbias + (idx >> 6) * kHidden + h * kHeadDim + (idx & 63), s_colsum[idx]);
+            s_colsum[idx] = 0.f;
+          }
+        }
+      }
     }
   }
 
@@ -402,7 +439,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
 template <int T>
 int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
-              int batch, cudaStream_t stream) {
+              float* dbias, int batch, cudaStream_t stream) {
   using Cfg = BtCfg<T>;
   static bool configured = false;
   auto kern = attention_bwd_tc_kernel<T>;
@@ -424,7 +461,7 @@ int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloa
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = batch * kHeads;
-  kern<<<units < sms ? units : sms, kBtThreads, Cfg::kSmemBytes, stream>>>(tm_qkv, tm_do, tm_o, lse2, dqkv, units);
+  kern<<<units < sms ? units : sms, kBtThreads, Cfg::kSmemBytes, stream>>>(tm_qkv, tm_do, tm_o, lse2, dqkv, dbias, units);
   return check_launch("attention_bwd_tc_kernel");
 }
 
@@ -437,13 +474,13 @@ bool attention_bwd_tc_supported(int tokens) {
 }
 
 int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
-                            __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream) {
+                            __nv_bfloat16* dqkv, float* dbias, int batch, int tokens, cudaStream_t stream) {
   if (batch <= 0) return kOk;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(o) & 15) || (reinterpret_cast<uintptr_t>(d_o) & 15) ||
       (reinterpret_cast<uintptr_t>(dqkv) & 15))
     return set_error(kErrBadArg, "attention_bwd_tc: pointers must be 16-byte aligned");
   switch (tokens) {
-    case 144: return launch_bt<144>(qkv, o, d_o, lse2, dqkv, batch, stream);
+    case 144: return launch_bt<144>(qkv, o, d_o, lse2, dqkv, dbias, batch, stream);
     default: return set_error(kErrUnsupported, "attention_bwd_tc: %d tokens not instantiated", tokens);
   }
 }

@@ -222,35 +222,49 @@ ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, c
                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate, long long gate_stride,
                    __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dgate_stride,
                    float* __restrict__ dbias, int tokens, int rows_per_cta) {
-  extern __shared__ __align__(16) float lg_smem[];     // [kLgWarps][768] x (dshift, dscale[, dgate, dbias])
+  extern __shared__ __align__(16) float lg_smem[];     // [quantity: dshift, dscale(, dgate, dbias)][kLgWarps][768], then two rows
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.y * rows_per_cta, t1 = min(tokens, t0 + rows_per_cta);
-  float4* acc_g = reinterpret_cast<float4*>(lg_smem + (2 * kLgWarps + warp) * kHidden);     // this warp's dgate sums
-  float4* acc_b = reinterpret_cast<float4*>(lg_smem + (3 * kLgWarps + warp) * kHidden);     // this warp's dbias sums
-  if constexpr (GATE) {
+  constexpr int kQ = GATE ? 4 : 2;
+  // per-warp running column sums live in shared memory (each lane owns its 24 columns: conflict-free 16-byte accesses), which
+  // leaves the registers to the row itself: EVERY global operand of a row - x, dxn, the previous dx, y - is requested before
+  // the first reduction, so a row costs one memory latency (the first version fetched dx / y chunk by chunk inside the output
+  // loop: ncu long_scoreboard 73 %, 94 us per launch)
+  const uint32_t acc0 = smem_u32(lg_smem + warp * kHidden) + 16u * lane;            // quantity q at acc0 + q * kLgWarps * 768 * 4
+  constexpr uint32_t kQStride = kLgWarps * kHidden * 4;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { acc_g[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f); acc_b[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  }
-  // the sample's scale (and gate) row: staged in shared memory and re-read per token row through volatile LDS, so the
-  // compiler cannot hoist 48 loop-invariant registers out of the row loop (it did: 128 registers + spills)
-  float* row_sc = lg_smem + (GATE ? 4 : 2) * kLgWarps * kHidden;
-  float* row_gt = row_sc + kHidden;
+  for (int q = 0; q < kQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(acc0 + q * kQStride + 512u * j), "f"(0.f) : "memory");
+  float* row_sc = lg_smem + kQ * kLgWarps * kHidden;   // 1 + scale[b] and gate[b]: re-read per row through volatile LDS so the
+  float* row_gt = row_sc + kHidden;                    // compiler cannot hoist 48 loop-invariant registers out of the row loop
   for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
     row_sc[c] = __ldg(scale + b * mod_stride + c) + 1.0f;
     if constexpr (GATE) row_gt[c] = __ldg(gate + b * gate_stride + c);
   }
   __syncthreads();
-  const uint32_t sc_s = smem_u32(row_sc), gt_s = smem_u32(row_gt);
-  float4 ssh[6], ssc[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) { ssh[j] = make_float4(0.f, 0.f, 0.f, 0.f); ssc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const uint32_t sc_s = smem_u32(row_sc) + 16u * lane, gt_s = smem_u32(row_gt) + 16u * lane;
+  auto acc_add = [&](int q, int j, float a0, float a1, float a2, float a3) {
+    float4 a = lds_f4(acc0 + q * kQStride + 512u * j);
+    a.x += a0; a.y += a1; a.z += a2; a.w += a3;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(acc0 + q * kQStride + 512u * j), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+  };
   for (int t = t0 + warp; t < t1; t += kLgWarps) {
     const long long row = static_cast<long long>(b) * tokens + t;
     const float4* xr = reinterpret_cast<const float4*>(x + row * kHidden);
     const float4* gr = reinterpret_cast<const float4*>(dxn + row * kHidden);
-    float4 v[6], g[6];
+    float4* dr = reinterpret_cast<float4*>(dx + row * kHidden);
+    float4 v[6], g[6], prev[6];
+    uint2 yv[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) { v[j] = __ldcs(xr + lane + 32 * j); g[j] = __ldcs(gr + lane + 32 * j); }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      prev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (accumulate) prev[j] = __ldcs(dr + lane + 32 * j);
+      if constexpr (GATE) yv[j] = __ldcs(reinterpret_cast<const uint2*>(y + row * kHidden) + lane + 32 * j);
+    }
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -265,50 +279,37 @@ ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, c
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {        // same arithmetic, in the same order, as ln_modulate_bwd_kernel
-      const float4 sc = lds_f4(sc_s + 16u * static_cast<uint32_t>(lane + 32 * j));      // 1 + scale
+      const float4 sc = lds_f4(sc_s + 512u * j);                                   // 1 + scale
       v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;
-      ssh[j].x += g[j].x; ssh[j].y += g[j].y; ssh[j].z += g[j].z; ssh[j].w += g[j].w;
-      ssc[j].x = fmaf(g[j].x, v[j].x, ssc[j].x); ssc[j].y = fmaf(g[j].y, v[j].y, ssc[j].y);
-      ssc[j].z = fmaf(g[j].z, v[j].z, ssc[j].z); ssc[j].w = fmaf(g[j].w, v[j].w, ssc[j].w);
+      acc_add(0, j, g[j].x, g[j].y, g[j].z, g[j].w);
+      acc_add(1, j, g[j].x * v[j].x, g[j].y * v[j].y, g[j].z * v[j].z, g[j].w * v[j].w);
       g[j].x *= sc.x; g[j].y *= sc.y; g[j].z *= sc.z; g[j].w *= sc.w;
       s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
       s2 += (g[j].x * v[j].x + g[j].y * v[j].y) + (g[j].z * v[j].z + g[j].w * v[j].w);
     }
     const float c1 = warp_sum_b(s1) * (1.0f / kHidden), c2 = warp_sum_b(s2) * (1.0f / kHidden);
-    float4* dr = reinterpret_cast<float4*>(dx + row * kHidden);
     uint2* db = dx_bf16 != nullptr ? reinterpret_cast<uint2*>(dx_bf16 + row * kHidden) : nullptr;
-    const uint2* yr = GATE ? reinterpret_cast<const uint2*>(y + row * kHidden) : nullptr;
     uint2* dyr = GATE ? reinterpret_cast<uint2*>(dy + row * kHidden) : nullptr;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       float4 o;
       o.x = rstd * (g[j].x - c1 - v[j].x * c2); o.y = rstd * (g[j].y - c1 - v[j].y * c2);
       o.z = rstd * (g[j].z - c1 - v[j].z * c2); o.w = rstd * (g[j].w - c1 - v[j].w * c2);
-      if (accumulate) {
-        const float4 prev = dr[lane + 32 * j];
-        o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
-      }
+      if (accumulate) { o.x += prev[j].x; o.y += prev[j].y; o.z += prev[j].z; o.w += prev[j].w; }
       dr[lane + 32 * j] = o;
       if (db != nullptr) { uint2 u; u.x = pack_bf16(o.x, o.y); u.y = pack_bf16(o.z, o.w); db[lane + 32 * j] = u; }
       if constexpr (GATE) {              // gate_bwd_kernel's arithmetic on the finished row
-        const float4 gt = lds_f4(gt_s + 16u * static_cast<uint32_t>(lane + 32 * j));
-        const uint2 yv = __ldcs(yr + lane + 32 * j);
-        const float y0 = __uint_as_float(yv.x << 16), y1 = __uint_as_float(yv.x & 0xffff0000u);
-        const float y2 = __uint_as_float(yv.y << 16), y3 = __uint_as_float(yv.y & 0xffff0000u);
-        float4 ag = acc_g[lane + 32 * j], ab = acc_b[lane + 32 * j];
-        ag.x = fmaf(o.x, y0, ag.x); ag.y = fmaf(o.y, y1, ag.y); ag.z = fmaf(o.z, y2, ag.z); ag.w = fmaf(o.w, y3, ag.w);
+        const float4 gt = lds_f4(gt_s + 512u * j);
+        const float y0 = __uint_as_float(yv[j].x << 16), y1 = __uint_as_float(yv[j].x & 0xffff0000u);
+        const float y2 = __uint_as_float(yv[j].y << 16), y3 = __uint_as_float(yv[j].y & 0xffff0000u);
+        acc_add(2, j, o.x * y0, o.y * y1, o.z * y2, o.w * y3);
         const float o0 = gt.x * o.x, o1 = gt.y * o.y, o2 = gt.z * o.z, o3 = gt.w * o.w;
-        ab.x += o0; ab.y += o1; ab.z += o2; ab.w += o3;
-        acc_g[lane + 32 * j] = ag; acc_b[lane + 32 * j] = ab;
+        acc_add(3, j, o0, o1, o2, o3);
         uint2 u; u.x = pack_bf16(o0, o1); u.y = pack_bf16(o2, o3);
         dyr[lane + 32 * j] = u;
       }
     }
   }
-  float4* red_sh = reinterpret_cast<float4*>(lg_smem + warp * kHidden);
-  float4* red_sc = reinterpret_cast<float4*>(lg_smem + (kLgWarps + warp) * kHidden);
-#pragma unroll
-  for (int j = 0; j < 6; ++j) { red_sh[lane + 32 * j] = ssh[j]; red_sc[lane + 32 * j] = ssc[j]; }
   __syncthreads();
   // cross-warp sums: thread -> 3 columns of each quantity; one atomicAdd per column, quantity and CTA
   for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
@@ -336,7 +337,7 @@ int launch_ln_gate_bwd(const float* x, const float* dxn, const float* scale, lon
   if (batch <= 0 || tokens <= 0) return kOk;
   const bool with_gate = y != nullptr;
   if (with_gate && (!gate || !dy || !dgate)) return set_error(kErrBadArg, "ln_gate_bwd: the gate half needs gate, dy and dgate");
-  int slices = (2 * 148 + batch - 1) / batch;                  // ~2 CTAs per SM
+  int slices = (2 * 148) / batch;                              // one wave of two CTAs per SM (rounding up would leave a short second wave)
   const int max_slices = (tokens + kLgWarps - 1) / kLgWarps;   // at least one row per warp
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;

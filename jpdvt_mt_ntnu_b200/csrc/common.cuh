@@ -67,7 +67,7 @@ struct GemmParams {
   const float* bias;     // [N]
   void* out;             // primary output, row-major, leading dimension ldo (elements)
   long long ldo;
-  float* out2;           // optional fp32 copy (EPI_BIAS_BF16_F32)
+  float* out2;           // optional fp32 copy (EPI_BIAS_BF16_F32); EPI_DGELU_BF16: optional [N] column sums of the output (bias gradient)
   const float* gate;     // sample b reads gate + b * gate_stride, [N] contiguous
   long long gate_stride;
   const float* xt;       // [M, 8] fp32                     (patch embed)
@@ -93,6 +93,8 @@ struct GemmParams {
   const float2* stats_in;
   const float* fold_u;
   int stats_slots;
+  int b_mn;                   // the B operand is given as [K, N] row-major (the contraction index is the ROW): data-gradient GEMMs read
+                              // nn.Linear's own [out, in] weight, dX = dY . W, instead of a transposed copy (MN-major UMMA operand)
   int reverse_m;              // walk the row blocks from the last to the first (set by launch_gemm from sweep_reverse())
 };
 
@@ -120,12 +122,12 @@ bool attention_tc_supported(int tokens);
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int tokens, cudaStream_t stream);
 // K-major bf16 [rows, cols] tensor map, {64 cols x box_rows} boxes, 128-byte swizzle (gemm.cu)
 int make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// dbias (nullable): the qkv Linear's bias gradient, dbias[c] += sum_rows dqkv[row, c] (accumulated with atomics)
 int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
-                         __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
-// attention_bwd_tc.cu: tcgen05 / TMEM backward for the sizes attention_bwd_tc_supported() names
+                         __nv_bfloat16* dqkv, float* dbias, int batch, int tokens, cudaStream_t stream);
 bool attention_bwd_tc_supported(int tokens);
 int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
-                            __nv_bfloat16* dqkv, int batch, int tokens, cudaStream_t stream);
+                            __nv_bfloat16* dqkv, float* dbias, int batch, int tokens, cudaStream_t stream);
 
 // fold.cu: W' = W (1 + scale), u = rowsum(W'), v = b + W . shift for the qkv and fc1 matrices of every block (mod row 0)
 int launch_fold_ln(const __nv_bfloat16* w_qkv, const __nv_bfloat16* w_fc1, const float* b_qkv, const float* b_fc1, const float* mod,

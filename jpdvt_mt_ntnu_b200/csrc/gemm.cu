@@ -150,9 +150,12 @@ __device__ __forceinline__ void bf16_math(float (&v)[64], const float* bias_smem
 }
 
 // 32 rows x 64 bf16 columns of this warp -> global, every store instruction writes 4 full 128-byte row segments.
+// colsum (DGELU only, nullable): colsum[n0 + c] += sum over the live rows of the bf16 values written - the bias gradient of the
+// layer whose pre-activation gradient this tile is (fc1: db1 = column sums of dh), folded in so that no pass re-reads dh.
 template <bool DGELU>
 __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)[64], __nv_bfloat16* out,
-                                                const __nv_bfloat16* aux, long long ldo, int row0, int n0, int M, int lane) {
+                                                const __nv_bfloat16* aux, long long ldo, int row0, int n0, int M, int lane,
+                                                float* colsum = nullptr) {
   const int sub = lane >> 3, ch = lane & 7;
   uint4 auxv[8];
   if constexpr (DGELU) {   // issue the coalesced gelu' loads first so their latency hides behind the staging round trip
@@ -163,6 +166,7 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
       if (row0 + r < M) auxv[it] = __ldg(reinterpret_cast<const uint4*>(aux + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch));
     }
   }
+  [[maybe_unused]] float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint8_t* mine = stage + lane * kStageRowBytes;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -185,8 +189,24 @@ __device__ __forceinline__ void store_bf16_tile(uint8_t* stage, const float (&v)
           uw[e] = pack_bf16(__uint_as_float(uw[e] << 16) * __uint_as_float(aw[e] << 16),
                             __uint_as_float(uw[e] & 0xffff0000u) * __uint_as_float(aw[e] & 0xffff0000u));
         u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { cs[2 * e] += __uint_as_float(uw[e] << 16); cs[2 * e + 1] += __uint_as_float(uw[e] & 0xffff0000u); }
       }
       *reinterpret_cast<uint4*>(out + static_cast<long long>(row0 + r) * ldo + n0 + 8 * ch) = u;
+    }
+  }
+  if constexpr (DGELU) {
+    if (colsum != nullptr) {             // lane (sub, ch): 8 columns x 8 of the warp's 32 rows -> sum over sub -> 2 vector red.adds
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+        cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+      }
+      if (sub == 0) {
+        float* dst = colsum + n0 + 8 * ch;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+      }
     }
   }
   __syncwarp();
@@ -218,7 +238,7 @@ __device__ __forceinline__ void stage_f32_tile(uint8_t* stage, const float (&v)[
   __syncwarp();
 }
 
-template <int BN, int EPI, int CS, int EW, int NB = 0>
+template <int BN, int EPI, int CS, int EW, int NB = 0, bool BMN = false>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_y, const GemmParams p) {
@@ -323,6 +343,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int hh = 0; hh < BM / 64; ++hh) tma_load_2d_pair(&tma_a, bar, sa + hh * 8192, row_a + 64 * hh, m0);
 #pragma unroll
             for (int hh = 0; hh < Cfg::kBRows / 64; ++hh) tma_load_2d_pair(&tma_b, bar, sb + hh * 8192, row_b + 64 * hh, m0);
+          } else if constexpr (BMN) {
+            // B = W [K, N] row-major (contraction rows, feature columns): {64 features x 64 contraction rows} boxes stacked
+            // along the feature dimension, exactly the weight-gradient mode's operand layout; A stays K-major
+            static_assert(!BMN || CS == 2, "the MN-major B operand is pair-only");
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(&tma_a, bar, sa, kb * BK, row_a);
+#pragma unroll
+            for (int hh = 0; hh < Cfg::kBRows / 64; ++hh) tma_load_2d_pair(&tma_b, bar, sb + hh * 8192, row_b + 64 * hh, kb * BK);
           } else if constexpr (CS == 2) {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
             const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
@@ -341,7 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN, WG ? 1 : 0, WG ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(CS * BM, BN, WG ? 1 : 0, (WG || BMN) ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int s = 0;; ++s) {
@@ -359,7 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: 16 elements = 32 B inside the swizzle row; MN-major: 16 contraction rows = two 1024 B atoms
             const uint64_t da = WG ? umma_desc_mn_sw128(a_addr + k * 2048) : umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t db = WG ? umma_desc_mn_sw128(b_addr + k * 2048) : umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            const uint64_t db = (WG || BMN) ? umma_desc_mn_sw128(b_addr + k * 2048) : umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
             if constexpr (CS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -794,7 +823,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             store_packed_tile(stage, gp, p.out_aux, p.ldo, row0, n0, p.M, lane);
           }
-          store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane);
+          store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane,
+                                                 EPI == EPI_DGELU_BF16 ? p.out2 : nullptr);
           if constexpr (EPI == EPI_BIAS_BF16_F32) {
             if (p.out2 != nullptr) {
 #pragma unroll
@@ -1188,14 +1218,15 @@ static int epi_warps(int epi) {
   return (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) ? 4 : 8;
 }
 
-template <int BN, int EPI, int EW, int NB = 0>
+template <int BN, int EPI, int EW, int NB = 0, bool BMN = false>
 static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                       cudaStream_t stream) {
   constexpr int CS = 2;
   using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
   static_assert(Cfg::kStages >= 3, "pipeline too shallow");
+  static_assert(!BMN || (BN / CS) % 64 == 0, "MN-major B boxes are 64 features wide");
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, EPI, CS, EW, NB>;
+  auto kern = gemm_kernel<BN, EPI, CS, EW, NB, BMN>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return set_error(kErrCuda, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(cudaGetLastError()));
@@ -1204,7 +1235,8 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_kmajor(&ta, a, p.M, p.K, lda, BM);
   if (rc != kOk) return rc;
-  rc = make_tmap_bf16_kmajor(&tb, w, p.N, p.K, ldw, Cfg::kBRows);
+  if constexpr (BMN) rc = make_tmap_bf16_kmajor(&tb, w, p.K, p.N, ldw, 64);   // W [K, N]: {64 features x 64 contraction rows} boxes
+  else rc = make_tmap_bf16_kmajor(&tb, w, p.N, p.K, ldw, Cfg::kBRows);
   if (rc != kOk) return rc;
   CUtensorMap tx = ta;                                       // residual-stream boxes (TMA residual epilogue only)
   if constexpr (NB > 0) {
@@ -1277,6 +1309,16 @@ int launch_gemm(int epi, const __nv_bfloat16* a, long long lda, const __nv_bfloa
   if ((lda % 8) != 0 || (ldw % 8) != 0) return set_error(kErrBadArg, "gemm: leading dimensions must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
     return set_error(kErrBadArg, "gemm: operand pointers must be 16-byte aligned");
+  if (p.b_mn) {          // data gradients: dX = dY . W with W as stored ([K, N] here); 256-wide tiles, three epilogues
+    if (p.N % 256 != 0 || (ldw % 8) != 0) return set_error(kErrBadArg, "gemm: the MN-major B operand needs N %% 256 == 0 (N=%d)", p.N);
+    if (epi == EPI_BIAS_F32) return launch_cfg<256, EPI_BIAS_F32, 8, 0, true>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_BIAS_BF16) return launch_cfg<256, EPI_BIAS_BF16, 4, 0, true>(a, lda, w, ldw, p, stream);
+    if (epi == EPI_DGELU_BF16) {
+      if (p.aux == nullptr) return set_error(kErrBadArg, "gemm: dgelu epilogue needs the pre-activations");
+      return launch_cfg<256, EPI_DGELU_BF16, 8, 0, true>(a, lda, w, ldw, p, stream);
+    }
+    return set_error(kErrBadArg, "gemm: epilogue %d has no MN-major B form", epi);
+  }
   const int bn_small = (p.stats_in == nullptr) ? small_tile_width(epi, p) : 0;
   if (bn_small == 192) {                                       // 192-wide tiles: the TMA-store and TMA-ring epilogues as they are
     if (epi == EPI_BIAS_BF16) return launch_cfg<192, EPI_BIAS_BF16, 4>(a, lda, w, ldw, p, stream);

@@ -21,11 +21,27 @@ inline long long n_mod_of(int depth) { return static_cast<long long>(depth) * 6 
 
 // out = a[M,K] . w[N,K]^T (+ bias or zeros) with the given epilogue
 int gemm(int epi, bfp a, long long lda, bfp w, long long ldw, const float* bias, void* out, long long ldo, long long m, int n,
-         int k, cudaStream_t st, float* out2 = nullptr, bfp aux = nullptr, const float* w2 = nullptr, const float* b2 = nullptr) {
+         int k, cudaStream_t st, float* out2 = nullptr, bfp aux = nullptr, const float* w2 = nullptr, const float* b2 = nullptr,
+         int b_mn = 0) {
   GemmParams p{};
   p.M = static_cast<int>(m); p.N = n; p.K = k; p.tokens = 1;
-  p.bias = bias; p.out = out; p.ldo = ldo; p.out2 = out2; p.aux = aux; p.w2 = w2; p.b2 = b2;
+  p.bias = bias; p.out = out; p.ldo = ldo; p.out2 = out2; p.aux = aux; p.w2 = w2; p.b2 = b2; p.b_mn = b_mn;
   return launch_gemm(epi, a, lda, w, ldw, p, st);
+}
+
+// JPDVT_DGRAD_MN=0: data-gradient GEMMs read transposed weight copies ([in, out], refreshed after every optimizer step) as
+// K-major operands (A/B knob); default: they read nn.Linear's own [out, in] weight as an MN-major B operand - no copies.
+bool dgrad_mn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JPDVT_DGRAD_MN"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// dX[m, n_in] = dY[m, k_out] . W, W = the layer's [k_out, n_in] weight (w) or its transposed copy (w_t)
+// colsum (dGELU form only, nullable): [n_in] column sums of the output, accumulated - the bias gradient of the layer below
+int dgrad(int epi, bfp dy, bfp w, bfp w_t, void* out, long long m, int n_in, int k_out, const float* zeros, cudaStream_t st,
+          bfp aux = nullptr, float* colsum = nullptr) {
+  if (dgrad_mn()) return gemm(epi, dy, k_out, w, n_in, zeros, out, n_in, m, n_in, k_out, st, colsum, aux, nullptr, nullptr, 1);
+  return gemm(epi, dy, k_out, w_t, k_out, zeros, out, n_in, m, n_in, k_out, st, colsum, aux);
 }
 
 // JPDVT_BWD_FUSED=0: separate LayerNorm-backward / gate-backward / partial-sum launches (A/B knob); default: each
@@ -53,10 +69,26 @@ int jpdvt_gemm_dgelu(const jpdvt_bf16* a, const jpdvt_bf16* w, const jpdvt_bf16*
   if (!a || !w || !pre || !out) return set_error(kErrBadArg, "gemm_dgelu: null pointer");
   return gemm(EPI_DGELU_BF16, BF(a), k, BF(w), k, nullptr, out, n, m, n, k, ST(stream), nullptr, BF(pre));
 }
+int jpdvt_gemm_dgrad(const jpdvt_bf16* dy, const jpdvt_bf16* w, const jpdvt_bf16* gprime_or_null, jpdvt_bf16* out_bf16_or_null,
+                     float* out_f32_or_null, float* colsum_or_null, int64_t m, int n_in, int k_out, void* stream) {
+  if (m == 0) return kOk;
+  if (!dy || !w || (!out_bf16_or_null == !out_f32_or_null)) return set_error(kErrBadArg, "gemm_dgrad: null pointer / exactly one output");
+  if (gprime_or_null && !out_bf16_or_null) return set_error(kErrBadArg, "gemm_dgrad: the dGELU form writes bf16");
+  if (colsum_or_null && !gprime_or_null) return set_error(kErrBadArg, "gemm_dgrad: column sums come with the dGELU form only");
+  static float* zeros = nullptr;       // the bias slot of the shared epilogues: 4 x 768 zeros, allocated once per process
+  if (zeros == nullptr) {
+    if (cudaMalloc(&zeros, 4 * kHidden * sizeof(float)) != cudaSuccess || cudaMemset(zeros, 0, 4 * kHidden * sizeof(float)) != cudaSuccess)
+      return set_error(kErrCuda, "gemm_dgrad: cannot allocate the zero bias");
+  }
+  if (n_in > 4 * kHidden) return set_error(kErrBadArg, "gemm_dgrad: n_in=%d > %d", n_in, 4 * kHidden);
+  const int epi = gprime_or_null ? EPI_DGELU_BF16 : (out_bf16_or_null ? EPI_BIAS_BF16 : EPI_BIAS_F32);
+  void* out = out_bf16_or_null ? static_cast<void*>(out_bf16_or_null) : static_cast<void*>(out_f32_or_null);
+  return gemm(epi, BF(dy), k_out, BF(w), n_in, zeros, out, n_in, m, n_in, k_out, ST(stream), colsum_or_null, BF(gprime_or_null), nullptr, nullptr, 1);
+}
 int jpdvt_attention_bwd(const jpdvt_bf16* qkv, const jpdvt_bf16* o, const jpdvt_bf16* d_o, const float* lse2, jpdvt_bf16* dqkv,
-                        int batch, int tokens, void* stream) {
+                        float* dbias_or_null, int batch, int tokens, void* stream) {
   if (!qkv || !o || !d_o || !lse2 || !dqkv) return set_error(kErrBadArg, "attention_bwd: null pointer");
-  return launch_attention_bwd(BF(qkv), BF(o), BF(d_o), lse2, BFM(dqkv), batch, tokens, ST(stream));
+  return launch_attention_bwd(BF(qkv), BF(o), BF(d_o), lse2, BFM(dqkv), dbias_or_null, batch, tokens, ST(stream));
 }
 int64_t jpdvt_bwd_part_floats(int batch, int tokens) { return bwd_part_floats(batch, tokens); }
 
@@ -198,12 +230,12 @@ int jpdvt_train_backward_head(const jpdvt_weights* w, const jpdvt_weights_t* wt,
   JP_TRY(launch_head_bwd(d_te, tp->headpre, w->w_head2, BFM(s->dpre), g->w_head2, g->b_head2, g->b_head1, M, st));
   JP_TRY(launch_wgrad(BF(s->dpre), 64, BF(tp->yfin), kHidden, g->w_head1, s->wgrad_scratch, M, 64, kHidden, st));
   // dy = dpre . W1 (+ the image head's gradient through unpatchify)
-  JP_TRY(gemm(EPI_BIAS_F32, BF(s->dpre), 64, BF(wt->w_head1_t), 64, s->zeros, s->dxn, kHidden, M, kHidden, 64, st));
+  JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dpre), BF(w->w_head1), BF(wt->w_head1_t), s->dxn, M, kHidden, 64, s->zeros, st));
   if (d_img != nullptr) JP_TRY(launch_unpatchify_bwd(d_img, s->dxn, batch, w->image_size, 1, st));
   JP_TRY(launch_cast_bf16(s->dxn, BFM(s->dy), X, st));
   JP_TRY(launch_colsum_f32(s->dxn, kHidden, M, kHidden, g->b_final, st));
   JP_TRY(launch_wgrad(BF(s->dy), kHidden, BF(tp->xnf), kHidden, g->w_final, s->wgrad_scratch, M, kHidden, kHidden, st));
-  JP_TRY(gemm(EPI_BIAS_F32, BF(s->dy), kHidden, BF(wt->w_final_t), kHidden, s->zeros, s->dxn, kHidden, M, kHidden, kHidden, st));
+  JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dy), BF(w->w_final), BF(wt->w_final_t), s->dxn, M, kHidden, kHidden, s->zeros, st));
   const float* mod = tp->mod + static_cast<long long>(depth) * 6 * kHidden;
   float* dmod = s->dmod + static_cast<long long>(depth) * 6 * kHidden;
   if (bwd_fused()) {
@@ -242,12 +274,11 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   const bool fused = bwd_fused();      // then dy = gate_mlp * dx came with the LayerNorm backward of the stage before
   if (!fused) JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   JP_TRY(launch_wgrad(dy, kHidden, h, H4, g->w_fc2 + static_cast<long long>(i) * kHidden * H4, s->wgrad_scratch, M, kHidden, static_cast<int>(H4), st));
-  JP_TRY(gemm(EPI_DGELU_BF16, dy, kHidden, BF(wt->w_fc2_t) + static_cast<long long>(i) * H4 * kHidden, kHidden, nullptr, dh, H4, M,
-              static_cast<int>(H4), kHidden, st, nullptr, hpre));
-  JP_TRY(launch_colsum_bf16(dh, H4, M, static_cast<int>(H4), g->b_fc1 + static_cast<long long>(i) * H4, st));
+  JP_TRY(dgrad(EPI_DGELU_BF16, dy, BF(w->w_fc2) + static_cast<long long>(i) * kHidden * H4, BF(wt->w_fc2_t) + static_cast<long long>(i) * H4 * kHidden,
+               dh, M, static_cast<int>(H4), kHidden, nullptr, st, hpre, g->b_fc1 + static_cast<long long>(i) * H4));   // + db_fc1 = column sums of dh
   JP_TRY(launch_wgrad(dh, H4, xn2, kHidden, g->w_fc1 + static_cast<long long>(i) * H4 * kHidden, s->wgrad_scratch, M, static_cast<int>(H4), kHidden, st));
-  JP_TRY(gemm(EPI_BIAS_F32, dh, H4, BF(wt->w_fc1_t) + static_cast<long long>(i) * kHidden * H4, H4, s->zeros, s->dxn, kHidden, M,
-              kHidden, static_cast<int>(H4), st));
+  JP_TRY(dgrad(EPI_BIAS_F32, dh, BF(w->w_fc1) + static_cast<long long>(i) * H4 * kHidden, BF(wt->w_fc1_t) + static_cast<long long>(i) * kHidden * H4,
+               s->dxn, M, kHidden, static_cast<int>(H4), s->zeros, st));
   // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(xn1)))     (models.py:120)
   if (fused) {
     JP_TRY(launch_ln_gate_bwd(tp->x + static_cast<long long>(2 * i + 1) * X, s->dxn, mod + 4 * kHidden, n_mod, s->dx, 1,
@@ -259,13 +290,14 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
     JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   }
   JP_TRY(launch_wgrad(dy, kHidden, att, kHidden, g->w_proj + static_cast<long long>(i) * kHidden * kHidden, s->wgrad_scratch, M, kHidden, kHidden, st));
-  JP_TRY(gemm(EPI_BIAS_BF16, dy, kHidden, BF(wt->w_proj_t) + static_cast<long long>(i) * kHidden * kHidden, kHidden, s->zeros, datt,
-              kHidden, M, kHidden, kHidden, st));
-  JP_TRY(launch_attention_bwd(qkv, att, datt, tp->lse2 + static_cast<long long>(i) * batch * kHeads * T, dqkv, batch, T, st));
-  JP_TRY(launch_colsum_bf16(dqkv, H3, M, static_cast<int>(H3), g->b_qkv + static_cast<long long>(i) * H3, st));
+  JP_TRY(dgrad(EPI_BIAS_BF16, dy, BF(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, BF(wt->w_proj_t) + static_cast<long long>(i) * kHidden * kHidden,
+               datt, M, kHidden, kHidden, s->zeros, st));
+  // dQ, dK, dV and (folded into the epilogue) the qkv bias gradient = column sums of dqkv
+  JP_TRY(launch_attention_bwd(qkv, att, datt, tp->lse2 + static_cast<long long>(i) * batch * kHeads * T, dqkv,
+                              g->b_qkv + static_cast<long long>(i) * H3, batch, T, st));
   JP_TRY(launch_wgrad(dqkv, H3, xn1, kHidden, g->w_qkv + static_cast<long long>(i) * H3 * kHidden, s->wgrad_scratch, M, static_cast<int>(H3), kHidden, st));
-  JP_TRY(gemm(EPI_BIAS_F32, dqkv, H3, BF(wt->w_qkv_t) + static_cast<long long>(i) * kHidden * H3, H3, s->zeros, s->dxn, kHidden, M,
-              kHidden, static_cast<int>(H3), st));
+  JP_TRY(dgrad(EPI_BIAS_F32, dqkv, BF(w->w_qkv) + static_cast<long long>(i) * H3 * kHidden, BF(wt->w_qkv_t) + static_cast<long long>(i) * kHidden * H3,
+               s->dxn, M, kHidden, static_cast<int>(H3), s->zeros, st));
   if (fused) {
     if (i == 0)     // bf16(dx0) for the patch-embedding weight gradient
       return launch_ln_gate_bwd(tp->x, s->dxn, mod + kHidden, n_mod, s->dx, 1, dmod, dmod + kHidden, n_mod, dy, nullptr, nullptr, 0,
@@ -306,8 +338,7 @@ int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt
   JP_TRY(launch_colsum_f32(s->dmod, n_mod, batch, static_cast<int>(n_mod), g->b_ada, st));
   JP_TRY(launch_cast_bf16(s->dmod, BFM(s->dmod_bf16), static_cast<long long>(batch) * n_mod, st));
   JP_TRY(launch_wgrad(BF(s->dmod_bf16), n_mod, BF(tp->silu_c_bf16), kHidden, g->w_ada, s->wgrad_scratch, batch, static_cast<int>(n_mod), kHidden, st));
-  JP_TRY(gemm(EPI_BIAS_F32, BF(s->dmod_bf16), n_mod, BF(wt->w_ada_t), n_mod, s->zeros, dsilu, kHidden, batch, kHidden,
-              static_cast<int>(n_mod), st));
+  JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dmod_bf16), BF(w->w_ada), BF(wt->w_ada_t), dsilu, batch, kHidden, static_cast<int>(n_mod), s->zeros, st));
   // c = W2 . silu(tpre) + b2 ; tpre = W0 . feat + b0                            (models.py:61-64)
   JP_TRY(launch_silu_bwd(dsilu, tp->c, dc, dc_bf, BH, st));
   JP_TRY(launch_colsum_f32(dc, kHidden, batch, kHidden, g->t_b2, st));

@@ -446,13 +446,32 @@ def gemm_dgelu(a, w, pre) -> torch.Tensor:
     return out
 
 
-def attention_bwd(qkv, o, d_o, lse2, batch: int, tokens: int) -> torch.Tensor:
+def gemm_dgrad(dy, w, gprime=None, out_dtype=torch.float32, with_colsum: bool = False):
+    """dX = dY . W from the layer's own [out, in] weight (MN-major B operand); `gprime`: multiply by gelu' (bf16 output);
+    `with_colsum` (dGELU form): also the column sums of the output -> (out, colsum [n_in])."""
+    lib = _lib_dev()
+    dy, w = _need(dy, torch.bfloat16, "dy"), _need(w, torch.bfloat16, "w")
+    m, k_out = dy.shape
+    n_in = w.shape[1]
+    if gprime is not None:
+        out_dtype = torch.bfloat16
+    out = torch.empty(m, n_in, device=dy.device, dtype=out_dtype)
+    cs = torch.zeros(n_in, device=dy.device, dtype=torch.float32) if with_colsum else None
+    check(lib.jpdvt_gemm_dgrad(ptr(dy), ptr(w), ptr(_need(gprime, torch.bfloat16, "gprime")) if gprime is not None else None,
+                               ptr(out) if out_dtype == torch.bfloat16 else None, ptr(out) if out_dtype == torch.float32 else None,
+                               ptr(cs), m, n_in, k_out, stream_ptr()), "gemm_dgrad")
+    return (out, cs) if with_colsum else out
+
+
+def attention_bwd(qkv, o, d_o, lse2, batch: int, tokens: int, with_bias_grad: bool = False):
+    """-> dqkv, or (dqkv, dbias [2304] = column sums of dqkv) with `with_bias_grad`."""
     lib = _lib_dev()
     dqkv = torch.empty_like(qkv)
+    dbias = torch.zeros(3 * HIDDEN, device=qkv.device, dtype=torch.float32) if with_bias_grad else None
     check(lib.jpdvt_attention_bwd(ptr(_need(qkv, torch.bfloat16, "qkv")), ptr(_need(o, torch.bfloat16, "o")),
                                   ptr(_need(d_o, torch.bfloat16, "d_o")), ptr(_need(lse2, torch.float32, "lse2")), ptr(dqkv),
-                                  batch, tokens, stream_ptr()), "attention_bwd")
-    return dqkv
+                                  ptr(dbias), batch, tokens, stream_ptr()), "attention_bwd")
+    return (dqkv, dbias) if with_bias_grad else dqkv
 
 
 def gate_bwd(dx, y, gate, tokens: int):

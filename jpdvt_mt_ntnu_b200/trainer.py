@@ -166,6 +166,12 @@ class Trainer:
         self.t_w2_bf16.copy_(self.p_views["t_w2"])
         d = self.model.depth
         bv = self.pb_views
+        if os.environ.get("JPDVT_DGRAD_MN", "1")[:1] != "0":
+            # the data-gradient GEMMs read the [out, in] weights themselves (MN-major B operand): only the small timestep-MLP
+            # matrix, whose operand copy is not part of jpdvt_weights, still gets a transposed bf16 copy
+            check(self.lib.jpdvt_transpose_bf16(ptr(self.t_w2_bf16), ptr(self.wt_t["t_w2_t"]), 1, HIDDEN, HIDDEN, st), "jpdvt_transpose_bf16")
+            self.model.__dict__["_epoch"] = self.model.__dict__.get("_epoch", 0) + 1
+            return
         for name, src, batch, rows, cols in (("w_qkv_t", bv["w_qkv"], d, 3 * HIDDEN, HIDDEN), ("w_proj_t", bv["w_proj"], d, HIDDEN, HIDDEN),
                                             ("w_fc1_t", bv["w_fc1"], d, 4 * HIDDEN, HIDDEN), ("w_fc2_t", bv["w_fc2"], d, HIDDEN, 4 * HIDDEN),
                                             ("w_final_t", bv["w_final"], 1, HIDDEN, HIDDEN), ("w_head1_t", bv["w_head1"], 1, 64, HIDDEN),

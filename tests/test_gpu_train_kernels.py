@@ -23,6 +23,26 @@ def test_wgrad_mn_major_gemm(ops, m, r, c):
     assert rel_l2(ops.gemm_wgrad(p, q), p.float().t() @ q.float()) < 1e-5       # fp32 accumulate, fp32 out, split-K reduce
 
 
+@pytest.mark.parametrize("m,k_out,n_in", [(4608, 768, 3072), (1000, 3072, 768), (432, 2304, 768), (300, 64, 768), (128, 768, 768),
+                                          (7, 1536, 768)])
+def test_dgrad_from_the_untransposed_weight(ops, m, k_out, n_in):
+    """dX = dY . W with W [out, in] read as an MN-major tcgen05 operand (no transposed weight copy): fp32, bf16 and dGELU
+    outputs against fp32 torch, and bit-identical to the K-major GEMM on the transposed copy (same products, same order)."""
+    torch.manual_seed(m + k_out)
+    dy = torch.randn(m, k_out, device="cuda").bfloat16()
+    w = (torch.randn(k_out, n_in, device="cuda") * 0.05).bfloat16()
+    ref = dy.float() @ w.float()
+    got = ops.gemm_dgrad(dy, w)
+    assert rel_l2(got, ref) < 1e-5
+    assert torch.equal(got, ops.gemm_bias_f32(dy, w.t().contiguous(), torch.zeros(n_in, device="cuda")))
+    assert rel_l2(ops.gemm_dgrad(dy, w, out_dtype=torch.bfloat16).float(), ref) < 5e-3
+    gp = torch.rand(m, n_in, device="cuda").bfloat16()
+    dh = ops.gemm_dgrad(dy, w, gprime=gp)
+    assert rel_l2(dh.float(), ref * gp.float()) < 5e-3
+    dh2, cs = ops.gemm_dgrad(dy, w, gprime=gp, with_colsum=True)      # bias gradient of the layer below, from the same epilogue
+    assert torch.equal(dh2, dh) and rel_l2(cs, dh.float().sum(0)) < 1e-5
+
+
 def test_dgelu_gate_ln_colsum(ops):
     torch.manual_seed(1)
     m, T = 432, 144
@@ -96,3 +116,7 @@ def test_attention_backward(ops, B, T):
     dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, T)
     for lo in (0, 768, 1536):
         assert rel_l2(dqkv[:, lo:lo + 768].float(), x.grad[:, lo:lo + 768]) < 6e-3
+    # the qkv bias gradient folded into the epilogue: column sums of exactly the bf16 values written
+    dqkv2, dbias = ops.attention_bwd(qkv, o, d_o, lse, B, T, with_bias_grad=True)
+    assert torch.equal(dqkv2, dqkv)
+    assert rel_l2(dbias, dqkv.float().sum(0)) < 1e-5
