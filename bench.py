@@ -353,8 +353,10 @@ def measure_strong(wl, total, world, rank, dev, steps, model=None, diffusion=Non
         one(cond, noise)
     ms, _ = _timed(lambda: one(cond, noise), steps, world, dev)
     ms_e2e, _ = _timed(lambda: one(cond_pin.to(dev, non_blocking=True), noise_pin.to(dev, non_blocking=True)).cpu(), steps, world, dev)
+    tflops = flops_per_forward((wl["size"] // 16) ** 2) * wl["steps"] * per * steps / (ms * 1e-3) / 1e12     # per GPU
     return {"workload": wl["name"].split(",")[0], "total_puzzles": per * world, "batch_per_gpu": per, "graph_replay": graph,
             "value": per * world * steps / (ms * 1e-3), "unit": "puzzles/s", "ms_per_pass": ms / steps,
+            "model_tflops_per_gpu": tflops, "model_frac_of_bf16_sustained": tflops / measured_peaks()["bf16_sustained"],
             "e2e": {"value": per * world * steps / (ms_e2e * 1e-3), "unit": "puzzles/s", "ms_per_pass": ms_e2e / steps}}
 
 
@@ -414,9 +416,11 @@ def run_ours(args, wl):
         del model
         torch.cuda.empty_cache()
         model = None
-        c5 = WORKLOADS["c5"]
-        strong["c5"] = measure_strong(c5, 128, world, rank, dev, 2)
-        torch.cuda.empty_cache()
+        # the other sampling configs of BASELINE.json (configs[3], [4]): 4x4 @256 px and 3x3 @288 px with missing pieces,
+        # 128 puzzles for the whole job each, so that every --gpus N line carries the whole reporting matrix
+        for key in ("c4", "c5"):
+            strong[key] = measure_strong(WORKLOADS[key], 128, world, rank, dev, 2)
+            torch.cuda.empty_cache()
     # ---- BASELINE.json's other metric: train img/s (configs[2]) with the NCCL gradient all-reduce at this N
     train = None
     if not args.no_extras and wl is WORKLOADS["c2"]:
