@@ -437,6 +437,302 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 256 (4x4 puzzles @256 px, BASELINE configs[3]): the score-sized tiles no longer fit shared memory next to the five
+// operand tiles, so a unit is walked as 2 key blocks x 2 query blocks of 128 x 128:
+//   per (kb, qb):  S^T = K[kb] Q[qb]^T, dP^T = V[kb] dO[qb]^T   -> TMEM columns [0,128), [128,256)
+//                  math warps (thread = key row): P^T, dS^T (bf16, K-major [key][query]) -> shared memory
+//                  dV[kb] += P^T dO[qb],  dK[kb] += dS^T Q[qb],  dQ[qb] += dS K[kb]      -> TMEM [256,320) [320,384) [384+64 qb, ..)
+// dV / dK of a key block leave TMEM after its second query block, the two dQ tiles at the end of the unit.  P^T lives where O
+// was (O is only needed for D[q] = sum_d dO O at the top of the unit).  The score MMAs of tile n+1 queue behind the gradient
+// MMAs of tile n, so they are done by the time the math warps come back for them.
+struct Bt256 {
+  static constexpr int T = 256;
+  static constexpr int kTile = T * 128;                       // 32 KB: one of Q / K / V / dO / O
+  static constexpr int kBlk = 128 * 128;                      // 64 queries of the 128-key P^T / dS^T tile
+  static constexpr int kOffQ = 0, kOffK = kTile, kOffV = 2 * kTile, kOffdO = 3 * kTile, kOffO = 4 * kTile;
+  static constexpr int kOffP = kOffO;                         // aliases O
+  static constexpr int kOffdS = 5 * kTile;
+  static constexpr int kOffStage = kOffdS + 2 * kBlk;         // 4 x 4 KB epilogue staging
+  static constexpr int kOffL = kOffStage + 4 * 4096;          // lse2[T], D[T]
+  static constexpr int kBarOff = kOffL + 2 * T * 4;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kInBytes = 5 * kTile;
+  static constexpr int kColS = 0, kColdP = 128, kColdV = 256, kColdK = 320, kColdQ = 384;
+  static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory");
+};
+
+__global__ void __launch_bounds__(kBtThreads, 1)
+attention_bwd_tc256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                           const __grid_constant__ CUtensorMap tm_o, const float* __restrict__ lse2, __nv_bfloat16* __restrict__ dqkv,
+                           float* __restrict__ dbias, int num_units) {
+  using Cfg = Bt256;
+  constexpr int T = Cfg::T;
+  extern __shared__ uint8_t att_bt_smem[];
+  uint8_t* smem = att_bt_smem + ((1024u - (smem_u32(att_bt_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* in_full = bars + 0;        // TMA: the unit's five tiles landed                                  (1 / unit)
+  uint64_t* s_full = bars + 1;         // MMA: S^T, dP^T of a tile are in TMEM                                (4 / unit)
+  uint64_t* p_full = bars + 2;         // math: P^T, dS^T of a tile are in shared memory, S^T / dP^T consumed (4 / unit, 4 arrivals)
+  uint64_t* g_done = bars + 3;         // MMA: the gradient MMAs of a tile have read P^T / dS^T               (4 / unit)
+  uint64_t* kv_drained = bars + 4;     // math: dV / dK of a key block have left TMEM                         (2 / unit, 4 arrivals)
+  uint64_t* epi_done = bars + 5;       // math: dQ has left TMEM                                              (1 / unit, 4 arrivals)
+  uint64_t* unit_done = bars + 6;      // MMA: every MMA of the unit has read its operand tiles               (1 / unit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  float* sL = reinterpret_cast<float*>(smem + Cfg::kOffL);
+  float* sD = sL + T;
+  __shared__ float s_colsum[3 * kHeadDim];
+  if (threadIdx.x < 3 * kHeadDim) s_colsum[threadIdx.x] = 0.f;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(in_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(g_done, 1); mbar_init(kv_drained, 4);
+    mbar_init(epi_done, 4); mbar_init(unit_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sdO = smem_u32(smem + Cfg::kOffdO), sO = smem_u32(smem + Cfg::kOffO), sdS = smem_u32(smem + Cfg::kOffdS),
+                 sP = smem_u32(smem + Cfg::kOffP);
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int b = unit / kHeads, h = unit - b * kHeads;
+        if (it > 0) mbar_wait_backoff(unit_done, static_cast<uint32_t>((it - 1) & 1), 64);
+        mbar_expect_tx(in_full, Cfg::kInBytes);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+        tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO, h * kHeadDim, b * T);
+        tma_load_2d(&tm_o, in_full, smem + Cfg::kOffO, h * kHeadDim, b * T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);               // S^T / dP^T: M = 128 keys, N = 128 queries
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHeadDim, 0, 1);   // dV, dK: A K-major, B (dO / Q) MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHeadDim, 1, 1);    // dQ: A (dS^T) and B (K) both MN-major
+      constexpr uint32_t kBlkW = Cfg::kBlk / 16;                            // P^T / dS^T block stride in descriptor units
+      constexpr uint32_t kHalfW = 128 * 128 / 16;                           // 128 rows of an operand tile in descriptor units
+      const uint32_t p_lo = desc_lo_k(sP), ds_lo = desc_lo_k(sdS), ds_mn = desc_lo_mn(sdS, Cfg::kBlk);
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        mbar_wait(in_full, static_cast<uint32_t>(it & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int n = 0; n < 4; ++n) {
+          const int kb = n >> 1, qb = n & 1;
+          const uint32_t g = static_cast<uint32_t>(it * 4 + n);
+          const uint32_t k_lo = desc_lo_k(sK + kb * Cfg::kBlk), v_lo = desc_lo_k(sV + kb * Cfg::kBlk);
+          const uint32_t q_lo = desc_lo_k(sQ + qb * Cfg::kBlk), do_lo = desc_lo_k(sdO + qb * Cfg::kBlk);
+          // ---- scores and their gradient for tile n (the TMEM columns were released by p_full of tile n - 1)
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColS, k_lo, q_lo, idesc_s);
+            else umma_lohi<true>(tmem_base + Cfg::kColS, k_lo + 2 * k, q_lo + 2 * k, idesc_s);
+          }
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColdP, v_lo, do_lo, idesc_s);
+            else umma_lohi<true>(tmem_base + Cfg::kColdP, v_lo + 2 * k, do_lo + 2 * k, idesc_s);
+          }
+          umma_commit(s_full);
+          // ---- gradients of tile n
+          mbar_wait(p_full, g & 1u);
+          if (n == 0 && it > 0) {                        // dV / dK of the previous unit's second key block, and its dQ, have left TMEM
+            mbar_wait(kv_drained, 1u);
+            mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));
+          }
+          if (n == 2) mbar_wait(kv_drained, 0u);         // ... of this unit's first key block
+          tc_fence_after();
+          const uint32_t do_mn = desc_lo_mn(sdO + qb * Cfg::kBlk, 8192), q_mn = desc_lo_mn(sQ + qb * Cfg::kBlk, 8192);
+          const uint32_t k_mn = desc_lo_mn(sK + kb * Cfg::kBlk, 8192);
+          (void)kHalfW;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                  // contraction over the tile's 128 queries
+            const uint32_t a = p_lo + (j >> 2) * kBlkW + (j & 3) * 2;
+            if (j == 0 && qb == 0) umma_lohi<false>(tmem_base + Cfg::kColdV, a, do_mn + j * 128, idesc_kv);
+            else umma_lohi<true>(tmem_base + Cfg::kColdV, a, do_mn + j * 128, idesc_kv);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = ds_lo + (j >> 2) * kBlkW + (j & 3) * 2;
+            if (j == 0 && qb == 0) umma_lohi<false>(tmem_base + Cfg::kColdK, a, q_mn + j * 128, idesc_kv);
+            else umma_lohi<true>(tmem_base + Cfg::kColdK, a, q_mn + j * 128, idesc_kv);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {                  // contraction over the tile's 128 keys
+            const uint32_t dq = tmem_base + Cfg::kColdQ + 64 * qb;
+            if (j == 0 && kb == 0) umma_lohi<false>(dq, ds_mn + j * 128, k_mn + j * 128, idesc_q);
+            else umma_lohi<true>(dq, ds_mn + j * 128, k_mn + j * 128, idesc_q);
+          }
+          umma_commit(g_done);
+        }
+        umma_commit(unit_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- math + epilogue warps
+    constexpr float sl2 = 0.125f * 1.4426950408889634f;
+    const int tid = threadIdx.x;                              // 0..127 = TMEM lane = key row inside the key block
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t stage = smem_u32(smem + Cfg::kOffStage) + static_cast<uint32_t>(warp) * 4096u;
+    const uint32_t csq = dbias != nullptr ? smem_u32(s_colsum) : 0u;
+    const uint32_t csk = csq ? csq + kHeadDim * 4 : 0u, csv = csq ? csq + 2 * kHeadDim * 4 : 0u;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const int b = unit / kHeads, h = unit - b * kHeads;
+      const float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+      __nv_bfloat16* base = dqkv + static_cast<long long>(b) * T * kQkvCols + h * kHeadDim;
+      mbar_wait(in_full, static_cast<uint32_t>(it & 1));
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {                     // D[q] and lse2[q]: two query rows per thread
+        const int q = tid + rep * 128;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t off = static_cast<uint32_t>(q) * 128u + static_cast<uint32_t>((j ^ (q & 7)) << 4);
+          const uint4 a = lds_u4(sdO + off), c = lds_u4(sO + off);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(cw[e] << 16), acc);
+            acc = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(cw[e] & 0xffff0000u), acc);
+          }
+        }
+        sD[q] = acc;
+        sL[q] = __ldg(lrow + q);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // D / lse complete; nobody reads O any more (P^T may overwrite it)
+#pragma unroll 1
+      for (int n = 0; n < 4; ++n) {
+        const int kb = n >> 1, qb = n & 1;
+        const uint32_t g = static_cast<uint32_t>(it * 4 + n);
+        mbar_wait(s_full, g & 1u);
+        if (g > 0) mbar_wait(g_done, (g - 1) & 1u);           // the previous tile's gradient MMAs have read P^T / dS^T
+        tc_fence_after();
+        {
+          uint32_t sa[16], da[16], sb[16], db[16];
+          tmem_ld_32x16(t_lane + Cfg::kColS, sa);
+          tmem_ld_32x16(t_lane + Cfg::kColdP, da);
+          tmem_ld_wait();
+          const uint32_t prow = sP + static_cast<uint32_t>(tid) * 128u, dsrow = sdS + static_cast<uint32_t>(tid) * 128u;
+          const int sw = tid & 7;
+          const float* lq = sL + qb * 128;
+          const float* dq = sD + qb * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t (&s_cur)[16] = (c & 1) ? sb : sa;
+            uint32_t (&d_cur)[16] = (c & 1) ? db : da;
+            uint32_t (&s_nxt)[16] = (c & 1) ? sa : sb;
+            uint32_t (&d_nxt)[16] = (c & 1) ? da : db;
+            if (c + 1 < 8) {
+              tmem_ld_32x16(t_lane + Cfg::kColS + 16 * (c + 1), s_nxt);
+              tmem_ld_32x16(t_lane + Cfg::kColdP + 16 * (c + 1), d_nxt);
+            }
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+              const int q0 = 16 * c + 8 * gg;
+              const float4 l0 = *reinterpret_cast<const float4*>(lq + q0), l1 = *reinterpret_cast<const float4*>(lq + q0 + 4);
+              const float4 e0 = *reinterpret_cast<const float4*>(dq + q0), e1 = *reinterpret_cast<const float4*>(dq + q0 + 4);
+              const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+              const float dv[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+              float p[8], ds[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                p[e] = ex2f(fmaf(__uint_as_float(s_cur[8 * gg + e]), sl2, -lv[e]));
+                ds[e] = p[e] * (__uint_as_float(d_cur[8 * gg + e]) - dv[e]) * 0.125f;
+              }
+              const int chunk = q0 >> 3;
+              const uint32_t off = static_cast<uint32_t>(chunk >> 3) * Cfg::kBlk + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4);
+              sts_u4(prow + off, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+              sts_u4(dsrow + off, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7])));
+            }
+            if (c + 1 < 8) tmem_ld_wait();
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        if (qb == 1) {                                        // the key block is complete: dV[kb], dK[kb] -> dqkv rows kb*128 + ...
+          mbar_wait(g_done, g & 1u);
+          tc_fence_after();
+          __nv_bfloat16* row0 = base + static_cast<long long>(kb * 128 + warp * 32) * kQkvCols;
+          store_acc_rows(t_lane + Cfg::kColdV, stage, row0 + 2 * kHidden, kQkvCols, 0, 32, lane, csv);
+          store_acc_rows(t_lane + Cfg::kColdK, stage, row0 + kHidden, kQkvCols, 0, 32, lane, csk);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(kv_drained);
+        }
+      }
+      // ---- dQ of both query blocks (g_done of the last tile was waited for above)
+#pragma unroll
+      for (int qb = 0; qb < 2; ++qb)
+        store_acc_rows(t_lane + Cfg::kColdQ + 64 * qb, stage, base + static_cast<long long>(qb * 128 + warp * 32) * kQkvCols, kQkvCols,
+                       0, 32, lane, csq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      if (dbias != nullptr) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int idx = k * 32 + lane;
+            atomicAdd(dbias + (idx >> 6) * kHidden + h * kHeadDim + (idx & 63), s_colsum[idx]);
+            s_colsum[idx] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_bt256(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
+                 float* dbias, int batch, cudaStream_t stream) {
+  using Cfg = Bt256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_bwd_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_bwd_tc256: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    configured = true;
+  }
+  CUtensorMap tm_qkv, tm_do, tm_o;
+  const long long rows = static_cast<long long>(batch) * Cfg::T;
+  int rc = make_tmap_bf16_kmajor(&tm_qkv, qkv, rows, kQkvCols, kQkvCols, Cfg::T);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tm_do, d_o, rows, kHidden, kHidden, Cfg::T);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tm_o, o, rows, kHidden, kHidden, Cfg::T);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  attention_bwd_tc256_kernel<<<units < sms ? units : sms, kBtThreads, Cfg::kSmemBytes, stream>>>(tm_qkv, tm_do, tm_o, lse2, dqkv, dbias, units);
+  return check_launch("attention_bwd_tc256_kernel");
+}
+
 template <int T>
 int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
               float* dbias, int batch, cudaStream_t stream) {
@@ -470,7 +766,7 @@ int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloa
 bool attention_bwd_tc_supported(int tokens) {
   static int legacy = -1;      // JPDVT_ATTN_BWD_LEGACY=1: the mma.sync backward for every size (A/B knob)
   if (legacy < 0) { const char* e = getenv("JPDVT_ATTN_BWD_LEGACY"); legacy = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return !legacy && tokens == 144;
+  return !legacy && (tokens == 144 || tokens == 256);
 }
 
 int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
@@ -481,6 +777,7 @@ int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, co
     return set_error(kErrBadArg, "attention_bwd_tc: pointers must be 16-byte aligned");
   switch (tokens) {
     case 144: return launch_bt<144>(qkv, o, d_o, lse2, dqkv, dbias, batch, stream);
+    case 256: return launch_bt256(qkv, o, d_o, lse2, dqkv, dbias, batch, stream);
     default: return set_error(kErrUnsupported, "attention_bwd_tc: %d tokens not instantiated", tokens);
   }
 }

@@ -19,7 +19,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-T = 144
+T = int(os.environ.get("T", "144"))
 for B in [int(v) for v in sys.argv[1:]] or [1, 2, 13]:
     torch.manual_seed(B)
     qkv = (torch.randn(B * T, 2304, device="cuda") * 1.2).bfloat16()
@@ -39,9 +39,9 @@ for B in [int(v) for v in sys.argv[1:]] or [1, 2, 13]:
     for part, name in enumerate(("dQ", "dK", "dV")):
         main = rel(d[:, :128, part] + gg[:, :128, part], gg[:, :128, part])
         tail = rel(d[:, 128:, part] + gg[:, 128:, part], gg[:, 128:, part])
-        print(f"    {name}: rows 0..127 {main:.3e}   rows 128..143 {tail:.3e}")
+        print(f"    {name}: rows 0..127 {main:.3e}   rows 128..{T - 1} {tail:.3e}")
 
-B = 128
+B = int(os.environ.get("TIME_BATCH", "128"))
 qkv = (torch.randn(B * T, 2304, device="cuda") * 1.2).bfloat16()
 d_o = torch.randn(B * T, 768, device="cuda").bfloat16()
 o, lse = ops.attention(qkv, B, T, return_lse=True)
@@ -55,4 +55,4 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 20 * 1e3
-print(f"attention_bwd B=128 T=144: {us:.1f} us per launch  ({5 * 2 * B * 12 * T * T * 64 / us / 1e6:.0f} TFLOP/s algorithmic)")
+print(f"attention_bwd B={B} T={T}: {us:.1f} us per launch  ({5 * 2 * B * 12 * T * T * 64 / us / 1e6:.0f} TFLOP/s algorithmic)")
