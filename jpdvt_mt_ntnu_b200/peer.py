@@ -31,6 +31,19 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int, int]:
     return chunk, rank * chunk, (rank + 1) * chunk
 
 
+def merge_ranges(ranges, limit: int = MAX_F32_RANGES):
+    """Sorted union of half-open index ranges (touching ranges are joined); raises if more than `limit` remain."""
+    merged = []
+    for b, e in sorted((int(b), int(e)) for b, e in ranges if e > b):
+        if merged and b <= merged[-1][1]:
+            merged[-1][1] = max(merged[-1][1], e)
+        else:
+            merged.append([b, e])
+    if len(merged) > limit:
+        raise _lib.JpdvtError(f"{len(merged)} fp32 ranges, the kernel takes {limit}")
+    return [tuple(r) for r in merged]
+
+
 def available(group=None) -> Tuple[bool, str]:
     """Can this process group use the peer-memory step?  (one node, 2..8 ranks, NCCL group, symmetric memory present)"""
     if not dist.is_initialized():
@@ -106,18 +119,11 @@ class PeerExchange:
     def set_f32_ranges(self, ranges) -> None:
         """Index ranges of the flat parameter space whose fp32 values every rank needs after a step (the parameters the
         kernels read in fp32: biases, timestep MLP, position head) - merged, at most MAX_F32_RANGES."""
-        merged = []
-        for b, e in sorted(ranges):
-            if merged and b <= merged[-1][1]:
-                merged[-1][1] = max(merged[-1][1], e)
-            else:
-                merged.append([b, e])
-        if len(merged) > MAX_F32_RANGES:
-            raise _lib.JpdvtError(f"{len(merged)} fp32 ranges, the kernel takes {MAX_F32_RANGES}")
+        merged = merge_ranges(ranges)
         self.struct.n_f32_ranges = len(merged)
         for k, (b, e) in enumerate(merged):
             self.struct.f32_ranges[2 * k], self.struct.f32_ranges[2 * k + 1] = b, e
-        self.f32_ranges = [tuple(r) for r in merged]
+        self.f32_ranges = merged
 
     def pull(self, names=("p", "m", "v", "ema")) -> None:
         """One-sided gather: copy every other owner's slice of the named fp32 state buffers into this rank's copy (peer

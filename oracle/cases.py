@@ -51,6 +51,8 @@ TRAINING_CASES = {
     "tiny96_mask": dict(size=96,  depth=2, batch=3, grid=3, wseed=32, seed=302, add_mask=True),
     "g4_128_mask": dict(size=128, depth=2, batch=2, grid=4, wseed=33, seed=303, add_mask=True),
     "d2_192":      dict(size=192, depth=2, batch=2, grid=3, wseed=34, seed=304, add_mask=False),
+    # 4x4 @256 px (T = 256, BASELINE configs[3]): the tiled tcgen05 attention backward end to end
+    "g4_256":      dict(size=256, depth=2, batch=2, grid=4, wseed=35, seed=305, add_mask=False),
 }
 
 GRAD_KEYS = [

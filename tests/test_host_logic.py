@@ -173,3 +173,34 @@ def test_documented_knobs_exist_in_the_sources():
     internal = {"JPDVT_FORCE_BUILD", "JPDVT_KEEP_NCCL_DEBUG"}          # build / bench plumbing, not A/B knobs
     undocumented = (read_in_c | read_in_py) - documented - internal
     assert not undocumented, f"read by the code but missing from DESIGN.md section 9: {sorted(undocumented)}"
+
+
+def test_peer_shard_bounds_and_f32_ranges():
+    """Host logic of the peer-memory optimizer step (jpdvt_mt_ntnu_b200/peer.py): the flat parameter space is cut into equal
+    contiguous slices of whole 2,048-parameter tiles that cover it exactly once; the fp32-replicated index ranges are the
+    sorted union of the non-bf16 fields."""
+    from jpdvt_mt_ntnu_b200 import peer
+    from jpdvt_mt_ntnu_b200._lib import JpdvtError, MAX_F32_RANGES
+    for total in (130747208, 2048, 2049, 5, 16 * 2048):
+        for world in (2, 3, 4, 8):
+            spans = [peer.shard_bounds(total, world, r) for r in range(world)]
+            chunk = spans[0][0]
+            assert chunk % 2048 == 0 and all(c == chunk for c, _, _ in spans)
+            assert spans[0][1] == 0 and all(spans[r][2] == spans[r + 1][1] for r in range(world - 1))
+            assert spans[-1][2] == world * chunk >= total > world * chunk - world * 2048
+    assert peer.merge_ranges([(10, 20), (0, 5), (20, 30), (28, 40), (50, 50), (60, 61)]) == [(0, 5), (10, 40), (60, 61)]
+    with pytest.raises(JpdvtError):
+        peer.merge_ranges([(3 * i, 3 * i + 1) for i in range(MAX_F32_RANGES + 1)])
+    # the JPDVT layout: everything that is not one of the eight bf16 matrices collapses into eight ranges
+    from jpdvt_mt_ntnu_b200.trainer import _BF16_FIELDS
+    from jpdvt_mt_ntnu_b200.training import _grad_layout
+    import math
+    off, ranges, f32_total = 0, [], 0
+    for name, shape in _grad_layout(12):
+        n = math.prod(shape)
+        if name not in _BF16_FIELDS:
+            ranges.append((off, off + n))
+            f32_total += n
+        off += n
+    merged = peer.merge_ranges(ranges)
+    assert len(merged) == 8 and sum(e - b for b, e in merged) == f32_total and off == 130747208
