@@ -103,6 +103,7 @@ struct TcCfg {
   static constexpr int kTmemCols = (!kDual && T + 64 <= 256) ? 256 : 512;
   static constexpr int kCtasPerSm = (T + 64 <= 256 && 2 * (kSmemBytes + 1024) <= 227 * 1024) ? 2 : 1;
   static_assert(kOffP % 1024 == 0 && kOffP1 % 1024 == 0 && kTileBytes % 1024 == 0, "operand tiles must stay 1024-byte aligned (swizzle atoms)");
+  static_assert(!kSplit || T + 64 + 32 <= kTmemCols, "transposed remainder scores need 32 TMEM columns behind O0");
 };
 
 // One softmax pass of the thread's S row (TMEM lane = row, columns [0,T)): exact row maximum, then
@@ -226,6 +227,81 @@ __device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_ro
   return (xch[64 + l] + xch[80 + l]) + (xch[96 + l] + xch[112 + l]);
 }
 
+// Transposed remainder (T = 144, opt-in - measured slower than the split form below, kept as the A/B): the scores of query rows 128..143 are produced as S_rem^T = K Q_rem^T - TMEM lane =
+// key, 16 columns = the remainder queries; a second group over the K rows shifted by 16 puts keys 128..143 into lanes 112..127 -
+// in 32 columns of their own, so their MMAs are issued right behind the main score tile instead of after its softmax has
+// released the columns (the untransposed form left every softmax warp waiting ~1,400 cycles per unit for them).  Each thread
+// then holds one key x 16 queries: row maximum and row sum are warp shuffles + one exchange through `xch`; the probabilities
+// go out as 2-byte stores into the compact K-major P tile (row = query, 2 KB per 64-key block), contiguous per warp and query.
+// Returns the row sum / sets ms_out for query (lane & 15).
+template <int T>
+__device__ __forceinline__ float softmax_rem_t_to_p(uint32_t t_lane, uint32_t col_r, uint32_t sP1, float* xch, int warp, int lane,
+                                                    float& ms_out) {
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  static_assert(T == 144, "transposed remainder: 128 + 16 tokens");
+  uint32_t a[16], b[16];
+  tmem_ld_32x16(t_lane + col_r, a);
+  tmem_ld_32x16(t_lane + col_r + 16, b);
+  tmem_ld_wait();
+  const bool tail = warp == 3 && lane >= 16;                 // lanes 112..127 of the shifted group hold keys 128..143
+  float m[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    m[q] = __uint_as_float(a[q]);
+    if (tail) m[q] = fmaxf(m[q], __uint_as_float(b[q]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(xch + warp * 16 + q) = make_float4(m[q], m[q + 1], m[q + 2], m[q + 3]);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  float ms[16];
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    const float4 x0 = *reinterpret_cast<const float4*>(xch + q), x1 = *reinterpret_cast<const float4*>(xch + 16 + q);
+    const float4 x2 = *reinterpret_cast<const float4*>(xch + 32 + q), x3 = *reinterpret_cast<const float4*>(xch + 48 + q);
+    ms[q] = fmaxf(fmaxf(x0.x, x1.x), fmaxf(x2.x, x3.x)) * sl2; ms[q + 1] = fmaxf(fmaxf(x0.y, x1.y), fmaxf(x2.y, x3.y)) * sl2;
+    ms[q + 2] = fmaxf(fmaxf(x0.z, x1.z), fmaxf(x2.z, x3.z)) * sl2; ms[q + 3] = fmaxf(fmaxf(x0.w, x1.w), fmaxf(x2.w, x3.w)) * sl2;
+  }
+  const int key = warp * 32 + lane, key2 = 128 + (lane & 15);
+  // element (q, key) of the compact P tile: block key >> 6, row q (128 B), 16-byte chunk ((key & 63) >> 3) ^ (q & 7)
+  const uint32_t base1 = sP1 + static_cast<uint32_t>(key >> 6) * 2048u + static_cast<uint32_t>(key & 7) * 2u;
+  const uint32_t base2 = sP1 + 2u * 2048u + static_cast<uint32_t>(key2 & 7) * 2u;
+  const uint32_t c1 = static_cast<uint32_t>((key & 63) >> 3), c2 = static_cast<uint32_t>((key2 & 63) >> 3);
+  float sm[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float p = ex2f(fmaf(__uint_as_float(a[q]), sl2, -ms[q]));
+    sm[q] = p;
+    const __nv_bfloat16 hb = __float2bfloat16_rn(p);
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(base1 + static_cast<uint32_t>(q) * 128u + ((c1 ^ static_cast<uint32_t>(q & 7)) << 4)),
+                 "h"(*reinterpret_cast<const uint16_t*>(&hb)) : "memory");
+    if (tail) {
+      const float p2 = ex2f(fmaf(__uint_as_float(b[q]), sl2, -ms[q]));
+      sm[q] += p2;
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(p2);
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(base2 + static_cast<uint32_t>(q) * 128u + ((c2 ^ static_cast<uint32_t>(q & 7)) << 4)),
+                   "h"(*reinterpret_cast<const uint16_t*>(&h2)) : "memory");
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], o);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(xch + 64 + warp * 16 + q) = make_float4(sm[q], sm[q + 1], sm[q + 2], sm[q + 3]);
+  }
+  const int l = lane & 15;
+  ms_out = fmaxf(fmaxf(xch[l], xch[16 + l]), fmaxf(xch[32 + l], xch[48 + l])) * sl2;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  return (xch[64 + l] + xch[80 + l]) + (xch[96 + l] + xch[112 + l]);
+}
+
 // O tile rows of this warp (TMEM lane = row, 64 fp32 columns) * inv -> bf16 -> global.  One thread per row would make every
 // store instruction touch 32 different lines, so the 32 x 128 B tile is transposed through a 4 KB staging tile (XOR-swizzled
 // 16-byte chunks, conflict free both ways) and leaves as 4 full 128-byte rows per instruction.
@@ -268,7 +344,7 @@ __device__ __forceinline__ void store_o_rows(const uint32_t (&a)[32], const uint
 // pipeline events of the first units into `trace` [role][unit][event]
 constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: MMA warp, softmax warp 0, softmax warp 3, TMA warp
 
-template <int T, bool TRACE>
+template <int T, bool TRACE, bool RT = false>     // RT: transposed remainder scores (T = 144), see softmax_rem_t_to_p
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
                     int num_units, int reverse, long long* __restrict__ trace) {
@@ -362,6 +438,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
         }
         umma_commit(&s_full[0]);
+        if constexpr (Cfg::kSplit && RT) {                     // remainder scores, transposed, into 32 columns of their own
+          constexpr uint32_t idesc_r = umma_idesc_bf16(128, 16);
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {                     // keys 0..127, then keys 16..143 (lanes 112..127 = keys 128..143)
+            const uint32_t a0 = k_lo + gq * 16 * 8, b0 = q_lo + 128 * 8;
+#pragma unroll
+            for (int k = 0; k < kHeadDim / 16; ++k) {
+              if (k == 0) umma_lohi<false>(tmem_base + (T + 64) + 16 * gq, a0, b0, idesc_r);
+              else umma_lohi<true>(tmem_base + (T + 64) + 16 * gq, a0 + 2 * k, b0 + 2 * k, idesc_r);
+            }
+          }
+          umma_commit(&s_full[1]);
+        }
         if constexpr (Cfg::kDual) {                            // second score tile right behind the first, into its own columns
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k) {
@@ -374,7 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mbar_wait(&p_full[0], ph);                            // softmax has consumed S and written P0
         mark(0, it, 4);
         tc_fence_after();
-        if constexpr (Cfg::kTiles == 2 && !Cfg::kDual) {        // remainder scores first: the softmax warps wait for them
+        if constexpr (Cfg::kTiles == 2 && !Cfg::kDual && !(Cfg::kSplit && RT)) {   // remainder scores first: the softmax warps wait for them
           if constexpr (Cfg::kSplit) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                       // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
@@ -444,7 +533,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         if constexpr (!Cfg::kSplit && !Cfg::kDual) mbar_wait(&o_full[0], ph);   // P1 would reuse P0: the O0 MMAs must have read it
         mark(role, it, 4);
         tc_fence_after();
-        if constexpr (Cfg::kSplit) {
+        if constexpr (Cfg::kSplit && RT) {
+          sum1 = softmax_rem_t_to_p<T>(t_lane, T + 64, sP1, xch, warp, lane, ms1);
+        } else if constexpr (Cfg::kSplit) {
           if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane, ms1);
           else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane, ms1);
         } else {
@@ -684,8 +775,12 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   static bool configured = false;
   static int trace_mode = -1;
   if (trace_mode < 0) { const char* e = getenv("JPDVT_ATTN_TRACE"); trace_mode = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  auto kern = attention_tc_kernel<T, false>;
-  auto kern_trace = attention_tc_kernel<T, true>;
+  static int rem_t = -1;            // JPDVT_ATTN_REM=transposed: remainder scores as K Q_rem^T in columns of their own (A/B knob;
+                                    // measured slower: 58.9 vs 54.1 us at B = 256 - DESIGN.md section 4); default: the split remainder
+  if (rem_t < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_t = (e != nullptr && e[0] == 't') ? 1 : 0; }
+  constexpr bool kCanRT = TcCfg<T>::kSplit;
+  auto kern = (kCanRT && rem_t) ? attention_tc_kernel<T, false, kCanRT> : attention_tc_kernel<T, false, false>;
+  auto kern_trace = (kCanRT && rem_t) ? attention_tc_kernel<T, true, kCanRT> : attention_tc_kernel<T, true, false>;
   if (!configured) {
     for (auto k : {kern, kern_trace}) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
