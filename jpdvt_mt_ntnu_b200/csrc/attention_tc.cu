@@ -227,6 +227,34 @@ __device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_ro
   return (xch[64 + l] + xch[80 + l]) + (xch[96 + l] + xch[112 + l]);
 }
 
+// Warp reduction of 16 per-lane values at once (value q of every lane -> one result per q): a butterfly that halves the value
+// count while it doubles the lanes folded in - 8 + 4 + 2 + 1 exchanges, then one across the last lane bit - 16 shuffles instead
+// of 16 x 5.  On return lanes 2q and 2q + 1 hold the reduction of value q over the 32 lanes.
+template <bool MAX>
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  auto op = [](float a, float b) { return MAX ? fmaxf(a, b) : a + b; };
+  float w8[8], w4[4], w2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
+    w8[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h8 ? w8[i] : w8[i + 4], keep = h8 ? w8[i + 4] : w8[i];
+    w4[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h4 ? w4[i] : w4[i + 2], keep = h4 ? w4[i + 2] : w4[i];
+    w2[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  const float send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
+  const float w1 = op(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  return op(w1, __shfl_xor_sync(0xffffffffu, w1, 1));       // value q = 8 h16 + 4 h8 + 2 h4 + h2 = lane >> 1
+}
+
 // Transposed remainder (T = 144, opt-in - measured slower than the split form below, kept as the A/B): the scores of query rows 128..143 are produced as S_rem^T = K Q_rem^T - TMEM lane =
 // key, 16 columns = the remainder queries; a second group over the K rows shifted by 16 puts keys 128..143 into lanes 112..127 -
 // in 32 columns of their own, so their MMAs are issued right behind the main score tile instead of after its softmax has
@@ -235,14 +263,12 @@ __device__ __forceinline__ float softmax_rem_to_p(uint32_t t_addr, uint32_t p_ro
 // go out as 2-byte stores into the compact K-major P tile (row = query, 2 KB per 64-key block), contiguous per warp and query.
 // Returns the row sum / sets ms_out for query (lane & 15).
 template <int T>
-__device__ __forceinline__ float softmax_rem_t_to_p(uint32_t t_lane, uint32_t col_r, uint32_t sP1, float* xch, int warp, int lane,
-                                                    float& ms_out) {
+__device__ __forceinline__ float softmax_rem_t_to_p(const uint32_t (&a)[16], const uint32_t (&b)[16], uint32_t sP1, float* xch, int warp,
+                                                    int lane, float& ms_out) {
+  // a, b: the thread's 16 + 16 score columns, read out of TMEM by the caller BEFORE it hands P0 to the MMA warp (a tcgen05.ld
+  // issued while the O0 MMAs run waits for them)
   constexpr float sl2 = 0.125f * 1.4426950408889634f;
   static_assert(T == 144, "transposed remainder: 128 + 16 tokens");
-  uint32_t a[16], b[16];
-  tmem_ld_32x16(t_lane + col_r, a);
-  tmem_ld_32x16(t_lane + col_r + 16, b);
-  tmem_ld_wait();
   const bool tail = warp == 3 && lane >= 16;                 // lanes 112..127 of the shifted group hold keys 128..143
   float m[16];
 #pragma unroll
@@ -250,14 +276,8 @@ __device__ __forceinline__ float softmax_rem_t_to_p(uint32_t t_lane, uint32_t co
     m[q] = __uint_as_float(a[q]);
     if (tail) m[q] = fmaxf(m[q], __uint_as_float(b[q]));
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) m[q] = fmaxf(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(xch + warp * 16 + q) = make_float4(m[q], m[q + 1], m[q + 2], m[q + 3]);
-  }
+  const float mq = warp_reduce16<true>(m, lane);
+  if ((lane & 1) == 0) xch[warp * 16 + (lane >> 1)] = mq;
   asm volatile("bar.sync 1, 128;" ::: "memory");
   float ms[16];
 #pragma unroll
@@ -288,14 +308,8 @@ __device__ __forceinline__ float softmax_rem_t_to_p(uint32_t t_lane, uint32_t co
                    "h"(*reinterpret_cast<const uint16_t*>(&h2)) : "memory");
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) sm[q] += __shfl_xor_sync(0xffffffffu, sm[q], o);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(xch + 64 + warp * 16 + q) = make_float4(sm[q], sm[q + 1], sm[q + 2], sm[q + 3]);
-  }
+  const float sq = warp_reduce16<false>(sm, lane);
+  if ((lane & 1) == 0) xch[64 + warp * 16 + (lane >> 1)] = sq;
   const int l = lane & 15;
   ms_out = fmaxf(fmaxf(xch[l], xch[16 + l]), fmaxf(xch[32 + l], xch[48 + l])) * sl2;
   asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -344,7 +358,10 @@ __device__ __forceinline__ void store_o_rows(const uint32_t (&a)[32], const uint
 // pipeline events of the first units into `trace` [role][unit][event]
 constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: MMA warp, softmax warp 0, softmax warp 3, TMA warp
 
-template <int T, bool TRACE, bool RT = false>     // RT: transposed remainder scores (T = 144), see softmax_rem_t_to_p
+// RT: transposed remainder scores (T = 144), see softmax_rem_t_to_p.  R2 (T = 144, split remainder): the 16 small remainder
+// MMAs are issued by TWO threads - groups 0, 1 by the MMA warp, groups 2, 3 by the TMA warp's lane - because issuing them
+// (60-90 cycles of single-thread work each) is what the softmax warps wait for between the two tiles.
+template <int T, bool TRACE, bool RT = false, bool R2 = false>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
                     int num_units, int reverse, long long* __restrict__ trace) {
@@ -370,7 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(qk_full, 1); mbar_init(v_full, 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], (t == 1 && R2) ? 2 : 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1); }
     mbar_init(epi_done, 4);
     fence_mbar_init();
   }
@@ -390,11 +407,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     // ---------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int it = 0;
+      [[maybe_unused]] auto issue_rem_half = [&](uint32_t ph_unit) {   // R2: quadrants 2, 3 <- rows 128..143 x keys [64, 96), [96, 144)
+        constexpr uint32_t idesc_a = umma_idesc_bf16(128, 32), idesc_b = umma_idesc_bf16(128, T - 96);
+        const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK);
+        mbar_wait(&p_full[0], ph_unit);                        // the softmax has consumed the main score tile
+        tc_fence_after();
+#pragma unroll
+        for (int j = 2; j < 4; ++j) {
+          const uint32_t idesc_j = j < 3 ? idesc_a : idesc_b;
+          const uint32_t a0 = q_lo + (128 - 32 * j) * 8, b0 = k_lo + 32 * j * 8;
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + 32 * j, a0, b0, idesc_j);
+            else umma_lohi<true>(tmem_base + 32 * j, a0 + 2 * k, b0 + 2 * k, idesc_j);
+          }
+        }
+        umma_commit(&s_full[1]);
+      };
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
         const int uu = reverse ? num_units - 1 - unit : unit;   // sweep direction: see sweep_reverse() in common.cuh
         const int b = uu / kHeads, h = uu - b * kHeads;
         const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
         mark(3, it, 0);
+        if constexpr (R2) {
+          if (it > 0) issue_rem_half(prev);                   // groups 2, 3 of the previous unit's remainder scores
+        }
         if (it > 0) mbar_wait(&s_full[kLast], prev);          // every score MMA of the previous unit has read Q, K
         mark(3, it, 1);
         mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
@@ -405,6 +442,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mark(3, it, 3);
         mbar_expect_tx(v_full, Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+      }
+      if constexpr (R2) {
+        if (it > 0) issue_rem_half(static_cast<uint32_t>((it - 1) & 1));   // the last unit's
       }
     }
     __syncwarp();
@@ -466,7 +506,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         if constexpr (Cfg::kTiles == 2 && !Cfg::kDual && !(Cfg::kSplit && RT)) {   // remainder scores first: the softmax warps wait for them
           if constexpr (Cfg::kSplit) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                       // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
+            for (int j = 0; j < (R2 ? 2 : 4); ++j) {            // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
               constexpr uint32_t idesc_a = umma_idesc_bf16(128, 32), idesc_b = umma_idesc_bf16(128, T - 96);
               const uint32_t idesc_j = j < 3 ? idesc_a : idesc_b;
               const uint32_t a0 = q_lo + (128 - 32 * j) * 8, b0 = k_lo + 32 * j * 8;
@@ -520,6 +560,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       tc_fence_after();
       float ms0, ms1 = 0.f;
       const float sum0 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms0);
+      [[maybe_unused]] uint32_t rem_a[16], rem_b[16];
+      if constexpr (Cfg::kSplit && RT) {                      // transposed remainder scores: long since in TMEM, read them now
+        mbar_wait(&s_full[1], ph);
+        tc_fence_after();
+        tmem_ld_32x16(t_lane + (T + 64), rem_a);
+        tmem_ld_32x16(t_lane + (T + 64) + 16, rem_b);
+        tmem_ld_wait();
+      }
       fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's reads
       tc_fence_before();
       __syncwarp();
@@ -534,7 +582,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mark(role, it, 4);
         tc_fence_after();
         if constexpr (Cfg::kSplit && RT) {
-          sum1 = softmax_rem_t_to_p<T>(t_lane, T + 64, sP1, xch, warp, lane, ms1);
+          sum1 = softmax_rem_t_to_p<T>(rem_a, rem_b, sP1, xch, warp, lane, ms1);
         } else if constexpr (Cfg::kSplit) {
           if (warp < 3) sum1 = softmax_rem_to_p<32>(t_lane + 32 * warp, sP1 + lane * 128, 4 * warp, lane & 7, xch, warp, lane, ms1);
           else sum1 = softmax_rem_to_p<T - 96>(t_lane + 96, sP1 + lane * 128, 12, lane & 7, xch, warp, lane, ms1);
@@ -778,9 +826,13 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   static int rem_t = -1;            // JPDVT_ATTN_REM=transposed: remainder scores as K Q_rem^T in columns of their own (A/B knob;
                                     // measured slower: 58.9 vs 54.1 us at B = 256 - DESIGN.md section 4); default: the split remainder
   if (rem_t < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_t = (e != nullptr && e[0] == 't') ? 1 : 0; }
+  static int rem_2 = -1;            // JPDVT_ATTN_REM=split: one thread issues all four remainder groups (A/B knob); default: two
+  if (rem_2 < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_2 = (e != nullptr && (e[0] == 's' || e[0] == 't')) ? 0 : 1; }
   constexpr bool kCanRT = TcCfg<T>::kSplit;
-  auto kern = (kCanRT && rem_t) ? attention_tc_kernel<T, false, kCanRT> : attention_tc_kernel<T, false, false>;
-  auto kern_trace = (kCanRT && rem_t) ? attention_tc_kernel<T, true, kCanRT> : attention_tc_kernel<T, true, false>;
+  auto kern = (kCanRT && rem_t) ? attention_tc_kernel<T, false, kCanRT, false>
+              : (kCanRT && rem_2) ? attention_tc_kernel<T, false, false, kCanRT> : attention_tc_kernel<T, false, false, false>;
+  auto kern_trace = (kCanRT && rem_t) ? attention_tc_kernel<T, true, kCanRT, false>
+                    : (kCanRT && rem_2) ? attention_tc_kernel<T, true, false, kCanRT> : attention_tc_kernel<T, true, false, false>;
   if (!configured) {
     for (auto k : {kern, kern_trace}) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
