@@ -108,9 +108,11 @@ struct TcCfg {
 
 // One softmax pass of the thread's S row (TMEM lane = row, columns [0,T)): exact row maximum, then
 // p = 2^((s - max) * log2(e) / 8) written as bf16 into the K-major swizzled P tile; returns sum(p) (fp32, unrounded p).
-template <int T, int TV = T>     // T columns are read (multiple of 16); columns >= TV are padding and get probability 0
+// PB: the 64-key blocks of the P row are announced one by one (blk_bar[0], blk_bar[1]: one arrival per warp) as soon as they are
+// in shared memory, so the MMA warp can issue their P V k-steps while the later blocks are still being computed.
+template <int T, int TV = T, bool PB = false>     // T columns are read (multiple of 16); columns >= TV are padding and get probability 0
 __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row_addr, uint32_t blk_stride, int sw, bool store,
-                                                  float& ms_out) {
+                                                  float& ms_out, uint64_t* blk_bar = nullptr, int lane = 0) {
   constexpr float sl2 = 0.125f * 1.4426950408889634f;       // head_dim^-0.5 * log2(e)
   constexpr int kFull = T / 32, kTail = T % 32;              // kTail is 0 or 16
   // chunk c = columns [32c, 32c+32) (the last one may be 16 wide); the load of chunk c+1 is in flight while chunk c is
@@ -180,6 +182,13 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
     const int n = (c < kFull) ? 32 : kTail;
 #pragma unroll
     for (int g = 0; g < n / 8; ++g) emit8(cur + 8 * g, c * 4 + g);
+    if constexpr (PB) {
+      if ((c & 1) == 1 && c + 1 < kChunks) {                  // keys [32 (c - 1), 32 (c + 1)) = one 64-key block of P is complete
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&blk_bar[c >> 1]);
+      }
+    }
     if (c + 1 < kChunks) tmem_ld_wait();
   }
   float s_even, s_odd;
@@ -382,6 +391,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   uint64_t* o_full = bars + 6;         // [2] MMA: O tile t is in TMEM
   uint64_t* epi_done = bars + 8;       // softmax warps: every TMEM read of the unit is done (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* pb_full = bars + 10;       // [2] R2: the first / second 64-key block of P0 is in shared memory (4 arrivals)
   float* xch = reinterpret_cast<float*>(smem + Cfg::kXchOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,6 +399,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     mbar_init(qk_full, 1); mbar_init(v_full, 1);
     for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], (t == 1 && R2) ? 2 : 1); mbar_init(&p_full[t], 4); mbar_init(&o_full[t], 1); }
     mbar_init(epi_done, 4);
+    mbar_init(&pb_full[0], 4); mbar_init(&pb_full[1], 4);
     fence_mbar_init();
   }
   if (warp == 5) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
@@ -464,14 +475,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O of the previous unit has left TMEM
         mark(0, it, 2);
         tc_fence_after();
-        auto issue_o = [&](uint32_t d_col, uint32_t pa_lo, uint32_t blk_words) {   // blk_words = P block stride / 16 bytes
+        auto issue_o = [&](uint32_t d_col, uint32_t pa_lo, uint32_t blk_words, int j0 = 0, int j1 = T / 16) {   // blk_words = P block stride / 16 bytes
 #pragma unroll
           for (int j = 0; j < T / 16; ++j) {
+            if (j < j0 || j >= j1) continue;
             const uint32_t a = pa_lo + (j >> 2) * blk_words + (j & 3) * 2, bq = v_lo + j * 128;
             if (j == 0) umma_lohi<false>(tmem_base + d_col, a, bq, idesc_o);
             else umma_lohi<true>(tmem_base + d_col, a, bq, idesc_o);
           }
         };
+        constexpr bool kPB = Cfg::kSplit && R2;                // P V k-steps of tile 0 issued per 64-key block of P0
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k) {
           if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
@@ -500,6 +513,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           umma_commit(&s_full[1]);
         }
         mark(0, it, 3);
+        if constexpr (kPB) {                                   // blocks 0 and 1 of P0 while the softmax is still on the later keys
+          mbar_wait(v_full, ph);
+          mbar_wait(&pb_full[0], ph);
+          tc_fence_after();
+          issue_o(Cfg::kColO0, p_lo, 1024, 0, 4);
+          mbar_wait(&pb_full[1], ph);
+          tc_fence_after();
+          issue_o(Cfg::kColO0, p_lo, 1024, 4, 8);
+        }
         mbar_wait(&p_full[0], ph);                            // softmax has consumed S and written P0
         mark(0, it, 4);
         tc_fence_after();
@@ -526,9 +548,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           umma_commit(&s_full[1]);
         }
         mark(0, it, 5);
-        mbar_wait(v_full, ph);
+        if constexpr (!kPB) mbar_wait(v_full, ph);
         mark(0, it, 6);
-        issue_o(Cfg::kColO0, p_lo, 1024);
+        if constexpr (kPB) issue_o(Cfg::kColO0, p_lo, 1024, 8, T / 16);
+        else issue_o(Cfg::kColO0, p_lo, 1024);
         umma_commit(&o_full[0]);
         mark(0, it, 7);
         if constexpr (Cfg::kTiles == 2) {
@@ -559,7 +582,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       mark(role, it, 1);
       tc_fence_after();
       float ms0, ms1 = 0.f;
-      const float sum0 = softmax_row_to_p<T>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms0);
+      const float sum0 = softmax_row_to_p<T, T, Cfg::kSplit && R2>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms0, pb_full, lane);
       [[maybe_unused]] uint32_t rem_a[16], rem_b[16];
       if constexpr (Cfg::kSplit && RT) {                      // transposed remainder scores: long since in TMEM, read them now
         mbar_wait(&s_full[1], ph);
@@ -826,8 +849,9 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   static int rem_t = -1;            // JPDVT_ATTN_REM=transposed: remainder scores as K Q_rem^T in columns of their own (A/B knob;
                                     // measured slower: 58.9 vs 54.1 us at B = 256 - DESIGN.md section 4); default: the split remainder
   if (rem_t < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_t = (e != nullptr && e[0] == 't') ? 1 : 0; }
-  static int rem_2 = -1;            // JPDVT_ATTN_REM=split: one thread issues all four remainder groups (A/B knob); default: two
-  if (rem_2 < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_2 = (e != nullptr && (e[0] == 's' || e[0] == 't')) ? 0 : 1; }
+  static int rem_2 = -1;            // JPDVT_ATTN_REM=pipelined: remainder MMAs issued by two threads + P V k-steps per 64-key block of
+                                    // P0 (A/B knob; shorter unit chain in the trace, same kernel time: DESIGN.md section 4)
+  if (rem_2 < 0) { const char* e = getenv("JPDVT_ATTN_REM"); rem_2 = (e != nullptr && e[0] == 'p') ? 1 : 0; }
   constexpr bool kCanRT = TcCfg<T>::kSplit;
   auto kern = (kCanRT && rem_t) ? attention_tc_kernel<T, false, kCanRT, false>
               : (kCanRT && rem_2) ? attention_tc_kernel<T, false, false, kCanRT> : attention_tc_kernel<T, false, false, false>;
