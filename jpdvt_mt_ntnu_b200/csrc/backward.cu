@@ -212,8 +212,19 @@ long long bwd_part_floats(int batch, int tokens) {
 // eight warps owns a slice of ONE sample's tokens, so the per-sample sums (dshift, dscale, dgate) leave through a
 // cross-warp reduction in shared memory and one atomicAdd per column and CTA - no partial buffers, no sum_parts /
 // colsum launches (ten launches per block become two).
-constexpr int kLgWarps = 8;
+constexpr int kLgWarps = 4;
+constexpr int kLgRowBytes = 3 * kHidden * 4 + kHidden * 2;      // x, dxn, previous dx (fp32) + y (bf16) of one token row: 10,752 B
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// Four warps per CTA, two CTAs per SM (eight warps with up to 255 registers each): a warp keeps its running column sums AND
+// the whole row in registers, and the NEXT row of the warp is already on its way into a shared-memory buffer (cp.async, two
+// buffers per warp) while the current one is processed, so no row waits on a memory latency.  History: v1 fetched the previous
+// dx / y chunk by chunk inside the output loop (ncu long_scoreboard 73 %, 94 us per launch at M = 18,432); v2 requested every
+// operand of a row up front but had to keep the sums in shared memory for lack of registers at 16 warps per SM (short_scoreboard
+// + mio 49 %, 69 us).
 template <bool GATE>
 __global__ void __launch_bounds__(kLgWarps * 32, 2)
 ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, const float* __restrict__ scale,
@@ -222,49 +233,60 @@ ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, c
                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate, long long gate_stride,
                    __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, long long dgate_stride,
                    float* __restrict__ dbias, int tokens, int rows_per_cta) {
-  extern __shared__ __align__(16) float lg_smem[];     // [quantity: dshift, dscale(, dgate, dbias)][kLgWarps][768], then two rows
+  extern __shared__ __align__(16) uint8_t lg_smem[];   // [warp][2] row buffers, then the sample's (1 + scale) and gate rows
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.y * rows_per_cta, t1 = min(tokens, t0 + rows_per_cta);
-  constexpr int kQ = GATE ? 4 : 2;
-  // per-warp running column sums live in shared memory (each lane owns its 24 columns: conflict-free 16-byte accesses), which
-  // leaves the registers to the row itself: EVERY global operand of a row - x, dxn, the previous dx, y - is requested before
-  // the first reduction, so a row costs one memory latency (the first version fetched dx / y chunk by chunk inside the output
-  // loop: ncu long_scoreboard 73 %, 94 us per launch)
-  const uint32_t acc0 = smem_u32(lg_smem + warp * kHidden) + 16u * lane;            // quantity q at acc0 + q * kLgWarps * 768 * 4
-  constexpr uint32_t kQStride = kLgWarps * kHidden * 4;
-#pragma unroll
-  for (int q = 0; q < kQ; ++q)
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(acc0 + q * kQStride + 512u * j), "f"(0.f) : "memory");
-  float* row_sc = lg_smem + kQ * kLgWarps * kHidden;   // 1 + scale[b] and gate[b]: re-read per row through volatile LDS so the
-  float* row_gt = row_sc + kHidden;                    // compiler cannot hoist 48 loop-invariant registers out of the row loop
+  float* row_sc = reinterpret_cast<float*>(lg_smem + 2 * kLgWarps * kLgRowBytes);
+  float* row_gt = row_sc + kHidden;
   for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
     row_sc[c] = __ldg(scale + b * mod_stride + c) + 1.0f;
     if constexpr (GATE) row_gt[c] = __ldg(gate + b * gate_stride + c);
   }
-  __syncthreads();
-  const uint32_t sc_s = smem_u32(row_sc) + 16u * lane, gt_s = smem_u32(row_gt) + 16u * lane;
-  auto acc_add = [&](int q, int j, float a0, float a1, float a2, float a3) {
-    float4 a = lds_f4(acc0 + q * kQStride + 512u * j);
-    a.x += a0; a.y += a1; a.z += a2; a.w += a3;
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(acc0 + q * kQStride + 512u * j), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-  };
-  for (int t = t0 + warp; t < t1; t += kLgWarps) {
+  const uint32_t buf0 = smem_u32(lg_smem + warp * 2 * kLgRowBytes);
+  // lane's 16-byte chunks: fp32 arrays chunk lane + 32 j (j < 6), bf16 y chunk lane + 32 j (j < 3)
+  auto prefetch = [&](int t, int which) {
     const long long row = static_cast<long long>(b) * tokens + t;
-    const float4* xr = reinterpret_cast<const float4*>(x + row * kHidden);
-    const float4* gr = reinterpret_cast<const float4*>(dxn + row * kHidden);
-    float4* dr = reinterpret_cast<float4*>(dx + row * kHidden);
-    float4 v[6], g[6], prev[6];
-    uint2 yv[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { v[j] = __ldcs(xr + lane + 32 * j); g[j] = __ldcs(gr + lane + 32 * j); }
+    const uint32_t dst = buf0 + which * kLgRowBytes + 16u * lane;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * kHidden) + lane;
+    const float4* gr = reinterpret_cast<const float4*>(dxn + row * kHidden) + lane;
+    const float4* pr = reinterpret_cast<const float4*>(dx + row * kHidden) + lane;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      prev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (accumulate) prev[j] = __ldcs(dr + lane + 32 * j);
-      if constexpr (GATE) yv[j] = __ldcs(reinterpret_cast<const uint2*>(y + row * kHidden) + lane + 32 * j);
+      cp_async16(dst + 512u * j, xr + 32 * j);
+      cp_async16(dst + 3072u + 512u * j, gr + 32 * j);
+      if (accumulate) cp_async16(dst + 6144u + 512u * j, pr + 32 * j);
     }
+    if constexpr (GATE) {
+      const uint4* yr = reinterpret_cast<const uint4*>(y + row * kHidden) + lane;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) cp_async16(dst + 9216u + 512u * j, yr + 32 * j);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float4 ssh[6], ssc[6], sg[6], sb[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    ssh[j] = make_float4(0.f, 0.f, 0.f, 0.f); ssc[j] = ssh[j]; sg[j] = ssh[j]; sb[j] = ssh[j];
+  }
+  int t = t0 + warp, it = 0;
+  if (t < t1) prefetch(t, 0);
+  __syncthreads();                                            // row_sc / row_gt are in place
+  const uint32_t sc_s = smem_u32(row_sc) + 16u * lane, gt_s = smem_u32(row_gt) + 16u * lane;
+  for (; t < t1; t += kLgWarps, ++it) {
+    const int which = it & 1;
+    __syncwarp();                                             // every lane is done with the buffer the next row goes into (the y
+    if (t + kLgWarps < t1) {                                  // halves are read by a different lane than the one that copied them)
+      prefetch(t + kLgWarps, which ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();                                             // ... and every lane's copies of the current row have landed
+    const long long row = static_cast<long long>(b) * tokens + t;
+    const uint32_t src = buf0 + which * kLgRowBytes + 16u * lane;
+    float4 v[6], g[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { v[j] = lds_f4(src + 512u * j); g[j] = lds_f4(src + 3072u + 512u * j); }
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -281,13 +303,15 @@ ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, c
     for (int j = 0; j < 6; ++j) {        // same arithmetic, in the same order, as ln_modulate_bwd_kernel
       const float4 sc = lds_f4(sc_s + 512u * j);                                   // 1 + scale
       v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;
-      acc_add(0, j, g[j].x, g[j].y, g[j].z, g[j].w);
-      acc_add(1, j, g[j].x * v[j].x, g[j].y * v[j].y, g[j].z * v[j].z, g[j].w * v[j].w);
+      ssh[j].x += g[j].x; ssh[j].y += g[j].y; ssh[j].z += g[j].z; ssh[j].w += g[j].w;
+      ssc[j].x = fmaf(g[j].x, v[j].x, ssc[j].x); ssc[j].y = fmaf(g[j].y, v[j].y, ssc[j].y);
+      ssc[j].z = fmaf(g[j].z, v[j].z, ssc[j].z); ssc[j].w = fmaf(g[j].w, v[j].w, ssc[j].w);
       g[j].x *= sc.x; g[j].y *= sc.y; g[j].z *= sc.z; g[j].w *= sc.w;
       s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
       s2 += (g[j].x * v[j].x + g[j].y * v[j].y) + (g[j].z * v[j].z + g[j].w * v[j].w);
     }
     const float c1 = warp_sum_b(s1) * (1.0f / kHidden), c2 = warp_sum_b(s2) * (1.0f / kHidden);
+    float4* dr = reinterpret_cast<float4*>(dx + row * kHidden);
     uint2* db = dx_bf16 != nullptr ? reinterpret_cast<uint2*>(dx_bf16 + row * kHidden) : nullptr;
     uint2* dyr = GATE ? reinterpret_cast<uint2*>(dy + row * kHidden) : nullptr;
 #pragma unroll
@@ -295,36 +319,55 @@ ln_gate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dxn, c
       float4 o;
       o.x = rstd * (g[j].x - c1 - v[j].x * c2); o.y = rstd * (g[j].y - c1 - v[j].y * c2);
       o.z = rstd * (g[j].z - c1 - v[j].z * c2); o.w = rstd * (g[j].w - c1 - v[j].w * c2);
-      if (accumulate) { o.x += prev[j].x; o.y += prev[j].y; o.z += prev[j].z; o.w += prev[j].w; }
+      if (accumulate) {
+        const float4 prev = lds_f4(src + 6144u + 512u * j);
+        o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+      }
       dr[lane + 32 * j] = o;
       if (db != nullptr) { uint2 u; u.x = pack_bf16(o.x, o.y); u.y = pack_bf16(o.z, o.w); db[lane + 32 * j] = u; }
       if constexpr (GATE) {              // gate_bwd_kernel's arithmetic on the finished row
         const float4 gt = lds_f4(gt_s + 512u * j);
-        const float y0 = __uint_as_float(yv[j].x << 16), y1 = __uint_as_float(yv[j].x & 0xffff0000u);
-        const float y2 = __uint_as_float(yv[j].y << 16), y3 = __uint_as_float(yv[j].y & 0xffff0000u);
-        acc_add(2, j, o.x * y0, o.y * y1, o.z * y2, o.w * y3);
+        // y: bf16 chunk (lane + 32 j') holds columns 8 (lane + 32 j') ..; this lane's fp32 columns 4 (lane + 32 j) .. +3 are the
+        // low or high half of y chunk (lane + 32 j) / 2 -> read the 8-byte half directly
+        uint2 yv;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(yv.x), "=r"(yv.y) : "r"(buf0 + which * kLgRowBytes + 9216u + 8u * (lane + 32 * j)));
+        const float y0 = __uint_as_float(yv.x << 16), y1 = __uint_as_float(yv.x & 0xffff0000u);
+        const float y2 = __uint_as_float(yv.y << 16), y3 = __uint_as_float(yv.y & 0xffff0000u);
+        sg[j].x = fmaf(o.x, y0, sg[j].x); sg[j].y = fmaf(o.y, y1, sg[j].y); sg[j].z = fmaf(o.z, y2, sg[j].z); sg[j].w = fmaf(o.w, y3, sg[j].w);
         const float o0 = gt.x * o.x, o1 = gt.y * o.y, o2 = gt.z * o.z, o3 = gt.w * o.w;
-        acc_add(3, j, o0, o1, o2, o3);
+        sb[j].x += o0; sb[j].y += o1; sb[j].z += o2; sb[j].w += o3;
         uint2 u; u.x = pack_bf16(o0, o1); u.y = pack_bf16(o2, o3);
         dyr[lane + 32 * j] = u;
       }
     }
   }
+  // cross-warp sums through the (now idle) row buffers: [quantity][warp][768] floats
   __syncthreads();
-  // cross-warp sums: thread -> 3 columns of each quantity; one atomicAdd per column, quantity and CTA
-  for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float* red = reinterpret_cast<float*>(lg_smem);
+  constexpr int kQ = GATE ? 4 : 2;
 #pragma unroll
-    for (int w = 0; w < kLgWarps; ++w) {
-      a0 += lg_smem[w * kHidden + c];
-      a1 += lg_smem[(kLgWarps + w) * kHidden + c];
-      if constexpr (GATE) { a2 += lg_smem[(2 * kLgWarps + w) * kHidden + c]; a3 += lg_smem[(3 * kLgWarps + w) * kHidden + c]; }
-    }
-    atomicAdd(dshift + b * dmod_stride + c, a0);
-    atomicAdd(dscale + b * dmod_stride + c, a1);
+  for (int j = 0; j < 6; ++j) {
+    reinterpret_cast<float4*>(red + (0 * kLgWarps + warp) * kHidden)[lane + 32 * j] = ssh[j];
+    reinterpret_cast<float4*>(red + (1 * kLgWarps + warp) * kHidden)[lane + 32 * j] = ssc[j];
     if constexpr (GATE) {
-      atomicAdd(dgate + b * dgate_stride + c, a2);
-      if (dbias != nullptr) atomicAdd(dbias + c, a3);
+      reinterpret_cast<float4*>(red + (2 * kLgWarps + warp) * kHidden)[lane + 32 * j] = sg[j];
+      reinterpret_cast<float4*>(red + (3 * kLgWarps + warp) * kHidden)[lane + 32 * j] = sb[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kHidden; c += kLgWarps * 32) {
+    float a[kQ];
+#pragma unroll
+    for (int qq = 0; qq < kQ; ++qq) {
+      a[qq] = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLgWarps; ++w) a[qq] += red[(qq * kLgWarps + w) * kHidden + c];
+    }
+    atomicAdd(dshift + b * dmod_stride + c, a[0]);
+    atomicAdd(dscale + b * dmod_stride + c, a[1]);
+    if constexpr (GATE) {
+      atomicAdd(dgate + b * dgate_stride + c, a[2]);
+      if (dbias != nullptr) atomicAdd(dbias + c, a[3]);
     }
   }
 }
@@ -343,11 +386,13 @@ int launch_ln_gate_bwd(const float* x, const float* dxn, const float* scale, lon
   if (slices < 1) slices = 1;
   const int rows = (tokens + slices - 1) / slices;
   slices = (tokens + rows - 1) / rows;
-  const size_t smem = (static_cast<size_t>(with_gate ? 4 : 2) * kLgWarps + 2) * kHidden * sizeof(float);
+  // row buffers (2 per warp; they also hold the 4 x kLgWarps x 768 floats of the closing reduction) + the scale / gate rows
+  static_assert(2 * kLgWarps * kLgRowBytes >= 4 * kLgWarps * kHidden * 4, "the reduction reuses the row buffers");
+  const size_t smem = static_cast<size_t>(2 * kLgWarps) * kLgRowBytes + 2 * kHidden * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(ln_gate_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * kLgWarps + 2) * kHidden * 4) != cudaSuccess ||
-        cudaFuncSetAttribute(ln_gate_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * kLgWarps + 2) * kHidden * 4) != cudaSuccess)
+    if (cudaFuncSetAttribute(ln_gate_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(ln_gate_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return set_error(kErrCuda, "ln_gate_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
