@@ -75,11 +75,16 @@ int jpdvt_gemm_dgrad(const jpdvt_bf16* dy, const jpdvt_bf16* w, const jpdvt_bf16
   if (!dy || !w || (!out_bf16_or_null == !out_f32_or_null)) return set_error(kErrBadArg, "gemm_dgrad: null pointer / exactly one output");
   if (gprime_or_null && !out_bf16_or_null) return set_error(kErrBadArg, "gemm_dgrad: the dGELU form writes bf16");
   if (colsum_or_null && !gprime_or_null) return set_error(kErrBadArg, "gemm_dgrad: column sums come with the dGELU form only");
-  static float* zeros = nullptr;       // the bias slot of the shared epilogues: 4 x 768 zeros, allocated once per process
-  if (zeros == nullptr) {
-    if (cudaMalloc(&zeros, 4 * kHidden * sizeof(float)) != cudaSuccess || cudaMemset(zeros, 0, 4 * kHidden * sizeof(float)) != cudaSuccess)
+  static float* zeros_of[64] = {};     // the bias slot of the shared epilogues: 4 x 768 zeros, allocated once per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return set_error(kErrUnsupported, "gemm_dgrad: device index %d", dev);
+  if (zeros_of[dev] == nullptr) {
+    if (cudaMalloc(&zeros_of[dev], 4 * kHidden * sizeof(float)) != cudaSuccess ||
+        cudaMemset(zeros_of[dev], 0, 4 * kHidden * sizeof(float)) != cudaSuccess)
       return set_error(kErrCuda, "gemm_dgrad: cannot allocate the zero bias");
   }
+  const float* zeros = zeros_of[dev];
   if (n_in > 4 * kHidden) return set_error(kErrBadArg, "gemm_dgrad: n_in=%d > %d", n_in, 4 * kHidden);
   const int epi = gprime_or_null ? EPI_DGELU_BF16 : (out_bf16_or_null ? EPI_BIAS_BF16 : EPI_BIAS_F32);
   void* out = out_bf16_or_null ? static_cast<void*>(out_bf16_or_null) : static_cast<void*>(out_f32_or_null);
