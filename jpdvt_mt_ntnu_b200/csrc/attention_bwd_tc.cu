@@ -733,6 +733,390 @@ int launch_bt256(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bf
   return check_launch("attention_bwd_tc256_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 324 (3x3 @288 px - the reference trainer's default image size): three key blocks x three query blocks of 128 (the last
+// of each 68 live).  dV / dK of ONE key block plus all three dQ tiles plus the score tiles would need 576 TMEM columns, so the
+// work item is (sample, head, key block): dV[kb], dK[kb] accumulate in TMEM over the item's three query blocks, while each
+// tile's dQ contribution dS K[kb] is a fresh 128 x 64 accumulator (double buffered) that the math warps write into the key
+// block's slice of an fp32 scratch; a closing pass adds the three slices and rounds them into dqkv's q columns.
+// D[q] = sum_d dO O comes from a small pre-pass (O is not loaded here).  TMEM: S^T 0, dP^T 128, dV 256, dK 320, dQ parts 384 / 448.
+struct Bt324 {
+  static constexpr int T = 324, TB = 3;                       // tokens, 128-row blocks
+  static constexpr int kBlk = 128 * 128;                      // 16 KB: 128 rows of an operand tile / 64 queries of P^T, dS^T
+  static constexpr int kOffK = 0, kOffV = kBlk, kOffQ = 2 * kBlk, kOffdO = kOffQ + TB * kBlk;
+  static constexpr int kOffP = kOffdO + TB * kBlk, kOffdS = kOffP + 2 * kBlk;
+  static constexpr int kOffStage = kOffdS + 2 * kBlk;         // 4 x 4 KB epilogue staging
+  static constexpr int kOffL = kOffStage + 4 * 4096;          // lse2[384], D[384]
+  static constexpr int kBarOff = kOffL + 2 * TB * 128 * 4;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kInBytes = (2 + 2 * TB) * kBlk;
+  static constexpr int kColS = 0, kColdP = 128, kColdV = 256, kColdK = 320, kColdQ = 384;
+  static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory");
+};
+
+// D[(b, h), q] = sum_d dO[b T + q, 64 h + d] * O[b T + q, 64 h + d]; one warp per token row, 8 lanes per head
+__global__ void __launch_bounds__(256)
+attn_bwd_d_kernel(const __nv_bfloat16* __restrict__ d_o, const __nv_bfloat16* __restrict__ o, float* __restrict__ dsum, long long rows,
+                  int tokens) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {                               // 16-byte chunk lane + 32 j = columns 8 (lane + 32 j) ..: head (lane + 32 j) / 8
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(d_o + row * kHidden) + lane + 32 * j);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(o + row * kHidden) + lane + 32 * j);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[j] = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(cw[e] << 16), acc[j]);
+      acc[j] = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(cw[e] & 0xffff0000u), acc[j]);
+    }
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+  }
+  const long long b = row / tokens;
+  const int q = static_cast<int>(row - b * tokens);
+  if ((lane & 7) == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int h = (lane >> 3) + 4 * j;
+      dsum[(b * kHeads + h) * tokens + q] = acc[j];
+    }
+  }
+}
+
+// dqkv[row, 0:768] = bf16(sum over the key-block slices of dq32[slice][row, :])
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_round_kernel(const float* __restrict__ dq32, long long slice_floats, int slices, __nv_bfloat16* __restrict__ dqkv, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = __ldcs(reinterpret_cast<const float4*>(dq32) + i);
+  for (int s = 1; s < slices; ++s) {
+    const float4 w = __ldcs(reinterpret_cast<const float4*>(dq32 + s * slice_floats) + i);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  const long long row = i / (kHidden / 4);
+  const int c4 = static_cast<int>(i - row * (kHidden / 4));
+  uint2 u;
+  u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+  reinterpret_cast<uint2*>(dqkv + row * kQkvCols)[c4] = u;
+}
+
+__global__ void __launch_bounds__(kBtThreads, 1)
+attention_bwd_tc324_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                           const float* __restrict__ lse2, const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dqkv,
+                           float* __restrict__ dq32, long long slice_floats, float* __restrict__ dbias, int num_items) {
+  using Cfg = Bt324;
+  constexpr int T = Cfg::T, TB = Cfg::TB;
+  extern __shared__ uint8_t att_bt_smem[];
+  uint8_t* smem = att_bt_smem + ((1024u - (smem_u32(att_bt_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* in_full = bars + 0;        // TMA: K[kb], V[kb], Q, dO of the item landed                         (1 / item)
+  uint64_t* s_full = bars + 1;         // MMA: S^T, dP^T of a tile are in TMEM                                 (3 / item)
+  uint64_t* p_full = bars + 2;         // math: P^T, dS^T of a tile are in shared memory (4 arrivals)          (3 / item)
+  uint64_t* g_done = bars + 3;         // MMA: the gradient MMAs of a tile are done                            (3 / item)
+  uint64_t* kv_drained = bars + 4;     // math: dV / dK of the item have left TMEM (4 arrivals)                (1 / item)
+  uint64_t* dq_drained = bars + 5;     // [2] math: the dQ partial in buffer b has left TMEM (4 arrivals)
+  uint64_t* item_done = bars + 7;      // MMA: every MMA of the item has read its operand tiles                (1 / item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sL = reinterpret_cast<float*>(smem + Cfg::kOffL);
+  float* sD = sL + TB * 128;
+  __shared__ float s_colsum[2 * kHeadDim];     // dK | dV column sums of the item
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 2 * kHeadDim) s_colsum[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(in_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(g_done, 1); mbar_init(kv_drained, 4);
+    mbar_init(&dq_drained[0], 4); mbar_init(&dq_drained[1], 4); mbar_init(item_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV), sQ = smem_u32(smem + Cfg::kOffQ),
+                 sdO = smem_u32(smem + Cfg::kOffdO), sP = smem_u32(smem + Cfg::kOffP), sdS = smem_u32(smem + Cfg::kOffdS);
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int unit = item / TB, kb = item - unit * TB;
+        const int b = unit / kHeads, h = unit - b * kHeads;
+        if (it > 0) mbar_wait_backoff(item_done, static_cast<uint32_t>((it - 1) & 1), 64);
+        mbar_expect_tx(in_full, Cfg::kInBytes);
+        // 128-row boxes; rows past the sample's 324 tokens belong to the next sample (finite values, masked below) or are
+        // zero-filled past the end of the tensor
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T + kb * 128);
+        tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T + kb * 128);
+#pragma unroll
+        for (int qb = 0; qb < TB; ++qb) {
+          tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffQ + qb * Cfg::kBlk, h * kHeadDim, b * T + qb * 128);
+          tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO + qb * Cfg::kBlk, h * kHeadDim, b * T + qb * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, kHeadDim, 0, 1);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHeadDim, 1, 1);
+      constexpr uint32_t kBlkW = Cfg::kBlk / 16;
+      const uint32_t p_lo = desc_lo_k(sP), ds_lo = desc_lo_k(sdS), ds_mn = desc_lo_mn(sdS, Cfg::kBlk);
+      const uint32_t k_lo = desc_lo_k(sK), v_lo = desc_lo_k(sV), k_mn = desc_lo_mn(sK, 8192);
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        mbar_wait(in_full, static_cast<uint32_t>(it & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int qb = 0; qb < TB; ++qb) {
+          const uint32_t g = static_cast<uint32_t>(it * TB + qb);
+          const uint32_t q_lo = desc_lo_k(sQ + qb * Cfg::kBlk), do_lo = desc_lo_k(sdO + qb * Cfg::kBlk);
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColS, k_lo, q_lo, idesc_s);
+            else umma_lohi<true>(tmem_base + Cfg::kColS, k_lo + 2 * k, q_lo + 2 * k, idesc_s);
+          }
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + Cfg::kColdP, v_lo, do_lo, idesc_s);
+            else umma_lohi<true>(tmem_base + Cfg::kColdP, v_lo + 2 * k, do_lo + 2 * k, idesc_s);
+          }
+          umma_commit(s_full);
+          mbar_wait(p_full, g & 1u);
+          if (qb == 0 && it > 0) mbar_wait(kv_drained, static_cast<uint32_t>((it - 1) & 1));   // dV / dK of the previous item have left TMEM
+          if (g >= 2) mbar_wait(&dq_drained[g & 1u], ((g >> 1) - 1u) & 1u);                      // ... and the dQ partial of tile g - 2
+          tc_fence_after();
+          const uint32_t do_mn = desc_lo_mn(sdO + qb * Cfg::kBlk, 8192), q_mn = desc_lo_mn(sQ + qb * Cfg::kBlk, 8192);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = p_lo + (j >> 2) * kBlkW + (j & 3) * 2;
+            if (j == 0 && qb == 0) umma_lohi<false>(tmem_base + Cfg::kColdV, a, do_mn + j * 128, idesc_kv);
+            else umma_lohi<true>(tmem_base + Cfg::kColdV, a, do_mn + j * 128, idesc_kv);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = ds_lo + (j >> 2) * kBlkW + (j & 3) * 2;
+            if (j == 0 && qb == 0) umma_lohi<false>(tmem_base + Cfg::kColdK, a, q_mn + j * 128, idesc_kv);
+            else umma_lohi<true>(tmem_base + Cfg::kColdK, a, q_mn + j * 128, idesc_kv);
+          }
+          const uint32_t dq = tmem_base + Cfg::kColdQ + 64 * (g & 1u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j == 0) umma_lohi<false>(dq, ds_mn + j * 128, k_mn + j * 128, idesc_q);
+            else umma_lohi<true>(dq, ds_mn + j * 128, k_mn + j * 128, idesc_q);
+          }
+          umma_commit(g_done);
+        }
+        umma_commit(item_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- math + epilogue warps
+    constexpr float sl2 = 0.125f * 1.4426950408889634f;
+    const int tid = threadIdx.x;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t stage = smem_u32(smem + Cfg::kOffStage) + static_cast<uint32_t>(warp) * 4096u;
+    const uint32_t csk = dbias != nullptr ? smem_u32(s_colsum) : 0u, csv = csk ? csk + kHeadDim * 4 : 0u;
+    // a drained dQ partial (this warp: 32 query rows x 64 fp32 columns) -> the item's key-block slice of the fp32 scratch,
+    // transposed through the staging tile 32 columns at a time so that every store writes four full 128-byte row segments.
+    // Plain stores: red.global.add into one buffer was the first form - 221 MB of L2 atomics per launch dominated the kernel.
+    auto drain_dq = [&](uint32_t g, int b, int h, int qb, int kb) {
+      uint32_t a[32], c[32];
+      tmem_ld_32x32(t_lane + Cfg::kColdQ + 64 * (g & 1u), a);
+      tmem_ld_32x32(t_lane + Cfg::kColdQ + 64 * (g & 1u) + 32, c);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_drained[g & 1u]);
+      const int q_first = qb * 128 + warp * 32;
+      const int live = T - q_first < 0 ? 0 : (T - q_first < 32 ? T - q_first : 32);
+      float* dst0 = dq32 + static_cast<long long>(kb) * slice_floats + (static_cast<long long>(b) * T + q_first) * kHidden + h * kHeadDim;
+      const uint32_t mine = stage + lane * 128, sw = lane & 7;
+      const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t (&r)[32] = half ? c : a;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts_u4(mine + ((j ^ sw) << 4), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub;
+          const uint4 u = lds_u4(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+          if (rr < live) *reinterpret_cast<uint4*>(dst0 + static_cast<long long>(rr) * kHidden + half * 32 + ch * 4) = u;
+        }
+        __syncwarp();
+      }
+    };
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int unit = item / TB, kb = item - unit * TB;
+      const int b = unit / kHeads, h = unit - b * kHeads;
+      const float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+      const float* drow = dsum + (static_cast<long long>(b) * kHeads + h) * T;
+      __nv_bfloat16* base = dqkv + static_cast<long long>(b) * T * kQkvCols + h * kHeadDim;
+      const int key = kb * 128 + tid;
+      const bool key_ok = key < T;
+      // lse / D of the unit's queries; dead queries get lse = +inf (probability 0) and D = 0.  The previous item's last reads of
+      // these arrays happened before its p_full arrivals, which every warp has passed.
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int rep = 0; rep < TB; ++rep) {
+        const int q = tid + rep * 128;
+        sL[q] = q < T ? __ldg(lrow + q) : INFINITY;
+        sD[q] = q < T ? __ldg(drow + q) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+      for (int qb = 0; qb < TB; ++qb) {
+        const uint32_t g = static_cast<uint32_t>(it * TB + qb);
+        mbar_wait(s_full, g & 1u);
+        if (g > 0) mbar_wait(g_done, (g - 1) & 1u);           // P^T / dS^T are free again; the dQ partial of tile g - 1 is complete
+        tc_fence_after();
+        {
+          uint32_t sa[16], da[16], sb[16], db[16];
+          tmem_ld_32x16(t_lane + Cfg::kColS, sa);
+          tmem_ld_32x16(t_lane + Cfg::kColdP, da);
+          tmem_ld_wait();
+          const uint32_t prow = sP + static_cast<uint32_t>(tid) * 128u, dsrow = sdS + static_cast<uint32_t>(tid) * 128u;
+          const int sw = tid & 7;
+          const float* lq = sL + qb * 128;
+          const float* dq = sD + qb * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t (&s_cur)[16] = (c & 1) ? sb : sa;
+            uint32_t (&d_cur)[16] = (c & 1) ? db : da;
+            uint32_t (&s_nxt)[16] = (c & 1) ? sa : sb;
+            uint32_t (&d_nxt)[16] = (c & 1) ? da : db;
+            if (c + 1 < 8) {
+              tmem_ld_32x16(t_lane + Cfg::kColS + 16 * (c + 1), s_nxt);
+              tmem_ld_32x16(t_lane + Cfg::kColdP + 16 * (c + 1), d_nxt);
+            }
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+              const int q0 = 16 * c + 8 * gg;
+              const float4 l0 = *reinterpret_cast<const float4*>(lq + q0), l1 = *reinterpret_cast<const float4*>(lq + q0 + 4);
+              const float4 e0 = *reinterpret_cast<const float4*>(dq + q0), e1 = *reinterpret_cast<const float4*>(dq + q0 + 4);
+              const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+              const float dv[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+              float p[8], ds[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {                   // dead key row or dead query column -> exactly 0 (garbage scores stay finite)
+                p[e] = key_ok ? ex2f(fmaf(__uint_as_float(s_cur[8 * gg + e]), sl2, -lv[e])) : 0.f;
+                ds[e] = (p[e] != 0.f) ? p[e] * (__uint_as_float(d_cur[8 * gg + e]) - dv[e]) * 0.125f : 0.f;
+              }
+              const int chunk = q0 >> 3;
+              const uint32_t off = static_cast<uint32_t>(chunk >> 3) * Cfg::kBlk + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4);
+              sts_u4(prow + off, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+              sts_u4(dsrow + off, make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7])));
+            }
+            if (c + 1 < 8) tmem_ld_wait();
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // while the gradient MMAs of this tile run: the dQ partial of the previous tile (complete: g_done(g - 1) above)
+        if (g > 0 && qb > 0) drain_dq(g - 1, b, h, qb - 1, kb);
+      }
+      // ---- end of the item: its last dQ partial, then dV[kb], dK[kb]
+      const uint32_t g_last = static_cast<uint32_t>(it * TB + TB - 1);
+      mbar_wait(g_done, g_last & 1u);
+      tc_fence_after();
+      drain_dq(g_last, b, h, TB - 1, kb);
+      const int row_first = kb * 128 + warp * 32;
+      const int live = T - row_first < 0 ? 0 : (T - row_first < 32 ? T - row_first : 32);
+      __nv_bfloat16* row0 = base + static_cast<long long>(row_first) * kQkvCols;
+      store_acc_rows(t_lane + Cfg::kColdV, stage, row0 + 2 * kHidden, kQkvCols, 0, live, lane, csv);
+      store_acc_rows(t_lane + Cfg::kColdK, stage, row0 + kHidden, kQkvCols, 0, live, lane, csk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kv_drained);
+      if (dbias != nullptr) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int idx = k * 32 + lane;                    // 0..63: dK columns, 64..127: dV columns
+            atomicAdd(dbias + (1 + (idx >> 6)) * kHidden + h * kHeadDim + (idx & 63), s_colsum[idx]);
+            s_colsum[idx] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_bt324(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
+                 float* dbias, float* scratch, int batch, cudaStream_t stream) {
+  using Cfg = Bt324;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_bwd_tc324_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_bwd_tc324: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    configured = true;
+  }
+  const long long rows = static_cast<long long>(batch) * Cfg::T;
+  const size_t dq_floats = static_cast<size_t>(rows) * kHidden, d_floats = static_cast<size_t>(batch) * kHeads * Cfg::T;
+  // scratch: 3 key-block slices of rows x 768 fp32 dQ partial sums (every live row of every slice is written: no memset) +
+  // batch x 12 x 324 fp32 for D; the caller's buffer, or stream-ordered memory
+  float* mine = nullptr;
+  if (scratch == nullptr) {
+    static bool pool_kept[64] = {};     // keep freed blocks in the device's stream-ordered pool: the next call reuses them
+    int pdev = 0;
+    cudaGetDevice(&pdev);
+    if (pdev >= 0 && pdev < 64 && !pool_kept[pdev]) {
+      cudaMemPool_t pool;
+      unsigned long long keep = ~0ull;
+      if (cudaDeviceGetDefaultMemPool(&pool, pdev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pool_kept[pdev] = true;
+    }
+    if (cudaMallocAsync(&mine, (Cfg::TB * dq_floats + d_floats) * sizeof(float), stream) != cudaSuccess)
+      return set_error(kErrCuda, "attention_bwd_tc324: cudaMallocAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    scratch = mine;
+  }
+  float* dq32 = scratch;
+  float* dsum = scratch + Cfg::TB * dq_floats;
+  int rc = kOk;
+  do {
+    attn_bwd_d_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(d_o, o, dsum, rows, Cfg::T);
+    if ((rc = check_launch("attn_bwd_d_kernel")) != kOk) break;
+    CUtensorMap tm_qkv, tm_do;
+    if ((rc = make_tmap_bf16_kmajor(&tm_qkv, qkv, rows, kQkvCols, kQkvCols, 128)) != kOk) break;
+    if ((rc = make_tmap_bf16_kmajor(&tm_do, d_o, rows, kHidden, kHidden, 128)) != kOk) break;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = batch * kHeads * Cfg::TB;
+    attention_bwd_tc324_kernel<<<items < sms ? items : sms, kBtThreads, Cfg::kSmemBytes, stream>>>(tm_qkv, tm_do, lse2, dsum, dqkv, dq32,
+                                                                                                  static_cast<long long>(dq_floats), dbias, items);
+    if ((rc = check_launch("attention_bwd_tc324_kernel")) != kOk) break;
+    const long long n4 = static_cast<long long>(dq_floats / 4);
+    attn_bwd_dq_round_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(dq32, static_cast<long long>(dq_floats), Cfg::TB, dqkv, n4);
+    if ((rc = check_launch("attn_bwd_dq_round_kernel")) != kOk) break;
+    if (dbias != nullptr) rc = launch_colsum_bf16(dqkv, kQkvCols, rows, kHidden, dbias, stream);     // the q third of the qkv bias gradient
+  } while (false);
+  if (mine != nullptr) cudaFreeAsync(mine, stream);
+  return rc;
+}
+
 template <int T>
 int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2, __nv_bfloat16* dqkv,
               float* dbias, int batch, cudaStream_t stream) {
@@ -766,7 +1150,7 @@ int launch_bt(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloa
 bool attention_bwd_tc_supported(int tokens) {
   static int legacy = -1;      // JPDVT_ATTN_BWD_LEGACY=1: the mma.sync backward for every size (A/B knob)
   if (legacy < 0) { const char* e = getenv("JPDVT_ATTN_BWD_LEGACY"); legacy = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return !legacy && (tokens == 144 || tokens == 256);
+  return !legacy && (tokens == 144 || tokens == 256 || tokens == 324);
 }
 
 int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, const __nv_bfloat16* d_o, const float* lse2,
@@ -778,6 +1162,7 @@ int launch_attention_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* o, co
   switch (tokens) {
     case 144: return launch_bt<144>(qkv, o, d_o, lse2, dqkv, dbias, batch, stream);
     case 256: return launch_bt256(qkv, o, d_o, lse2, dqkv, dbias, batch, stream);
+    case 324: return launch_bt324(qkv, o, d_o, lse2, dqkv, dbias, nullptr, batch, stream);
     default: return set_error(kErrUnsupported, "attention_bwd_tc: %d tokens not instantiated", tokens);
   }
 }

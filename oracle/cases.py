@@ -53,6 +53,8 @@ TRAINING_CASES = {
     "d2_192":      dict(size=192, depth=2, batch=2, grid=3, wseed=34, seed=304, add_mask=False),
     # 4x4 @256 px (T = 256, BASELINE configs[3]): the tiled tcgen05 attention backward end to end
     "g4_256":      dict(size=256, depth=2, batch=2, grid=4, wseed=35, seed=305, add_mask=False),
+    # 3x3 @288 px (T = 324, the reference trainer's default --image-size) with masked pieces: the key-block-item backward
+    "d2_288_mask": dict(size=288, depth=2, batch=2, grid=3, wseed=36, seed=306, add_mask=True),
 }
 
 GRAD_KEYS = [

@@ -102,8 +102,8 @@ def test_ln_gate_bwd_fused(ops, B, T):
     assert rel_l2(only[0], xx.grad) < 1e-5 and only[4] is None
 
 
-@pytest.mark.parametrize("B,T", [(2, 144), (1, 144), (13, 144), (40, 144), (3, 9), (2, 256), (13, 256), (40, 256), (1, 324), (2, 100),
-                                 (1, 36)])
+@pytest.mark.parametrize("B,T", [(2, 144), (1, 144), (13, 144), (40, 144), (3, 9), (2, 256), (13, 256), (40, 256), (1, 324), (5, 324),
+                                 (13, 324), (2, 100), (1, 36)])
 def test_attention_backward(ops, B, T):
     torch.manual_seed(T)
     qkv = (torch.randn(B * T, 2304, device="cuda") * 1.2).bfloat16()
