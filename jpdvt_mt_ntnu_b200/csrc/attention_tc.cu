@@ -665,6 +665,355 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// T = 144 with EIGHT softmax warps per CTA (opt-in, JPDVT_ATTN_WARPS=8 - built on the hypothesis that the four-warp kernel is
+// bound by the latency of its math warps' instruction streams; parity-green and SLOWER, 57.8 vs 54.0 us at B = 256, so that is
+// not the bound either: DESIGN.md section 4).  Warps w
+// and w + 4 share a TMEM lane quadrant - the same 32 query rows - and split the COLUMNS: keys [0,80) / [80,144) of the score
+// row (row maximum and row sum meet through shared memory), 16-key halves of each remainder group, columns [0,32) / [32,64)
+// of the output rows.  Twice the warps per scheduler, half the work per warp.  Layout, barriers and MMA / TMA roles are the
+// four-warp kernel's (split remainder); warps 0-7 softmax, warp 8 TMA, warp 9 MMA.
+constexpr int kTc8Threads = 320;
+struct Tc8Cfg {
+  using Base = TcCfg<144>;
+  static constexpr int T = 144;
+  static constexpr int kXchOff = Base::kBarOff + 128;
+  // floats: row max [2][128], row sum [2][128] of the main tile; row max [8][16], row sum [8][16] of the remainder
+  static constexpr int kXchBytes = (4 * 128 + 2 * 8 * 16) * 4;
+  static constexpr int kSmemBytes = kXchOff + kXchBytes + 1024;
+  static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
+};
+
+__global__ void __launch_bounds__(kTc8Threads, 2)
+attention_tc8_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                     int num_units, int reverse) {
+  using Cfg = TcCfg<144>;
+  constexpr int T = 144;
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;         // [2]
+  uint64_t* p_full = bars + 4;         // [2] 8 arrivals
+  uint64_t* o_full = bars + 6;         // [2]
+  uint64_t* epi_done = bars + 8;       // 8 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xmax = reinterpret_cast<float*>(smem + Tc8Cfg::kXchOff);   // [2][128]
+  float* xsum = xmax + 256;                                        // [2][128]
+  float* rmax = xsum + 256;                                        // [8][16]
+  float* rsum = rmax + 128;                                        // [8][16]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 8); mbar_init(&o_full[t], 1); }
+    mbar_init(epi_done, 8);
+    fence_mbar_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sP = smem_u32(smem + Cfg::kOffP), sP1 = smem_u32(smem + Cfg::kOffP1);
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int uu = reverse ? num_units - 1 - unit : unit;
+        const int b = uu / kHeads, h = uu - b * kHeads;
+        const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        if (it > 0) mbar_wait(&s_full[1], prev);              // every score MMA of the previous unit has read Q, K
+        mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
+        tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        if (it > 0) mbar_wait(&o_full[1], prev);              // ... and every P V MMA has read V
+        mbar_expect_tx(v_full, Cfg::kTileBytes);
+        tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);
+      constexpr uint32_t idesc_a = umma_idesc_bf16(128, 32), idesc_b = umma_idesc_bf16(128, T - 96);
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), p_lo = desc_lo_k(sP), v_lo = desc_lo_mn(sV), p1_lo = desc_lo_k(sP1);
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        mbar_wait(qk_full, ph);
+        if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
+        }
+        umma_commit(&s_full[0]);
+        mbar_wait(&p_full[0], ph);                            // the main score tile is consumed, P0 is in shared memory
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                         // quadrant j <- rows 128..143 x keys [32j, 32j + n_j)
+          const uint32_t idesc_j = j < 3 ? idesc_a : idesc_b;
+          const uint32_t a0 = q_lo + (128 - 32 * j) * 8, b0 = k_lo + 32 * j * 8;
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            if (k == 0) umma_lohi<false>(tmem_base + 32 * j, a0, b0, idesc_j);
+            else umma_lohi<true>(tmem_base + 32 * j, a0 + 2 * k, b0 + 2 * k, idesc_j);
+          }
+        }
+        umma_commit(&s_full[1]);
+        mbar_wait(v_full, ph);
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {
+          const uint32_t a = p_lo + (j >> 2) * 1024 + (j & 3) * 2, bq = v_lo + j * 128;
+          if (j == 0) umma_lohi<false>(tmem_base + Cfg::kColO0, a, bq, idesc_o);
+          else umma_lohi<true>(tmem_base + Cfg::kColO0, a, bq, idesc_o);
+        }
+        umma_commit(&o_full[0]);
+        mbar_wait(&p_full[1], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {
+          const uint32_t a = p1_lo + (j >> 2) * 128 + (j & 3) * 2, bq = v_lo + j * 128;
+          if (j == 0) umma_lohi<false>(tmem_base + Cfg::kColO1, a, bq, idesc_o);
+          else umma_lohi<true>(tmem_base + Cfg::kColO1, a, bq, idesc_o);
+        }
+        umma_commit(&o_full[1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- softmax + epilogue
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int r_tile = quad * 32 + lane;
+    const int nch = half ? 4 : 5, cbase = half ? 80 : 0;      // this warp's 16-column chunks of the score row
+    const int pair_bar = 3 + quad;                            // named barrier of the two warps that share a lane quadrant
+    const int sw = r_tile & 7;
+    const uint32_t p_row = sP + r_tile * 128;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      const int uu = reverse ? num_units - 1 - unit : unit;
+      const int b = uu / kHeads, h = uu - b * kHeads;
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+      // ---- main tile: row maximum over this warp's columns, exchanged with the sibling warp
+      mbar_wait(&s_full[0], ph);
+      tc_fence_after();
+      uint32_t ra[16], rb[16];
+      float m0 = -INFINITY, m1 = -INFINITY;
+      tmem_ld_32x16(t_lane + cbase, ra);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch) {
+          uint32_t (&cur)[16] = (c & 1) ? rb : ra;
+          uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
+          if (c + 1 < nch) tmem_ld_32x16(t_lane + cbase + 16 * (c + 1), nxt);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+          }
+          if (c + 1 < nch) tmem_ld_wait();
+        }
+      }
+      tmem_ld_32x16(t_lane + cbase, ra);                      // second pass: its first chunk is in flight during the exchange
+      xmax[half * 128 + r_tile] = fmaxf(m0, m1);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float ms0 = fmaxf(xmax[r_tile], xmax[128 + r_tile]) * sl2;
+      // ---- probabilities of this warp's columns -> P0 (bf16, K-major swizzled), partial row sum
+      uint64_t sum2 = f2_pack(0.f, 0.f);
+      const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms0, -ms0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < nch) {
+          uint32_t (&cur)[16] = (c & 1) ? rb : ra;
+          uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
+          if (c + 1 < nch) tmem_ld_32x16(t_lane + cbase + 16 * (c + 1), nxt);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {                       // 8 keys -> one 16-byte chunk of the P row
+            float p[8];
+            uint64_t e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a, bb;
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[8 * g + 2 * j]), __uint_as_float(cur[8 * g + 2 * j + 1])), sl2p, nmsp), a, bb);
+              p[2 * j] = ex2f(a); p[2 * j + 1] = ex2f(bb);
+              e[j] = f2_pack(p[2 * j], p[2 * j + 1]);
+            }
+            sum2 = f2_add(sum2, f2_add(f2_add(e[0], e[1]), f2_add(e[2], e[3])));
+            const int chunk = (cbase >> 3) + 2 * c + g;
+            sts_u4(p_row + static_cast<uint32_t>(chunk >> 3) * 16384u + static_cast<uint32_t>(((chunk & 7) ^ sw) << 4),
+                   make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+          }
+          if (c + 1 < nch) tmem_ld_wait();
+        }
+      }
+      {
+        float s_even, s_odd;
+        f2_unpack(sum2, s_even, s_odd);
+        xsum[half * 128 + r_tile] = s_even + s_odd;            // read after the remainder's CTA-wide barriers below
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[0]);
+      // ---- remainder rows 128..143 (lanes 0..15 of every quadrant): group `quad` = keys [32 quad, 32 quad + n), split in two
+      mbar_wait(&s_full[1], ph);
+      tc_fence_after();
+      const int rc0 = 32 * quad + 16 * half;                  // first key of this warp's slice; quad 3 / half 1 takes 32 keys
+      const bool wide = (quad == 3 && half == 1);
+      uint32_t sa[16], sb2[16];
+      tmem_ld_32x16(t_lane + rc0, sa);
+      if (wide) tmem_ld_32x16(t_lane + rc0 + 16, sb2);
+      tmem_ld_wait();
+      float rm0 = -INFINITY, rm1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        rm0 = fmaxf(rm0, __uint_as_float(sa[j])); rm1 = fmaxf(rm1, __uint_as_float(sa[j + 1]));
+        if (wide) { rm0 = fmaxf(rm0, __uint_as_float(sb2[j])); rm1 = fmaxf(rm1, __uint_as_float(sb2[j + 1])); }
+      }
+      const int l = lane & 15;
+      if (lane < 16) rmax[warp * 16 + lane] = fmaxf(rm0, rm1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float mx = rmax[l];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, rmax[w * 16 + l]);
+      const float ms1 = mx * sl2;
+      float rs = 0.f;
+      {
+        const uint32_t p1_row = sP1 + lane * 128;
+        const int swr = lane & 7;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[j] = ex2f(fmaf(__uint_as_float(sa[8 * g + j]), sl2, -ms1));
+          rs += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+          const int ch = (rc0 >> 3) + g;
+          if (lane < 16) sts_u4(p1_row + static_cast<uint32_t>(ch >> 3) * 2048u + static_cast<uint32_t>(((ch & 7) ^ swr) << 4),
+                                make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+        }
+        if (wide) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = ex2f(fmaf(__uint_as_float(sb2[8 * g + j]), sl2, -ms1));
+            rs += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            const int ch = (rc0 >> 3) + 2 + g;
+            if (lane < 16) sts_u4(p1_row + static_cast<uint32_t>(ch >> 3) * 2048u + static_cast<uint32_t>(((ch & 7) ^ swr) << 4),
+                                  make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+          }
+        }
+      }
+      if (lane < 16) rsum[warp * 16 + lane] = rs;
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float sum1 = rsum[l];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) sum1 += rsum[w * 16 + l];
+      const float sum0 = xsum[r_tile] + xsum[128 + r_tile];     // both halves were written before the barriers above
+      if (lse2 != nullptr) {
+        float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+        if (half == 0) lrow[r_tile] = ms0 + log2f(sum0);
+        if (warp == 0 && lane < 16) lrow[128 + lane] = ms1 + log2f(sum1);
+      }
+      // ---- outputs: this warp's 32 columns of its 32 rows.  O0 into registers BEFORE P1 is handed over (a tcgen05.ld issued
+      // while the O1 MMAs run waits for them)
+      uint32_t oa[32];
+      mbar_wait(&o_full[0], ph);
+      tc_fence_after();
+      tmem_ld_32x32(t_lane + Cfg::kColO0 + 32 * half, oa);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[1]);
+      auto store_half = [&](const uint32_t (&o)[32], float inv, __nv_bfloat16* dst_row0, int live_rows) {
+        // 32 rows x 32 bf16 columns (64 B per row) through a 2 KB staging tile in the idle P0 buffer: 16-byte chunk c of row r
+        // sits at r * 64 + ((c ^ (r >> 1)) & 3) * 16; every store instruction then writes 8 rows x 64 contiguous bytes
+        const uint32_t stg = sP + static_cast<uint32_t>(warp) * 2048u;
+        const uint32_t mine = stg + lane * 64;
+        const uint32_t swz = static_cast<uint32_t>(lane >> 1) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts_u4(mine + ((static_cast<uint32_t>(j) ^ swz) << 4),
+                 make_uint4(pack_bf16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+                            pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv)));
+        __syncwarp();
+        const int sub = lane >> 2, ch = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + sub;
+          uint4 u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                       : "r"(stg + r * 64 + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(r >> 1) & 3u)) << 4)));
+          if (r < live_rows) *reinterpret_cast<uint4*>(dst_row0 + static_cast<long long>(r) * kHidden + 32 * half + ch * 8) = u;
+        }
+        __syncwarp();
+      };
+      store_half(oa, 1.0f / sum0, obase + static_cast<long long>(quad * 32) * kHidden, T - quad * 32 < 32 ? T - quad * 32 : 32);
+      if (quad == 0) {                                         // O1 rows 128..143 sit in lanes 0..15 of quadrant 0: warps 0 and 4
+        mbar_wait(&o_full[1], ph);
+        tc_fence_after();
+        tmem_ld_32x32(t_lane + Cfg::kColO1 + 32 * half, oa);
+        tmem_ld_wait();
+        store_half(oa, 1.0f / sum1, obase + static_cast<long long>(128) * kHidden, 16);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_tc8(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
+  constexpr int T = 144;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc8Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_tc8: cudaFuncSetAttribute(smem=%d) failed: %s", Tc8Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    cudaFuncSetAttribute(attention_tc8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  CUtensorMap tm;
+  const long long rows = static_cast<long long>(batch) * T;
+  int rc = make_tmap_bf16_kmajor(&tm, qkv, rows, kQkvCols, kQkvCols, T);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  const int grid = units < 2 * sms ? units : 2 * sms;
+  if (launch_pdl(attention_tc8_kernel, dim3(grid), dim3(kTc8Threads), Tc8Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse()) != cudaSuccess)
+    return set_error(kErrCuda, "attention_tc8_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return check_launch("attention_tc8_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Longer sequences (T = 324 @288 px): keys padded to TP = 336 (a multiple of 16, columns >= T masked to probability 0), the
 // score tile is 128 x TP fp32 = TP TMEM columns (two MMAs per k-step, N <= 256 each), so one score tile at a time: the
 // ceil(T / 128) query tiles of a unit run one after the other, O in its own 64 columns, one CTA per SM.
@@ -874,7 +1223,9 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = batch * kHeads;
-  const int slots = sms * Cfg::kCtasPerSm;
+  static int cta_cap = -1;          // JPDVT_ATTN_CTAS=1: one CTA per SM (the experiment behind DESIGN.md section 4: 76 vs 54 us)
+  if (cta_cap < 0) { const char* e = getenv("JPDVT_ATTN_CTAS"); cta_cap = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  const int slots = sms * (cta_cap ? 1 : Cfg::kCtasPerSm);
   const int grid = units < slots ? units : slots;
   if (trace_mode) {   // developer path: synchronous, prints the event clocks of CTA 0 (relative to its first event)
     constexpr int n = kTraceRoles * kTraceUnits * kTraceEvents;
@@ -914,7 +1265,12 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return set_error(kErrBadArg, "attention_tc: pointers must be 16-byte aligned");
   switch (tokens) {
-    case 144: return launch_tc<144>(qkv, out, lse2, batch, stream);
+    case 144: {
+      static int warps8 = -1;       // JPDVT_ATTN_WARPS=8: the eight-softmax-warp kernel (A/B knob; measured slower: 57.8 vs 54.0 us at
+                                    // B = 256 - DESIGN.md section 4); default: four
+      if (warps8 < 0) { const char* e = getenv("JPDVT_ATTN_WARPS"); warps8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
+      return warps8 ? launch_tc8(qkv, out, lse2, batch, stream) : launch_tc<144>(qkv, out, lse2, batch, stream);
+    }
     case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
     case 324: return launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
