@@ -50,7 +50,8 @@ class Trainer:
         # full optimizer pass on every rank.  "stage": one all-reduce per backward stage (overlaps the rest of the backward,
         # but the NCCL kernels then compete for SMs with the persistent one-CTA-per-SM GEMMs - measured slower).
         mode = allreduce or os.environ.get("JPDVT_TRAIN_ALLREDUCE")
-        if mode is None:
+        auto = mode is None
+        if auto:
             mode = "peer" if (self.world > 1 and peer.available(process_group)[0]) else "end"
         if mode not in ("stage", "end", "peer"):
             raise ValueError(f"allreduce must be 'peer', 'end' or 'stage', got {mode!r}")
@@ -74,7 +75,22 @@ class Trainer:
         if self.allreduce == "peer" and self.world > 1:
             # every flat buffer lives in this rank's symmetric block: the peers read the gradients, write the bf16 operands
             # (and the few fp32 values the kernels read directly) and can read the owner's slice of the fp32 state
-            self.px = peer.PeerExchange(self.total, dev, process_group)
+            try:
+                self.px = peer.PeerExchange(self.total, dev, process_group)
+            except Exception as e:  # noqa: BLE001  (no peer access between these GPUs, VMM handles refused, ...)
+                if not auto:
+                    raise
+                self.px, why = None, e
+            if auto:
+                # the ranks must agree: if the mapping failed anywhere, everybody takes the NCCL path
+                ok = torch.tensor([1 if self.px is not None else 0], device=dev, dtype=torch.int32)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+                if int(ok.item()) == 0:
+                    if self.px is None and (dist.get_rank(process_group) == 0):
+                        import warnings
+                        warnings.warn(f"peer-memory optimizer step unavailable ({why}); falling back to the NCCL all-reduce")
+                    self.px, self.allreduce = None, "end"
+        if self.px is not None:
             self.p_flat, self.m_flat, self.v_flat = self.px.p, self.px.m, self.px.v
             self.pb_flat = self.px.weights_bf16
         else:
