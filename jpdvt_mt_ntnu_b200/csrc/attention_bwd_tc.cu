@@ -208,6 +208,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
         tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO, h * kHeadDim, b * T);
         tma_load_2d(&tm_o, in_full, smem + Cfg::kOffO, h * kHeadDim, b * T);
+        // the next unit's five tiles towards L2: its loads can only be issued when this unit's last MMA has read the buffers
+        if (unit + static_cast<int>(gridDim.x) < num_units) {
+          const int nu = unit + static_cast<int>(gridDim.x), nb = nu / kHeads, nh = nu - nb * kHeads;
+          tma_prefetch_2d(&tm_qkv, kHidden + nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, 2 * kHidden + nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_do, nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_o, nh * kHeadDim, nb * T);
+        }
       }
     }
     __syncwarp();
@@ -513,6 +522,14 @@ attention_bwd_tc256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
         tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO, h * kHeadDim, b * T);
         tma_load_2d(&tm_o, in_full, smem + Cfg::kOffO, h * kHeadDim, b * T);
+        if (unit + static_cast<int>(gridDim.x) < num_units) {       // the next unit's tiles towards L2
+          const int nu = unit + static_cast<int>(gridDim.x), nb = nu / kHeads, nh = nu - nb * kHeads;
+          tma_prefetch_2d(&tm_qkv, kHidden + nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, 2 * kHidden + nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_do, nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_o, nh * kHeadDim, nb * T);
+        }
       }
     }
     __syncwarp();
@@ -857,6 +874,17 @@ attention_bwd_tc324_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         for (int qb = 0; qb < TB; ++qb) {
           tma_load_2d(&tm_qkv, in_full, smem + Cfg::kOffQ + qb * Cfg::kBlk, h * kHeadDim, b * T + qb * 128);
           tma_load_2d(&tm_do, in_full, smem + Cfg::kOffdO + qb * Cfg::kBlk, h * kHeadDim, b * T + qb * 128);
+        }
+        if (item + static_cast<int>(gridDim.x) < num_items) {       // the next item's tiles towards L2
+          const int ni = item + static_cast<int>(gridDim.x), nunit = ni / TB, nkb = ni - nunit * TB;
+          const int nb = nunit / kHeads, nh = nunit - nb * kHeads;
+          tma_prefetch_2d(&tm_qkv, kHidden + nh * kHeadDim, nb * T + nkb * 128);
+          tma_prefetch_2d(&tm_qkv, 2 * kHidden + nh * kHeadDim, nb * T + nkb * 128);
+#pragma unroll
+          for (int qb = 0; qb < TB; ++qb) {
+            tma_prefetch_2d(&tm_qkv, nh * kHeadDim, nb * T + qb * 128);
+            tma_prefetch_2d(&tm_do, nh * kHeadDim, nb * T + qb * 128);
+          }
         }
       }
     }

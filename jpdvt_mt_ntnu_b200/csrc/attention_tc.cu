@@ -373,7 +373,7 @@ constexpr int kTraceUnits = 6, kTraceEvents = 10, kTraceRoles = 4;   // roles: M
 template <int T, bool TRACE, bool RT = false, bool R2 = false>
 __global__ void __launch_bounds__(kTcThreads, TcCfg<T>::kCtasPerSm)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                    int num_units, int reverse, long long* __restrict__ trace) {
+                    int num_units, int reverse, long long* __restrict__ trace, int l2_prefetch) {
   using Cfg = TcCfg<T>;
   auto mark = [&](int role, int it, int ev) {
     if constexpr (TRACE) {
@@ -453,6 +453,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mark(3, it, 3);
         mbar_expect_tx(v_full, Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+        // the next unit's Q / K / V towards L2 now: their loads are only issued when this unit's MMAs have released the
+        // buffers, and that latency sits on the unit chain (2,860 cycles from HBM under load)
+        if (l2_prefetch && unit + static_cast<int>(gridDim.x) < num_units) {
+          const int nu = reverse ? num_units - 1 - (unit + static_cast<int>(gridDim.x)) : unit + static_cast<int>(gridDim.x);
+          const int nb = nu / kHeads, nh = nu - nb * kHeads;
+          tma_prefetch_2d(&tm_qkv, nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, kHidden + nh * kHeadDim, nb * T);
+          tma_prefetch_2d(&tm_qkv, 2 * kHidden + nh * kHeadDim, nb * T);
+        }
       }
       if constexpr (R2) {
         if (it > 0) issue_rem_half(static_cast<uint32_t>((it - 1) & 1));   // the last unit's
@@ -1223,6 +1232,9 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = batch * kHeads;
+  static int l2pf = -1;             // JPDVT_ATTN_L2PF=1: TMA L2 prefetch of the next unit's tiles (A/B knob; measured neutral: with two
+                                    // CTAs per SM the other CTA already covers the load latency - 54.9 vs 54.2 us at B = 256)
+  if (l2pf < 0) { const char* e = getenv("JPDVT_ATTN_L2PF"); l2pf = (e != nullptr && e[0] == '1') ? 1 : 0; }
   static int cta_cap = -1;          // JPDVT_ATTN_CTAS=1: one CTA per SM (the experiment behind DESIGN.md section 4: 76 vs 54 us)
   if (cta_cap < 0) { const char* e = getenv("JPDVT_ATTN_CTAS"); cta_cap = (e != nullptr && e[0] == '1') ? 1 : 0; }
   const int slots = sms * (cta_cap ? 1 : Cfg::kCtasPerSm);
@@ -1232,7 +1244,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
     long long* d = nullptr;
     cudaMalloc(&d, n * sizeof(long long));
     cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
-    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d);
+    kern_trace<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d, l2pf);
     long long h[n];
     cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -1251,7 +1263,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
       }
     return check_launch("attention_tc_kernel<trace>");
   }
-  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(), static_cast<long long*>(nullptr)) != cudaSuccess)
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(), static_cast<long long*>(nullptr), l2pf) != cudaSuccess)
     return set_error(kErrCuda, "attention_tc_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("attention_tc_kernel");
 }
