@@ -562,16 +562,20 @@ def measure_training(wl, batch, steps, warmup, world, rank, dev):
     kw = dict(block_size=S // G, patch_size=16, add_mask=False, grid_size=G)
     torch.manual_seed(rank)
 
+    # the whole step replayed from a CUDA graph (no host in the loop, train_JPDVT.py:340-372) where the exchange allows it:
+    # one GPU or the peer-memory step; an NCCL all-reduce stays on host-issued launches.  JPDVT_TRAIN_GRAPH=0: never.
+    graph = os.environ.get("JPDVT_TRAIN_GRAPH", "1")[:1] != "0" and (world == 1 or trainer.px is not None)
+
     def one_step(xin):
         t = torch.randint(0, diffusion.num_timesteps, (batch,), device=dev)          # train_JPDVT.py:354
-        return trainer.step(xin, t, piece, **kw)
+        return trainer.step(xin, t, piece, graph=graph, **kw)
 
     from jpdvt_mt_ntnu_b200 import _lib
     for _ in range(max(warmup, 3)):
         one_step(x)
-    n0 = _lib.launch_count()
+    n0 = _lib.launch_count() + trainer.replayed_launches
     ms, loss = _timed(lambda: one_step(x), steps, world, dev)
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() + trainer.replayed_launches - n0
     # end to end through the trainer's own host-side pieces: every step's batch comes from pinned host memory (copied one
     # step ahead on a copy stream - BatchPrefetcher), every step's loss goes back to the host (pinned ring - LossLog)
     from jpdvt_mt_ntnu_b200.trainer import BatchPrefetcher, LossLog
@@ -592,7 +596,7 @@ def measure_training(wl, batch, steps, warmup, world, rank, dev):
            "e2e": {"value": batch * world * steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
            "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12, "final_loss": float(loss_h),
-           "gpu_launches": launches}
+           "gpu_launches": launches, "graph_replay": graph}
     del trainer, model
     torch.cuda.empty_cache()
     return out

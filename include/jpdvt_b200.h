@@ -445,6 +445,8 @@ typedef struct jpdvt_peer_step {
   int64_t f32_ranges[2 * JPDVT_MAX_F32_RANGES];
   uint32_t* local_sync;          /* device uint32, zero before the first call (CTA counter of this rank) */
   int32_t* status;               /* device int32, stays zero unless a barrier timed out */
+  uint32_t* epoch_dev;           /* optional device uint32: when set, the barrier token is *epoch_dev + 1 and the kernel stores it back
+                                  * (a CUDA-graph replay cannot carry a changing kernel parameter); must agree across the ranks */
 } jpdvt_peer_step;
 /* p, m, v, ema: this rank's full-length flat fp32 buffers - only [shard_begin, shard_end) is read and written (the fp32
  * master state of a parameter lives on its owner, except the f32_ranges, which every rank receives; gather the rest for
@@ -453,6 +455,15 @@ typedef struct jpdvt_peer_step {
 int jpdvt_adamw_ema_peer(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, int64_t step,
                          float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
                          void* stream);
+/* The two optimizer steps with the step count (Adam's bias corrections) read from DEVICE memory instead of a host argument -
+ * what a CUDA-graph replay of the whole training step needs (train_JPDVT.py:340-376 without the host in the loop).  The caller
+ * increments *step_dev (stream ordered) before the call; the peer form also takes its barrier token from px->epoch_dev. */
+int jpdvt_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema_or_null, jpdvt_bf16* p_bf16_or_null, int64_t n,
+                        const int64_t* step_dev, float grad_scale, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float ema_decay, void* stream);
+int jpdvt_adamw_ema_peer_dev(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, const int64_t* step_dev,
+                             float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             float ema_decay, void* stream);
 /* out[b][c][r] = in[b][r][c]: refreshes the [in, out] weight copies of jpdvt_weights_t after an optimizer step. */
 int jpdvt_transpose_bf16(const jpdvt_bf16* in, jpdvt_bf16* out, int batch, int rows, int cols, void* stream);
 

@@ -75,7 +75,7 @@ class PeerStep(C.Structure):
                 ("weights_bf16", c_void_p * MAX_PEERS), ("params", c_void_p * MAX_PEERS), ("signals", c_void_p * MAX_PEERS),
                 ("grads_mc", c_void_p), ("weights_mc", c_void_p), ("params_mc", c_void_p), ("n_f32_ranges", C.c_int32),
                 ("reserved", C.c_int32), ("f32_ranges", C.c_int64 * (2 * MAX_F32_RANGES)), ("local_sync", c_void_p),
-                ("status", c_void_p)]
+                ("status", c_void_p), ("epoch_dev", c_void_p)]
 
 
 # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables, 4: timestep-MLP
@@ -134,6 +134,8 @@ PROTOTYPES = {
                                    C.POINTER(Grads), P, P],
     "jpdvt_adamw_ema": [P, P, P, P, P, P, c_int64, c_int64] + [C.c_float] * 7 + [P],
     "jpdvt_adamw_ema_peer": [C.POINTER(PeerStep), P, P, P, P, c_int64] + [C.c_float] * 7 + [P],
+    "jpdvt_adamw_ema_peer_dev": [C.POINTER(PeerStep), P, P, P, P, P] + [C.c_float] * 7 + [P],
+    "jpdvt_adamw_ema_dev": [P, P, P, P, P, P, c_int64, P] + [C.c_float] * 7 + [P],
     "jpdvt_transpose_bf16": [P, P, c_int, c_int, c_int, P],
     "jpdvt_denoiser_forward": [C.POINTER(Weights), C.POINTER(Workspace), P, P, P, P, P, P, P, c_int, P],
     "jpdvt_sample_loop": [C.POINTER(Weights), C.POINTER(Workspace), C.POINTER(Sampler), P, P, c_int, c_int, c_int, P],

@@ -12,10 +12,24 @@ namespace jp {
 
 // AdamW exactly as torch.optim.AdamW (decoupled weight decay, bias correction via step-dependent scalars computed on the
 // host): p *= 1 - lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// step_ptr != null: the step count lives on the device (a CUDA-graph replay of the training step cannot carry step-dependent
+// scalars as kernel parameters) and the two bias-correction factors are derived from it, once per block
 __global__ void __launch_bounds__(256)
 adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ ema, __nv_bfloat16* __restrict__ p_bf16, long long n4, float grad_scale, float lr,
-                 float beta1, float beta2, float eps, float weight_decay, float step_size, float inv_sqrt_bc2, float ema_decay) {
+                 float beta1, float beta2, float eps, float weight_decay, float step_size, float inv_sqrt_bc2, float ema_decay,
+                 const long long* __restrict__ step_ptr) {
+  if (step_ptr != nullptr) {
+    __shared__ float s_corr[2];
+    if (threadIdx.x == 0) {
+      const double st = static_cast<double>(*step_ptr);
+      s_corr[0] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), st)));
+      s_corr[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(beta2), st)));
+    }
+    __syncthreads();
+    step_size = s_corr[0];
+    inv_sqrt_bc2 = s_corr[1];
+  }
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -84,7 +98,20 @@ int jpdvt_adamw_ema(float* p, const float* g, float* m, float* v, float* ema_or_
   const long long n4 = n / 4;
   adamw_ema_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, ema_or_null, reinterpret_cast<__nv_bfloat16*>(p_bf16_or_null), n4, grad_scale, lr, beta1, beta2, eps,
-      weight_decay, step_size, inv_sqrt_bc2, ema_decay);
+      weight_decay, step_size, inv_sqrt_bc2, ema_decay, nullptr);
+  return check_launch("adamw_ema_kernel");
+}
+
+int jpdvt_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema_or_null, jpdvt_bf16* p_bf16_or_null, int64_t n,
+                        const int64_t* step_dev, float grad_scale, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float ema_decay, void* stream) {
+  if (n == 0) return kOk;
+  if (!p || !g || !m || !v || !step_dev) return set_error(kErrBadArg, "adamw_ema_dev: null pointer");
+  if (n & 3) return set_error(kErrBadArg, "adamw_ema_dev: element count must be a multiple of 4");
+  const long long n4 = n / 4;
+  adamw_ema_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, ema_or_null, reinterpret_cast<__nv_bfloat16*>(p_bf16_or_null), n4, grad_scale, lr, beta1, beta2, eps,
+      weight_decay, 0.f, 0.f, ema_decay, reinterpret_cast<const long long*>(step_dev));
   return check_launch("adamw_ema_kernel");
 }
 

@@ -72,7 +72,25 @@ __device__ __forceinline__ bool wait_flags(const uint32_t* flags, int world, int
 
 struct AdamHyper {
   float grad_scale, lr, beta1, beta2, eps, weight_decay, step_size, inv_sqrt_bc2, ema_decay;
+  const long long* step_dev;      // != null: step count on the device, bias corrections derived in the kernel (graph replay)
 };
+
+// step-dependent scalars of one launch: from the host (parameters) or from the device-side counters
+struct StepScalars { uint32_t epoch; float step_size, inv_sqrt_bc2; };
+__device__ __forceinline__ StepScalars step_scalars(const jpdvt_peer_step& px, const AdamHyper& h) {
+  __shared__ StepScalars sc;
+  if (threadIdx.x == 0) {
+    sc.epoch = px.epoch_dev != nullptr ? *reinterpret_cast<volatile uint32_t*>(px.epoch_dev) + 1u : px.epoch;
+    sc.step_size = h.step_size; sc.inv_sqrt_bc2 = h.inv_sqrt_bc2;
+    if (h.step_dev != nullptr) {
+      const double st = static_cast<double>(*h.step_dev);
+      sc.step_size = static_cast<float>(static_cast<double>(h.lr) / (1.0 - pow(static_cast<double>(h.beta1), st)));
+      sc.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(h.beta2), st)));
+    }
+  }
+  __syncthreads();
+  return sc;
+}
 
 template <bool MC>
 __global__ void __launch_bounds__(256)
@@ -82,13 +100,15 @@ peer_adamw_ema_kernel(const jpdvt_peer_step px, float* __restrict__ p, float* __
   const unsigned long long timeout_ns = static_cast<unsigned long long>(px.timeout_ms) * 1000000ull;
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(px.signals[rank]);
   __shared__ int s_last;
+  const StepScalars sc = step_scalars(px, h);
+  const uint32_t epoch = sc.epoch;
 
   // ---- barrier A: the gradients of every rank are final -------------------------------------------------------------
   if (blockIdx.x == 0 && threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
     __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(px.signals[threadIdx.x]) + rank, px.epoch);
+    st_release_sys(reinterpret_cast<uint32_t*>(px.signals[threadIdx.x]) + rank, epoch);
   }
-  if (!wait_flags(my_flags, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 1);
+  if (!wait_flags(my_flags, world, rank, epoch, timeout_ns)) atomicExch(px.status, 1);
   __syncthreads();
 
   // ---- my slice: reduce, update, broadcast ---------------------------------------------------------------------------
@@ -132,8 +152,8 @@ peer_adamw_ema_kernel(const jpdvt_peer_step px, float* __restrict__ p, float* __
       pa[k] *= wd_mul;
       ma[k] = h.beta1 * ma[k] + (1.0f - h.beta1) * gk;
       va[k] = h.beta2 * va[k] + (1.0f - h.beta2) * gk * gk;
-      const float denom = sqrtf(va[k]) * h.inv_sqrt_bc2 + h.eps;
-      pa[k] -= h.step_size * (ma[k] / denom);
+      const float denom = sqrtf(va[k]) * sc.inv_sqrt_bc2 + h.eps;
+      pa[k] -= sc.step_size * (ma[k] / denom);
     }
     reinterpret_cast<float4*>(p + i)[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
     reinterpret_cast<float4*>(p + i)[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
@@ -191,9 +211,11 @@ peer_adamw_ema_kernel(const jpdvt_peer_step px, float* __restrict__ p, float* __
     if (threadIdx.x == 0) *px.local_sync = 0u;                              // ready for the next call (stream ordered)
     if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) {
       __threadfence_system();
-      st_release_sys(reinterpret_cast<uint32_t*>(px.signals[threadIdx.x]) + JPDVT_MAX_PEERS + rank, px.epoch);
+      st_release_sys(reinterpret_cast<uint32_t*>(px.signals[threadIdx.x]) + JPDVT_MAX_PEERS + rank, epoch);
     }
-    if (!wait_flags(my_flags + JPDVT_MAX_PEERS, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 2);
+    if (!wait_flags(my_flags + JPDVT_MAX_PEERS, world, rank, epoch, timeout_ns)) atomicExch(px.status, 2);
+    __syncthreads();
+    if (threadIdx.x == 0 && px.epoch_dev != nullptr) *px.epoch_dev = epoch;      // every CTA of this launch has read the old value
   }
 }
 
@@ -235,11 +257,13 @@ peer_adamw_ema_bulk_kernel(const jpdvt_peer_step px, float* __restrict__ p, floa
     fence_mbar_init();
   }
   // ---- barrier A ---------------------------------------------------------------------------------------------------
+  const StepScalars sc = step_scalars(px, h);
+  const uint32_t epoch = sc.epoch;
   if (blockIdx.x == 0 && tid < world && tid != rank) {
     __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + rank, px.epoch);
+    st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + rank, epoch);
   }
-  if (!wait_flags(my_flags, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 1);
+  if (!wait_flags(my_flags, world, rank, epoch, timeout_ns)) atomicExch(px.status, 1);
   __syncthreads();
 
   const long long t0 = px.shard_begin / kTile, t1 = px.shard_end / kTile;   // tiles of my slice
@@ -297,8 +321,8 @@ peer_adamw_ema_bulk_kernel(const jpdvt_peer_step px, float* __restrict__ p, floa
       pa[k] *= wd_mul;
       ma[k] = h.beta1 * ma[k] + (1.0f - h.beta1) * gk;
       va[k] = h.beta2 * va[k] + (1.0f - h.beta2) * gk * gk;
-      const float denom = sqrtf(va[k]) * h.inv_sqrt_bc2 + h.eps;
-      pa[k] -= h.step_size * (ma[k] / denom);
+      const float denom = sqrtf(va[k]) * sc.inv_sqrt_bc2 + h.eps;
+      pa[k] -= sc.step_size * (ma[k] / denom);
     }
     reinterpret_cast<float4*>(p + i)[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
     reinterpret_cast<float4*>(p + i)[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
@@ -354,9 +378,11 @@ peer_adamw_ema_bulk_kernel(const jpdvt_peer_step px, float* __restrict__ p, floa
     if (tid == 0) *px.local_sync = 0u;
     if (tid < world && tid != rank) {
       __threadfence_system();
-      st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + JPDVT_MAX_PEERS + rank, px.epoch);
+      st_release_sys(reinterpret_cast<uint32_t*>(px.signals[tid]) + JPDVT_MAX_PEERS + rank, epoch);
     }
-    if (!wait_flags(my_flags + JPDVT_MAX_PEERS, world, rank, px.epoch, timeout_ns)) atomicExch(px.status, 2);
+    if (!wait_flags(my_flags + JPDVT_MAX_PEERS, world, rank, epoch, timeout_ns)) atomicExch(px.status, 2);
+    __syncthreads();
+    if (threadIdx.x == 0 && px.epoch_dev != nullptr) *px.epoch_dev = epoch;      // every CTA of this launch has read the old value
   }
 }
 
@@ -366,16 +392,33 @@ using namespace jp;
 
 extern "C" {
 
+static int peer_step_impl(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, int64_t step,
+                          const int64_t* step_dev, float grad_scale, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float ema_decay, void* stream);
+
 int jpdvt_adamw_ema_peer(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, int64_t step,
                          float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
                          void* stream) {
+  if (step < 1) return set_error(kErrBadArg, "adamw_ema_peer: step counts from 1");
+  return peer_step_impl(px, p, m, v, ema_or_null, step, nullptr, grad_scale, lr, beta1, beta2, eps, weight_decay, ema_decay, stream);
+}
+
+int jpdvt_adamw_ema_peer_dev(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, const int64_t* step_dev,
+                             float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             float ema_decay, void* stream) {
+  if (!step_dev || !px || !px->epoch_dev) return set_error(kErrBadArg, "adamw_ema_peer_dev: device step / epoch counters required");
+  return peer_step_impl(px, p, m, v, ema_or_null, 1, step_dev, grad_scale, lr, beta1, beta2, eps, weight_decay, ema_decay, stream);
+}
+
+static int peer_step_impl(const jpdvt_peer_step* px, float* p, float* m, float* v, float* ema_or_null, int64_t step,
+                          const int64_t* step_dev, float grad_scale, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float ema_decay, void* stream) {
   if (!px || !p || !m || !v) return set_error(kErrBadArg, "adamw_ema_peer: null pointer");
   if (px->world < 2 || px->world > JPDVT_MAX_PEERS || px->rank < 0 || px->rank >= px->world)
     return set_error(kErrBadArg, "adamw_ema_peer: world=%d rank=%d (2..%d ranks)", px->world, px->rank, JPDVT_MAX_PEERS);
   if ((px->shard_begin & 7) || (px->shard_end & 7) || px->shard_end < px->shard_begin)
     return set_error(kErrBadArg, "adamw_ema_peer: the slice [%lld, %lld) must be multiples of 8 parameters",
                      static_cast<long long>(px->shard_begin), static_cast<long long>(px->shard_end));
-  if (step < 1) return set_error(kErrBadArg, "adamw_ema_peer: step counts from 1");
   if (!px->local_sync || !px->status) return set_error(kErrBadArg, "adamw_ema_peer: null sync / status word");
   const bool mc = px->grads_mc != nullptr && px->weights_mc != nullptr && px->params_mc != nullptr;
   if (px->n_f32_ranges < 0 || px->n_f32_ranges > JPDVT_MAX_F32_RANGES)
@@ -391,6 +434,7 @@ int jpdvt_adamw_ema_peer(const jpdvt_peer_step* px, float* p, float* m, float* v
   h.step_size = static_cast<float>(lr / bc1);
   h.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
   h.ema_decay = ema_decay;
+  h.step_dev = reinterpret_cast<const long long*>(step_dev);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -424,6 +424,21 @@ class GaussianDiffusion:
             img = out["sample"]
 
     # ------------------------------------------------------------------ training
+    @staticmethod
+    def draw_scramble(batch: int, grid: int, add_mask: bool):
+        """The host-side draws of one training step in the reference's order (gaussian_diffusion.py:757, 777-783): the piece
+        permutation (numpy) and, with add_mask, per sample r = randint(0, G) zeroed slots (numpy + `random`).
+        -> (perm int32 [G*G], keep float32 [B, G*G] or None)."""
+        n = grid * grid
+        perm = th.as_tensor(np.random.permutation(n), dtype=th.int32)
+        keep = None
+        if add_mask:
+            keep = th.ones(batch, n)
+            for i in range(batch):
+                r = np.random.randint(0, grid)
+                keep[i, random.sample(range(n), r)] = 0
+        return perm, keep
+
     def _to_device_async(self, host: "th.Tensor", device) -> "th.Tensor":
         """Small host-drawn tables (the step's permutation, the mask slots) -> device WITHOUT a stream sync: a pageable
         host-to-device copy blocks the host until the stream has drained, i.e. once per training step (measured: 10 of the
@@ -471,10 +486,13 @@ class GaussianDiffusion:
         B = x_start.shape[0]
         G, n = grid_size, grid_size * grid_size
         draws = getattr(self, "_draws", None)      # parity tests inject the reference's CPU draws here
+        dev_draws = getattr(self, "_device_draws", None)   # Trainer's CUDA-graph step: permutation / mask slots already on the device
         noise_x = th.randn_like(x_start) if draws is None else draws["noise_x"].to(x_start.device)
-        perm = np.random.permutation(n) if draws is None else np.asarray(draws["perm"])
+        perm = None if dev_draws is not None else (np.random.permutation(n) if draws is None else np.asarray(draws["perm"]))
         keep_slots = None
-        if add_mask:
+        if dev_draws is not None:
+            keep_slots = dev_draws.get("keep") if add_mask else None
+        elif add_mask:
             if draws is not None:
                 keep_slots = draws["masks"].clone()
             else:
@@ -483,10 +501,13 @@ class GaussianDiffusion:
                     r = np.random.randint(0, G)
                     keep_slots[i, random.sample(range(n), r)] = 0
         on_gpu = x_start.device.type == "cuda"
-        perm_dev = (self._to_device_async(th.as_tensor(np.asarray(perm), dtype=th.int32), x_start.device) if on_gpu
-                    else th.as_tensor(np.asarray(perm), dtype=th.int32))
-        if keep_slots is not None and on_gpu:
-            keep_slots = self._to_device_async(keep_slots.to(th.float32), x_start.device)
+        if dev_draws is not None:
+            perm_dev = dev_draws["perm"]
+        else:
+            perm_dev = (self._to_device_async(th.as_tensor(np.asarray(perm), dtype=th.int32), x_start.device) if on_gpu
+                        else th.as_tensor(np.asarray(perm), dtype=th.int32))
+            if keep_slots is not None and on_gpu:
+                keep_slots = self._to_device_async(keep_slots.to(th.float32), x_start.device)
         x0 = self._scramble(x_start, perm_dev, G, block_size)
         tok = block_size // patch_size
         te = time_emb_start.to(x_start.device).float().expand(B, -1, -1)[:, perm_dev.long()]

@@ -112,6 +112,9 @@ class PeerExchange:
         s.n_f32_ranges, s.reserved = 0, 0
         s.local_sync = self.flags.data_ptr() + 4 * (2 * MAX_PEERS)
         s.status = self.flags.data_ptr() + 4 * (2 * MAX_PEERS + 1)
+        # the barrier token lives on the device (the kernel reads *epoch_dev + 1 and stores it back), so a CUDA-graph replay
+        # of the step needs no changing kernel parameter; every rank starts from 0 and steps in lockstep
+        s.epoch_dev = self.flags.data_ptr() + 4 * (2 * MAX_PEERS + 2)
         self.struct = s
         self.epoch = 0
         self.handle.barrier()                       # every rank's block is zeroed and mapped before anyone's first step

@@ -98,6 +98,9 @@ class Trainer:
             self.m_flat = torch.zeros(self.total, **f32)
             self.v_flat = torch.zeros(self.total, **f32)
             self.pb_flat = torch.zeros(self.total, device=dev, dtype=torch.bfloat16)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)     # the step count on the device (graph replays read it)
+        self._graphs: Dict = {}
+        self.replayed_launches = 0   # library kernels run from graph replays (the host-side launch counter does not see them)
         self._stale = set()          # peer mode: fp32 state buffers whose non-owned slices are behind the owners'
         self.p_views, self.pb_views, self.offsets = {}, {}, {}
         off = 0
@@ -168,6 +171,7 @@ class Trainer:
         steps = torch.tensor([self.step_count], dtype=torch.int64, device=self.device)
         parallel.broadcast_state((self.p_flat, self.ema_flat, self.m_flat, self.v_flat, steps), self.group)
         self.step_count = int(steps.item())
+        self.step_dev.fill_(self.step_count)
         self.pb_flat.copy_(self.p_flat)
 
     # ------------------------------------------------------------------ derived operand copies
@@ -214,24 +218,41 @@ class Trainer:
                 self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     # ------------------------------------------------------------------ one optimisation step
-    def step(self, x: torch.Tensor, t: torch.Tensor, time_emb: torch.Tensor, **loss_kwargs) -> torch.Tensor:
-        """x [B,3,S,S] in [-1,1], t int64 [B], time_emb [1,G*G,8]  ->  mean loss (device scalar, no host sync)."""
+    def step(self, x: torch.Tensor, t: torch.Tensor, time_emb: torch.Tensor, graph: bool = False, **loss_kwargs) -> torch.Tensor:
+        """x [B,3,S,S] in [-1,1], t int64 [B], time_emb [1,G*G,8]  ->  mean loss (device scalar, no host sync).
+        graph=True: the whole step - scramble, q_sample, forward, loss, backward, gradient exchange, AdamW + EMA, operand
+        refresh (train_JPDVT.py:340-372) - is replayed from a CUDA graph; see `_step_graphed`."""
+        if graph:
+            return self._step_graphed(x, t, time_emb, **loss_kwargs)
+        return self._step_body(x, t, time_emb, None, False, **loss_kwargs)
+
+    def _step_body(self, x, t, time_emb, device_draws, dev_step: bool, **loss_kwargs) -> torch.Tensor:
         model = self.model
         model.__dict__["_stage_hook"] = self._on_stage
         self._works = []
-        terms = self.diffusion.training_losses(model, x, t, time_emb, None, **loss_kwargs)
+        self.diffusion.__dict__["_device_draws"] = device_draws
+        try:
+            terms = self.diffusion.training_losses(model, x, t, time_emb, None, **loss_kwargs)
+        finally:
+            self.diffusion.__dict__["_device_draws"] = None
         loss = terms["loss"].mean()
         loss.backward()
         flat = self.engine.last_flat
         self.step_count += 1
+        self.step_dev.add_(1)
+        hyper = (1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.ema_decay)
+        st = _lib.stream_ptr(self.device)
         if self.px is not None:
             # one kernel: sum of every rank's gradients for my slice (peer memory), AdamW + EMA on the slice, bf16 operands
             # (+ the fp32 biases) written to every rank; its two in-kernel barriers are the only synchronisation
             with _lib.on_device(self.device):
-                check(self.lib.jpdvt_adamw_ema_peer(C.byref(self.px.next_epoch()), ptr(self.p_flat), ptr(self.m_flat), ptr(self.v_flat),
-                                                    ptr(self.ema_flat), self.step_count, 1.0 / self.world, self.lr, self.betas[0],
-                                                    self.betas[1], self.eps, self.weight_decay, self.ema_decay,
-                                                    _lib.stream_ptr(self.device)), "jpdvt_adamw_ema_peer")
+                state = (ptr(self.p_flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat))
+                if dev_step:
+                    check(self.lib.jpdvt_adamw_ema_peer_dev(C.byref(self.px.struct), *state, ptr(self.step_dev), *hyper, st),
+                          "jpdvt_adamw_ema_peer_dev")
+                else:
+                    check(self.lib.jpdvt_adamw_ema_peer(C.byref(self.px.next_epoch()), *state, self.step_count, *hyper, st),
+                          "jpdvt_adamw_ema_peer")
             self._stale = {"p", "m", "v", "ema"}
         else:
             if self.world > 1 and self.allreduce == "end":
@@ -240,15 +261,79 @@ class Trainer:
                 wk.wait()
             self._works = []
             with _lib.on_device(self.device):
-                check(self.lib.jpdvt_adamw_ema(ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat),
-                                               ptr(self.pb_flat), self.total, self.step_count, 1.0 / self.world, self.lr, self.betas[0],
-                                               self.betas[1], self.eps, self.weight_decay, self.ema_decay,
-                                               _lib.stream_ptr(self.device)), "jpdvt_adamw_ema")
+                state = (ptr(self.p_flat), ptr(flat), ptr(self.m_flat), ptr(self.v_flat), ptr(self.ema_flat), ptr(self.pb_flat), self.total)
+                if dev_step:
+                    check(self.lib.jpdvt_adamw_ema_dev(*state, ptr(self.step_dev), *hyper, st), "jpdvt_adamw_ema_dev")
+                else:
+                    check(self.lib.jpdvt_adamw_ema(*state, self.step_count, *hyper, st), "jpdvt_adamw_ema")
         self._refresh_derived()
         for p in model.parameters():
             p.grad = None
         self.engine.last_flat = None
         return loss.detach()
+
+    # ------------------------------------------------------------------ the step from a CUDA graph
+    def _step_graphed(self, x, t, time_emb, **kw) -> torch.Tensor:
+        """Host-free training step.  Per (batch shape, loss keywords): call 1 runs eagerly (every lazy initialisation of the
+        library happens outside a capture), call 2 captures the step on static input buffers and replays it, later calls
+        only copy the inputs in and replay.  What changes from step to step reaches the graph through device memory: the
+        batch, the timesteps, the host-drawn permutation / mask slots (copied into static buffers before the replay, in
+        the reference's RNG order), torch's graph-safe Philox state for the two noise draws, and the step count /
+        barrier token of the optimizer kernels (`step_dev`, `epoch_dev`).  Not for the NCCL exchange modes."""
+        if self.world > 1 and self.px is None:
+            raise _lib.JpdvtError("Trainer.step(graph=True) needs the peer-memory exchange (or one GPU), not an NCCL all-reduce")
+        grid = int(kw.get("grid_size", 3))
+        add_mask = bool(kw.get("add_mask", False))
+        key = (tuple(x.shape), x.dtype, tuple(time_emb.shape), tuple(sorted(kw.items())))
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = {"warm": True}
+            return self._step_body(x, t, time_emb, None, False, **kw)
+        B, n = x.shape[0], grid * grid
+        if "graph" not in ent:
+            dev = self.device
+            ent["x"] = torch.empty(x.shape, device=dev, dtype=torch.float32)
+            ent["t"] = torch.empty(B, device=dev, dtype=torch.int64)
+            ent["piece"] = time_emb.to(device=dev, dtype=torch.float32).clone()
+            ent["perm"] = torch.empty(n, device=dev, dtype=torch.int32)
+            ent["keep"] = torch.empty(B, n, device=dev, dtype=torch.float32) if add_mask else None
+            ent["perm_pin"] = torch.empty(n, dtype=torch.int32).pin_memory()
+            ent["keep_pin"] = torch.empty(B, n, dtype=torch.float32).pin_memory() if add_mask else None
+            ent["done"] = torch.cuda.Event()
+        else:
+            ent["done"].synchronize()           # the previous replay has read the pinned staging buffers
+        inj = getattr(self.diffusion, "_draws", None)     # parity tests inject the reference's draws (device noise tensors)
+        if inj is not None:
+            perm = torch.as_tensor(inj["perm"], dtype=torch.int32)
+            keep = inj["masks"].to(torch.float32) if add_mask else None
+        else:
+            perm, keep = self.diffusion.draw_scramble(B, grid, add_mask)
+        ent["perm_pin"].copy_(perm)
+        with _lib.on_device(self.device):
+            ent["x"].copy_(x, non_blocking=True)
+            ent["t"].copy_(t, non_blocking=True)
+            ent["perm"].copy_(ent["perm_pin"], non_blocking=True)
+            if add_mask:
+                ent["keep_pin"].copy_(keep)
+                ent["keep"].copy_(ent["keep_pin"], non_blocking=True)
+            if "graph" not in ent:
+                draws = {"perm": ent["perm"], "keep": ent["keep"]}
+                count, works = self.step_count, self._works
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    ent["loss"] = self._step_body(ent["x"], ent["t"], ent["piece"], draws, True, **kw)
+                ent["graph"], ent["launches"] = g, _lib.launch_count() - n0      # library kernels per replay
+                # the capture executed nothing: undo its host-side bookkeeping, the replay below is this call's step
+                self.step_count, self._works = count, works
+            ent["graph"].replay()
+            ent["done"].record(torch.cuda.current_stream(self.device))
+        self.step_count += 1
+        self.replayed_launches += ent["launches"]
+        if self.px is not None:
+            self._stale = {"p", "m", "v", "ema"}
+        self.model.__dict__["_epoch"] = self.model.__dict__.get("_epoch", 0) + 1
+        return ent["loss"]
 
     # ------------------------------------------------------------------ peer mode: the fp32 state is owned slice by slice
     def sync_state(self, names=("p", "m", "v", "ema")) -> None:
@@ -376,6 +461,8 @@ class Trainer:
         if ckpt.get("train_steps") is not None and ckpt.get("opt") is None:
             self.step_count = int(ckpt["train_steps"])
         self.pb_flat.copy_(self.p_flat)
+        self.step_dev.fill_(self.step_count)
+        self._graphs.clear()
         self._stale = set()           # every rank has just loaded the whole state
         # (pos_embed: self.pos is a view of the module's frozen buffer, updated in place by load_state_dict)
         self._sync_replicas()

@@ -52,13 +52,20 @@ def _build(seed, dev, load_state):
     return m.to(dev)
 
 
-def _one_step(trainer, diffusion, x, t, piece, draws, steps=1):
+def _one_step(trainer, diffusion, x, t, piece, draws, steps=1, graph=False):
     kw = dict(block_size=CASE["size"] // CASE["grid"], patch_size=16, add_mask=CASE["add_mask"], grid_size=CASE["grid"])
     loss = None
+    if graph:      # a captured step reads the injected noise from fixed device tensors
+        draws = dict(draws, noise_x=draws["noise_x"].to(x.device), noise_te=draws["noise_te"].to(x.device))
     for _ in range(steps):
         diffusion._draws = draws
-        loss = trainer.step(x, t, piece, **kw)
+        loss = trainer.step(x, t, piece, graph=graph, **kw)
     return loss
+
+
+def _steps(mode):
+    # graph: call 1 runs eagerly, call 2 captures and replays, call 3 only replays
+    return 3 if mode.endswith("graph") else 2
 
 
 def _worker(rank, world, port, backend, out_path, mode="end"):
@@ -96,8 +103,11 @@ def _worker(rank, world, port, backend, out_path, mode="end"):
         draws = _draws(CASE)
         half = CASE["batch"] // world
         lo, hi = rank * half, (rank + 1) * half
-        loss = _one_step(tr, d, x[lo:hi].to(dev), t[lo:hi].to(dev), piece.to(dev), _slice(draws, lo, hi), steps=2)
+        loss = _one_step(tr, d, x[lo:hi].to(dev), t[lo:hi].to(dev), piece.to(dev), _slice(draws, lo, hi), steps=_steps(mode),
+                         graph=mode.endswith("graph"))
         tr.check_peers()
+        if mode.endswith("graph"):
+            assert len(tr._graphs) == 1 and "graph" in next(iter(tr._graphs.values())), "the step was not replayed from a CUDA graph"
         if tr.px is not None:
             # the fp32 state is owned slice by slice; rank 0 alone assembles a checkpoint (one-sided peer reads), as the
             # reference's rank-0-only torch.save does under DDP (train_JPDVT.py:409-417)
@@ -125,14 +135,15 @@ def _worker(rank, world, port, backend, out_path, mode="end"):
         dist.destroy_process_group()
 
 
-MODES = ["end", "peer", "peer-mc", "peer-thread"]
+MODES = ["end", "peer", "peer-mc", "peer-thread", "peer-graph"]
 
 
 @pytest.mark.parametrize("mode", MODES)
 def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path, mode):
     """`end`: NCCL SUM all-reduce + the full optimizer pass on every rank.  `peer*`: the fused reduce-scatter + AdamW/EMA +
     all-gather kernel over NVLink peer memory (csrc/peer_optim.cu) - bulk async copies (default), multimem instructions,
-    per-thread peer loads / stores.  Needs two GPUs with symmetric memory, skipped on a one-GPU box."""
+    per-thread peer loads / stores; `peer-graph`: the whole step, exchange included, replayed from a CUDA graph (step count
+    and barrier token read from device memory).  Needs two GPUs with symmetric memory, skipped on a one-GPU box."""
     from conftest import rel_l2
     from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
     from jpdvt_mt_ntnu_b200.trainer import Trainer
@@ -151,8 +162,8 @@ def test_two_rank_step_equals_one_rank_step_on_the_whole_batch(cuda, tmp_path, m
     tr = Trainer(model, d, lr=1e-3, weight_decay=0.0, ema_decay=0.999)
     p0 = tr.p_flat.clone().cpu()
     x, t, piece = cases.training_inputs(CASE)
-    loss = _one_step(tr, d, x.to(dev), t.to(dev), piece.to(dev), _draws(CASE), steps=2)
-    assert two["step"] == tr.step_count == 2
+    loss = _one_step(tr, d, x.to(dev), t.to(dev), piece.to(dev), _draws(CASE), steps=_steps(mode))
+    assert two["step"] == tr.step_count == _steps(mode)
     # loss of the second step: mean over the whole batch == mean of the two half-batch means
     assert abs(two["loss"].item() - loss.item()) <= 2e-3 * abs(loss.item())
     # first / second moments after two steps are linear / quadratic in the averaged gradients

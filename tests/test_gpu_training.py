@@ -154,6 +154,51 @@ def test_fused_trainer_matches_stock_adamw_and_ema(cuda):
     assert rel_l2(a, b) < 5e-2
 
 
+def test_graphed_step_matches_eager_step(cuda):
+    """Trainer.step(graph=True) - the whole of train_JPDVT.py:340-372 (scramble, q_sample, forward, loss, backward, AdamW,
+    EMA, operand refresh) replayed from one CUDA graph, with the batch, the host-drawn permutation / mask slots, torch's
+    Philox state and the optimizer's step count reaching it through device memory - against the eager step under the same
+    seeds: five steps on five different batches, per-step losses and the final parameters / moments / EMA agree to the
+    rounding of the unordered fp32 weight-gradient reductions."""
+    import random
+    import numpy as np
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT
+    from jpdvt_mt_ntnu_b200.trainer import Trainer
+    case = cases.TRAINING_CASES["tiny96"]
+    kw = dict(block_size=32, patch_size=16, add_mask=True, grid_size=3)
+    g = torch.Generator().manual_seed(17)
+    n_steps, batch = 5, 6
+    xs = [(torch.rand(batch, 3, 96, 96, generator=g) * 2 - 1).cuda() for _ in range(n_steps)]
+    ts = [torch.randint(0, 1000, (batch,), generator=g).cuda() for _ in range(n_steps)]
+    piece = cases.training_inputs(case)[2].cuda()
+
+    def run(graph):
+        m = DiT(input_size=96, depth=2, hidden_size=768, patch_size=16, num_heads=12)
+        m.load_state_dict(cases.state_for(case))
+        d = create_diffusion("")
+        tr = Trainer(m.cuda(), d, lr=1e-3, weight_decay=0.01, ema_decay=0.99)
+        torch.manual_seed(5), np.random.seed(5), random.seed(5)
+        losses = [tr.step(xs[i], ts[i], piece, graph=graph, **kw).clone() for i in range(n_steps)]
+        torch.cuda.synchronize()
+        return tr, torch.stack(losses).cpu()
+
+    eager, l_eager = run(False)
+    graphed, l_graph = run(True)
+    ent = next(iter(graphed._graphs.values()))
+    assert len(graphed._graphs) == 1 and isinstance(ent.get("graph"), torch.cuda.CUDAGraph)
+    assert graphed.step_count == eager.step_count == n_steps and int(graphed.step_dev.item()) == n_steps
+    assert torch.allclose(l_graph, l_eager, rtol=2e-3, atol=0), (l_graph, l_eager)
+    assert len(set(l_eager.tolist())) == n_steps                 # the five batches really differ
+    assert rel_l2(graphed.m_flat, eager.m_flat) < 2e-2
+    assert rel_l2(graphed.v_flat, eager.v_flat) < 4e-2
+    assert rel_l2(graphed.p_flat, eager.p_flat) < 2e-3
+    assert rel_l2(graphed.ema_flat, eager.ema_flat) < 1e-4
+    # another batch shape gets its own graph; the NCCL exchange modes are refused (test_gpu_trainer_ddp covers peer-graph)
+    graphed.step(xs[0][:4], ts[0][:4], piece, graph=True, **kw)
+    assert len(graphed._graphs) == 2
+
+
 def test_trainer_checkpoint_resume_in_reference_format(cuda, tmp_path):
     """save_checkpoint writes the reference trainer's dict (train_JPDVT.py:410-416); a fresh Trainer that loads it
     continues where the first one stood (same next step: parameters, EMA, moments, step count), and the
