@@ -160,6 +160,83 @@ def cpu_port_puzzles_per_s(wl, sample_batch=16, sample_steps=2):
     return sample_batch / total, cores, f"{sample_batch} puzzles x {sample_steps} of {wl['steps']} diffusion steps + assignment, scaled x{wl['steps']}/{sample_steps}", t_steps + t_assign
 
 
+REF_STAGED = os.path.join(ROOT, "baseline", "_ref", "image_model")
+_REF_MODULES = {}
+
+
+def staged_reference():
+    """The UNMODIFIED reference modules (image_model/models.py, diffusion/, inference.py) from the git-ignored staging
+    directory baseline/_ref/ (tools/stage_reference.sh copies them there in the build container; the directory travels to the
+    GPU box with the snapshot).  The two packages they import that this image lacks (timm, matplotlib) come from the stand-ins
+    the golden generator uses (oracle/standins).  None when the staging directory is absent or does not import."""
+    if "mods" in _REF_MODULES:
+        return _REF_MODULES["mods"]
+    mods = None
+    if os.path.isfile(os.path.join(REF_STAGED, "models.py")):
+        saved = list(sys.path)
+        sys.path[:0] = [os.path.join(ROOT, "oracle", "standins"), REF_STAGED]
+        try:
+            import importlib
+            mods = tuple(importlib.import_module(n) for n in ("models", "diffusion", "inference"))
+        except Exception as e:  # noqa: BLE001  (a missing third-party import on this box: the port is the fallback)
+            print(f"[bench] staged reference not importable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+            mods = None
+        finally:
+            sys.path[:] = saved
+    _REF_MODULES["mods"] = mods
+    return mods
+
+
+def cpu_reference_puzzles_per_s(wl, sample_batch=16, sample_steps=2):
+    """The reference's own CPU path on a BOUNDED sample, through its stock calls: `DiT_models["JPDVT"]`, `create_diffusion`,
+    `p_sample_loop_progressive` (stopped after `sample_steps` of the 250 steps - every step is identical work) and the
+    assignment snippet of inference.py:294-306 (`rearrange`, sklearn `pairwise_distances`, `find_permutation`), scaled to
+    the full step count.  Falls back to the oracle port when baseline/_ref is not staged.  -> (..., kind)"""
+    mods = staged_reference()
+    if mods is None:
+        return cpu_port_puzzles_per_s(wl, sample_batch, sample_steps) + ("port",)
+    import itertools
+    import torch
+    from einops import rearrange
+    from sklearn.metrics import pairwise_distances
+    from oracle import jpdvt_oracle as orc          # seeded weights only (the same state the GPU arm loads)
+    ref_models, ref_diffusion, ref_inference = mods
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, G = wl["size"], wl["grid"]
+    tok = S // (16 * G)
+    key = ("ref", S)
+    if key not in _CPU_CACHE:
+        m = ref_models.DiT_models["JPDVT"](input_size=S)
+        m.load_state_dict(orc.seeded_state(m.state_dict(), seed=1234))
+        m.train()                                    # inference.py:213-214 (a no-op: no dropout / batch norm)
+        _CPU_CACHE[key] = m
+    model = _CPU_CACHE[key]
+    diffusion = ref_diffusion.create_diffusion(str(wl["steps"]))
+    cond, noise, _ = synthetic_inputs(wl, sample_batch)
+
+    def steps(n):
+        gen = diffusion.p_sample_loop_progressive(model.forward, cond, noise.shape, noise, clip_denoised=False, model_kwargs=None,
+                                                  device="cpu", progress=False)
+        return list(itertools.islice(gen, n))[-1]
+    with torch.no_grad():
+        steps(1)                                     # warm-up (thread pools, allocator)
+        t0 = time.perf_counter()
+        out = steps(sample_steps)
+        t_steps = time.perf_counter() - t0
+        canon = torch.tensor(ref_models.get_2d_sincos_pos_embed(8, G)).unsqueeze(0).float()
+        t0 = time.perf_counter()
+        for b in range(sample_batch):
+            lat = rearrange(out["sample"][b], "(p1 h1 p2 w1) d -> (p1 p2) (h1 w1) d", p1=G, p2=G, h1=tok, w1=tok).mean(1)
+            dist = pairwise_distances(lat.cpu().numpy(), canon[0].cpu().numpy(), metric="manhattan")
+            ref_inference.find_permutation(dist)
+        t_assign = time.perf_counter() - t0
+    total = t_steps / sample_steps * wl["steps"] + t_assign
+    sample = (f"unmodified reference modules (baseline/_ref, timm stand-in): {sample_batch} puzzles x {sample_steps} of {wl['steps']} "
+              f"diffusion steps + assignment, scaled x{wl['steps']}/{sample_steps}")
+    return sample_batch / total, cores, sample, t_steps + t_assign, "reference"
+
+
 def stock_torch_gpu_puzzles_per_s(wl, batch, precision="fp32", sample_steps=5):
     """SURVEY.md 8(d) "same box" comparator: the oracle's stock torch ops (what the reference's fp32 nn.Modules execute)
     moved to cuda:0 - cuBLAS / ATen kernels, none of this repo's - on the bench batch, `sample_steps` of the 250 steps
@@ -211,8 +288,9 @@ def run_reference_gpu(args, wl):
 
 
 def run_reference(args, wl):
-    """`--impl reference`: the reference path's CPU implementation (oracle port; the Python reference cannot travel to
-    the GPU box) on the host cores.  Rank 0 only."""
+    """`--impl reference`: the reference path's CPU implementation on the host cores - the unmodified reference modules
+    from the staged baseline/_ref when the snapshot carries them (`kind: "reference"`), else the oracle port
+    (`kind: "port"`).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -220,7 +298,7 @@ def run_reference(args, wl):
         return run_reference_gpu(args, wl)
     vals, spent = [], 0.0
     for i in range(args.warmup + args.steps):
-        v, cores, sample, dt = cpu_port_puzzles_per_s(wl, sample_batch=16, sample_steps=2)
+        v, cores, sample, dt, kind = cpu_reference_puzzles_per_s(wl, sample_batch=16, sample_steps=2)
         if i >= args.warmup:
             vals.append(v); spent += dt
     value = statistics.mean(vals)
@@ -229,7 +307,7 @@ def run_reference(args, wl):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * spent / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": sampling_config(wl, args.batch or wl["batch"]),
-        "cpu_baseline": {"value": value, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "puzzles/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "puzzles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -448,8 +526,8 @@ def run_ours(args, wl):
         roof, breakdown = kernel_roofline(model, wl, batch, peaks)
         cpu_obj, stock = None, None
         if world == 1:           # reported at N=1 only (torchrun pins the ranks to one host thread each)
-            cpu_v, cores, sample, _ = cpu_port_puzzles_per_s(wl)
-            cpu_obj = {"value": cpu_v, "unit": "puzzles/s", "cores": cores, "kind": "port", "sample": sample}
+            cpu_v, cores, sample, _, kind = cpu_reference_puzzles_per_s(wl)
+            cpu_obj = {"value": cpu_v, "unit": "puzzles/s", "cores": cores, "kind": kind, "sample": sample}
             if not args.no_extras:
                 del model
                 torch.cuda.empty_cache()
