@@ -458,11 +458,13 @@ int jpdvt_mse_loss_bwd(const float* te_out, const float* te_tgt, int64_t per_te,
 }
 int jpdvt_assign_from_scores(const double* scores, int batch, int n, double sentinel, int32_t* order, int32_t* pred,
                              void* stream) {
+  if (batch == 0) return kOk;
   if (!scores || !order || !pred) return set_error(kErrBadArg, "assign_from_scores: null pointer");
   return launch_assign_scores(scores, batch, n, sentinel, order, pred, ST(stream));
 }
 int jpdvt_assign_greedy_l1(const float* latents, const float* canon, int batch, int grid, int tokens_per_side,
                            double sentinel, int32_t* order, int32_t* pred, double* scores_out_or_null, void* stream) {
+  if (batch == 0) return kOk;
   if (!latents || !canon || !order || !pred) return set_error(kErrBadArg, "assign_greedy_l1: null pointer");
   return launch_assign_latents(latents, canon, batch, grid, tokens_per_side, sentinel, order, pred, scores_out_or_null, ST(stream));
 }
@@ -489,6 +491,7 @@ int jpdvt_score_placements(const int32_t* pred, const int32_t* truth, int batch,
 int jpdvt_denoiser_forward(const jpdvt_weights* w_host, const jpdvt_workspace* ws_host, const float* img,
                            const int64_t* t, const int32_t* step_ptr, const int32_t* map, const float* x_t,
                            float* te_out, float* img_out_or_null, int batch, void* stream) {
+  if (batch == 0) return kOk;   // empty batch: nothing to launch (torch hands out null pointers for empty tensors)
   if (!img || !x_t || !te_out) return set_error(kErrBadArg, "denoiser_forward: null pointer");
   if (!t && !step_ptr) return set_error(kErrBadArg, "denoiser_forward: need t or step_ptr");
   return forward_impl(w_host, ws_host, img, t, step_ptr, map, x_t, te_out, img_out_or_null, batch, ST(stream));
@@ -496,6 +499,7 @@ int jpdvt_denoiser_forward(const jpdvt_weights* w_host, const jpdvt_workspace* w
 
 int jpdvt_sample_loop(const jpdvt_weights* w, const jpdvt_workspace* ws, const jpdvt_sampler* s, const float* condition,
                       const float* noise, int batch, int first_step, int last_step, void* stream) {
+  if (batch == 0) return kOk;   // an empty shard of puzzles (inference_ddp.py:325 with fewer images than ranks): no-op
   if (!w || !ws || !s || !condition || !noise) return set_error(kErrBadArg, "sample_loop: null pointer");
   if (!s->step_ids || !s->timestep_map || !s->coef1 || !s->coef2 || !s->logvar || !s->x0 || !s->sample)
     return set_error(kErrBadArg, "sample_loop: sampler struct has null members");

@@ -484,6 +484,8 @@ class GaussianDiffusion:
         if model_kwargs is None:
             model_kwargs = {}
         B = x_start.shape[0]
+        if B == 0:
+            raise ValueError("training_losses: empty batch (the reference's loader drops incomplete batches, drop_last=True, train_JPDVT.py:311-319)")
         G, n = grid_size, grid_size * grid_size
         draws = getattr(self, "_draws", None)      # parity tests inject the reference's CPU draws here
         dev_draws = getattr(self, "_device_draws", None)   # Trainer's CUDA-graph step: permutation / mask slots already on the device

@@ -182,6 +182,8 @@ class DenoiserEngine:
         batches the ~23,000 launches of a 250-step loop are launch- and gap-bound, the graph removes the host from the loop.
         Inputs are copied into graph-owned buffers; the returned tensors are copies."""
         n_steps = tables["num_steps"]
+        if condition.shape[0] == 0:                                  # an empty shard: nothing to capture
+            return self.sample_loop(tables, condition, noise, step_noise, chain=chain)
         strided = step_noise is not None and step_noise.dim() == noise.dim() + 1 and step_noise.shape[0] > 1
         # The graph bakes in raw pointers to the packed weights and the schedule tables: key on the weights' generation
         # counter (ids are reused after a re-pack) and on the tables' storage, and pin both objects in the entry.

@@ -255,3 +255,51 @@ def test_in_kernel_step_noise_chain_mode_statistics(cuda):
     assert torch.equal(a, a2)
     b = d.p_sample_loop(m.forward, cond.cuda(), noise.shape, noise.cuda(), clip_denoised=False, chain=True)
     assert torch.isfinite(b).all() and not torch.equal(a, b)
+
+
+def test_empty_and_single_puzzle_batches_and_batch_invariance(cuda):
+    """Edge cases of the sampling path end to end.  An empty shard of puzzles (inference_ddp.py:325 with fewer images than
+    ranks) runs through p_sample_loop and the assignment as a no-op with the reference's shapes ([0, T, 8] / [0, G*G]); a
+    single puzzle (M = 144 rows, less than one GEMM tile) works; and a puzzle's latents do not depend on its neighbours in
+    the batch: rows of a batch-5 run are bit-identical to the same puzzles run as batches of 1 and 2 (every kernel reduces
+    within a row or within one (sample, head) unit), with plain launches and from a CUDA graph."""
+    import pytest as _pytest
+    from jpdvt_mt_ntnu_b200 import assignment
+    from jpdvt_mt_ntnu_b200.diffusion import create_diffusion
+    from jpdvt_mt_ntnu_b200.models import DiT, get_2d_sincos_pos_embed
+    from jpdvt_mt_ntnu_b200.weights import seeded_state
+    size, grid = 192, 3
+    T = (size // 16) ** 2
+    model = DiT(input_size=size, depth=2, hidden_size=768, patch_size=16, num_heads=12)
+    model.load_state_dict(seeded_state(model.state_dict(), seed=7))
+    model.cuda()
+    d = create_diffusion("4")
+    g = torch.Generator().manual_seed(0)
+    full = (torch.rand(5, 3, size, size, generator=g) * 2 - 1).cuda()
+    noise1 = torch.randn(1, T, 8, generator=g).cuda()
+
+    def run(B, graph):
+        with torch.no_grad():
+            out = d.p_sample_loop(model.forward, full[:B], (B, T, 8), noise1.repeat(B, 1, 1), clip_denoised=False, graph=graph)
+            order, pred = assignment.solve_puzzles(out, grid)
+        return out, order, pred
+
+    ref, ref_order, ref_pred = run(5, False)
+    for B in (0, 1, 2):
+        for graph in (False, True):
+            out, order, pred = run(B, graph)
+            assert tuple(out.shape) == (B, T, 8) and tuple(order.shape) == (B, grid * grid) == tuple(pred.shape)
+            assert torch.equal(out, ref[:B]) and torch.equal(pred, ref_pred[:B]) and torch.equal(order, ref_order[:B])
+    with torch.no_grad():
+        img, te = model(full[:0], torch.zeros(0, dtype=torch.long, device="cuda"), noise1[:0])
+    assert tuple(img.shape) == (0, 3, size, size) and tuple(te.shape) == (0, T, 8)
+    # training: the reference's loader never yields an empty batch (drop_last=True); here it is a clear error, not a crash
+    piece = torch.tensor(get_2d_sincos_pos_embed(8, grid)).unsqueeze(0).float().cuda()
+    with _pytest.raises(ValueError, match="empty batch"):
+        create_diffusion("").training_losses(model, full[:0], torch.zeros(0, dtype=torch.long, device="cuda"), piece, None,
+                                             block_size=size // grid, patch_size=16, add_mask=False, grid_size=grid)
+    t1 = torch.randint(0, 1000, (1,), device="cuda")
+    loss = create_diffusion("").training_losses(model, full[:1], t1, piece, None, block_size=size // grid, patch_size=16,
+                                                add_mask=True, grid_size=grid)["loss"]
+    loss.mean().backward()
+    assert tuple(loss.shape) == (1,) and torch.isfinite(loss).all()
