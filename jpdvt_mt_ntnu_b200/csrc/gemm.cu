@@ -1416,15 +1416,33 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   reinterpret_cast<float4*>(out)[i] = acc;
 }
 
+// Split of the contraction (the M = batch x tokens rows) over work items.  One work item = one 256 x BN tile of dW over
+// `kb_per` 64-row blocks; the CTA pairs take items round robin, so the launch lasts rounds x (kb_per + per-item overhead) with
+// rounds = ceil(tiles x split / pairs).  The first plan aimed at "about two items per pair" (s = ceil(148 / tiles)) and landed
+// between waves: fc1 / fc2 (36 tiles) got 5 splits = 180 items = 2.43 waves on 74 pairs, qkv (27 tiles) 6 splits = 162 items =
+// 2.19 waves - a quarter of the SM time idle in the last round (ncu: SMs active 74 % of the launch).  Now every split count
+// up to 16 is costed and the cheapest wins (ties: fewer splits = fewer reduction boxes): 36 tiles -> 2 splits (72 items, one
+// full wave), 27 tiles -> 8 splits (216 items, 2.92 waves), 9 tiles -> 8 or 16.  JPDVT_WGRAD_SPLIT=<n> forces a count (A/B).
 static void wgrad_plan(long long m, int out_rows, int n_cols, int* split, int* split_len) {
   const int bn = (n_cols % 256 == 0) ? 256 : 128;
   const int tiles = ((out_rows + 255) / 256) * (n_cols / bn);
   const int kb_total = static_cast<int>((m + BK - 1) / BK);
-  int s = (2 * (num_sms() / 2) + tiles - 1) / tiles;     // aim at ~2 work items per CTA pair
-  if (s > 16) s = 16;
-  if (s > kb_total) s = kb_total;
-  if (s < 1) s = 1;
-  const int kb_per = (kb_total + s - 1) / s;
+  const int pairs = num_sms() / 2;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("JPDVT_WGRAD_SPLIT"); forced = (e != nullptr) ? atoi(e) : 0; }
+  constexpr int kItemOverhead = 2;          // per work item, in k-block times: accumulator hand-over, first operand boxes
+  int best_s = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 16 && s <= kb_total; ++s) {
+    const int kb_per = (kb_total + s - 1) / s;
+    const int n_split = (kb_total + kb_per - 1) / kb_per;
+    if (n_split != s) continue;               // the same plan as a smaller s
+    const int rounds = (tiles * n_split + pairs - 1) / pairs;
+    const long long cost = static_cast<long long>(rounds) * (kb_per + kItemOverhead);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
+  }
+  if (forced > 0) best_s = forced < kb_total ? forced : kb_total;
+  const int kb_per = (kb_total + best_s - 1) / best_s;
   *split = (kb_total + kb_per - 1) / kb_per;
   *split_len = kb_per * BK;
 }
