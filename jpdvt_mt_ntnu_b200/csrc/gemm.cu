@@ -32,7 +32,8 @@ constexpr int kStageWarpBytes = 32 * kStageRowBytes;      // one 32-row transpos
 constexpr int kXBoxBytes = 32 * 32 * 4;                   // one residual box: 32 rows x 32 fp32 columns (128-byte swizzled rows)
 
 // NB > 0: per-warp ring of NB residual boxes instead of the staging tiles; LNS: room for the LayerNorm row statistics
-template <int BN, int CS, int EW, int NB = 0, bool LNS = false>
+// SB: staging tiles per epilogue warp (2 for the epilogue that hands TWO 32 x 64 bf16 boxes per chunk to the TMA)
+template <int BN, int CS, int EW, int NB = 0, bool LNS = false, int SB = 1>
 struct GemmCfg {
   static constexpr int kThreads = 64 + EW * 32;
   static constexpr int kBRows = BN / CS;                  // W rows this CTA loads
@@ -44,7 +45,7 @@ struct GemmCfg {
   // its ring needs the room to keep the five pipeline stages)
   static constexpr int kVecWarpBytes = NB > 0 ? 0 : 3 * kColsPerWarp * 4;
   static constexpr int kLnStatsBytes = LNS ? 2 * 2 * BM * 8 : 0;      // EPI_RESID_LN_F32: (mean, M2) per row, column half, M-block parity
-  static constexpr int kStagingBytes = NB > 0 ? EW * NB * kXBoxBytes : EW * kStageWarpBytes;
+  static constexpr int kStagingBytes = NB > 0 ? EW * NB * kXBoxBytes : EW * SB * kStageWarpBytes;
   // staging + barriers + align slack (+ the head epilogue's static arrays, absent from the ring variant)
   static constexpr int kFixedBytes = kStagingBytes + EW * kVecWarpBytes + kLnStatsBytes + 256 + 1024 + (NB > 0 ? 0 : 2304);
   static constexpr int kStagesRaw = (kMaxSmem - kFixedBytes) / kStageBytes;
@@ -242,7 +243,8 @@ template <int BN, int EPI, int CS, int EW, int NB = 0, bool BMN = false>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_y, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
+  constexpr int SB = (EPI == EPI_BIAS_GELU_GRAD_BF16) ? 2 : 1;
+  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32, SB>;
   static_assert((NB > 0) == (EPI == EPI_RESID_TMA_F32 || EPI == EPI_RESID_LN_TMA_F32 || EPI == EPI_RESID_TMA_XB_F32),
                 "the residual ring belongs to the TMA residual epilogues");
   constexpr int kColsPerWarp = Cfg::kColsPerWarp;
@@ -403,7 +405,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2 .. 2+EW)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    uint8_t* stage = stage_buf + (warp - 2) * kStageWarpBytes;
+    uint8_t* stage = stage_buf + (warp - 2) * SB * kStageWarpBytes;
     const int col_base = ((warp - 2) >> 2) * kColsPerWarp;   // first accumulator column of this warp
     int acc = 0; uint32_t acc_phase = 0;
     __shared__ float s_w2[kLatent * 64];
@@ -821,6 +823,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               v[j] = y0; v[j + 1] = y1;
               gp[j >> 1] = pack_bf16(d0, d1);
             }
+            if (p.tma_out) {
+              // both 32 x 64 bf16 tiles leave as 4 KB boxes of 128-byte swizzled rows (row per thread, conflict free) through
+              // the TMA - the form that took the sampling fc1 epilogue off the critical path; the warp's two staging tiles
+              // hold the derivative box and the activation box, refilled once the previous chunk's stores have read them
+              const uint32_t sb0 = smem_u32(stage), sb1 = sb0 + kStageWarpBytes;
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+              const uint32_t mine0 = sb0 + lane * 128, sw0 = ((sb0 >> 7) + lane) & 7;
+              const uint32_t mine1 = sb1 + lane * 128, sw1 = ((sb1 >> 7) + lane) & 7;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                sts_u4_shared(mine0 + ((j ^ sw0) << 4), gp[4 * j], gp[4 * j + 1], gp[4 * j + 2], gp[4 * j + 3]);
+                sts_u4_shared(mine1 + ((j ^ sw1) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tma_y, stage, n0, row0);
+                tma_store_2d(&tma_x, stage + kStageWarpBytes, n0, row0);
+                tma_store_commit();
+              }
+              continue;
+            }
             store_packed_tile(stage, gp, p.out_aux, p.ldo, row0, n0, p.M, lane);
           }
           store_bf16_tile<EPI == EPI_DGELU_BF16>(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out), p.aux, p.ldo, row0, n0, p.M, lane,
@@ -1117,7 +1143,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }   // !kLNX
   }
 
-  if constexpr (kXR || kLNX || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_WGRAD_F32) {
+  if constexpr (kXR || kLNX || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_GRAD_BF16 || EPI == EPI_WGRAD_F32) {
     if (warp >= 2 && lane == 0) tma_store_wait<0>();          // bulk stores read this CTA's shared memory: drain before exit
   }
   tc_fence_before();
@@ -1215,14 +1241,14 @@ static int epi_warps(int epi) {
     forced = (e == nullptr) ? 0 : (e[0] == '4' ? 4 : 8);
   }
   if (forced) return forced;
-  return (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16) ? 4 : 8;
+  return (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_GELU_GRAD_BF16) ? 4 : 8;
 }
 
 template <int BN, int EPI, int EW, int NB = 0, bool BMN = false>
 static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* w, long long ldw, const GemmParams& p,
                       cudaStream_t stream) {
   constexpr int CS = 2;
-  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32>;
+  using Cfg = GemmCfg<BN, CS, EW, NB, EPI == EPI_RESID_LN_F32, (EPI == EPI_BIAS_GELU_GRAD_BF16) ? 2 : 1>;
   static_assert(Cfg::kStages >= 3, "pipeline too shallow");
   static_assert(!BMN || (BN / CS) % 64 == 0, "MN-major B boxes are 64 features wide");
   static bool attr_set = false;
@@ -1258,6 +1284,18 @@ static int launch_cfg(const __nv_bfloat16* a, long long lda, const __nv_bfloat16
   if constexpr (EPI == EPI_RESID_LN_TMA_F32) {
     rc = make_tmap_bf16_box32(&ty, p.ln_out, p.M, p.N, p.ldo);
     if (rc != kOk) return rc;
+  }
+  if constexpr (EPI == EPI_BIAS_GELU_GRAD_BF16) {            // training fc1: activation boxes through tx, derivative boxes through ty
+    static int tma_out = -1;
+    if (tma_out < 0) { const char* e = getenv("JPDVT_GEMM_TMA_OUT"); tma_out = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    pp.tma_out = (tma_out && (p.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.out_aux != nullptr &&
+                  (reinterpret_cast<uintptr_t>(p.out_aux) & 15) == 0) ? 1 : 0;
+    if (pp.tma_out) {
+      rc = make_tmap_bf16_kmajor(&tx, p.out, p.M, p.N, p.ldo, 32);
+      if (rc != kOk) return rc;
+      rc = make_tmap_bf16_kmajor(&ty, p.out_aux, p.M, p.N, p.ldo, 32);
+      if (rc != kOk) return rc;
+    }
   }
   const int tiles = ((p.M + CS * BM - 1) / (CS * BM)) * (p.N / BN);
   const int max_groups = num_sms() / CS;
