@@ -297,25 +297,34 @@ class Trainer:
             ent["piece"] = time_emb.to(device=dev, dtype=torch.float32).clone()
             ent["perm"] = torch.empty(n, device=dev, dtype=torch.int32)
             ent["keep"] = torch.empty(B, n, device=dev, dtype=torch.float32) if add_mask else None
-            ent["perm_pin"] = torch.empty(n, dtype=torch.int32).pin_memory()
-            ent["keep_pin"] = torch.empty(B, n, dtype=torch.float32).pin_memory() if add_mask else None
-            ent["done"] = torch.cuda.Event()
-        else:
-            ent["done"].synchronize()           # the previous replay has read the pinned staging buffers
+            # host-drawn tables are staged through a ring of pinned slots: a slot is rewritten only after the copy that read it
+            # has run, so the host runs up to `ring` steps ahead of the device instead of waiting for every replay
+            ent["ring"] = 8
+            ent["perm_pin"] = torch.empty(ent["ring"], n, dtype=torch.int32).pin_memory()
+            ent["keep_pin"] = torch.empty(ent["ring"], B, n, dtype=torch.float32).pin_memory() if add_mask else None
+            ent["copied"] = [None] * ent["ring"]
+            ent["slot"] = 0
+        slot = ent["slot"]
+        ent["slot"] = (slot + 1) % ent["ring"]
+        if ent["copied"][slot] is not None:
+            ent["copied"][slot].synchronize()
         inj = getattr(self.diffusion, "_draws", None)     # parity tests inject the reference's draws (device noise tensors)
         if inj is not None:
             perm = torch.as_tensor(inj["perm"], dtype=torch.int32)
             keep = inj["masks"].to(torch.float32) if add_mask else None
         else:
             perm, keep = self.diffusion.draw_scramble(B, grid, add_mask)
-        ent["perm_pin"].copy_(perm)
+        ent["perm_pin"][slot].copy_(perm)
         with _lib.on_device(self.device):
             ent["x"].copy_(x, non_blocking=True)
             ent["t"].copy_(t, non_blocking=True)
-            ent["perm"].copy_(ent["perm_pin"], non_blocking=True)
+            ent["perm"].copy_(ent["perm_pin"][slot], non_blocking=True)
             if add_mask:
-                ent["keep_pin"].copy_(keep)
-                ent["keep"].copy_(ent["keep_pin"], non_blocking=True)
+                ent["keep_pin"][slot].copy_(keep)
+                ent["keep"].copy_(ent["keep_pin"][slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            ent["copied"][slot] = ev
             if "graph" not in ent:
                 draws = {"perm": ent["perm"], "keep": ent["keep"]}
                 count, works = self.step_count, self._works
@@ -327,7 +336,6 @@ class Trainer:
                 # the capture executed nothing: undo its host-side bookkeeping, the replay below is this call's step
                 self.step_count, self._works = count, works
             ent["graph"].replay()
-            ent["done"].record(torch.cuda.current_stream(self.device))
         self.step_count += 1
         self.replayed_launches += ent["launches"]
         if self.px is not None:
