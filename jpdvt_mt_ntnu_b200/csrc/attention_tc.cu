@@ -22,6 +22,7 @@
 // CTAs per SM, so one CTA's loads / MMA latencies hide behind the other's softmax.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <initializer_list>
 
 #include "common.cuh"
@@ -1198,6 +1199,401 @@ int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int
   return check_launch("attention_tc_seq_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 144, hybrid form (JPDVT_ATTN_REM=hybrid): the 128-row main tile on tcgen05 as above, the 16-row remainder on the softmax
+// warps themselves with mma.sync (registers), so that NO tcgen05 instruction is spent on it.
+//
+// Why: a tcgen05.mma costs the same with 16 live rows as with 128, so the remainder doubled the tensor-pipe time and the
+// operand traffic of a unit (16 score MMAs + 9 P V MMAs at M = 128 for 16 rows), its scores aliased the main tile's TMEM
+// columns (issued only after the main softmax), its output aliased them again (so the next unit's scores had to wait for this
+// unit's epilogue), and Q / K stayed busy until those late MMAs had read them (the next unit's load latency sat on the chain).
+// Here a softmax warp computes S_rem[16, its keys] = Q_rem K^T with mma.sync.m16n8k16 straight from the TMA-swizzled Q / K tiles
+// (ldmatrix) while the main score MMAs run, the four warps exchange row maximum / row sum through shared memory and leave the
+// bf16 probabilities in a 4.8 KB row-major tile; after the main softmax each warp multiplies that tile with ITS 16 output
+// columns of V (ldmatrix.trans) while the tensor core runs the main P V, and writes its 16 x 16 outputs directly.  Consequences
+// for the pipeline: Q / K are released ~400 cycles into a unit (the next unit's loads hide behind the main softmax), the
+// TMEM score columns are free as soon as the main softmax has read them, so the MMA warp issues the NEXT unit's scores right
+// behind this unit's P V - they are done before the softmax warps come back from the epilogue.
+constexpr int kHmPRowBytes = 304;                           // 144 keys x 2 B + 16 B: conflict-free ldmatrix rows / 4-byte stores
+static_assert(16 * kHmPRowBytes <= TcCfg<144>::kP1Bytes, "the remainder's probability tile reuses the compact P1 slot");
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of 16-byte chunk `ch` of row `row` in a TMA SWIZZLE_128B tile of 128-byte rows (1024-byte aligned base)
+__device__ __forceinline__ uint32_t swz128(int row, int ch) { return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4)); }
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.mma with the A operand in TENSOR MEMORY (K-major: lane = row, two bf16 per 32-bit column), B from shared memory
+template <bool ACC>
+__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi)
+      : "memory");
+}
+
+// softmax_row_to_p with the probabilities going back into TENSOR MEMORY instead of shared memory: the bf16 pairs of keys
+// [32c, 32c + 32) overwrite columns [16c, 16c + 16) of the thread's own score row - columns whose scores this thread has
+// already read (chunk c is in registers, the load in flight is chunk c + 1 at columns >= 32c + 32) - and the P V MMAs read
+// them as their A operand straight from there: no shared-memory tile, no store / operand-read traffic for P at all.
+template <int T>
+__device__ __forceinline__ float softmax_row_to_tmem(uint32_t t_row, float& ms_out) {
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  constexpr int kFull = T / 32, kTail = T % 32;
+  static_assert(kTail == 0 || kTail == 16, "token count must be a multiple of 16");
+  constexpr int kChunks = kFull + (kTail ? 1 : 0);
+  uint32_t ra[32], rb[32];
+  auto load_chunk = [&](uint32_t (&r)[32], int c) {
+    if (c < kFull) tmem_ld_32x32(t_row + c * 32, r);
+    else tmem_ld_32x16(t_row + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
+  };
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  load_chunk(ra, 0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+#pragma unroll
+    for (int j = 0; j < n; j += 8) {
+      m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+      m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+      m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
+      m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+    }
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  load_chunk(ra, 0);
+  const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+  ms_out = ms;
+  uint64_t sum2 = f2_pack(0.f, 0.f);
+  const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms, -ms);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2p, nmsp), a, b);
+      const float pa = ex2f(a), pb = ex2f(b);
+      sum2 = f2_add(sum2, f2_pack(pa, pb));
+      pk[j] = pack_bf16(pa, pb);
+    }
+    if (c < kFull) tmem_st_32x16(t_row + c * 16, pk);
+    else tmem_st_32x8(t_row + c * 16, pk);
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  tmem_st_wait();
+  float s_even, s_odd;
+  f2_unpack(sum2, s_even, s_odd);
+  return s_even + s_odd;
+}
+
+// PT: the main tile's probabilities live in tensor memory (softmax_row_to_tmem, A-from-TMEM MMAs) instead of a shared-memory tile
+template <bool PT>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                    int num_units, int reverse) {
+  constexpr int T = 144;
+  using Cfg = TcCfg<T>;
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;        // TMA: Q and K landed
+  uint64_t* v_full = bars + 1;         // TMA: V landed
+  uint64_t* s_full = bars + 2;         // MMA: main scores are in TMEM (and the score MMAs have read Q, K)
+  uint64_t* p_full = bars + 3;         // softmax warps: P0 is in shared memory, the score columns are free (4 arrivals)
+  uint64_t* o_full = bars + 4;         // MMA: O0 is in TMEM (and the P V MMAs have read V, P0)
+  uint64_t* epi_done = bars + 5;       // softmax warps: O0 has left TMEM (4 arrivals)
+  uint64_t* qk_read = bars + 6;        // softmax warps: the remainder's ldmatrix reads of Q, K are done (4 arrivals)
+  uint64_t* v_read = bars + 7;         // softmax warps: the remainder's ldmatrix reads of V are done (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kXchOff);   // [2][4][16]: row maximum / row sum of the remainder per warp
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(epi_done, 4); mbar_init(qk_read, 4); mbar_init(v_read, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sP = smem_u32(smem + Cfg::kOffP), sPr = smem_u32(smem + Cfg::kOffP1);
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int uu = reverse ? num_units - 1 - unit : unit;
+        const int b = uu / kHeads, h = uu - b * kHeads;
+        const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        if (it > 0) { mbar_wait(s_full, prev); mbar_wait(qk_read, prev); }     // tensor core and ldmatrix are done with Q, K
+        mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
+        tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
+        tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        if (it > 0) { mbar_wait(o_full, prev); mbar_wait(v_read, prev); }      // ... and with V
+        mbar_expect_tx(v_full, Cfg::kTileBytes);
+        tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);   // B = V, MN-major
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), p_lo = desc_lo_k(sP), v_lo = desc_lo_mn(sV);
+      auto issue_s = [&]() {
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
+        }
+        umma_commit(s_full);
+      };
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        if (it == 0) {
+          mbar_wait(qk_full, 0);
+          tc_fence_after();
+          issue_s();
+        }
+        mbar_wait(p_full, ph);                                  // P0 written, score columns read
+        mbar_wait(v_full, ph);
+        if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O0 of the previous unit has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {
+          const uint32_t bq = v_lo + j * 128;
+          if constexpr (PT) {                                  // A = P out of tensor memory: key step j = columns [8j, 8j + 8)
+            if (j == 0) umma_ts_lohi<false>(tmem_base + Cfg::kColO0, tmem_base + 8 * j, bq, idesc_o);
+            else umma_ts_lohi<true>(tmem_base + Cfg::kColO0, tmem_base + 8 * j, bq, idesc_o);
+          } else {
+            const uint32_t a = p_lo + (j >> 2) * 1024 + (j & 3) * 2;
+            if (j == 0) umma_lohi<false>(tmem_base + Cfg::kColO0, a, bq, idesc_o);
+            else umma_lohi<true>(tmem_base + Cfg::kColO0, a, bq, idesc_o);
+          }
+        }
+        umma_commit(o_full);
+        if (unit + static_cast<int>(gridDim.x) < num_units) {  // the next unit's scores, behind this unit's P V on the tensor pipe
+          mbar_wait(qk_full, ph ^ 1u);
+          if constexpr (PT) mbar_wait(o_full, ph);             // the scores overwrite the columns the P V MMAs read P from
+          tc_fence_after();
+          issue_s();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- softmax + remainder + epilogue
+    constexpr float sl2 = 0.125f * 1.4426950408889634f;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r_tile = warp * 32 + lane;
+    const int g = lane >> 2, tq = lane & 3, li = lane >> 3, lr = lane & 7;
+    // remainder scores: warp 0 takes keys [0, 48), warps 1..3 32 keys each - whole 16-key steps for the P V contraction
+    const int key0 = (warp == 0) ? 0 : 16 + 32 * warp;
+    const int npairs = (warp == 0) ? 3 : 2;                    // pairs of 8-key tiles
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      const int uu = reverse ? num_units - 1 - unit : unit;
+      const int b = uu / kHeads, h = uu - b * kHeads;
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+
+      // ---- remainder scores S_rem[16, my keys] = Q[128:144] K[my keys]^T, fp32 in registers
+      mbar_wait(qk_full, ph);
+      float sr[3][2][4];
+#pragma unroll
+      for (int pp = 0; pp < 3; ++pp)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) { sr[pp][nt][0] = sr[pp][nt][1] = sr[pp][nt][2] = sr[pp][nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qa[4];
+        ldsm_x4(qa, sQ + swz128(128 + (li & 1) * 8 + lr, ks * 2 + (li >> 1)));
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp) {
+          if (pp < npairs) {
+            uint32_t kf[4];
+            ldsm_x4(kf, sK + swz128(key0 + 16 * pp + (li >> 1) * 8 + lr, ks * 2 + (li & 1)));
+            mma_bf16(sr[pp][0], qa, kf[0], kf[1]);
+            mma_bf16(sr[pp][1], qa, kf[2], kf[3]);
+          }
+        }
+      }
+      float mlo = -INFINITY, mhi = -INFINITY;                   // rows 128 + g and 128 + g + 8
+#pragma unroll
+      for (int pp = 0; pp < 3; ++pp) {
+        if (pp < npairs) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            mlo = fmaxf(mlo, fmaxf(sr[pp][nt][0], sr[pp][nt][1]));
+            mhi = fmaxf(mhi, fmaxf(sr[pp][nt][2], sr[pp][nt][3]));
+          }
+        }
+      }
+      mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 1)); mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 2));
+      mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1)); mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+      if (tq == 0) { xch[warp * 16 + g] = mlo; xch[warp * 16 + g + 8] = mhi; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qk_read);                      // every ldmatrix of Q / K has delivered (the maxima depend on them)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float ms_lo = fmaxf(fmaxf(xch[g], xch[16 + g]), fmaxf(xch[32 + g], xch[48 + g])) * sl2;
+      const float ms_hi = fmaxf(fmaxf(xch[g + 8], xch[24 + g]), fmaxf(xch[40 + g], xch[56 + g])) * sl2;
+      float slo = 0.f, shi = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < 3; ++pp) {
+        if (pp < npairs) {
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const float p0 = ex2f(fmaf(sr[pp][nt][0], sl2, -ms_lo)), p1 = ex2f(fmaf(sr[pp][nt][1], sl2, -ms_lo));
+            const float p2 = ex2f(fmaf(sr[pp][nt][2], sl2, -ms_hi)), p3 = ex2f(fmaf(sr[pp][nt][3], sl2, -ms_hi));
+            slo += p0 + p1; shi += p2 + p3;
+            const uint32_t col = static_cast<uint32_t>(key0 + 16 * pp + 8 * nt + 2 * tq) * 2u;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sPr + g * kHmPRowBytes + col), "r"(pack_bf16(p0, p1)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sPr + (g + 8) * kHmPRowBytes + col), "r"(pack_bf16(p2, p3)) : "memory");
+          }
+        }
+      }
+      slo += __shfl_xor_sync(0xffffffffu, slo, 1); slo += __shfl_xor_sync(0xffffffffu, slo, 2);
+      shi += __shfl_xor_sync(0xffffffffu, shi, 1); shi += __shfl_xor_sync(0xffffffffu, shi, 2);
+      if (tq == 0) { xch[64 + warp * 16 + g] = slo; xch[64 + warp * 16 + g + 8] = shi; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // probabilities and row sums of all four warps are in place
+
+      // ---- main tile: S out of TMEM, P0 into shared memory
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      float ms0, sum0;
+      if constexpr (PT) {
+        sum0 = softmax_row_to_tmem<T>(t_lane, ms0);
+      } else {
+        sum0 = softmax_row_to_p<T, T, false>(t_lane, sP + r_tile * 128, 16384, r_tile & 7, true, ms0);
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      // ---- remainder outputs: O_rem[16, my 16 columns] = P_rem[16, 144] V[144, my columns] while the tensor core runs the main P V
+      mbar_wait(v_full, ph);
+      float orr[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { orr[nt][0] = orr[nt][1] = orr[nt][2] = orr[nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < T / 16; ++ks) {
+        uint32_t pa[4], vf[4];
+        ldsm_x4(pa, sPr + static_cast<uint32_t>(((li & 1) * 8 + lr) * kHmPRowBytes + (ks * 2 + (li >> 1)) * 16));
+        ldsm_x4_trans(vf, sV + swz128(16 * ks + (li & 1) * 8 + lr, 2 * warp + (li >> 1)));
+        mma_bf16(orr[0], pa, vf[0], vf[1]);
+        mma_bf16(orr[1], pa, vf[2], vf[3]);
+      }
+      const float sum_lo = (xch[64 + g] + xch[80 + g]) + (xch[96 + g] + xch[112 + g]);
+      const float sum_hi = (xch[72 + g] + xch[88 + g]) + (xch[104 + g] + xch[120 + g]);
+      const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_read);                       // (the accumulators feed the stores below: the ldmatrix reads are done)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = 16 * warp + 8 * nt + 2 * tq;
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(128 + g) * kHidden + col) = pack_bf16(orr[nt][0] * inv_lo, orr[nt][1] * inv_lo);
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(136 + g) * kHidden + col) = pack_bf16(orr[nt][2] * inv_hi, orr[nt][3] * inv_hi);
+      }
+      if (lse2 != nullptr) {   // training: log2-domain log-sum-exp of the scaled scores, [B, 12, T]
+        float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+        lrow[r_tile] = ms0 + log2f(sum0);
+        if (warp == 0 && tq == 0) { lrow[128 + g] = ms_lo + log2f(sum_lo); lrow[136 + g] = ms_hi + log2f(sum_hi); }
+      }
+
+      // ---- main output
+      uint32_t oa[32], ob[32];
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      load_o_row(t_lane + Cfg::kColO0, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      store_o_rows(oa, ob, 1.0f / sum0, sP + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, bool p_in_tmem, cudaStream_t stream) {
+  using Cfg = TcCfg<144>;
+  static bool configured = false;
+  auto kern = p_in_tmem ? attention_hm_kernel<true> : attention_hm_kernel<false>;
+  if (!configured) {
+    for (auto k : {attention_hm_kernel<true>, attention_hm_kernel<false>}) {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+        return set_error(kErrCuda, "attention_hm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                         cudaGetErrorString(cudaGetLastError()));
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    configured = true;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_kmajor(&tm, qkv, static_cast<long long>(batch) * 144, kQkvCols, kQkvCols, 144);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  const int slots = sms * 2;
+  const int grid = units < slots ? units : slots;
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse()) != cudaSuccess)
+    return set_error(kErrCuda, "attention_hm_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return check_launch("attention_hm_kernel");
+}
+
 template <int T>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = TcCfg<T>;
@@ -1281,6 +1677,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
       static int warps8 = -1;       // JPDVT_ATTN_WARPS=8: the eight-softmax-warp kernel (A/B knob; measured slower: 57.8 vs 54.0 us at
                                     // B = 256 - DESIGN.md section 4); default: four
       if (warps8 < 0) { const char* e = getenv("JPDVT_ATTN_WARPS"); warps8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
+      static int hybrid = -1;       // JPDVT_ATTN_REM=hybrid: main tile on tcgen05, the 16-row remainder on mma.sync (attention_hm_kernel);
+                                    // JPDVT_ATTN_REM=hybrid-tmem: the same with the main tile's probabilities kept in tensor memory
+      if (hybrid < 0) { const char* e = getenv("JPDVT_ATTN_REM"); hybrid = (e == nullptr || e[0] != 'h') ? 0 : (strstr(e, "tmem") != nullptr ? 2 : 1); }
+      if (hybrid) return launch_hm(qkv, out, lse2, batch, hybrid == 2, stream);
       return warps8 ? launch_tc8(qkv, out, lse2, batch, stream) : launch_tc<144>(qkv, out, lse2, batch, stream);
     }
     case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
