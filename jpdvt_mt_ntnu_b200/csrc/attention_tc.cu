@@ -1324,12 +1324,18 @@ __device__ __forceinline__ float softmax_row_to_tmem(uint32_t t_row, float& ms_o
 }
 
 // PT: the main tile's probabilities live in tensor memory (softmax_row_to_tmem, A-from-TMEM MMAs) instead of a shared-memory tile
-template <bool PT>
+template <bool PT, bool TRACE = false>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                    int num_units, int reverse) {
+                    int num_units, int reverse, long long* __restrict__ trace = nullptr) {
   constexpr int T = 144;
   using Cfg = TcCfg<T>;
+  auto mark = [&](int role, int it, int ev) {                 // developer path (JPDVT_ATTN_TRACE=1): clocks of CTA 0
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < kTraceUnits && role >= 0)
+        trace[(role * kTraceUnits + it) * kTraceEvents + ev] = clock64();
+    }
+  };
   extern __shared__ uint8_t att_tc_smem[];
   uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
@@ -1369,11 +1375,15 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         const int uu = reverse ? num_units - 1 - unit : unit;
         const int b = uu / kHeads, h = uu - b * kHeads;
         const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        mark(3, it, 0);
         if (it > 0) { mbar_wait(s_full, prev); mbar_wait(qk_read, prev); }     // tensor core and ldmatrix are done with Q, K
+        mark(3, it, 1);
         mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
         tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        mark(3, it, 2);
         if (it > 0) { mbar_wait(o_full, prev); mbar_wait(v_read, prev); }      // ... and with V
+        mark(3, it, 3);
         mbar_expect_tx(v_full, Cfg::kTileBytes);
         tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
       }
@@ -1401,9 +1411,12 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           tc_fence_after();
           issue_s();
         }
+        mark(0, it, 0);
         mbar_wait(p_full, ph);                                  // P0 written, score columns read
+        mark(0, it, 1);
         mbar_wait(v_full, ph);
         if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O0 of the previous unit has left TMEM
+        mark(0, it, 2);
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < T / 16; ++j) {
@@ -1418,11 +1431,15 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           }
         }
         umma_commit(o_full);
+        mark(0, it, 3);
         if (unit + static_cast<int>(gridDim.x) < num_units) {  // the next unit's scores, behind this unit's P V on the tensor pipe
           mbar_wait(qk_full, ph ^ 1u);
+          mark(0, it, 4);
           if constexpr (PT) mbar_wait(o_full, ph);             // the scores overwrite the columns the P V MMAs read P from
+          mark(0, it, 5);
           tc_fence_after();
           issue_s();
+          mark(0, it, 6);
         }
       }
     }
@@ -1444,7 +1461,10 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
 
       // ---- remainder scores S_rem[16, my keys] = Q[128:144] K[my keys]^T, fp32 in registers
+      const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
+      mark(role, it, 0);
       mbar_wait(qk_full, ph);
+      mark(role, it, 1);
       float sr[3][2][4];
 #pragma unroll
       for (int pp = 0; pp < 3; ++pp)
@@ -1502,9 +1522,11 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       shi += __shfl_xor_sync(0xffffffffu, shi, 1); shi += __shfl_xor_sync(0xffffffffu, shi, 2);
       if (tq == 0) { xch[64 + warp * 16 + g] = slo; xch[64 + warp * 16 + g + 8] = shi; }
       asm volatile("bar.sync 1, 128;" ::: "memory");           // probabilities and row sums of all four warps are in place
+      mark(role, it, 2);
 
       // ---- main tile: S out of TMEM, P0 into shared memory
       mbar_wait(s_full, ph);
+      mark(role, it, 3);
       tc_fence_after();
       float ms0, sum0;
       if constexpr (PT) {
@@ -1516,9 +1538,11 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      mark(role, it, 4);
 
       // ---- remainder outputs: O_rem[16, my 16 columns] = P_rem[16, 144] V[144, my columns] while the tensor core runs the main P V
       mbar_wait(v_full, ph);
+      mark(role, it, 5);
       float orr[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) { orr[nt][0] = orr[nt][1] = orr[nt][2] = orr[nt][3] = 0.f; }
@@ -1549,13 +1573,17 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 
       // ---- main output
       uint32_t oa[32], ob[32];
+      mark(role, it, 6);
       mbar_wait(o_full, ph);
+      mark(role, it, 7);
       tc_fence_after();
       load_o_row(t_lane + Cfg::kColO0, oa, ob);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(epi_done);
+      mark(role, it, 8);
       store_o_rows(oa, ob, 1.0f / sum0, sP + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
+      mark(role, it, 9);
     }
   }
 
@@ -1567,12 +1595,269 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   }
 }
 
-int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, bool p_in_tmem, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 144, remainder-warp form (JPDVT_ATTN_REM=warp): as the hybrid kernel with the probabilities in tensor memory, but the
+// 16-row remainder is the job of ONE warp of its own - the former TMA warp, idle but for three bulk loads per unit - which
+// runs it flash-attention-2 style entirely in registers (scores of all 144 keys as mma.sync accumulators, exact softmax with
+// quad shuffles, the probabilities re-used as A fragments, 16 x 64 outputs written from the accumulators): no shared-memory
+// tile, no barrier with the softmax warps.  The trace of the hybrid kernel showed why: the four softmax warps spent 1,500 +
+// 1,100 of a unit's 6,400 cycles on the remainder (two named barriers, dependent mma.sync chains), i.e. the remainder sat on
+// the unit chain although nothing of the main tile depends on it.  Roles:
+//   warps 0-3 : main tile only - S out of TMEM, P back into TMEM, O0 out of TMEM -> global
+//   warp 4    : remainder rows 128..143 (all 32 lanes) + the Q / K loads of the next unit (lane 0)
+//   warp 5    : MMA issuer + the V load of the next unit (lane 0)
+template <bool TRACE>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                    int num_units, int reverse, long long* __restrict__ trace) {
+  constexpr int T = 144;
+  using Cfg = TcCfg<T>;
+  auto mark = [&](int role, int it, int ev) {                 // developer path (JPDVT_ATTN_TRACE=1): clocks of CTA 0
+    if constexpr (TRACE) {
+      if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < kTraceUnits && role >= 0)
+        trace[(role * kTraceUnits + it) * kTraceEvents + ev] = clock64();
+    }
+  };
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;        // TMA: Q and K landed
+  uint64_t* v_full = bars + 1;         // TMA: V landed
+  uint64_t* s_full = bars + 2;         // MMA: main scores are in TMEM (and the score MMAs have read Q, K)
+  uint64_t* p_full = bars + 3;         // softmax warps: P is in TMEM, the scores are consumed (4 arrivals)
+  uint64_t* o_full = bars + 4;         // MMA: O0 is in TMEM (and the P V MMAs have read V and P)
+  uint64_t* epi_done = bars + 5;       // softmax warps: O0 has left TMEM (4 arrivals)
+  uint64_t* v_read = bars + 6;         // remainder warp: its ldmatrix reads of V are done (1 arrival)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(epi_done, 4); mbar_init(v_read, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sP = smem_u32(smem + Cfg::kOffP);
+  auto unit_bh = [&](int unit, int& b, int& h) {
+    const int uu = reverse ? num_units - 1 - unit : unit;
+    b = uu / kHeads; h = uu - b * kHeads;
+  };
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- remainder rows + Q / K loads
+    constexpr float sl2 = 0.125f * 1.4426950408889634f;
+    const int g = lane >> 2, tq = lane & 3, li = lane >> 3, lr = lane & 7;
+    auto load_qk = [&](int unit) {
+      int b, h;
+      unit_bh(unit, b, h);
+      mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
+      tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T);
+      tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+    };
+    if (lane == 0 && static_cast<int>(blockIdx.x) < num_units) load_qk(blockIdx.x);
+    __syncwarp();
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      int b, h;
+      unit_bh(unit, b, h);
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+      mark(3, it, 0);
+      mbar_wait(qk_full, ph);
+      mark(3, it, 1);
+      // ---- S_rem[16, 144] = Q[128:144] K^T: 18 accumulator tiles of 8 keys
+      float sr[18][4];
+#pragma unroll
+      for (int j = 0; j < 18; ++j) { sr[j][0] = sr[j][1] = sr[j][2] = sr[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qa[4];
+        ldsm_x4(qa, sQ + swz128(128 + (li & 1) * 8 + lr, ks * 2 + (li >> 1)));
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+          uint32_t kf[4];
+          ldsm_x4(kf, sK + swz128(16 * pp + (li >> 1) * 8 + lr, ks * 2 + (li & 1)));
+          mma_bf16(sr[2 * pp], qa, kf[0], kf[1]);
+          mma_bf16(sr[2 * pp + 1], qa, kf[2], kf[3]);
+        }
+      }
+      float mlo = -INFINITY, mhi = -INFINITY;                   // rows 128 + g and 136 + g
+#pragma unroll
+      for (int j = 0; j < 18; ++j) {
+        mlo = fmaxf(mlo, fmaxf(sr[j][0], sr[j][1]));
+        mhi = fmaxf(mhi, fmaxf(sr[j][2], sr[j][3]));
+      }
+      mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 1)); mlo = fmaxf(mlo, __shfl_xor_sync(0xffffffffu, mlo, 2));
+      mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1)); mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+      // every ldmatrix of Q / K has delivered (the maxima depend on all of them): once the main score MMAs have read the tiles
+      // too, the next unit's Q / K may land - a whole main softmax ahead of their use
+      if (lane == 0 && unit + static_cast<int>(gridDim.x) < num_units) {
+        mbar_wait(s_full, ph);
+        load_qk(unit + gridDim.x);
+      }
+      __syncwarp();
+      mark(3, it, 2);
+      const float ms_lo = mlo * sl2, ms_hi = mhi * sl2;
+      float slo = 0.f, shi = 0.f;
+      uint32_t pf[9][4];                                        // the probabilities as A fragments of the P V contraction
+#pragma unroll
+      for (int j = 0; j < 18; ++j) {
+        const float p0 = ex2f(fmaf(sr[j][0], sl2, -ms_lo)), p1 = ex2f(fmaf(sr[j][1], sl2, -ms_lo));
+        const float p2 = ex2f(fmaf(sr[j][2], sl2, -ms_hi)), p3 = ex2f(fmaf(sr[j][3], sl2, -ms_hi));
+        slo += p0 + p1; shi += p2 + p3;
+        pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      slo += __shfl_xor_sync(0xffffffffu, slo, 1); slo += __shfl_xor_sync(0xffffffffu, slo, 2);
+      shi += __shfl_xor_sync(0xffffffffu, shi, 1); shi += __shfl_xor_sync(0xffffffffu, shi, 2);
+      // ---- O_rem[16, 64] = P_rem V
+      mbar_wait(v_full, ph);
+      mark(3, it, 3);
+      float orr[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { orr[j][0] = orr[j][1] = orr[j][2] = orr[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 9; ++ks) {
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vf[4];
+          ldsm_x4_trans(vf, sV + swz128(16 * ks + (li & 1) * 8 + lr, dp * 2 + (li >> 1)));
+          mma_bf16(orr[2 * dp], pf[ks], vf[0], vf[1]);
+          mma_bf16(orr[2 * dp + 1], pf[ks], vf[2], vf[3]);
+        }
+      }
+      const float inv_lo = 1.0f / slo, inv_hi = 1.0f / shi;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                            // the accumulators feed the stores: every ldmatrix of V has delivered
+        const int col = 8 * j + 2 * tq;
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(128 + g) * kHidden + col) = pack_bf16(orr[j][0] * inv_lo, orr[j][1] * inv_lo);
+        *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(136 + g) * kHidden + col) = pack_bf16(orr[j][2] * inv_hi, orr[j][3] * inv_hi);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_read);
+      if (lse2 != nullptr && tq == 0) {
+        float* lrow = lse2 + (static_cast<long long>(b) * kHeads + h) * T;
+        lrow[128 + g] = ms_lo + log2f(slo);
+        lrow[136 + g] = ms_hi + log2f(shi);
+      }
+      mark(3, it, 4);
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer + V loads
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);   // B = V, MN-major
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), v_lo = desc_lo_mn(sV);
+      auto issue_s = [&]() {
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
+        }
+        umma_commit(s_full);
+      };
+      auto load_v = [&](int unit) {
+        int b, h;
+        unit_bh(unit, b, h);
+        mbar_expect_tx(v_full, Cfg::kTileBytes);
+        tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+      };
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        if (it == 0) {
+          load_v(unit);
+          mbar_wait(qk_full, 0);
+          tc_fence_after();
+          issue_s();
+        }
+        mark(0, it, 0);
+        mbar_wait(p_full, ph);                                  // P written, score columns read
+        mark(0, it, 1);
+        mbar_wait(v_full, ph);
+        if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O0 of the previous unit has left TMEM
+        mark(0, it, 2);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {                      // A = P out of tensor memory: key step j = columns [8j, 8j + 8)
+          if (j == 0) umma_ts_lohi<false>(tmem_base + Cfg::kColO0, tmem_base + 8 * j, v_lo + j * 128, idesc_o);
+          else umma_ts_lohi<true>(tmem_base + Cfg::kColO0, tmem_base + 8 * j, v_lo + j * 128, idesc_o);
+        }
+        umma_commit(o_full);
+        mark(0, it, 3);
+        if (unit + static_cast<int>(gridDim.x) < num_units) {
+          mbar_wait(o_full, ph);                                // P V has read V and P: V may be replaced, the scores may overwrite P
+          mbar_wait(v_read, ph);                                // ... and the remainder warp has read V
+          mark(0, it, 4);
+          load_v(unit + gridDim.x);
+          mbar_wait(qk_full, ph ^ 1u);
+          mark(0, it, 5);
+          tc_fence_after();
+          issue_s();                                            // the next unit's scores: done before the softmax warps are back
+          mark(0, it, 6);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- main tile: softmax + epilogue
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r_tile = warp * 32 + lane;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      int b, h;
+      unit_bh(unit, b, h);
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+      const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
+      mark(role, it, 0);
+      mbar_wait(s_full, ph);
+      mark(role, it, 1);
+      tc_fence_after();
+      float ms0;
+      const float sum0 = softmax_row_to_tmem<T>(t_lane, ms0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      mark(role, it, 2);
+      if (lse2 != nullptr) lse2[(static_cast<long long>(b) * kHeads + h) * T + r_tile] = ms0 + log2f(sum0);
+      uint32_t oa[32], ob[32];
+      mbar_wait(o_full, ph);
+      mark(role, it, 3);
+      tc_fence_after();
+      load_o_row(t_lane + Cfg::kColO0, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      mark(role, it, 4);
+      store_o_rows(oa, ob, 1.0f / sum0, sP + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
+      mark(role, it, 5);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int mode, cudaStream_t stream) {
   using Cfg = TcCfg<144>;
   static bool configured = false;
-  auto kern = p_in_tmem ? attention_hm_kernel<true> : attention_hm_kernel<false>;
+  const bool p_in_tmem = mode == 2;
+  auto kern = mode == 3 ? attention_rw_kernel<false> : (p_in_tmem ? attention_hm_kernel<true, false> : attention_hm_kernel<false, false>);
   if (!configured) {
-    for (auto k : {attention_hm_kernel<true>, attention_hm_kernel<false>}) {
+    for (auto k : {attention_hm_kernel<true, false>, attention_hm_kernel<false, false>, attention_rw_kernel<false>}) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
         return set_error(kErrCuda, "attention_hm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
                          cudaGetErrorString(cudaGetLastError()));
@@ -1589,7 +1874,36 @@ int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   const int units = batch * kHeads;
   const int slots = sms * 2;
   const int grid = units < slots ? units : slots;
-  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse()) != cudaSuccess)
+  static int trace_mode = -1;
+  if (trace_mode < 0) { const char* e = getenv("JPDVT_ATTN_TRACE"); trace_mode = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  if (trace_mode) {   // developer path: synchronous, prints the event clocks of CTA 0 (relative to its first event)
+    auto kt = mode == 3 ? attention_rw_kernel<true> : (p_in_tmem ? attention_hm_kernel<true, true> : attention_hm_kernel<false, true>);
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    constexpr int n = kTraceRoles * kTraceUnits * kTraceEvents;
+    long long* d = nullptr;
+    cudaMalloc(&d, n * sizeof(long long));
+    cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
+    kt<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d);
+    long long hbuf[n];
+    cudaMemcpyAsync(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    cudaFree(d);
+    long long t0 = 0;
+    for (int i = 0; i < n; ++i) if (hbuf[i] != 0 && (t0 == 0 || hbuf[i] < t0)) t0 = hbuf[i];
+    const char* names[kTraceRoles] = {"mma  ", "sm_w0", "sm_w3", "tma  "};
+    for (int r = 0; r < kTraceRoles; ++r)
+      for (int u = 0; u < kTraceUnits; ++u) {
+        fprintf(stderr, "trace %s unit %d:", names[r], u);
+        for (int e = 0; e < kTraceEvents; ++e) {
+          const long long v = hbuf[(r * kTraceUnits + u) * kTraceEvents + e];
+          fprintf(stderr, " %7lld", v ? v - t0 : -1LL);
+        }
+        fprintf(stderr, "\n");
+      }
+    return check_launch("attention_hm_kernel<trace>");
+  }
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(), static_cast<long long*>(nullptr)) != cudaSuccess)
     return set_error(kErrCuda, "attention_hm_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("attention_hm_kernel");
 }
@@ -1678,9 +1992,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
                                     // B = 256 - DESIGN.md section 4); default: four
       if (warps8 < 0) { const char* e = getenv("JPDVT_ATTN_WARPS"); warps8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
       static int hybrid = -1;       // JPDVT_ATTN_REM=hybrid: main tile on tcgen05, the 16-row remainder on mma.sync (attention_hm_kernel);
-                                    // JPDVT_ATTN_REM=hybrid-tmem: the same with the main tile's probabilities kept in tensor memory
-      if (hybrid < 0) { const char* e = getenv("JPDVT_ATTN_REM"); hybrid = (e == nullptr || e[0] != 'h') ? 0 : (strstr(e, "tmem") != nullptr ? 2 : 1); }
-      if (hybrid) return launch_hm(qkv, out, lse2, batch, hybrid == 2, stream);
+                                    // JPDVT_ATTN_REM=hybrid-tmem: the same with the main tile's probabilities kept in tensor memory; JPDVT_ATTN_REM=warp: the
+                                    // remainder as one warp's register-resident job (attention_rw_kernel)
+      if (hybrid < 0) { const char* e = getenv("JPDVT_ATTN_REM"); hybrid = (e == nullptr) ? 0 : (e[0] == 'w' ? 3 : (e[0] != 'h' ? 0 : (strstr(e, "tmem") != nullptr ? 2 : 1))); }
+      if (hybrid) return launch_hm(qkv, out, lse2, batch, hybrid, stream);
       return warps8 ? launch_tc8(qkv, out, lse2, batch, stream) : launch_tc<144>(qkv, out, lse2, batch, stream);
     }
     case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
