@@ -1609,7 +1609,7 @@ attention_hm_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 template <bool TRACE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                    int num_units, int reverse, long long* __restrict__ trace) {
+                    int num_units, int reverse, long long* __restrict__ trace, int sms) {
   constexpr int T = 144;
   using Cfg = TcCfg<T>;
   auto mark = [&](int role, int it, int ev) {                 // developer path (JPDVT_ATTN_TRACE=1): clocks of CTA 0
@@ -1631,6 +1631,11 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The two CTAs of an SM would both put their remainder warp on the same SM sub-partition (warp index mod 4), where their
+  // mma.sync streams share one legacy tensor pipe (30 cycles per HMMA in the trace); the second CTA of an SM (blocks are dealt
+  // breadth first) therefore swaps the two single-warp roles, so that the remainder warps sit on sub-partitions 0 and 1.
+  const bool swap_roles = ((static_cast<int>(blockIdx.x) / sms) & 1) != 0;
+  const int rem_warp = swap_roles ? 5 : 4, mma_warp = swap_roles ? 4 : 5;
   if (threadIdx.x == 0) {
     mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     mbar_init(epi_done, 4); mbar_init(v_read, 1);
@@ -1651,7 +1656,7 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     b = uu / kHeads; h = uu - b * kHeads;
   };
 
-  if (warp == 4) {
+  if (warp == rem_warp) {
     // ---------------------------------------------------------------------------------------------- remainder rows + Q / K loads
     constexpr float sl2 = 0.125f * 1.4426950408889634f;
     const int g = lane >> 2, tq = lane & 3, li = lane >> 3, lr = lane & 7;
@@ -1750,7 +1755,7 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       }
       mark(3, it, 4);
     }
-  } else if (warp == 5) {
+  } else if (warp == mma_warp) {
     // ---------------------------------------------------------------------------------------------- MMA issuer + V loads
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
@@ -1855,9 +1860,13 @@ int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   using Cfg = TcCfg<144>;
   static bool configured = false;
   const bool p_in_tmem = mode == 2;
-  auto kern = mode == 3 ? attention_rw_kernel<false> : (p_in_tmem ? attention_hm_kernel<true, false> : attention_hm_kernel<false, false>);
+  auto kern = p_in_tmem ? attention_hm_kernel<true, false> : attention_hm_kernel<false, false>;
   if (!configured) {
-    for (auto k : {attention_hm_kernel<true, false>, attention_hm_kernel<false, false>, attention_rw_kernel<false>}) {
+    for (auto k : {attention_rw_kernel<false>, attention_rw_kernel<true>}) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    for (auto k : {attention_hm_kernel<true, false>, attention_hm_kernel<false, false>}) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
         return set_error(kErrCuda, "attention_hm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
                          cudaGetErrorString(cudaGetLastError()));
@@ -1877,14 +1886,15 @@ int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
   static int trace_mode = -1;
   if (trace_mode < 0) { const char* e = getenv("JPDVT_ATTN_TRACE"); trace_mode = (e != nullptr && e[0] == '1') ? 1 : 0; }
   if (trace_mode) {   // developer path: synchronous, prints the event clocks of CTA 0 (relative to its first event)
-    auto kt = mode == 3 ? attention_rw_kernel<true> : (p_in_tmem ? attention_hm_kernel<true, true> : attention_hm_kernel<false, true>);
+    auto kt = p_in_tmem ? attention_hm_kernel<true, true> : attention_hm_kernel<false, true>;
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     constexpr int n = kTraceRoles * kTraceUnits * kTraceEvents;
     long long* d = nullptr;
     cudaMalloc(&d, n * sizeof(long long));
     cudaMemsetAsync(d, 0, n * sizeof(long long), stream);
-    kt<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d);
+    if (mode == 3) attention_rw_kernel<true><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d, sms);
+    else kt<<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, 0, d);
     long long hbuf[n];
     cudaMemcpyAsync(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -1902,6 +1912,12 @@ int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int bat
         fprintf(stderr, "\n");
       }
     return check_launch("attention_hm_kernel<trace>");
+  }
+  if (mode == 3) {
+    if (launch_pdl(attention_rw_kernel<false>, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(),
+                   static_cast<long long*>(nullptr), sms) != cudaSuccess)
+      return set_error(kErrCuda, "attention_rw_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return check_launch("attention_rw_kernel");
   }
   if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tm, out, lse2, units, sweep_reverse(), static_cast<long long*>(nullptr)) != cudaSuccess)
     return set_error(kErrCuda, "attention_hm_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1991,10 +2007,12 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
       static int warps8 = -1;       // JPDVT_ATTN_WARPS=8: the eight-softmax-warp kernel (A/B knob; measured slower: 57.8 vs 54.0 us at
                                     // B = 256 - DESIGN.md section 4); default: four
       if (warps8 < 0) { const char* e = getenv("JPDVT_ATTN_WARPS"); warps8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
-      static int hybrid = -1;       // JPDVT_ATTN_REM=hybrid: main tile on tcgen05, the 16-row remainder on mma.sync (attention_hm_kernel);
+      static int hybrid = -1;       // default (JPDVT_ATTN_REM unset or =warp): attention_rw_kernel, 42 us at B = 256; =split: the round-1 kernel
+                                    // (54 us; every remainder MMA on tcgen05); =transposed / =pipelined: its variants (launch_tc);
+                                    // JPDVT_ATTN_REM=hybrid: main tile on tcgen05, the 16-row remainder on mma.sync (attention_hm_kernel);
                                     // JPDVT_ATTN_REM=hybrid-tmem: the same with the main tile's probabilities kept in tensor memory; JPDVT_ATTN_REM=warp: the
                                     // remainder as one warp's register-resident job (attention_rw_kernel)
-      if (hybrid < 0) { const char* e = getenv("JPDVT_ATTN_REM"); hybrid = (e == nullptr) ? 0 : (e[0] == 'w' ? 3 : (e[0] != 'h' ? 0 : (strstr(e, "tmem") != nullptr ? 2 : 1))); }
+      if (hybrid < 0) { const char* e = getenv("JPDVT_ATTN_REM"); hybrid = (e == nullptr || e[0] == 'w') ? 3 : (e[0] != 'h' ? 0 : (strstr(e, "tmem") != nullptr ? 2 : 1)); }
       if (hybrid) return launch_hm(qkv, out, lse2, batch, hybrid, stream);
       return warps8 ? launch_tc8(qkv, out, lse2, batch, stream) : launch_tc<144>(qkv, out, lse2, batch, stream);
     }
