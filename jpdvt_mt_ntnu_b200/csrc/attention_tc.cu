@@ -1856,6 +1856,181 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 256 (4x4 @256 px), query-tile form (default; JPDVT_ATTN_QT=0 restores the dual-tile kernel above): what the T = 144
+// rewrite taught, applied to the size without a remainder.  The dual-tile kernel holds a whole (sample, head) unit per CTA -
+// two 128 x 256 score tiles in 512 TMEM columns, two 64 KB probability tiles in shared memory - so an SM runs ONE chain.
+// Here the work item is (unit, 128-query tile): Q tile 16 KB + K 32 KB + V 32 KB, the scores in columns [0, 256), the bf16
+// probabilities written back over columns [0, 128) (tcgen05.st; A-from-TMEM MMAs), the output accumulator in the score tile's
+// dead columns [128, 192) - 256 TMEM columns and < 100 KB of shared memory, i.e. two independent chains per SM, and no
+// shared-memory traffic for P at all.  K / V are fetched once per item (twice per unit); the two items of a unit run on
+// neighbouring CTAs at the same time, so the second fetch is an L2 hit.
+template <int T>
+struct QtCfg {
+  static_assert(T == 256, "instantiated for 256 tokens");
+  static constexpr int kQBytes = 128 * 128, kKvBytes = T * 128;
+  static constexpr int kOffQ = 0, kOffK = kQBytes, kOffV = kQBytes + kKvBytes, kOffStage = kQBytes + 2 * kKvBytes;
+  static constexpr int kBarOff = kOffStage + 4 * 4096;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kColP = 0, kColO = T / 2;             // P: T / 2 columns of bf16 pairs; O behind them, inside the score tile
+  static_assert(kColO + kHeadDim <= T && T <= 256, "TMEM columns");
+  static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
+};
+
+template <int T>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_qt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int num_items, int reverse) {
+  using Cfg = QtCfg<T>;
+  constexpr int kQt = T / 128;                                // query tiles per unit
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;        // TMA: Q tile and K landed
+  uint64_t* v_full = bars + 1;         // TMA: V landed
+  uint64_t* s_full = bars + 2;         // MMA: scores are in TMEM (and the score MMAs have read Q, K)
+  uint64_t* p_full = bars + 3;         // softmax warps: P is in TMEM, the scores are consumed (4 arrivals)
+  uint64_t* o_full = bars + 4;         // MMA: O is in TMEM (and the P V MMAs have read V and P)
+  uint64_t* epi_done = bars + 5;       // softmax warps: O has left TMEM (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(epi_done, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sStage = smem_u32(smem + Cfg::kOffStage);
+  auto item_bhq = [&](int item, int& b, int& h, int& qt) {
+    const int ii = reverse ? num_items - 1 - item : item;
+    const int uu = ii / kQt;
+    qt = ii - uu * kQt;
+    b = uu / kHeads; h = uu - b * kHeads;
+  };
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int b, h, qt;
+        item_bhq(item, b, h, qt);
+        const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        if (it > 0) mbar_wait(s_full, prev);                  // the score MMAs of the previous item have read Q, K
+        mbar_expect_tx(qk_full, Cfg::kQBytes + Cfg::kKvBytes);
+        tma_load_2d(&tm_q, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * T + qt * 128);
+        tma_load_2d(&tm_kv, qk_full, smem + Cfg::kOffK, kHidden + h * kHeadDim, b * T);
+        if (it > 0) mbar_wait(o_full, prev);                  // ... and its P V MMAs have read V
+        mbar_expect_tx(v_full, Cfg::kKvBytes);
+        tma_load_2d(&tm_kv, v_full, smem + Cfg::kOffV, 2 * kHidden + h * kHeadDim, b * T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, T);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);   // B = V, MN-major
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), v_lo = desc_lo_mn(sV);
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        mbar_wait(qk_full, ph);
+        if (it > 0) mbar_wait(epi_done, static_cast<uint32_t>((it - 1) & 1));   // O of the previous item (inside the score tile) has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, ph);                                  // P written, score columns read
+        mbar_wait(v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {                      // A = P out of tensor memory: key step j = columns [8j, 8j + 8)
+          if (j == 0) umma_ts_lohi<false>(tmem_base + Cfg::kColO, tmem_base + Cfg::kColP + 8 * j, v_lo + j * 128, idesc_o);
+          else umma_ts_lohi<true>(tmem_base + Cfg::kColO, tmem_base + Cfg::kColP + 8 * j, v_lo + j * 128, idesc_o);
+        }
+        umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------------------------------------- softmax + epilogue
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r_tile = warp * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      int b, h, qt;
+      item_bhq(item, b, h, qt);
+      __nv_bfloat16* obase = out + (static_cast<long long>(b) * T + qt * 128) * kHidden + h * kHeadDim;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      float ms0;
+      const float sum0 = softmax_row_to_tmem<T>(t_lane, ms0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (lse2 != nullptr) lse2[(static_cast<long long>(b) * kHeads + h) * T + qt * 128 + r_tile] = ms0 + log2f(sum0);
+      uint32_t oa[32], ob[32];
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      load_o_row(t_lane + Cfg::kColO, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      store_o_rows(oa, ob, 1.0f / sum0, sStage + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <int T>
+int launch_qt(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
+  using Cfg = QtCfg<T>;
+  static bool configured = false;
+  auto kern = attention_qt_kernel<T>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_qt: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  CUtensorMap tq, tkv;
+  const long long rows = static_cast<long long>(batch) * T;
+  int rc = make_tmap_bf16_kmajor(&tq, qkv, rows, kQkvCols, kQkvCols, 128);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tkv, qkv, rows, kQkvCols, kQkvCols, T);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = batch * kHeads * (T / 128);
+  const int slots = sms * 2;
+  const int grid = items < slots ? items : slots;
+  if (launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tq, tkv, out, lse2, items, sweep_reverse()) != cudaSuccess)
+    return set_error(kErrCuda, "attention_qt_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return check_launch("attention_qt_kernel");
+}
+
 int launch_hm(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, int mode, cudaStream_t stream) {
   using Cfg = TcCfg<144>;
   static bool configured = false;
@@ -2016,7 +2191,12 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
       if (hybrid) return launch_hm(qkv, out, lse2, batch, hybrid, stream);
       return warps8 ? launch_tc8(qkv, out, lse2, batch, stream) : launch_tc<144>(qkv, out, lse2, batch, stream);
     }
-    case 256: return launch_tc<256>(qkv, out, lse2, batch, stream);
+    case 256: {
+      static int qt = -1;           // JPDVT_ATTN_QT=0: the dual-tile kernel (one unit per CTA, P tiles in shared memory) instead of the
+                                    // query-tile kernel (attention_qt_kernel: two chains per SM, P in tensor memory)
+      if (qt < 0) { const char* e = getenv("JPDVT_ATTN_QT"); qt = (e != nullptr && e[0] == '0') ? 0 : 1; }
+      return qt ? launch_qt<256>(qkv, out, lse2, batch, stream) : launch_tc<256>(qkv, out, lse2, batch, stream);
+    }
     case 324: return launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
   }
