@@ -1814,15 +1814,34 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     __syncwarp();
   } else {
     // ---------------------------------------------------------------------------------------------- main tile: softmax + epilogue
+    // Software pipeline: the output of unit n - 1 is drained AFTER the softmax of unit n, so the warps do not sit out the P V
+    // latency (p_full -> nine MMAs -> o_full, ~800 cycles in the trace) between a unit's softmax and its own epilogue.  The
+    // P V MMAs of unit n wait for that drain (epi_done), the scores of unit n + 1 for the P V MMAs of unit n (o_full).
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const int r_tile = warp * 32 + lane;
-    int it = 0;
+    const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
+    auto drain = [&](int it_prev, int unit_prev, float inv) {
+      int b, h;
+      unit_bh(unit_prev, b, h);
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
+      uint32_t oa[32], ob[32];
+      mbar_wait(o_full, static_cast<uint32_t>(it_prev & 1));
+      mark(role, it_prev, 3);
+      tc_fence_after();
+      load_o_row(t_lane + Cfg::kColO0, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      mark(role, it_prev, 4);
+      store_o_rows(oa, ob, inv, sP + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
+      mark(role, it_prev, 5);
+    };
+    int it = 0, unit_prev = -1;
+    float inv_prev = 0.f;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const uint32_t ph = static_cast<uint32_t>(it & 1);
       int b, h;
       unit_bh(unit, b, h);
-      __nv_bfloat16* obase = out + static_cast<long long>(b) * T * kHidden + h * kHeadDim;
-      const int role = (warp == 0) ? 1 : (warp == 3) ? 2 : -1;
       mark(role, it, 0);
       mbar_wait(s_full, ph);
       mark(role, it, 1);
@@ -1834,18 +1853,11 @@ attention_rw_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       if (lane == 0) mbar_arrive(p_full);
       mark(role, it, 2);
       if (lse2 != nullptr) lse2[(static_cast<long long>(b) * kHeads + h) * T + r_tile] = ms0 + log2f(sum0);
-      uint32_t oa[32], ob[32];
-      mbar_wait(o_full, ph);
-      mark(role, it, 3);
-      tc_fence_after();
-      load_o_row(t_lane + Cfg::kColO0, oa, ob);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(epi_done);
-      mark(role, it, 4);
-      store_o_rows(oa, ob, 1.0f / sum0, sP + static_cast<uint32_t>(warp) * 4096u, obase + static_cast<long long>(warp * 32) * kHidden, 32, lane);
-      mark(role, it, 5);
+      if (it > 0) drain(it - 1, unit_prev, inv_prev);
+      unit_prev = unit;
+      inv_prev = 1.0f / sum0;
     }
+    if (it > 0) drain(it - 1, unit_prev, inv_prev);
   }
 
   tc_fence_before();
