@@ -353,7 +353,9 @@ def kernel_roofline(model, wl, batch, peaks):
         "gemm_fc1 (tcgen05, bias+gelu)": (lambda: ops.gemm_bias_gelu(xn, W["w_fc1"][0], W["b_fc1"][0]), 2.0 * M * 768 * 3072, "flop"),
         "gemm_fc2 (tcgen05, gated residual via TMA ring)": (lambda: ops.gemm_bias_gate_residual(x, hid, W["w_fc2"][0], W["b_fc2"][0], gate, T), 2.0 * M * 3072 * 768, "flop"),
         "gemm_proj (tcgen05, gated residual via TMA ring)": (lambda: ops.gemm_bias_gate_residual(x, xn, W["w_proj"][0], W["b_proj"][0], gate, T), 2.0 * M * 768 * 768, "flop"),
-        "attention (tcgen05, S/O in TMEM)": (lambda: ops.attention(qkv, batch, T), 4.0 * batch * 12 * T * T * 64, "flop"),
+        # HBM-bound since the remainder-warp / P-in-TMEM kernels: algorithmic bytes = qkv in (2304 bf16) + output (768 bf16) per row
+        "attention (tcgen05 + TMEM, HBM-bound)": (lambda: ops.attention(qkv, batch, T), M * (2304 + 768) * 2.0, "byte"),
+        "proj as bytes (fp32 residual RMW + bf16 operand)": (lambda: ops.gemm_bias_gate_residual(x, xn, W["w_proj"][0], W["b_proj"][0], gate, T), M * 768 * (4.0 + 4.0 + 2.0), "byte"),
         "ln_modulate (fp32->bf16)": (lambda: ops.ln_modulate(x, shift, scale, T), M * 768 * 6.0, "byte"),
     }
     out = {}

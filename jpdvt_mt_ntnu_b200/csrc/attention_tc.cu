@@ -197,6 +197,103 @@ __device__ __forceinline__ float softmax_row_to_p(uint32_t t_row, uint32_t p_row
   return sum + (s_even + s_odd);
 }
 
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.mma with the A operand in TENSOR MEMORY (K-major: lane = row, two bf16 per 32-bit column), B from shared memory
+template <bool ACC>
+__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi)
+      : "memory");
+}
+
+// softmax_row_to_p with the probabilities going back into TENSOR MEMORY instead of shared memory: the bf16 pairs of keys
+// [32c, 32c + 32) overwrite columns [16c, 16c + 16) of the thread's own score row - columns whose scores this thread has
+// already read (chunk c is in registers, the load in flight is chunk c + 1 at columns >= 32c + 32) - and the P V MMAs read
+// them as their A operand straight from there: no shared-memory tile, no store / operand-read traffic for P at all.
+template <int T, int TV = T>      // T columns are read (multiple of 16); columns >= TV are padding and get probability 0
+__device__ __forceinline__ float softmax_row_to_tmem(uint32_t t_row, float& ms_out) {
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  constexpr int kFull = T / 32, kTail = T % 32;
+  static_assert(kTail == 0 || kTail == 16, "token count must be a multiple of 16");
+  constexpr int kChunks = kFull + (kTail ? 1 : 0);
+  uint32_t ra[32], rb[32];
+  auto load_chunk = [&](uint32_t (&r)[32], int c) {
+    if (c < kFull) tmem_ld_32x32(t_row + c * 32, r);
+    else tmem_ld_32x16(t_row + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
+  };
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  load_chunk(ra, 0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+#pragma unroll
+    for (int j = 0; j < n; j += 8) {
+      if (c * 32 + j + 8 <= TV) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c * 32 + j + e < TV) m0 = fmaxf(m0, __uint_as_float(cur[j + e]));
+      }
+    }
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  load_chunk(ra, 0);
+  const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+  ms_out = ms;
+  uint64_t sum2 = f2_pack(0.f, 0.f);
+  const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms, -ms);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2p, nmsp), a, b);
+      float pa = ex2f(a), pb = ex2f(b);
+      if (c * 32 + 2 * j >= TV) pa = 0.f;                      // padded keys (compile-time after unrolling)
+      if (c * 32 + 2 * j + 1 >= TV) pb = 0.f;
+      sum2 = f2_add(sum2, f2_pack(pa, pb));
+      pk[j] = pack_bf16(pa, pb);
+    }
+    if (c < kFull) tmem_st_32x16(t_row + c * 16, pk);
+    else tmem_st_32x8(t_row + c * 16, pk);
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  tmem_st_wait();
+  float s_even, s_odd;
+  f2_unpack(sum2, s_even, s_odd);
+  return s_even + s_odd;
+}
+
 // Split remainder: this warp's NCJ key columns of the 16 remainder rows (live in lanes 0..15 of the warp's TMEM quadrant).
 // Row maximum and row sum are combined across the four warps through `xch`; p goes out as bf16 into the compact P tile
 // (row = lane, 2 KB per 64-key block).  Returns the full row sum.
@@ -1043,7 +1140,9 @@ struct SeqCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory");
 };
 
-template <int TP, int TV>
+// PT: the probabilities go back into tensor memory over the consumed score columns (softmax_row_to_tmem) and the P V MMAs read
+// them from there; the output of tile n - 1 is drained after the softmax of tile n (as in attention_rw_kernel)
+template <int TP, int TV, bool PT = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
                         int num_units, int reverse) {
@@ -1109,6 +1208,7 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
         for (int t = 0; t < kTiles; ++t, ++tile_no) {
           const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
           if (tile_no > 0) mbar_wait(p_full, ph ^ 1);            // the previous tile's softmax has consumed the score columns
+          if constexpr (PT) { if (tile_no > 0) mbar_wait(o_full, ph ^ 1); }   // ... and its P V MMAs the probabilities written over them
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k) {                // S[:, 0:N1) and S[:, N1:TP) of query rows [128 t, 128 t + 128)
@@ -1124,9 +1224,15 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < TP / 16; ++j) {
-            const uint32_t a = p_lo + (j >> 2) * 1024 + (j & 3) * 2, bq = v_lo + j * 128;
-            if (j == 0) umma_lohi<false>(tmem_base + TP, a, bq, idesc_o);
-            else umma_lohi<true>(tmem_base + TP, a, bq, idesc_o);
+            const uint32_t bq = v_lo + j * 128;
+            if constexpr (PT) {
+              if (j == 0) umma_ts_lohi<false>(tmem_base + TP, tmem_base + 8 * j, bq, idesc_o);
+              else umma_ts_lohi<true>(tmem_base + TP, tmem_base + 8 * j, bq, idesc_o);
+            } else {
+              const uint32_t a = p_lo + (j >> 2) * 1024 + (j & 3) * 2;
+              if (j == 0) umma_lohi<false>(tmem_base + TP, a, bq, idesc_o);
+              else umma_lohi<true>(tmem_base + TP, a, bq, idesc_o);
+            }
           }
           umma_commit(o_full);
           if (t == kTiles - 1) umma_commit(v_free);
@@ -1138,6 +1244,20 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const int r_tile = warp * 32 + lane;
     long long tile_no = 0;
+    // PT: the previous tile's output is drained after this tile's softmax
+    [[maybe_unused]] __nv_bfloat16* prev_dst = nullptr;
+    [[maybe_unused]] float prev_inv = 0.f;
+    [[maybe_unused]] int prev_live = 0;
+    [[maybe_unused]] auto drain = [&](uint32_t ph_prev) {
+      mbar_wait(o_full, ph_prev);
+      tc_fence_after();
+      uint32_t oa[32], ob[32];
+      load_o_row(t_lane + TP, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
+      store_o_rows(oa, ob, prev_inv, sP + static_cast<uint32_t>(warp) * 4096u, prev_dst, prev_live, lane);
+    };
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int uu = reverse ? num_units - 1 - unit : unit;
       const int b = uu / kHeads, h = uu - b * kHeads;
@@ -1145,6 +1265,22 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
       for (int t = 0; t < kTiles; ++t, ++tile_no) {
         const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
         mbar_wait(s_full, ph);
+        if constexpr (PT) {
+          tc_fence_after();
+          float ms;
+          const float sum = softmax_row_to_tmem<TP, TV>(t_lane, ms);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+          const int row = t * 128 + r_tile;
+          if (lse2 != nullptr && row < TV) lse2[(static_cast<long long>(b) * kHeads + h) * TV + row] = ms + log2f(sum);
+          if (tile_no > 0) drain(ph ^ 1);
+          const int live = TV - (t * 128 + warp * 32);
+          prev_dst = obase + static_cast<long long>(t * 128 + warp * 32) * kHidden;
+          prev_inv = 1.0f / sum;
+          prev_live = live < 0 ? 0 : (live < 32 ? live : 32);
+          continue;
+        }
         if (tile_no > 0) mbar_wait(o_full, ph ^ 1);               // the previous tile's P V MMAs have read the P buffer
         tc_fence_after();
         float ms;
@@ -1168,6 +1304,7 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
                      obase + static_cast<long long>(t * 128 + warp * 32) * kHidden, live < 0 ? 0 : (live < 32 ? live : 32), lane);
       }
     }
+    if constexpr (PT) { if (tile_no > 0) drain(static_cast<uint32_t>((tile_no - 1) & 1)); }
   }
   tc_fence_before();
   __syncthreads();
@@ -1181,7 +1318,9 @@ template <int TP, int TV>
 int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = SeqCfg<TP, TV>;
   static bool configured = false;
-  auto kern = attention_tc_seq_kernel<TP, TV>;
+  static int pt = -1;               // JPDVT_ATTN_SEQ_TMEM=0: probabilities through the shared-memory P tile (the first form) instead of TMEM
+  if (pt < 0) { const char* e = getenv("JPDVT_ATTN_SEQ_TMEM"); pt = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  auto kern = pt ? attention_tc_seq_kernel<TP, TV, true> : attention_tc_seq_kernel<TP, TV, false>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return set_error(kErrCuda, "attention_tc_seq: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
@@ -1233,95 +1372,6 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 }
 // byte offset of 16-byte chunk `ch` of row `row` in a TMA SWIZZLE_128B tile of 128-byte rows (1024-byte aligned base)
 __device__ __forceinline__ uint32_t swz128(int row, int ch) { return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4)); }
-
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// tcgen05.mma with the A operand in TENSOR MEMORY (K-major: lane = row, two bf16 per 32-bit column), B from shared memory
-template <bool ACC>
-__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(kDescHi)
-      : "memory");
-}
-
-// softmax_row_to_p with the probabilities going back into TENSOR MEMORY instead of shared memory: the bf16 pairs of keys
-// [32c, 32c + 32) overwrite columns [16c, 16c + 16) of the thread's own score row - columns whose scores this thread has
-// already read (chunk c is in registers, the load in flight is chunk c + 1 at columns >= 32c + 32) - and the P V MMAs read
-// them as their A operand straight from there: no shared-memory tile, no store / operand-read traffic for P at all.
-template <int T>
-__device__ __forceinline__ float softmax_row_to_tmem(uint32_t t_row, float& ms_out) {
-  constexpr float sl2 = 0.125f * 1.4426950408889634f;
-  constexpr int kFull = T / 32, kTail = T % 32;
-  static_assert(kTail == 0 || kTail == 16, "token count must be a multiple of 16");
-  constexpr int kChunks = kFull + (kTail ? 1 : 0);
-  uint32_t ra[32], rb[32];
-  auto load_chunk = [&](uint32_t (&r)[32], int c) {
-    if (c < kFull) tmem_ld_32x32(t_row + c * 32, r);
-    else tmem_ld_32x16(t_row + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
-  };
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-  load_chunk(ra, 0);
-  tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
-    const int n = (c < kFull) ? 32 : kTail;
-#pragma unroll
-    for (int j = 0; j < n; j += 8) {
-      m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
-      m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
-      m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
-      m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
-    }
-    if (c + 1 < kChunks) tmem_ld_wait();
-  }
-  load_chunk(ra, 0);
-  const float ms = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
-  ms_out = ms;
-  uint64_t sum2 = f2_pack(0.f, 0.f);
-  const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms, -ms);
-  tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
-    const int n = (c < kFull) ? 32 : kTail;
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < n / 2; ++j) {
-      float a, b;
-      f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2p, nmsp), a, b);
-      const float pa = ex2f(a), pb = ex2f(b);
-      sum2 = f2_add(sum2, f2_pack(pa, pb));
-      pk[j] = pack_bf16(pa, pb);
-    }
-    if (c < kFull) tmem_st_32x16(t_row + c * 16, pk);
-    else tmem_st_32x8(t_row + c * 16, pk);
-    if (c + 1 < kChunks) tmem_ld_wait();
-  }
-  tmem_st_wait();
-  float s_even, s_odd;
-  f2_unpack(sum2, s_even, s_odd);
-  return s_even + s_odd;
-}
 
 // PT: the main tile's probabilities live in tensor memory (softmax_row_to_tmem, A-from-TMEM MMAs) instead of a shared-memory tile
 template <bool PT, bool TRACE = false>
