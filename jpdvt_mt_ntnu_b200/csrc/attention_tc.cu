@@ -5,6 +5,14 @@
 // and T = 256 (256 px), inference and training forward (optionally writes the per-row log-sum-exp the backward reads);
 // the mma.sync kernel in attention.cu keeps the other sizes.
 //
+// Kernels of this file, by token count (defaults; DESIGN.md section 4 has the measurements):
+//   T = 144 : attention_rw_kernel    - main 128-row tile on tcgen05 with the probabilities kept in TMEM (A-from-TMEM MMAs), the
+//                                      16-row remainder on one warp's mma.sync; attention_tc_kernel<144> / attention_hm_kernel /
+//                                      attention_tc8_kernel are the earlier forms, kept as A/B opt-ins (JPDVT_ATTN_REM, JPDVT_ATTN_WARPS)
+//   T = 256 : attention_qt_kernel    - work item = (unit, 128-query tile), P in TMEM, two CTAs per SM (attention_tc_kernel<256>: opt-in)
+//   T = 324 : attention_tc_seq_kernel - keys padded to 336, one score tile at a time, P in TMEM
+// The description below is the first tcgen05 form (attention_tc_kernel), whose building blocks the others share.
+//
 // One CTA works on one (sample, head) unit at a time, several units per CTA (persistent grid):
 //   warps 0-3 : softmax + output epilogue; warp w owns TMEM lanes [32w, 32w+32) = 32 query rows of a 128-row tile
 //   warp 4    : TMA producer - Q, K, V of the head straight out of the fused QKV activation [B*T, 2304]
