@@ -109,7 +109,7 @@ void set_sweep_reverse(int reverse);
 // dW[wg_rows, n_cols] (fp32) = P[M, wg_rows]^T . Q[M, n_cols]   (both bf16 row-major); `partial` is scratch of
 // split * wg_rows * n_cols floats (see wgrad_scratch_floats)
 int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* qmat, long long ldq, float* out,
-                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream);
+                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream, bool out_zeroed = false);
 long long wgrad_scratch_floats(long long m, int out_rows, int n_cols);
 
 // a: bf16 [M, K] row-major (lda elements); w: bf16 [N, K] row-major (nn.Linear layout)

@@ -1520,8 +1520,10 @@ static int launch_wgrad_cfg(const __nv_bfloat16* pmat, long long ldp, const __nv
   return check_launch("gemm_kernel<wgrad>");
 }
 
+// out_zeroed: the caller has already zero-filled `out` on this stream (the training backward's flat gradient buffer is cleared
+// once per step), so the split path need not clear it again before its reduction boxes add into it
 int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* qmat, long long ldq, float* out,
-                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream) {
+                 float* partial, long long m, int out_rows, int n_cols, cudaStream_t stream, bool out_zeroed) {
   if (out_rows <= 0 || n_cols <= 0) return kOk;
   if (m <= 0) return set_error(kErrBadArg, "wgrad: empty contraction");
   if (n_cols % 128 != 0) return set_error(kErrBadArg, "wgrad: n_cols=%d must be a multiple of 128", n_cols);
@@ -1535,7 +1537,7 @@ int launch_wgrad(const __nv_bfloat16* pmat, long long ldp, const __nv_bfloat16* 
   if (tma_red < 0) { const char* e = getenv("JPDVT_WGRAD_TMA_REDUCE"); tma_red = (e != nullptr && e[0] == '0') ? 0 : 1; }
   if (p.split > 1 && tma_red && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (n_cols % 4) == 0) {
     // splits accumulate straight into the gradient with TMA reduction boxes
-    if (cudaMemsetAsync(out, 0, static_cast<size_t>(out_rows) * n_cols * sizeof(float), stream) != cudaSuccess)
+    if (!out_zeroed && cudaMemsetAsync(out, 0, static_cast<size_t>(out_rows) * n_cols * sizeof(float), stream) != cudaSuccess)
       return set_error(kErrCuda, "wgrad: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
     p.out = out;
     p.tma_out = 1;

@@ -233,13 +233,13 @@ int jpdvt_train_backward_head(const jpdvt_weights* w, const jpdvt_weights_t* wt,
   const long long M = tp->rows, X = M * kHidden, n_mod = n_mod_of(depth);
   // te = W2 silu(pre) + b2, pre = W1 y + b1 (models.py:288-290)
   JP_TRY(launch_head_bwd(d_te, tp->headpre, w->w_head2, BFM(s->dpre), g->w_head2, g->b_head2, g->b_head1, M, st));
-  JP_TRY(launch_wgrad(BF(s->dpre), 64, BF(tp->yfin), kHidden, g->w_head1, s->wgrad_scratch, M, 64, kHidden, st));
+  JP_TRY(launch_wgrad(BF(s->dpre), 64, BF(tp->yfin), kHidden, g->w_head1, s->wgrad_scratch, M, 64, kHidden, st, true));
   // dy = dpre . W1 (+ the image head's gradient through unpatchify)
   JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dpre), BF(w->w_head1), BF(wt->w_head1_t), s->dxn, M, kHidden, 64, s->zeros, st));
   if (d_img != nullptr) JP_TRY(launch_unpatchify_bwd(d_img, s->dxn, batch, w->image_size, 1, st));
   JP_TRY(launch_cast_bf16(s->dxn, BFM(s->dy), X, st));
   JP_TRY(launch_colsum_f32(s->dxn, kHidden, M, kHidden, g->b_final, st));
-  JP_TRY(launch_wgrad(BF(s->dy), kHidden, BF(tp->xnf), kHidden, g->w_final, s->wgrad_scratch, M, kHidden, kHidden, st));
+  JP_TRY(launch_wgrad(BF(s->dy), kHidden, BF(tp->xnf), kHidden, g->w_final, s->wgrad_scratch, M, kHidden, kHidden, st, true));
   JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dy), BF(w->w_final), BF(wt->w_final_t), s->dxn, M, kHidden, kHidden, s->zeros, st));
   const float* mod = tp->mod + static_cast<long long>(depth) * 6 * kHidden;
   float* dmod = s->dmod + static_cast<long long>(depth) * 6 * kHidden;
@@ -278,10 +278,10 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
   // ---- MLP branch: x_out = x_mid + gate_mlp * fc2(gelu(fc1(xn2)))            (models.py:121)
   const bool fused = bwd_fused();      // then dy = gate_mlp * dx came with the LayerNorm backward of the stage before
   if (!fused) JP_TRY(launch_gate_bwd(s->dx, y2, mod + 5 * kHidden, n_mod, dy, dmod + 5 * kHidden, n_mod, g->b_fc2 + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
-  JP_TRY(launch_wgrad(dy, kHidden, h, H4, g->w_fc2 + static_cast<long long>(i) * kHidden * H4, s->wgrad_scratch, M, kHidden, static_cast<int>(H4), st));
+  JP_TRY(launch_wgrad(dy, kHidden, h, H4, g->w_fc2 + static_cast<long long>(i) * kHidden * H4, s->wgrad_scratch, M, kHidden, static_cast<int>(H4), st, true));
   JP_TRY(dgrad(EPI_DGELU_BF16, dy, BF(w->w_fc2) + static_cast<long long>(i) * kHidden * H4, BF(wt->w_fc2_t) + static_cast<long long>(i) * H4 * kHidden,
                dh, M, static_cast<int>(H4), kHidden, nullptr, st, hpre, g->b_fc1 + static_cast<long long>(i) * H4));   // + db_fc1 = column sums of dh
-  JP_TRY(launch_wgrad(dh, H4, xn2, kHidden, g->w_fc1 + static_cast<long long>(i) * H4 * kHidden, s->wgrad_scratch, M, static_cast<int>(H4), kHidden, st));
+  JP_TRY(launch_wgrad(dh, H4, xn2, kHidden, g->w_fc1 + static_cast<long long>(i) * H4 * kHidden, s->wgrad_scratch, M, static_cast<int>(H4), kHidden, st, true));
   JP_TRY(dgrad(EPI_BIAS_F32, dh, BF(w->w_fc1) + static_cast<long long>(i) * H4 * kHidden, BF(wt->w_fc1_t) + static_cast<long long>(i) * kHidden * H4,
                s->dxn, M, kHidden, static_cast<int>(H4), s->zeros, st));
   // ---- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(xn1)))     (models.py:120)
@@ -294,13 +294,13 @@ int jpdvt_train_backward_block(const jpdvt_weights* w, const jpdvt_weights_t* wt
                                   dmod + 3 * kHidden, dmod + 4 * kHidden, n_mod, nullptr, s->part, batch, T, st));
     JP_TRY(launch_gate_bwd(s->dx, y1, mod + 2 * kHidden, n_mod, dy, dmod + 2 * kHidden, n_mod, g->b_proj + static_cast<long long>(i) * kHidden, s->part, batch, T, st));
   }
-  JP_TRY(launch_wgrad(dy, kHidden, att, kHidden, g->w_proj + static_cast<long long>(i) * kHidden * kHidden, s->wgrad_scratch, M, kHidden, kHidden, st));
+  JP_TRY(launch_wgrad(dy, kHidden, att, kHidden, g->w_proj + static_cast<long long>(i) * kHidden * kHidden, s->wgrad_scratch, M, kHidden, kHidden, st, true));
   JP_TRY(dgrad(EPI_BIAS_BF16, dy, BF(w->w_proj) + static_cast<long long>(i) * kHidden * kHidden, BF(wt->w_proj_t) + static_cast<long long>(i) * kHidden * kHidden,
                datt, M, kHidden, kHidden, s->zeros, st));
   // dQ, dK, dV and (folded into the epilogue) the qkv bias gradient = column sums of dqkv
   JP_TRY(launch_attention_bwd(qkv, att, datt, tp->lse2 + static_cast<long long>(i) * batch * kHeads * T, dqkv,
                               g->b_qkv + static_cast<long long>(i) * H3, batch, T, st));
-  JP_TRY(launch_wgrad(dqkv, H3, xn1, kHidden, g->w_qkv + static_cast<long long>(i) * H3 * kHidden, s->wgrad_scratch, M, static_cast<int>(H3), kHidden, st));
+  JP_TRY(launch_wgrad(dqkv, H3, xn1, kHidden, g->w_qkv + static_cast<long long>(i) * H3 * kHidden, s->wgrad_scratch, M, static_cast<int>(H3), kHidden, st, true));
   JP_TRY(dgrad(EPI_BIAS_F32, dqkv, BF(w->w_qkv) + static_cast<long long>(i) * H3 * kHidden, BF(wt->w_qkv_t) + static_cast<long long>(i) * kHidden * H3,
                s->dxn, M, kHidden, static_cast<int>(H3), s->zeros, st));
   if (fused) {
@@ -328,7 +328,7 @@ int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt
   const long long M = tp->rows, n_mod = n_mod_of(depth);
   const long long BH = static_cast<long long>(batch) * kHidden;
   // x0 = cols . Wp^T + b_patch + b_in + pos + x_t . Win^T                      (models.py:280-281); s->dy holds bf16(dx0)
-  JP_TRY(launch_wgrad(BF(s->dy), kHidden, BF(tp->cols), kHidden, g->w_patch, s->wgrad_scratch, M, kHidden, kHidden, st));
+  JP_TRY(launch_wgrad(BF(s->dy), kHidden, BF(tp->cols), kHidden, g->w_patch, s->wgrad_scratch, M, kHidden, kHidden, st, true));
   JP_TRY(launch_colsum_f32(s->dx, kHidden, M, kHidden, g->b_patch, st));
   JP_TRY(cudaMemcpyAsync(g->b_in, g->b_patch, kHidden * sizeof(float), cudaMemcpyDeviceToDevice, st) == cudaSuccess
              ? kOk : set_error(kErrCuda, "train_backward_embed: bias copy failed"));
@@ -342,18 +342,18 @@ int jpdvt_train_backward_embed(const jpdvt_weights* w, const jpdvt_weights_t* wt
   bfm dc_bf = BFM(s->small_bf16), hid_bf = BFM(s->small_bf16) + BH, dtpre_bf = BFM(s->small_bf16) + 2 * BH, feat_bf = BFM(s->small_bf16) + 3 * BH;
   JP_TRY(launch_colsum_f32(s->dmod, n_mod, batch, static_cast<int>(n_mod), g->b_ada, st));
   JP_TRY(launch_cast_bf16(s->dmod, BFM(s->dmod_bf16), static_cast<long long>(batch) * n_mod, st));
-  JP_TRY(launch_wgrad(BF(s->dmod_bf16), n_mod, BF(tp->silu_c_bf16), kHidden, g->w_ada, s->wgrad_scratch, batch, static_cast<int>(n_mod), kHidden, st));
+  JP_TRY(launch_wgrad(BF(s->dmod_bf16), n_mod, BF(tp->silu_c_bf16), kHidden, g->w_ada, s->wgrad_scratch, batch, static_cast<int>(n_mod), kHidden, st, true));
   JP_TRY(dgrad(EPI_BIAS_F32, BF(s->dmod_bf16), BF(w->w_ada), BF(wt->w_ada_t), dsilu, batch, kHidden, static_cast<int>(n_mod), s->zeros, st));
   // c = W2 . silu(tpre) + b2 ; tpre = W0 . feat + b0                            (models.py:61-64)
   JP_TRY(launch_silu_bwd(dsilu, tp->c, dc, dc_bf, BH, st));
   JP_TRY(launch_colsum_f32(dc, kHidden, batch, kHidden, g->t_b2, st));
   JP_TRY(launch_silu_fwd_bf16(tp->tpre, hid_bf, BH, st));
-  JP_TRY(launch_wgrad(dc_bf, kHidden, hid_bf, kHidden, g->t_w2, s->wgrad_scratch, batch, kHidden, kHidden, st));
+  JP_TRY(launch_wgrad(dc_bf, kHidden, hid_bf, kHidden, g->t_w2, s->wgrad_scratch, batch, kHidden, kHidden, st, true));
   JP_TRY(gemm(EPI_BIAS_F32, dc_bf, kHidden, BF(wt->t_w2_t), kHidden, s->zeros, dhid, kHidden, batch, kHidden, kHidden, st));
   JP_TRY(launch_silu_bwd(dhid, tp->tpre, dtpre, dtpre_bf, BH, st));
   JP_TRY(launch_colsum_f32(dtpre, kHidden, batch, kHidden, g->t_b0, st));
   JP_TRY(launch_cast_bf16(tp->feat, feat_bf, static_cast<long long>(batch) * 256, st));
-  JP_TRY(launch_wgrad(dtpre_bf, kHidden, feat_bf, 256, g->t_w0, s->wgrad_scratch, batch, kHidden, 256, st));
+  JP_TRY(launch_wgrad(dtpre_bf, kHidden, feat_bf, 256, g->t_w0, s->wgrad_scratch, batch, kHidden, 256, st, true));
   return kOk;
 }
 
