@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define JPDVT_ABI_VERSION 5
+#define JPDVT_ABI_VERSION 6
 #define JPDVT_HIDDEN 768
 #define JPDVT_LATENT 8
 

@@ -80,8 +80,9 @@ class PeerStep(C.Structure):
 
 # JPDVT_ABI_VERSION in include/jpdvt_b200.h (2: LayerNorm-fold buffers, 3: per-step conditioning tables, 4: timestep-MLP
 # scratch of its own, hoisted embedding, in-kernel Philox noise, loss kernels, tcgen05 attention backward, 5: peer-memory
-# optimizer step)
-ABI_VERSION = 5
+# optimizer step, 6: device-side step count / barrier token for the graph-replayed training step - jpdvt_peer_step.epoch_dev,
+# jpdvt_adamw_ema_dev, jpdvt_adamw_ema_peer_dev)
+ABI_VERSION = 6
 
 P = c_void_p
 # name -> argument types (all return int status); kept in one table so tests can check it against the header

@@ -123,7 +123,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/jpdvt_b200.h but not exported"
     assert set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS) == declared
-    assert lib.jpdvt_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.jpdvt_abi_version() == _lib.ABI_VERSION == 6
     assert isinstance(lib.jpdvt_last_error_string(), bytes)
 
 
