@@ -204,3 +204,27 @@ def test_peer_shard_bounds_and_f32_ranges():
         off += n
     merged = peer.merge_ranges(ranges)
     assert len(merged) == 8 and sum(e - b for b, e in merged) == f32_total and off == 130747208
+
+
+def test_wgrad_split_plan_fills_whole_waves():
+    """The weight-gradient GEMMs' contraction split (csrc/gemm.cu: wgrad_plan, read back through the scratch-size query - a pure
+    host function, 148 SMs assumed without a device): the number of work items tiles x splits must land just under a whole
+    number of waves on the 74 CTA pairs, not between waves.  At the C3 shapes (M = 128 x 144 rows): fc1 / fc2 have 36 output
+    tiles -> 2 splits = 72 items (one wave; the first plan's 5 splits = 180 items = 2.43 waves left a quarter of the SM time
+    idle), qkv 27 tiles -> 8 splits = 216 items (2.92 waves), proj 9 tiles -> 8 splits = 72 items."""
+    lib = _lib.load()
+    m = 128 * 144
+    pairs = 74
+    for name, (rows, cols), want in (("qkv", (2304, 768), 8), ("proj", (768, 768), 8), ("fc1", (3072, 768), 2), ("fc2", (768, 3072), 2)):
+        floats = int(lib.jpdvt_wgrad_scratch_floats(m, rows, cols))
+        split = floats // (rows * cols) if floats else 1
+        assert split == want, (name, split)
+        tiles = ((rows + 255) // 256) * (cols // 256)
+        items = tiles * split
+        waves = -(-items // pairs)
+        assert items / (waves * pairs) > 0.95, (name, items, waves)
+    # tiny contractions (the conditioning layers: m = batch rows) never split below one 64-row block per item
+    for rows, cols in ((768, 768), (768, 256)):
+        floats = int(lib.jpdvt_wgrad_scratch_floats(128, rows, cols))
+        split = floats // (rows * cols) if floats else 1
+        assert 1 <= split <= 2
