@@ -228,3 +228,25 @@ def test_wgrad_split_plan_fills_whole_waves():
         floats = int(lib.jpdvt_wgrad_scratch_floats(128, rows, cols))
         split = floats // (rows * cols) if floats else 1
         assert 1 <= split <= 2
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints ONE JSON line with the contract's
+    keys; `cpu_baseline.kind` says which CPU implementation was timed: the unmodified reference modules from the staged
+    baseline/_ref when the snapshot carries them, the oracle port otherwise."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "puzzles/sec (3x3 @192px sampling)" and line["unit"] == "puzzles/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "image_model", "models.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and "scaled x250/2" in line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "puzzles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("JPDVT 3x3 @192px sampling") and line["config"]["batch_per_gpu"] == 256
