@@ -1322,6 +1322,276 @@ attention_tc_seq_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 324, eight softmax warps (default; JPDVT_ATTN_SEQ_WARPS=4 restores the kernel above): with 336 score columns one SM can
+// hold one chain only, and that chain is the softmax of a 336-column row per thread (two passes, ~5,000 cycles per tile).  Here
+// two threads share a row: warps 0-3 take keys [0, 176), warps 4-7 keys [176, 336) of the same 128 rows (same TMEM lane
+// quadrant: warp index mod 4), exchange the row maximum and the row sum through shared memory (one 64-thread named barrier per
+// quadrant each), and write their probabilities to tensor memory - the first half over the score columns it has itself read
+// ([0, 88)), the second half into free columns behind O ([400, 480)), because its natural place lies inside the columns the
+// first warp may still be reading.  The P V MMAs take k-steps 0..10 from the first region and 11..20 from the second.  The
+// output tile is drained by warps 0-3 as before (after the next tile's softmax).
+constexpr int kSeq8Threads = 320;                           // 8 softmax warps + TMA warp + MMA warp
+
+// columns [0, NC) of the score row at t_src: maximum over the valid ones
+template <int NC, int NV>
+__device__ __forceinline__ float row_max_tmem(uint32_t t_src) {
+  static_assert(NC % 16 == 0 && NV <= NC, "column count");
+  constexpr int kFull = NC / 32, kTail = NC % 32, kChunks = kFull + (kTail ? 1 : 0);
+  uint32_t ra[32], rb[32];
+  auto load_chunk = [&](uint32_t (&r)[32], int c) {
+    if (c < kFull) tmem_ld_32x32(t_src + c * 32, r);
+    else tmem_ld_32x16(t_src + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
+  };
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  load_chunk(ra, 0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+#pragma unroll
+    for (int j = 0; j < n; j += 8) {
+      if (c * 32 + j + 8 <= NV) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3])));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[j + 4]), __uint_as_float(cur[j + 5])));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[j + 6]), __uint_as_float(cur[j + 7])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c * 32 + j + e < NV) m0 = fmaxf(m0, __uint_as_float(cur[j + e]));
+      }
+    }
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// p = 2^(s * log2(e)/8 - ms) of columns [0, NC) at t_src as bf16 pairs into columns [0, NC / 2) at t_dst (t_dst may be t_src: the
+// pairs of chunk c land on columns the thread has already read); columns >= NV get probability 0; returns the sum
+template <int NC, int NV>
+__device__ __forceinline__ float row_exp_to_tmem(uint32_t t_src, uint32_t t_dst, float ms) {
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  constexpr int kFull = NC / 32, kTail = NC % 32, kChunks = kFull + (kTail ? 1 : 0);
+  uint32_t ra[32], rb[32];
+  auto load_chunk = [&](uint32_t (&r)[32], int c) {
+    if (c < kFull) tmem_ld_32x32(t_src + c * 32, r);
+    else tmem_ld_32x16(t_src + c * 32, reinterpret_cast<uint32_t (&)[16]>(r));
+  };
+  uint64_t sum2 = f2_pack(0.f, 0.f);
+  const uint64_t sl2p = f2_pack(sl2, sl2), nmsp = f2_pack(-ms, -ms);
+  load_chunk(ra, 0);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    if (c + 1 < kChunks) load_chunk(nxt, c + 1);
+    const int n = (c < kFull) ? 32 : kTail;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      float a, b;
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2p, nmsp), a, b);
+      float pa = ex2f(a), pb = ex2f(b);
+      if (c * 32 + 2 * j >= NV) pa = 0.f;
+      if (c * 32 + 2 * j + 1 >= NV) pb = 0.f;
+      sum2 = f2_add(sum2, f2_pack(pa, pb));
+      pk[j] = pack_bf16(pa, pb);
+    }
+    if (c < kFull) tmem_st_32x16(t_dst + c * 16, pk);
+    else tmem_st_32x8(t_dst + c * 16, pk);
+    if (c + 1 < kChunks) tmem_ld_wait();
+  }
+  tmem_st_wait();
+  float s_even, s_odd;
+  f2_unpack(sum2, s_even, s_odd);
+  return s_even + s_odd;
+}
+
+template <int TP, int TV>
+__global__ void __launch_bounds__(kSeq8Threads, 1)
+attention_seq8_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
+                      int num_units, int reverse) {
+  using Cfg = SeqCfg<TP, TV>;
+  constexpr int kTiles = Cfg::kTiles;
+  constexpr int kNA = 176, kNB = TP - kNA;                    // key split between the two warps of a row (whole 16-key steps)
+  constexpr int kColO = TP, kColPB = TP + 64;                 // O behind the scores, the second half's probabilities behind O
+  static_assert(TP == 336 && kNB % 16 == 0 && TV > kNA && kColPB + kNB / 2 <= 512, "laid out for 324 tokens padded to 336");
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;         // MMA: scores of the current tile ready   (once per tile)
+  uint64_t* p_full = bars + 3;         // softmax warps: P written, S consumed    (once per tile, 8 arrivals)
+  uint64_t* o_full = bars + 4;         // MMA: O of the current tile ready        (once per tile)
+  uint64_t* o_read = bars + 5;         // warps 0-3: O read out of TMEM           (once per tile, 4 arrivals)
+  uint64_t* qk_free = bars + 6;        // MMA: every score MMA of the unit has read Q, K
+  uint64_t* v_free = bars + 7;         // MMA: every P V MMA of the unit has read V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::kOffP);   // [2][2][128] row maximum / row sum per half (the P tile's slot is free)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_read, 4);
+    mbar_init(qk_free, 1); mbar_init(v_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tm_qkv);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV),
+                 sStage = smem_u32(smem + Cfg::kOffP) + 4096u;      // output staging behind the exchange words
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int uu = reverse ? num_units - 1 - unit : unit;
+        const int b = uu / kHeads, h = uu - b * kHeads;
+        if (it > 0) mbar_wait_backoff(qk_free, static_cast<uint32_t>((it - 1) & 1), 100);
+        mbar_expect_tx(qk_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffQ + part * Cfg::kBoxRows * 128, h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+          tma_load_2d(&tm_qkv, qk_full, smem + Cfg::kOffK + part * Cfg::kBoxRows * 128, kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+        }
+        if (it > 0) mbar_wait_backoff(v_free, static_cast<uint32_t>((it - 1) & 1), 100);
+        mbar_expect_tx(v_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+          tma_load_2d(&tm_qkv, v_full, smem + Cfg::kOffV + part * Cfg::kBoxRows * 128, 2 * kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s1 = umma_idesc_bf16(128, Cfg::kN1), idesc_s2 = umma_idesc_bf16(128, Cfg::kN2);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), v_lo = desc_lo_mn(sV);
+      int it = 0;
+      long long tile_no = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        mbar_wait(qk_full, static_cast<uint32_t>(it & 1));
+        for (int t = 0; t < kTiles; ++t, ++tile_no) {
+          const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
+          if (tile_no > 0) { mbar_wait(p_full, ph ^ 1); mbar_wait(o_full, ph ^ 1); }   // scores consumed, P read by the previous P V
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+            const uint32_t a = q_lo + t * 128 * 8 + 2 * k;
+            if (k == 0) { umma_lohi<false>(tmem_base, a, k_lo, idesc_s1); umma_lohi<false>(tmem_base + Cfg::kN1, a, k_lo + Cfg::kN1 * 8, idesc_s2); }
+            else { umma_lohi<true>(tmem_base, a, k_lo + 2 * k, idesc_s1); umma_lohi<true>(tmem_base + Cfg::kN1, a, k_lo + Cfg::kN1 * 8 + 2 * k, idesc_s2); }
+          }
+          umma_commit(s_full);
+          if (t == kTiles - 1) umma_commit(qk_free);
+          mbar_wait(p_full, ph);
+          if (t == 0) mbar_wait(v_full, static_cast<uint32_t>(it & 1));
+          if (tile_no > 0) mbar_wait(o_read, ph ^ 1);            // the previous tile's O has left TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < TP / 16; ++j) {                    // key step j: first half's pairs at [8j, 8j + 8), second half's behind O
+            const uint32_t a = (j < kNA / 16) ? tmem_base + 8 * j : tmem_base + kColPB + 8 * (j - kNA / 16);
+            if (j == 0) umma_ts_lohi<false>(tmem_base + kColO, a, v_lo + j * 128, idesc_o);
+            else umma_ts_lohi<true>(tmem_base + kColO, a, v_lo + j * 128, idesc_o);
+          }
+          umma_commit(o_full);
+          if (t == kTiles - 1) umma_commit(v_free);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3, half = warp >> 2;                // TMEM lane quadrant / which half of the keys
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int r_tile = quad * 32 + lane;
+    float* xmax = xch + half * 128 + r_tile;                    // mine; the partner's is xch[(1 - half) * 128 + r_tile]
+    float* xsum = xch + 256 + half * 128 + r_tile;
+    const float* pmax = xch + (1 - half) * 128 + r_tile;
+    const float* psum = xch + 256 + (1 - half) * 128 + r_tile;
+    long long tile_no = 0;
+    __nv_bfloat16* prev_dst = nullptr;
+    float prev_inv = 0.f;
+    int prev_live = 0;
+    auto drain = [&](uint32_t ph_prev) {                        // warps 0-3 only
+      mbar_wait(o_full, ph_prev);
+      tc_fence_after();
+      uint32_t oa[32], ob[32];
+      load_o_row(t_lane + kColO, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
+      store_o_rows(oa, ob, prev_inv, sStage + static_cast<uint32_t>(quad) * 4096u, prev_dst, prev_live, lane);
+    };
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int uu = reverse ? num_units - 1 - unit : unit;
+      const int b = uu / kHeads, h = uu - b * kHeads;
+      __nv_bfloat16* obase = out + static_cast<long long>(b) * TV * kHidden + h * kHeadDim;
+      for (int t = 0; t < kTiles; ++t, ++tile_no) {
+        const uint32_t ph = static_cast<uint32_t>(tile_no & 1);
+        mbar_wait(s_full, ph);
+        tc_fence_after();
+        const float mx = half == 0 ? row_max_tmem<kNA, kNA>(t_lane) : row_max_tmem<kNB, TV - kNA>(t_lane + kNA);
+        *xmax = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float ms = fmaxf(mx, *pmax) * sl2;
+        const float part = half == 0 ? row_exp_to_tmem<kNA, kNA>(t_lane, t_lane, ms)
+                                     : row_exp_to_tmem<kNB, TV - kNA>(t_lane + kNA, t_lane + kColPB, ms);
+        *xsum = part;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if (half == 0) {
+          const float sum = part + *psum;
+          const int row = t * 128 + r_tile;
+          if (lse2 != nullptr && row < TV) lse2[(static_cast<long long>(b) * kHeads + h) * TV + row] = ms + log2f(sum);
+          if (tile_no > 0) drain(ph ^ 1);
+          const int live = TV - (t * 128 + quad * 32);
+          prev_dst = obase + static_cast<long long>(t * 128 + quad * 32) * kHidden;
+          prev_inv = 1.0f / sum;
+          prev_live = live < 0 ? 0 : (live < 32 ? live : 32);
+        }
+      }
+    }
+    if (half == 0 && tile_no > 0) drain(static_cast<uint32_t>((tile_no - 1) & 1));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int TP, int TV>
+int launch_seq8(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
+  using Cfg = SeqCfg<TP, TV>;
+  static bool configured = false;
+  auto kern = attention_seq8_kernel<TP, TV>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_seq8: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    configured = true;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_kmajor(&tm, qkv, static_cast<long long>(batch) * TV, kQkvCols, kQkvCols, Cfg::kBoxRows);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int units = batch * kHeads;
+  kern<<<units < sms ? units : sms, kSeq8Threads, Cfg::kSmemBytes, stream>>>(tm, out, lse2, units, sweep_reverse());
+  return check_launch("attention_seq8_kernel");
+}
+
 template <int TP, int TV>
 int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = SeqCfg<TP, TV>;
@@ -2267,7 +2537,11 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
       if (qt < 0) { const char* e = getenv("JPDVT_ATTN_QT"); qt = (e != nullptr && e[0] == '0') ? 0 : 1; }
       return qt ? launch_qt<256>(qkv, out, lse2, batch, stream) : launch_tc<256>(qkv, out, lse2, batch, stream);
     }
-    case 324: return launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
+    case 324: {
+      static int w8 = -1;           // JPDVT_ATTN_SEQ_WARPS=8: two threads per score row (attention_seq8_kernel); default: four softmax warps
+      if (w8 < 0) { const char* e = getenv("JPDVT_ATTN_SEQ_WARPS"); w8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
+      return w8 ? launch_seq8<336, 324>(qkv, out, lse2, batch, stream) : launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
+    }
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
   }
 }
