@@ -10,7 +10,8 @@
 //                                      16-row remainder on one warp's mma.sync; attention_tc_kernel<144> / attention_hm_kernel /
 //                                      attention_tc8_kernel are the earlier forms, kept as A/B opt-ins (JPDVT_ATTN_REM, JPDVT_ATTN_WARPS)
 //   T = 256 : attention_qt_kernel    - work item = (unit, 128-query tile), P in TMEM, two CTAs per SM (attention_tc_kernel<256>: opt-in)
-//   T = 324 : attention_tc_seq_kernel - keys padded to 336, one score tile at a time, P in TMEM
+//   T = 324 : attention_ks_kernel    - work item = (unit, 128-query tile), keys in two blocks with the online-softmax rescale of O in
+//                                      TMEM, two CTAs per SM (attention_tc_seq_kernel / attention_seq8_kernel: the earlier forms, opt-in)
 // The description below is the first tcgen05 form (attention_tc_kernel), whose building blocks the others share.
 //
 // One CTA works on one (sample, head) unit at a time, several units per CTA (persistent grid):
@@ -1592,6 +1593,229 @@ int launch_seq8(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int b
   return check_launch("attention_seq8_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// T = 324, key-split form (default; JPDVT_ATTN_SEQ_SPLIT=0 restores the sequential-tile kernel): two chains per SM for the size whose score row (336 columns) does not
+// fit a 256-column CTA.  Work item = (unit, 128-query tile); the keys go through in two blocks - [0, 176) and [176, 336) - with
+// the online-softmax rule between them: block 0 gives m0, P0 = 2^(S0 - m0), O = P0 V0; block 1 gives m1 = max(m0, rowmax S1),
+// P1 = 2^(S1 - m1), and the accumulator is rescaled by a = 2^(m0 - m1) IN tensor memory (tcgen05.ld, scale, tcgen05.st - one
+// 64-column round trip per row) before O += P1 V1; the row sum follows l = a l0 + l1.  TMEM per CTA: scores / probabilities of
+// the current block in columns [0, 176), O in [176, 240); shared memory: Q tile 16 KB + K 42 KB + V 42 KB (the output staging
+// tile re-uses V once the second P V has read it) - two CTAs per SM.  Every per-block barrier completes exactly twice per item,
+// so block 0 always waits on parity 0 and block 1 on parity 1.
+struct KsCfg {
+  static constexpr int TV = 324, TP = 336, kNA = 176, kNB = TP - kNA, kVB = TV - kNA;     // valid keys of block 1
+  static constexpr int kQBytes = 128 * 128, kKvBytes = TP * 128, kBoxRows = TP / 2;
+  static constexpr int kOffQ = 0, kOffK = kQBytes, kOffV = kQBytes + kKvBytes;
+  static constexpr int kBarOff = kOffV + kKvBytes;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kColO = kNA;
+  static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kNA % 16 == 0 && kNB % 16 == 0 && kColO + kHeadDim <= 256, "layout");
+  static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
+};
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+attention_ks_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int num_items, int reverse) {
+  using Cfg = KsCfg;
+  constexpr int TV = Cfg::TV, kQt = 3;
+  constexpr float sl2 = 0.125f * 1.4426950408889634f;
+  extern __shared__ uint8_t att_tc_smem[];
+  uint8_t* smem = att_tc_smem + ((1024u - (smem_u32(att_tc_smem) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* qk_full = bars + 0;        // TMA: Q tile and K landed                              (once per item)
+  uint64_t* v_full = bars + 1;         // TMA: V landed                                         (once per item)
+  uint64_t* s_full = bars + 2;         // MMA: scores of the current key block are in TMEM      (twice per item)
+  uint64_t* p_full = bars + 3;         // softmax warps: P of the block written (block 1: O rescaled too), 4 arrivals (twice per item)
+  uint64_t* o_full = bars + 4;         // MMA: the block's P V MMAs are done                    (twice per item)
+  uint64_t* o_read = bars + 5;         // softmax warps: O has left TMEM, 4 arrivals            (once per item)
+  uint64_t* qk_free = bars + 6;        // MMA: both score blocks have read Q, K                 (once per item)
+  uint64_t* v_free = bars + 7;         // MMA: both P V blocks have read V                      (once per item)
+  uint64_t* stage_free = bars + 8;     // softmax warps: the staging tile inside V is done, 4 arrivals (once per item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(o_read, 4); mbar_init(qk_free, 1); mbar_init(v_free, 1); mbar_init(stage_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+  const uint32_t sQ = smem_u32(smem + Cfg::kOffQ), sK = smem_u32(smem + Cfg::kOffK), sV = smem_u32(smem + Cfg::kOffV);
+  auto item_bhq = [&](int item, int& b, int& h, int& qt) {
+    const int ii = reverse ? num_items - 1 - item : item;
+    const int uu = ii / kQt;
+    qt = ii - uu * kQt;
+    b = uu / kHeads; h = uu - b * kHeads;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int b, h, qt;
+        item_bhq(item, b, h, qt);
+        const uint32_t prev = static_cast<uint32_t>((it - 1) & 1);
+        if (it > 0) mbar_wait(qk_free, prev);
+        mbar_expect_tx(qk_full, Cfg::kQBytes + Cfg::kKvBytes);
+        tma_load_2d(&tm_q, qk_full, smem + Cfg::kOffQ, h * kHeadDim, b * TV + qt * 128);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+          tma_load_2d(&tm_kv, qk_full, smem + Cfg::kOffK + part * Cfg::kBoxRows * 128, kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+        if (it > 0) { mbar_wait(v_free, prev); mbar_wait(stage_free, prev); }
+        mbar_expect_tx(v_full, Cfg::kKvBytes);
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+          tma_load_2d(&tm_kv, v_full, smem + Cfg::kOffV + part * Cfg::kBoxRows * 128, 2 * kHidden + h * kHeadDim, b * TV + part * Cfg::kBoxRows);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s0 = umma_idesc_bf16(128, Cfg::kNA), idesc_s1 = umma_idesc_bf16(128, Cfg::kNB);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim, 0, 1);
+      const uint32_t q_lo = desc_lo_k(sQ), k_lo = desc_lo_k(sK), v_lo = desc_lo_mn(sV);
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it & 1);
+        mbar_wait(qk_full, ph);
+        if (it > 0) mbar_wait(o_full, 1);                       // the previous item's second P V has read its probabilities
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {                 // block 0: keys [0, 176)
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo, idesc_s0);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + 2 * k, idesc_s0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, 0);
+        mbar_wait(v_full, ph);
+        if (it > 0) mbar_wait(o_read, static_cast<uint32_t>((it - 1) & 1));   // the previous item's O has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < Cfg::kNA / 16; ++j) {
+          if (j == 0) umma_ts_lohi<false>(tmem_base + Cfg::kColO, tmem_base + 8 * j, v_lo + j * 128, idesc_o);
+          else umma_ts_lohi<true>(tmem_base + Cfg::kColO, tmem_base + 8 * j, v_lo + j * 128, idesc_o);
+        }
+        umma_commit(o_full);
+        mbar_wait(o_full, 0);                                   // P0 has been read: the second score block may overwrite it
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {                 // block 1: keys [176, 336)
+          if (k == 0) umma_lohi<false>(tmem_base, q_lo, k_lo + Cfg::kNA * 8, idesc_s1);
+          else umma_lohi<true>(tmem_base, q_lo + 2 * k, k_lo + Cfg::kNA * 8 + 2 * k, idesc_s1);
+        }
+        umma_commit(s_full);
+        umma_commit(qk_free);
+        mbar_wait(p_full, 1);                                   // P1 written and O rescaled
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < Cfg::kNB / 16; ++j)
+          umma_ts_lohi<true>(tmem_base + Cfg::kColO, tmem_base + 8 * j, v_lo + (Cfg::kNA / 16 + j) * 128, idesc_o);
+        umma_commit(o_full);
+        umma_commit(v_free);
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r_tile = warp * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t ph = static_cast<uint32_t>(it & 1);
+      int b, h, qt;
+      item_bhq(item, b, h, qt);
+      // ---- block 0
+      mbar_wait(s_full, 0);
+      tc_fence_after();
+      const float ms0 = row_max_tmem<Cfg::kNA, Cfg::kNA>(t_lane) * sl2;
+      const float l0 = row_exp_to_tmem<Cfg::kNA, Cfg::kNA>(t_lane, t_lane, ms0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- block 1
+      mbar_wait(s_full, 1);
+      tc_fence_after();
+      const float ms1 = fmaxf(ms0, row_max_tmem<Cfg::kNB, Cfg::kVB>(t_lane) * sl2);
+      const float alpha = ex2f(ms0 - ms1);
+      const float l1 = row_exp_to_tmem<Cfg::kNB, Cfg::kVB>(t_lane, t_lane, ms1);
+      const float lsum = fmaf(l0, alpha, l1);
+      if (!__all_sync(0xffffffffu, alpha == 1.0f)) {            // rescale the accumulator of block 0 (its P V is done: the second
+        uint32_t oa[32], ob[32];                                //  score block is only issued behind it)
+        load_o_row(t_lane + Cfg::kColO, oa, ob);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          oa[j] = __float_as_uint(__uint_as_float(oa[j]) * alpha);
+          ob[j] = __float_as_uint(__uint_as_float(ob[j]) * alpha);
+        }
+        tmem_st_32x16(t_lane + Cfg::kColO, reinterpret_cast<const uint32_t (&)[16]>(oa[0]));
+        tmem_st_32x16(t_lane + Cfg::kColO + 16, reinterpret_cast<const uint32_t (&)[16]>(oa[16]));
+        tmem_st_32x16(t_lane + Cfg::kColO + 32, reinterpret_cast<const uint32_t (&)[16]>(ob[0]));
+        tmem_st_32x16(t_lane + Cfg::kColO + 48, reinterpret_cast<const uint32_t (&)[16]>(ob[16]));
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      const int row = qt * 128 + r_tile;
+      if (lse2 != nullptr && row < TV) lse2[(static_cast<long long>(b) * kHeads + h) * TV + row] = ms1 + log2f(lsum);
+      // ---- output
+      uint32_t oa[32], ob[32];
+      mbar_wait(o_full, 1);
+      tc_fence_after();
+      load_o_row(t_lane + Cfg::kColO, oa, ob);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
+      const int live = TV - (qt * 128 + warp * 32);
+      store_o_rows(oa, ob, 1.0f / lsum, sV + static_cast<uint32_t>(warp) * 4096u,
+                   out + (static_cast<long long>(b) * TV + qt * 128 + warp * 32) * kHidden + h * kHeadDim,
+                   live < 0 ? 0 : (live < 32 ? live : 32), lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_free);
+      (void)ph;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_ks(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
+  using Cfg = KsCfg;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return set_error(kErrCuda, "attention_ks: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(cudaGetLastError()));
+    cudaFuncSetAttribute(attention_ks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  CUtensorMap tq, tkv;
+  const long long rows = static_cast<long long>(batch) * Cfg::TV;
+  int rc = make_tmap_bf16_kmajor(&tq, qkv, rows, kQkvCols, kQkvCols, 128);
+  if (rc != kOk) return rc;
+  rc = make_tmap_bf16_kmajor(&tkv, qkv, rows, kQkvCols, kQkvCols, Cfg::kBoxRows);
+  if (rc != kOk) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = batch * kHeads * 3;
+  const int slots = sms * 2;
+  const int grid = items < slots ? items : slots;
+  if (launch_pdl(attention_ks_kernel, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, stream, tq, tkv, out, lse2, items, sweep_reverse()) != cudaSuccess)
+    return set_error(kErrCuda, "attention_ks_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return check_launch("attention_ks_kernel");
+}
+
 template <int TP, int TV>
 int launch_tc_seq(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse2, int batch, cudaStream_t stream) {
   using Cfg = SeqCfg<TP, TV>;
@@ -2540,6 +2764,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* lse
     case 324: {
       static int w8 = -1;           // JPDVT_ATTN_SEQ_WARPS=8: two threads per score row (attention_seq8_kernel); default: four softmax warps
       if (w8 < 0) { const char* e = getenv("JPDVT_ATTN_SEQ_WARPS"); w8 = (e != nullptr && e[0] == '8') ? 1 : 0; }
+      static int ks = -1;           // default: key-split form, two chains per SM (attention_ks_kernel, 96.6 us at B = 128);
+                                    // JPDVT_ATTN_SEQ_SPLIT=0: the sequential-tile kernel (121.5 us)
+      if (ks < 0) { const char* e = getenv("JPDVT_ATTN_SEQ_SPLIT"); ks = (e != nullptr && e[0] == '0') ? 0 : 1; }
+      if (ks) return launch_ks(qkv, out, lse2, batch, stream);
       return w8 ? launch_seq8<336, 324>(qkv, out, lse2, batch, stream) : launch_tc_seq<336, 324>(qkv, out, lse2, batch, stream);
     }
     default: return set_error(kErrUnsupported, "attention_tc: %d tokens not instantiated", tokens);
